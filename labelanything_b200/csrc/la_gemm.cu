@@ -1,0 +1,297 @@
+// labelanything_b200 — tcgen05 GEMM with fused bias / activation epilogue (sm_100a).
+//
+//   out[M, N] = act( A[M, K] @ W[N, K]^T + bias[N] )          A, W bf16 (K contiguous); fp32 accumulate
+//
+// This is the one dense-contraction kernel behind every nn.Linear / 1x1 conv / (im2col'd) conv /
+// stride==kernel ConvTranspose on the hot path:
+//   reference call sites: label_anything/models/image_encoder.py:227-228,242,253 (qkv / proj),
+//   common.py:28-37 (MLPBlock), common.py:82-85,108-110,146 (Attention projections),
+//   build_lam.py:150-171 (neck), mask_decoder.py:206-255 (upscaling / spatial convs).
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0   : TMA producer   — A and W tiles (128B-swizzled boxes) into a STAGES-deep smem ring
+//   warp 1   : MMA issuer     — one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into TMEM
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue       — tcgen05.ld -> bias/activation -> swizzled smem staging -> TMA store
+// The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
+// the mainloop of tile i+1.
+#include "la_common.cuh"
+#include "../../include/labelanything_b200.h"
+
+namespace la {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int EPI_WARP_BYTES = 2 * 4096;  // two 32-row x 128-byte staging buffers per epilogue warp
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+};
+
+template <int BLOCK_N, typename OutT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                         const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N,
+                         int K, int act) {
+  using S = GemmSmem<BLOCK_N>;
+  constexpr int CHUNK = 128 / (int)sizeof(OutT);  // output columns per staging row (128 bytes)
+  constexpr int NCHUNK = BLOCK_N / CHUNK;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + S::STAGES * S::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + S::EPI_BYTES);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full = empty_bar + S::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_blks = (N + BLOCK_N - 1) / BLOCK_N;
+  const int m_blks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int num_tiles = n_blks * m_blks;
+  const int k_blks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_blks) * GEMM_BLOCK_M;
+        const int n0 = (tile % n_blks) * BLOCK_N;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + S::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          tma_load_2d(a_dst, &tm_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+          tma_load_2d(b_dst, &tm_w, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < k_blks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t b_base = a_base + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+            const uint64_t a_desc = umma_smem_desc_sw128(a_base + k * GEMM_UMMA_K * 2);
+            const uint64_t b_desc = umma_smem_desc_sw128(b_base + k * GEMM_UMMA_K * 2);
+            umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------- epilogue -----------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* my_stage = epi_smem + q * S::EPI_WARP_BYTES;
+    int it = 0;
+    uint32_t chunk_ctr = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / n_blks) * GEMM_BLOCK_M;
+      const int n0 = (tile % n_blks) * BLOCK_N;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
+        const int col0 = c * CHUNK;
+        float v[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK / 32; ++j) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + col0 + j * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[j * 32 + i] = __uint_as_float(r[i]);
+        }
+        if (c == NCHUNK - 1) {
+          // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < CHUNK; i += 4) {
+            const int col = n0 + col0 + i;
+            if (col + 3 < N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+              v[i] += b.x;
+              v[i + 1] += b.y;
+              v[i + 2] += b.z;
+              v[i + 3] += b.w;
+            }
+          }
+        }
+        if (act == LA_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i) v[i] = gelu_erf(v[i]);
+        } else if (act == LA_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        // staging buffer (double-buffered): make sure the TMA store issued two chunks ago has read it
+        uint8_t* buf = my_stage + (chunk_ctr & 1) * 4096;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* row_ptr = buf + lane * 128;
+        if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            uint4 pk;
+            pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+            pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+            pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+            pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(row_ptr + ((g ^ (lane & 7)) << 4)) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 pk = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            *reinterpret_cast<float4*>(row_ptr + ((g ^ (lane & 7)) << 4)) = pk;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_out, buf, n0 + col0, m0 + q * 32);
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, S::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, typename OutT>
+static int launch_gemm(cudaStream_t stream, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
+                       const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int act) {
+  using S = GemmSmem<BLOCK_N>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT>;
+  LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  const int n_blks = (N + BLOCK_N - 1) / BLOCK_N;
+  const int m_blks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int tiles = n_blks * m_blks;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tm_a, tm_w, tm_out, bias, M, N, K, act);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+}  // namespace la
+
+extern "C" int la_gemm_bf16(void* stream, const void* a, long long lda, const void* w, long long ldw,
+                            const float* bias, void* out, long long ldo, int out_dtype, int M, int N, int K,
+                            int act) {
+  using namespace la;
+  LA_CHECK_ARG(a && w && out, "la_gemm_bf16: null pointer");
+  LA_CHECK_ARG(M > 0 && N > 0 && K > 0, "la_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  LA_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "la_gemm_bf16: K/lda/ldw must be multiples of 8");
+  LA_CHECK_ARG(N % 8 == 0, "la_gemm_bf16: N must be a multiple of 8 (got %d)", N);
+  LA_CHECK_ARG(out_dtype == LA_DTYPE_BF16 || out_dtype == LA_DTYPE_F32, "la_gemm_bf16: bad out_dtype %d", out_dtype);
+  LA_CHECK_ARG((ldo * (out_dtype == LA_DTYPE_BF16 ? 2 : 4)) % 16 == 0, "la_gemm_bf16: ldo must give 16B rows");
+  LA_CHECK_ARG((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) %
+                       16 ==
+                   0,
+               "la_gemm_bf16: pointers must be 16-byte aligned");
+  LA_CHECK_ARG(act >= LA_ACT_NONE && act <= LA_ACT_RELU, "la_gemm_bf16: bad act %d", act);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const int block_n = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+  CUtensorMap tm_a, tm_w, tm_out;
+  int rc = make_tensor_map_2d(&tm_a, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)M,
+                              (uint64_t)lda * 2, GEMM_BLOCK_K, GEMM_BLOCK_M, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_w, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2,
+                          GEMM_BLOCK_K, (uint32_t)block_n, Swizzle::B128);
+  if (rc) return rc;
+  if (out_dtype == LA_DTYPE_BF16) {
+    rc = make_tensor_map_2d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)N, (uint64_t)M,
+                            (uint64_t)ldo * 2, 64, 32, Swizzle::B128);
+    if (rc) return rc;
+    if (block_n == 256) return launch_gemm<256, __nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+    if (block_n == 128) return launch_gemm<128, __nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+    return launch_gemm<64, __nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+  } else {
+    rc = make_tensor_map_2d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)N, (uint64_t)M,
+                            (uint64_t)ldo * 4, 32, 32, Swizzle::B128);
+    if (rc) return rc;
+    if (block_n == 256) return launch_gemm<256, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+    if (block_n == 128) return launch_gemm<128, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+    return launch_gemm<64, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+  }
+}
