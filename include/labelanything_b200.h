@@ -50,6 +50,50 @@ int la_device_check(void); /* LA_OK iff the current device is sm_100 */
 int la_gemm_bf16(void* stream, const void* a, long long lda, const void* w, long long ldw, const float* bias,
                  void* out, long long ldo, int out_dtype, int M, int N, int K, int act);
 
+/* ---- fused attention ----------------------------------------------------------------------------- */
+/* Multi-head self-attention, head_dim 64, over n_seq sequences of seq_len tokens stored as consecutive rows
+ * of the packed projection matrix `qkv` [rows_total, ld_qkv] (bf16).  Head h reads q/k/v at columns
+ * {q,k,v}_off + 64*h.  softmax(scale * q k^T + bias) v -> out [.., ld_out] bf16 at columns 64*h.
+ * Optional decomposed relative-position bias (bias_h/bias_w != NULL): fp32 tables [n_heads][rows_total][ldb]
+ * with table[h][row][grid_hw-1 - q_pos + k_pos] = q_row(h) . rel_pos[q_pos - k_pos + grid_hw-1], i.e. the
+ * product of the head's q rows with the REVERSED rel_pos table (computed with la_gemm_bf16); grid_hw = 64
+ * (global blocks, seq_len 4096) or 14 (windowed blocks, seq_len 196).
+ * out_mode 0: out row = sequence*seq_len + token.  out_mode 1: window un-partition — sequence = image*nwin^2
+ * + window, token (ty,tx) of window (wy,wx) goes to image row (wy*14+ty)*img_hw + wx*14+tx, padded
+ * positions are dropped.
+ *   label_anything/models/image_encoder.py:239-255,282-304,340-376; transformers modeling_vit.py:199-250 */
+int la_attention_bf16(void* stream, const void* qkv, long long ld_qkv, long long rows_total, int q_off, int k_off,
+                      int v_off, int n_seq, int seq_len, int n_heads, float scale, const float* bias_h,
+                      const float* bias_w, int ldb, int grid_hw, void* out, long long ld_out, int out_mode,
+                      int nwin, int img_hw);
+
+/* ---- streaming row kernels ----------------------------------------------------------------------- */
+/* x = x_in[(row % x_mod) if x_mod > 0 else row] + delta[row]  (fp32 + bf16); optionally stored to x_out (may
+ * alias x_in); y = LayerNorm(x) * gamma + beta (biased variance, `eps`), or a plain cast when gamma == NULL;
+ * y stored as bf16 / fp32 (y_dtype) with a row remapping:
+ *   map_mode 0: identity.
+ *   map_mode 1: `rows` counts OUTPUT rows in window-partitioned order (image, wy, wx, ty, tx) for win x win
+ *               windows, nwin per side, over an hw x hw grid; rows that fall in the zero padding are written
+ *               as zeros (F.pad happens after norm1).  image_encoder.py:183-187,258-279
+ *   map_mode 2: drop token 0 (CLS) of every seq_len-token sequence.  build_encoder.py:98
+ *   image_encoder.py:181-197; common.py:42-54; transformers modeling_vit.py:325-346,416 */
+int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const void* delta, float* x_out,
+                     const float* gamma, const float* beta, float eps, void* y_out, int y_dtype, long long rows,
+                     int d, int map_mode, int seq_len, int win, int nwin, int hw);
+
+/* x[img, tok, :] = (tok < n_cls ? cls : patch[img, tok - n_cls, :]) + pos[tok, :]; patch bf16, x fp32.
+ *   image_encoder.py:112-114; transformers modeling_vit.py:109-125 */
+int la_embed_tokens(void* stream, const void* patch, const float* cls, const float* pos, float* x, long long n_img,
+                    int tokens_per_img, int n_cls, int d);
+
+/* images [n_img, channels, size, size] fp32 (NCHW) -> [n_img*(size/16)^2, channels*256] bf16 patch rows,
+ * column = c*256 + ky*16 + kx (matches Conv2d weight.flatten(1)).  image_encoder.py:402-410 */
+int la_im2col_patch16(void* stream, const float* images, void* out, long long n_img, int channels, int size);
+
+/* token-major bf16 map [n_img, height, width, channels] -> [n_img*height*width, 9*channels] bf16 rows,
+ * column = (ky*3+kx)*channels + c, zero padding 1.  build_lam.py:162-168; mask_decoder.py:241-247 */
+int la_im2col_3x3(void* stream, const void* in, void* out, long long n_img, int height, int width, int channels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,504 @@
+// labelanything_b200 — fused multi-head self-attention (QK^T -> [+ decomposed rel-pos bias] -> softmax -> PV)
+// on tcgen05 tensor cores, head_dim = 64 (sm_100a).
+//
+// Replaces the materialised attention of the reference's ViT blocks:
+//   label_anything/models/image_encoder.py:239-255 (Attention.forward), 340-376 (add_decomposed_rel_pos),
+//   258-304 (window partition / unpartition — folded into the output row mapping), and the HF ViT
+//   self-attention used by the MAE encoders (transformers/models/vit/modeling_vit.py:199-250).
+//
+// One CTA owns 256 consecutive query rows of one (sequence, head): two 128-row Q tiles ("A", "B") that
+// ping-pong on the tensor core while their softmax warpgroups run on the CUDA cores (FlashAttention-style
+// online softmax, accumulator O kept in TMEM and rescaled only when the running max grows by > 2^8).
+//   warp 0      : TMA producer (Q once; K and V tiles through two independent smem rings)
+//   warp 1      : MMA issuer   (S = Q K^T into TMEM;  O += P V with P staged in smem, V as MN-major operand)
+//   warp 2      : TMEM allocator
+//   warps 4-7   : softmax + epilogue for Q tile A     warps 8-11: same for Q tile B
+// The decomposed relative-position bias  rel_h[q, kh] + rel_w[q, kw]  is read from fp32 tables produced
+// by la_gemm_bf16 (q_head @ reversed_table^T), already shifted so that entry (gh-1 - qh + kh) is the bias
+// of key row kh for a query in grid row qh.
+#include "la_common.cuh"
+
+namespace la {
+
+constexpr int ATT_THREADS = 384;
+constexpr int ATT_D = 64;
+constexpr int ATT_KV_STAGES = 3;
+
+enum AttBias : int { ATT_BIAS_NONE = 0, ATT_BIAS_GLOBAL64 = 1, ATT_BIAS_WINDOW14 = 2 };
+
+struct AttParams {
+  int n_seq, seq_len, n_heads;
+  int q_off, k_off, v_off;  // column (element) offsets of head 0 inside a qkv row
+  long long rows_total;     // rows in the qkv matrix
+  float scale_log2;         // softmax scale * log2(e)
+  // rel-pos bias tables: [n_heads][rows_total][ldb] fp32 (nullptr for ATT_BIAS_NONE)
+  const float* bias_h;
+  const float* bias_w;
+  int ldb;
+  // output
+  __nv_bfloat16* out;
+  long long ld_out;
+  int out_mode;  // 0: row = seq*seq_len + t ; 1: window unpartition
+  int win, nwin, img_hw;  // out_mode 1: window size, windows per side, un-padded grid side
+};
+
+template <int KV_TILE>
+struct AttSmem {
+  static constexpr int Q_BYTES = 2 * 128 * 128;             // two Q tiles, 128 rows x 128 B
+  static constexpr int KV_BYTES = KV_TILE * 128;            // one K or V tile
+  static constexpr int KV_SLOT = ((KV_BYTES + 1023) / 1024) * 1024;
+  static constexpr int P_BYTES = 2 * 16384;                 // per Q tile: two K-blocks of 128 rows x 128 B
+  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_V = OFF_K + ATT_KV_STAGES * KV_SLOT;
+  static constexpr int OFF_P = OFF_V + ATT_KV_STAGES * KV_SLOT;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <int KV_TILE, int BIAS>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                     const AttParams p) {
+  using S = AttSmem<KV_TILE>;
+  constexpr int GW = BIAS == ATT_BIAS_GLOBAL64 ? 64 : (BIAS == ATT_BIAS_WINDOW14 ? 14 : 1);
+  constexpr int NCH = (KV_TILE + 31) / 32;  // 32-column chunks per S row (last one may be 16 wide)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* bar_q = bars;                          // 1
+  uint64_t* full_k = bars + 1;                     // ATT_KV_STAGES
+  uint64_t* empty_k = full_k + ATT_KV_STAGES;
+  uint64_t* full_v = empty_k + ATT_KV_STAGES;
+  uint64_t* empty_v = full_v + ATT_KV_STAGES;
+  uint64_t* bar_s = empty_v + ATT_KV_STAGES;       // 2
+  uint64_t* bar_p = bar_s + 2;                     // 2
+  uint64_t* bar_o = bar_p + 2;                     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qpair = blockIdx.x;
+  const int head = blockIdx.y;
+  const int seq = blockIdx.z;
+  const int NT = (p.seq_len + KV_TILE - 1) / KV_TILE;
+  const long long seq_row0 = static_cast<long long>(seq) * p.seq_len;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < ATT_KV_STAGES; ++s) {
+      mbar_init(&full_k[s], 1);
+      mbar_init(&empty_k[s], 1);
+      mbar_init(&full_v[s], 1);
+      mbar_init(&empty_v[s], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&bar_s[x], 1);
+      mbar_init(&bar_p[x], 128);
+      mbar_init(&bar_o[x], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+  const uint32_t TM_S = 0, TM_O = 256;
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ------------------------------------
+    if (lane == 0) {
+      const int q_row = static_cast<int>(seq_row0) + qpair * 256;
+      mbar_arrive_expect_tx(bar_q, S::Q_BYTES);
+      tma_load_2d(smem, &tm_q, bar_q, p.q_off + head * ATT_D, q_row);
+      tma_load_2d(smem + 16384, &tm_q, bar_q, p.q_off + head * ATT_D, q_row + 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < NT; ++j) {
+        const int kv_row = static_cast<int>(seq_row0) + j * KV_TILE;
+        mbar_wait(&empty_k[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_k[stage], S::KV_BYTES);
+        tma_load_2d(smem + S::OFF_K + stage * S::KV_SLOT, &tm_kv, &full_k[stage], p.k_off + head * ATT_D, kv_row);
+        mbar_wait(&empty_v[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_v[stage], S::KV_BYTES);
+        tma_load_2d(smem + S::OFF_V + stage * S::KV_SLOT, &tm_kv, &full_v[stage], p.v_off + head * ATT_D, kv_row);
+        if (++stage == ATT_KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer --------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, KV_TILE, 0, 0);  // S = Q K^T   (both K-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (V is MN-major)
+      const uint32_t q_base = smem_u32(smem);
+      const uint32_t p_base = smem_u32(smem + S::OFF_P);
+
+      auto issue_s = [&](int x, int kstage) {
+        const uint32_t k_base = smem_u32(smem + S::OFF_K + kstage * S::KV_SLOT);
+#pragma unroll
+        for (int ks = 0; ks < ATT_D / 16; ++ks) {
+          umma_bf16_ss(tmem_base + TM_S + x * 128, umma_smem_desc_sw128(q_base + x * 16384 + ks * 32),
+                       umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int x, int vstage, bool acc) {
+        const uint32_t v_base = smem_u32(smem + S::OFF_V + vstage * S::KV_SLOT);
+#pragma unroll
+        for (int ks = 0; ks < KV_TILE / 16; ++ks) {
+          const uint32_t a_addr = p_base + x * S::P_BYTES + (ks >> 2) * 16384 + (ks & 3) * 32;
+          umma_bf16_ss(tmem_base + TM_O + x * 64, umma_smem_desc_sw128(a_addr),
+                       umma_smem_desc_sw128(v_base + ks * 2048), idesc_o, (acc || ks > 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(bar_q, 0);
+      mbar_wait(&full_k[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      umma_commit(&bar_s[0]);
+      issue_s(1, 0);
+      umma_commit(&bar_s[1]);
+      umma_commit(&empty_k[0]);
+
+      int kstage = 0, vstage = 0;
+      uint32_t kphase = 0, vphase = 0;
+      for (int j = 0; j < NT; ++j) {
+        int kstage_next = kstage + 1;
+        uint32_t kphase_next = kphase;
+        if (kstage_next == ATT_KV_STAGES) {
+          kstage_next = 0;
+          kphase_next ^= 1;
+        }
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(&bar_p[x], j & 1);
+          if (x == 0) mbar_wait(&full_v[vstage], vphase);
+          tc_fence_after();
+          issue_pv(x, vstage, j > 0);
+          if (x == 1) umma_commit(&empty_v[vstage]);
+          if (j + 1 < NT) {
+            if (x == 0) {
+              mbar_wait(&full_k[kstage_next], kphase_next);
+              tc_fence_after();
+            }
+            issue_s(x, kstage_next);
+            umma_commit(&bar_s[x]);
+            if (x == 1) umma_commit(&empty_k[kstage_next]);
+          } else {
+            umma_commit(&bar_o[x]);
+          }
+        }
+        kstage = kstage_next;
+        kphase = kphase_next;
+        if (++vstage == ATT_KV_STAGES) {
+          vstage = 0;
+          vphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------ softmax + epilogue ------------------------------
+    const int x = (warp - 4) >> 2;     // Q tile: 0 = A, 1 = B
+    const int quarter = warp & 3;      // TMEM lane quarter
+    const int r = quarter * 32 + lane;  // row inside the Q tile
+    const int t = qpair * 256 + x * 128 + r;  // token index inside the sequence
+    const bool row_valid = t < p.seq_len;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + TM_S + x * 128;
+    const uint32_t t_o = tmem_base + lane_addr + TM_O + x * 64;
+    uint8_t* p_row = smem + S::OFF_P + x * S::P_BYTES + r * 128;
+    const float sl2 = p.scale_log2;
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    // ---- rel-pos bias prologue: per-row tables in registers (already in log2 units) ----
+    float rw2[GW];
+    float rh2w[BIAS == ATT_BIAS_WINDOW14 ? 16 : 1];
+    const float* bh_row = nullptr;
+    if constexpr (BIAS != ATT_BIAS_NONE) {
+      const int tt = row_valid ? t : 0;
+      const int qh = tt / GW, qw = tt % GW;
+      const long long brow = (static_cast<long long>(head) * p.rows_total + seq_row0 + tt) * p.ldb;
+      const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
+      bh_row = p.bias_h + brow + (GW - 1 - qh);
+#pragma unroll
+      for (int i = 0; i < GW; ++i) rw2[i] = __ldg(bw_row + i) * LOG2E;
+      if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rh2w[i] = i < 14 ? __ldg(bh_row + i) * LOG2E : 0.0f;
+      }
+    } else {
+      rw2[0] = 0.0f;
+      rh2w[0] = 0.0f;
+    }
+
+    float m_used = -INFINITY;
+    float l_sum = 0.0f;
+
+    for (int j = 0; j < NT; ++j) {
+      const int valid = p.seq_len - j * KV_TILE;  // keys of this tile that exist (may exceed KV_TILE)
+      const bool partial = valid < KV_TILE;
+      // per-tile rel_h terms
+      float rh2[BIAS == ATT_BIAS_GLOBAL64 ? 2 : (BIAS == ATT_BIAS_WINDOW14 ? 8 : 1)];
+      if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
+        rh2[0] = __ldg(bh_row + 2 * j) * LOG2E;
+        rh2[1] = __ldg(bh_row + 2 * j + 1) * LOG2E;
+      } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rh2[i] = (j == 0) ? rh2w[i] : rh2w[8 + i];
+      } else {
+        rh2[0] = 0.0f;
+      }
+
+      mbar_wait(&bar_s[x], j & 1);
+      tc_fence_after();
+
+      // ---- pass 1: row max of the biased, scaled scores ----
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        constexpr int W32 = 32;
+        const int width = (c * 32 + 32 <= KV_TILE) ? 32 : 16;
+        uint32_t sv[W32];
+        if (c * 32 + 32 <= KV_TILE) {
+          tmem_ld_32x32b_x32(t_s + c * 32, sv);
+        } else {
+          uint32_t s16[16];
+          tmem_ld_32x32b_x16(t_s + c * 32, s16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sv[i] = s16[i];
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < W32; ++i) {
+          if (i < width) {
+            const int col = c * 32 + i;
+            float tv;
+            if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
+              tv = fmaf(__uint_as_float(sv[i]), sl2, rw2[col % 64] + rh2[col / 64]);
+            } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+              tv = fmaf(__uint_as_float(sv[i]), sl2, rw2[col % 14] + rh2[col / 14]);
+            } else {
+              tv = __uint_as_float(sv[i]) * sl2;
+            }
+            if (partial && col >= valid) tv = -INFINITY;
+            mx = fmaxf(mx, tv);
+          }
+        }
+      }
+
+      // ---- running max with lazy rescale (threshold 8 in log2 units => P <= 256) ----
+      float alpha = 1.0f;
+      bool need = false;
+      if (j == 0) {
+        m_used = mx;
+      } else if (mx > m_used + 8.0f) {
+        alpha = ex2_approx(m_used - mx);
+        m_used = mx;
+        need = true;
+      }
+      if (__any_sync(0xffffffffu, need)) {
+        // O of this Q tile is complete up to tile j-1 (bar_s[x] of tile j was committed after PV(j-1)).
+#pragma unroll
+        for (int hseg = 0; hseg < 2; ++hseg) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(t_o + hseg * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st_32x32b_x32(t_o + hseg * 32, ov);
+        }
+        tmem_st_wait();
+        l_sum *= alpha;
+      }
+
+      // ---- pass 2: P = exp2(t - m_used) -> bf16 -> swizzled smem (A operand of the PV MMA) ----
+      const float neg_m = -m_used;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        constexpr int W32 = 32;
+        const int width = (c * 32 + 32 <= KV_TILE) ? 32 : 16;
+        uint32_t sv[W32];
+        if (c * 32 + 32 <= KV_TILE) {
+          tmem_ld_32x32b_x32(t_s + c * 32, sv);
+        } else {
+          uint32_t s16[16];
+          tmem_ld_32x32b_x16(t_s + c * 32, s16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sv[i] = s16[i];
+        }
+        tmem_ld_wait();
+        float pv[W32];
+#pragma unroll
+        for (int i = 0; i < W32; ++i) {
+          if (i < width) {
+            const int col = c * 32 + i;
+            float tv;
+            if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
+              tv = fmaf(__uint_as_float(sv[i]), sl2, rw2[col % 64] + (rh2[col / 64] + neg_m));
+            } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+              tv = fmaf(__uint_as_float(sv[i]), sl2, rw2[col % 14] + (rh2[col / 14] + neg_m));
+            } else {
+              tv = fmaf(__uint_as_float(sv[i]), sl2, neg_m);
+            }
+            float e = ex2_approx(tv);
+            if (partial && col >= valid) e = 0.0f;
+            pv[i] = e;
+            l_sum += e;
+          } else {
+            pv[i] = 0.0f;
+          }
+        }
+        // 32 columns = 64 bytes = four 16-byte groups of K-block (c >> 1)
+        uint8_t* blk = p_row + (c >> 1) * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g * 8 < width) {
+            uint4 pk;
+            pk.x = pack_bf16(pv[g * 8 + 0], pv[g * 8 + 1]);
+            pk.y = pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]);
+            pk.z = pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]);
+            pk.w = pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]);
+            const int grp = (c & 1) * 4 + g;
+            *reinterpret_cast<uint4*>(blk + ((grp ^ (r & 7)) << 4)) = pk;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bar_p[x]);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global (with the window-unpartition row mapping) ----
+    mbar_wait(&bar_o[x], 0);
+    tc_fence_after();
+    long long out_row = -1;
+    if (row_valid) {
+      if (p.out_mode == 0) {
+        out_row = seq_row0 + t;
+      } else {
+        const int per_img = p.nwin * p.nwin;
+        const int img = seq / per_img, wi = seq % per_img;
+        const int y = (wi / p.nwin) * p.win + t / p.win;
+        const int xx = (wi % p.nwin) * p.win + t % p.win;
+        if (y < p.img_hw && xx < p.img_hw)
+          out_row = (static_cast<long long>(img) * p.img_hw + y) * p.img_hw + xx;
+      }
+    }
+    const float inv_l = 1.0f / l_sum;
+#pragma unroll
+    for (int hseg = 0; hseg < 2; ++hseg) {
+      uint32_t ov[32];
+      tmem_ld_32x32b_x32(t_o + hseg * 32, ov);
+      tmem_ld_wait();
+      if (out_row >= 0) {
+        __nv_bfloat16* dst = p.out + out_row * p.ld_out + head * ATT_D + hseg * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(ov[g * 8 + 0]) * inv_l, __uint_as_float(ov[g * 8 + 1]) * inv_l);
+          pk.y = pack_bf16(__uint_as_float(ov[g * 8 + 2]) * inv_l, __uint_as_float(ov[g * 8 + 3]) * inv_l);
+          pk.z = pack_bf16(__uint_as_float(ov[g * 8 + 4]) * inv_l, __uint_as_float(ov[g * 8 + 5]) * inv_l);
+          pk.w = pack_bf16(__uint_as_float(ov[g * 8 + 6]) * inv_l, __uint_as_float(ov[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int KV_TILE, int BIAS>
+static int launch_attention(cudaStream_t stream, const void* qkv, long long ld_qkv, const AttParams& p) {
+  using S = AttSmem<KV_TILE>;
+  CUtensorMap tm_q, tm_kv;
+  int rc = make_tensor_map_2d(&tm_q, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_qkv,
+                              (uint64_t)p.rows_total, (uint64_t)ld_qkv * 2, 64, 128, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_kv, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_qkv, (uint64_t)p.rows_total,
+                          (uint64_t)ld_qkv * 2, 64, KV_TILE, Swizzle::B128);
+  if (rc) return rc;
+  auto kern = attention_fwd_kernel<KV_TILE, BIAS>;
+  LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  dim3 grid((p.seq_len + 255) / 256, p.n_heads, p.n_seq);
+  kern<<<grid, ATT_THREADS, S::TOTAL, stream>>>(tm_q, tm_kv, p);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+}  // namespace la
+
+extern "C" int la_attention_bf16(void* stream, const void* qkv, long long ld_qkv, long long rows_total, int q_off,
+                                 int k_off, int v_off, int n_seq, int seq_len, int n_heads, float scale,
+                                 const float* bias_h, const float* bias_w, int ldb, int grid_hw, void* out,
+                                 long long ld_out, int out_mode, int nwin, int img_hw) {
+  using namespace la;
+  LA_CHECK_ARG(qkv && out, "la_attention_bf16: null pointer");
+  LA_CHECK_ARG(n_seq > 0 && seq_len > 0 && n_heads > 0, "la_attention_bf16: empty problem");
+  LA_CHECK_ARG(n_seq <= 65535 && n_heads <= 65535, "la_attention_bf16: n_seq/n_heads exceed the grid limits");
+  LA_CHECK_ARG(ld_qkv % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+               "la_attention_bf16: strides/offsets must be multiples of 8 elements");
+  LA_CHECK_ARG(rows_total >= static_cast<long long>(n_seq) * seq_len, "la_attention_bf16: rows_total too small");
+  LA_CHECK_ARG(rows_total < (1ll << 31), "la_attention_bf16: rows_total exceeds TMA coordinate range");
+  const bool has_bias = bias_h != nullptr || bias_w != nullptr;
+  LA_CHECK_ARG(!has_bias || (bias_h && bias_w), "la_attention_bf16: bias_h and bias_w must come together");
+  AttParams p;
+  p.n_seq = n_seq;
+  p.seq_len = seq_len;
+  p.n_heads = n_heads;
+  p.q_off = q_off;
+  p.k_off = k_off;
+  p.v_off = v_off;
+  p.rows_total = rows_total;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.bias_h = bias_h;
+  p.bias_w = bias_w;
+  p.ldb = ldb;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out;
+  p.out_mode = out_mode;
+  p.win = grid_hw;
+  p.nwin = nwin;
+  p.img_hw = img_hw;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!has_bias) {
+    LA_CHECK_ARG(out_mode == 0, "la_attention_bf16: window output mapping needs the window bias mode");
+    return launch_attention<128, ATT_BIAS_NONE>(st, qkv, ld_qkv, p);
+  }
+  if (grid_hw == 64) {
+    LA_CHECK_ARG(seq_len == 4096 && ldb >= 127 && out_mode == 0,
+                 "la_attention_bf16: 64x64 rel-pos mode expects seq_len 4096, ldb >= 127");
+    return launch_attention<128, ATT_BIAS_GLOBAL64>(st, qkv, ld_qkv, p);
+  }
+  if (grid_hw == 14) {
+    LA_CHECK_ARG(seq_len == 196 && ldb >= 27, "la_attention_bf16: 14x14 rel-pos mode expects seq_len 196, ldb >= 27");
+    LA_CHECK_ARG(out_mode == 0 || (nwin > 0 && img_hw > 0 && n_seq % (nwin * nwin) == 0),
+                 "la_attention_bf16: bad window-unpartition parameters");
+    return launch_attention<112, ATT_BIAS_WINDOW14>(st, qkv, ld_qkv, p);
+  }
+  set_last_error("la_attention_bf16: unsupported rel-pos grid %d (built for 64 and 14)", grid_hw);
+  return LA_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,312 @@
+// labelanything_b200 — HBM-bound row kernels of the ViT encoder and neck (sm_100a).
+//
+//   la_add_layernorm : residual add (fp32 stream + bf16 branch output) fused with LayerNorm and with the
+//                      window-partition / zero-pad / CLS-drop row remapping, one warp per token row.
+//                      reference: image_encoder.py:181-197 (x = shortcut + attn; x + mlp(norm2(x))),
+//                      258-279 (window_partition incl. F.pad), common.py:42-54 (LayerNorm2d == per-token LN
+//                      in token-major layout), HF modeling_vit.py:325-346,416.
+//   la_embed_tokens  : x[img, tok] = (cls | patch-GEMM row) + pos_embed[tok]   image_encoder.py:112-114,
+//                      HF modeling_vit.py:109-125.
+//   la_im2col_patch  : NCHW fp32 image -> [tokens, 3*P*P] bf16 rows for the patch-embed GEMM
+//                      (stride == kernel conv, image_encoder.py:402-410).
+//   la_im2col_3x3    : token-major bf16 feature map -> [tokens, 9*C] rows (zero padded) for 3x3 convs
+//                      (build_lam.py:162-168, mask_decoder.py:241-247).
+// All are pure streaming kernels: 16-byte vectorised, coalesced along the channel dimension, grid sized in
+// multiples of the SM count; the roofline that bounds them is HBM bandwidth.
+#include "la_common.cuh"
+
+namespace la {
+
+constexpr int ROW_MAXV = 10;  // float4 per lane -> rows up to 1280 channels
+
+struct AddLnParams {
+  const float* x_in;            // [x_rows, d] fp32 or nullptr
+  long long x_mod;              // >0: x_in row = src_row % x_mod (broadcast table)
+  const __nv_bfloat16* delta;   // [rows, d] or nullptr
+  float* x_out;                 // [rows, d] or nullptr
+  const float* gamma;           // nullptr -> no normalisation (plain cast)
+  const float* beta;
+  float eps;
+  void* y_out;                  // nullptr -> skip
+  int y_f32;                    // 0 bf16, 1 fp32
+  long long rows;               // source rows (map 0, 2) ; output rows (map 1)
+  int d;
+  int map_mode;                 // 0 identity, 1 window partition with zero pad, 2 drop first token per sequence
+  int seq_len;                  // map 2
+  int win, nwin, hw;            // map 1
+};
+
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int nv = p.d >> 7;           // full float4 groups per lane
+  const int tail = (p.d & 127) >> 2;  // leftover float4s (< 32)
+
+  for (long long row = warp_global; row < p.rows; row += n_warps) {
+    long long src = row, dst = row;
+    bool pad = false, write_y = p.y_out != nullptr;
+    if (p.map_mode == 1) {
+      const int w2 = p.win * p.win;
+      const long long widx = row / w2;
+      const int tin = static_cast<int>(row % w2);
+      const int per_img = p.nwin * p.nwin;
+      const long long img = widx / per_img;
+      const int wi = static_cast<int>(widx % per_img);
+      const int y = (wi / p.nwin) * p.win + tin / p.win;
+      const int x = (wi % p.nwin) * p.win + tin % p.win;
+      pad = (y >= p.hw) || (x >= p.hw);
+      src = (img * p.hw + y) * p.hw + x;
+    } else if (p.map_mode == 2) {
+      const long long s = row / p.seq_len;
+      const int tin = static_cast<int>(row % p.seq_len);
+      write_y = write_y && tin > 0;
+      dst = row - s - 1;
+    }
+    const size_t ebytes = p.y_f32 ? 4 : 2;
+    uint8_t* yrow = static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(dst) * p.d * ebytes;
+    if (pad) {
+      // zero row (padding token of a window): F.pad after norm1, image_encoder.py:271-275
+      if (p.y_f32) {
+        for (int i = lane; i < p.d / 4; i += 32) reinterpret_cast<float4*>(yrow)[i] = make_float4(0, 0, 0, 0);
+      } else {
+        for (int i = lane; i < p.d / 8; i += 32) reinterpret_cast<uint4*>(yrow)[i] = make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
+    float4 v[ROW_MAXV + 1];
+    const long long xrow = p.x_mod > 0 ? src % p.x_mod : src;
+    const float4* xin = p.x_in ? reinterpret_cast<const float4*>(p.x_in + xrow * p.d) : nullptr;
+    const uint2* din = p.delta ? reinterpret_cast<const uint2*>(p.delta + src * p.d) : nullptr;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i <= ROW_MAXV; ++i) {
+      const bool on = (i < nv) || (i == nv && lane < tail);
+      float4 a = make_float4(0, 0, 0, 0);
+      if (on) {
+        const int idx = i * 32 + lane;
+        if (xin) a = xin[idx];
+        if (din) {
+          const uint2 dv = din[idx];
+          const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
+          const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
+          a.x += __low2float(d01);
+          a.y += __high2float(d01);
+          a.z += __low2float(d23);
+          a.w += __high2float(d23);
+        }
+        if (p.x_out) reinterpret_cast<float4*>(p.x_out + src * p.d)[idx] = a;
+      }
+      v[i] = a;
+      sum += a.x + a.y + a.z + a.w;
+    }
+    if (!write_y) continue;
+    float mean = 0.f, rstd = 1.f;
+    if (p.gamma) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      mean = sum / p.d;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i <= ROW_MAXV; ++i) {
+        const bool on = (i < nv) || (i == nv && lane < tail);
+        if (on) {
+          const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+          sq += dx * dx + dy * dy + dz * dz + dw * dw;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      rstd = rsqrtf(sq / p.d + p.eps);
+    }
+#pragma unroll
+    for (int i = 0; i <= ROW_MAXV; ++i) {
+      const bool on = (i < nv) || (i == nv && lane < tail);
+      if (on) {
+        const int idx = i * 32 + lane;
+        float4 o = v[i];
+        if (p.gamma) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + idx);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta) + idx);
+          o.x = (o.x - mean) * rstd * g.x + b.x;
+          o.y = (o.y - mean) * rstd * g.y + b.y;
+          o.z = (o.z - mean) * rstd * g.z + b.z;
+          o.w = (o.w - mean) * rstd * g.w + b.w;
+        }
+        if (p.y_f32) {
+          reinterpret_cast<float4*>(yrow)[idx] = o;
+        } else {
+          uint2 pk;
+          pk.x = pack_bf16(o.x, o.y);
+          pk.y = pack_bf16(o.z, o.w);
+          reinterpret_cast<uint2*>(yrow)[idx] = pk;
+        }
+      }
+    }
+  }
+}
+
+// x[img*T + tok, :] = (tok < n_cls ? cls : patch[img*(T-n_cls) + tok - n_cls, :]) + pos[tok, :]
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const __nv_bfloat16* __restrict__ patch, const float* __restrict__ cls,
+                    const float* __restrict__ pos, float* __restrict__ x, long long n_img, int T, int n_cls, int d) {
+  const int dv = d >> 2;
+  const long long total = n_img * T * dv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % dv);
+    const long long rt = i / dv;
+    const int tok = static_cast<int>(rt % T);
+    const long long img = rt / T;
+    float4 a;
+    if (tok < n_cls) {
+      a = __ldg(reinterpret_cast<const float4*>(cls) + c4);
+    } else {
+      const uint2 pv =
+          reinterpret_cast<const uint2*>(patch + (img * (T - n_cls) + tok - n_cls) * static_cast<long long>(d))[c4];
+      const __nv_bfloat162 p01 = *reinterpret_cast<const __nv_bfloat162*>(&pv.x);
+      const __nv_bfloat162 p23 = *reinterpret_cast<const __nv_bfloat162*>(&pv.y);
+      a = make_float4(__low2float(p01), __high2float(p01), __low2float(p23), __high2float(p23));
+    }
+    if (pos) {
+      const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(tok) * d) + c4);
+      a.x += pe.x;
+      a.y += pe.y;
+      a.z += pe.z;
+      a.w += pe.w;
+    }
+    reinterpret_cast<float4*>(x)[i] = a;
+  }
+}
+
+// images [I, C, S, S] fp32 -> rows [I * (S/P)^2, C*P*P] bf16, column = c*P*P + ky*P + kx   (P == 16)
+__global__ void __launch_bounds__(256)
+im2col_patch16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, long long n_img, int C, int S) {
+  const int g = S / 16;
+  // one thread handles 8 consecutive kx (half a patch row): 32 B in, 16 B out
+  const long long total = n_img * C * S * (S / 8);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xs = static_cast<int>(i % (S / 8));
+    long long r = i / (S / 8);
+    const int y = static_cast<int>(r % S);
+    r /= S;
+    const int c = static_cast<int>(r % C);
+    const long long im = r / C;
+    const float4* src = reinterpret_cast<const float4*>(img + ((im * C + c) * S + y) * S + xs * 8);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    const int px = xs >> 1, half = xs & 1, py = y >> 4, ky = y & 15;
+    const long long row = (im * g + py) * g + px;
+    uint4 pk;
+    pk.x = pack_bf16(a.x, a.y);
+    pk.y = pack_bf16(a.z, a.w);
+    pk.z = pack_bf16(b.x, b.y);
+    pk.w = pack_bf16(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + row * (C * 256) + c * 256 + ky * 16 + half * 8) = pk;
+  }
+}
+
+// in [I, H, W, C] bf16 -> out [I*H*W, 9*C] bf16, column = (ky*3 + kx)*C + c, zero padded borders
+__global__ void __launch_bounds__(256)
+im2col_3x3_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n_img, int H,
+                  int W, int C) {
+  const int cv = C >> 3;  // uint4 per pixel
+  const long long total = n_img * H * W * 9 * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cv);
+    long long r = i / cv;
+    const int tap = static_cast<int>(r % 9);
+    r /= 9;
+    const int x = static_cast<int>(r % W);
+    r /= W;
+    const int y = static_cast<int>(r % H);
+    const long long im = r / H;
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      v = __ldg(reinterpret_cast<const uint4*>(in + ((im * H + yy) * W + xx) * static_cast<long long>(C)) + c8);
+    reinterpret_cast<uint4*>(out)[i] = v;
+  }
+}
+
+static int grid_for(long long work_items, int block, int per_sm) {
+  long long blocks = (work_items + block - 1) / block;
+  const long long cap = static_cast<long long>(sm_count()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace la
+
+extern "C" {
+
+int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const void* delta, float* x_out,
+                     const float* gamma, const float* beta, float eps, void* y_out, int y_dtype, long long rows,
+                     int d, int map_mode, int seq_len, int win, int nwin, int hw) {
+  using namespace la;
+  LA_CHECK_ARG(rows > 0 && d > 0, "la_add_layernorm: empty problem");
+  LA_CHECK_ARG(d % 8 == 0 && d <= 128 * ROW_MAXV + 124, "la_add_layernorm: d=%d unsupported (multiple of 8, <= 1404)", d);
+  LA_CHECK_ARG(x_in || delta, "la_add_layernorm: need x_in and/or delta");
+  LA_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "la_add_layernorm: gamma/beta must come together");
+  LA_CHECK_ARG(map_mode >= 0 && map_mode <= 2, "la_add_layernorm: bad map_mode");
+  LA_CHECK_ARG(map_mode != 1 || (win > 0 && nwin > 0 && hw > 0 && rows % (static_cast<long long>(win) * win * nwin * nwin) == 0),
+               "la_add_layernorm: bad window parameters");
+  LA_CHECK_ARG(map_mode != 2 || (seq_len > 1 && rows % seq_len == 0), "la_add_layernorm: bad seq_len");
+  AddLnParams p;
+  p.x_in = x_in;
+  p.x_mod = x_mod;
+  p.delta = static_cast<const __nv_bfloat16*>(delta);
+  p.x_out = x_out;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.eps = eps;
+  p.y_out = y_out;
+  p.y_f32 = y_dtype == LA_DTYPE_F32;
+  p.rows = rows;
+  p.d = d;
+  p.map_mode = map_mode;
+  p.seq_len = seq_len;
+  p.win = win;
+  p.nwin = nwin;
+  p.hw = hw;
+  const int grid = grid_for(rows * 32, 256, 8);
+  add_layernorm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+int la_embed_tokens(void* stream, const void* patch, const float* cls, const float* pos, float* x, long long n_img,
+                    int tokens_per_img, int n_cls, int d) {
+  using namespace la;
+  LA_CHECK_ARG(patch && x && n_img > 0 && tokens_per_img > n_cls && d % 4 == 0, "la_embed_tokens: bad arguments");
+  LA_CHECK_ARG(n_cls == 0 || cls, "la_embed_tokens: cls token missing");
+  const long long total = n_img * tokens_per_img * (d / 4);
+  embed_tokens_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(patch), cls, pos, x, n_img, tokens_per_img, n_cls, d);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+int la_im2col_patch16(void* stream, const float* images, void* out, long long n_img, int channels, int size) {
+  using namespace la;
+  LA_CHECK_ARG(images && out && n_img > 0 && channels > 0 && size % 16 == 0, "la_im2col_patch16: bad arguments");
+  const long long total = n_img * channels * size * (size / 8);
+  im2col_patch16_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      images, static_cast<__nv_bfloat16*>(out), n_img, channels, size);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+int la_im2col_3x3(void* stream, const void* in, void* out, long long n_img, int height, int width, int channels) {
+  using namespace la;
+  LA_CHECK_ARG(in && out && n_img > 0 && height > 0 && width > 0 && channels % 8 == 0, "la_im2col_3x3: bad arguments");
+  const long long total = n_img * height * width * 9 * (channels / 8);
+  im2col_3x3_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n_img, height, width, channels);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+}  // extern "C"

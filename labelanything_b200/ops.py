@@ -46,3 +46,81 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act
         DT_BF16 if out.dtype == torch.bfloat16 else DT_F32, M, N, K, act)
     _native.check(rc, "gemm")
     return out
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def attention(qkv: torch.Tensor, n_seq: int, seq_len: int, n_heads: int, scale: float, out: torch.Tensor,
+              q_off: int, k_off: int, v_off: int, bias_h: torch.Tensor | None = None,
+              bias_w: torch.Tensor | None = None, grid_hw: int = 0, out_mode: int = 0, nwin: int = 0,
+              img_hw: int = 0) -> torch.Tensor:
+    """Fused MHSA (head_dim 64) over the packed projection matrix `qkv` [rows, ld] bf16; see the C header."""
+    _require_cuda(qkv, out, bias_h, bias_w)
+    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1
+    assert out.dtype == torch.bfloat16 and out.dim() == 2 and out.stride(1) == 1
+    ldb = 0
+    if bias_h is not None:
+        assert bias_h.dtype == torch.float32 and bias_w.dtype == torch.float32
+        assert bias_h.is_contiguous() and bias_w.is_contiguous() and bias_h.shape == bias_w.shape
+        assert bias_h.shape[0] == n_heads and bias_h.shape[1] == qkv.shape[0]
+        ldb = bias_h.shape[2]
+    rc = _native.lib().la_attention_bf16(
+        _stream(qkv), qkv.data_ptr(), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, n_seq, seq_len, n_heads,
+        float(scale), _ptr(bias_h), _ptr(bias_w), ldb, grid_hw, out.data_ptr(), out.stride(0), out_mode, nwin,
+        img_hw)
+    _native.check(rc, "attention")
+    return out
+
+
+def add_layernorm(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: torch.Tensor | None,
+                  beta: torch.Tensor | None, eps: float, *, rows: int, d: int, x_out: torch.Tensor | None = None,
+                  y_out: torch.Tensor | None = None, x_mod: int = 0, map_mode: int = 0, seq_len: int = 0,
+                  win: int = 0, nwin: int = 0, hw: int = 0) -> None:
+    """x = x_in + delta (-> x_out); y = LN(x) (-> y_out, bf16 or fp32) with optional row remapping."""
+    _require_cuda(x_in, delta, gamma, beta, x_out, y_out)
+    ref = x_in if x_in is not None else delta
+    for t in (x_in, x_out, gamma, beta):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    assert delta is None or (delta.dtype == torch.bfloat16 and delta.is_contiguous())
+    assert y_out is None or (y_out.is_contiguous() and y_out.dtype in (torch.bfloat16, torch.float32))
+    rc = _native.lib().la_add_layernorm(
+        _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(x_out), _ptr(gamma), _ptr(beta), float(eps),
+        _ptr(y_out), DT_F32 if (y_out is not None and y_out.dtype == torch.float32) else DT_BF16, rows, d,
+        map_mode, seq_len, win, nwin, hw)
+    _native.check(rc, "add_layernorm")
+
+
+def embed_tokens(patch: torch.Tensor, cls: torch.Tensor | None, pos: torch.Tensor | None, x: torch.Tensor,
+                 n_img: int, tokens_per_img: int, n_cls: int, d: int) -> torch.Tensor:
+    _require_cuda(patch, cls, pos, x)
+    assert patch.dtype == torch.bfloat16 and patch.is_contiguous() and x.dtype == torch.float32 and x.is_contiguous()
+    rc = _native.lib().la_embed_tokens(_stream(x), patch.data_ptr(), _ptr(cls), _ptr(pos), x.data_ptr(), n_img,
+                                       tokens_per_img, n_cls, d)
+    _native.check(rc, "embed_tokens")
+    return x
+
+
+def im2col_patch16(images: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """images [I, C, S, S] fp32 -> [I*(S/16)^2, C*256] bf16."""
+    _require_cuda(images, out)
+    assert images.dtype == torch.float32 and images.is_contiguous() and images.dim() == 4
+    I, C, S, S2 = images.shape
+    assert S == S2 and S % 16 == 0
+    if out is None:
+        out = torch.empty((I * (S // 16) ** 2, C * 256), dtype=torch.bfloat16, device=images.device)
+    rc = _native.lib().la_im2col_patch16(_stream(images), images.data_ptr(), out.data_ptr(), I, C, S)
+    _native.check(rc, "im2col_patch16")
+    return out
+
+
+def im2col_3x3(x: torch.Tensor, n_img: int, h: int, w: int, c: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """token-major bf16 [n_img*h*w, c] -> [n_img*h*w, 9c] bf16 (zero pad 1)."""
+    _require_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == n_img * h * w * c
+    if out is None:
+        out = torch.empty((n_img * h * w, 9 * c), dtype=torch.bfloat16, device=x.device)
+    rc = _native.lib().la_im2col_3x3(_stream(x), x.data_ptr(), out.data_ptr(), n_img, h, w, c)
+    _native.check(rc, "im2col_3x3")
+    return out

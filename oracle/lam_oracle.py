@@ -27,7 +27,7 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 SD = Dict[str, Tensor]
 
-NULL, NEGATIVE, POSITIVE = -1, 0, 1  # label_anything/data/utils.py:25-28 (Label)
+POSITIVE, NULL, NEGATIVE = 1, 0, -1  # label_anything/data/utils.py:25-28 (Label)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -255,7 +255,10 @@ def dense_pe(gauss: Tensor, h: int, w: int) -> Tensor:
 
 
 def embed_points(sd: SD, name: str, coords: Tensor, labels: Tensor, pad: bool, image_size: int) -> Tensor:
-    """coords [S,P,2] (x,y px), labels [S,P] in {1,0,-1} -> [S,P(+1),D].  prompt_encoder.py:83-103,648-654"""
+    """coords [S,P,2] (x,y px), labels [S,P] in {1,0,-1} -> [S,P(+1),D].  prompt_encoder.py:83-103,648-654.
+
+    The padding point appended when there are no boxes carries label -1, which in this code base is
+    Label.NEGATIVE (not "null" as in SAM) -- it therefore receives PE + point_embeddings[0]; restated as is."""
     gauss = sd[name + ".pe_layer.positional_encoding_gaussian_matrix"]
     pts = coords + 0.5
     if pad:
@@ -347,7 +350,7 @@ def prompt_encoder(sd: SD, name: str, cfg: dict, image_embeddings: Tensor,
     pos = dense_pe(gauss, gh, gw)
 
     if class_rows is not None:  # RandomMatrixEncoder.forward_with_rows, prompt_encoder.py:250-264
-        code = sd[name + ".class_encoder.pos_embedding"][0, 0, class_rows]  # [C, D]
+        code = sd[name + ".class_encoder.pos_embedding"][0, 0, class_rows[:C]]  # [C, D]
         src = (src.view(B, M, C, D, h, w) + code.view(1, 1, C, D, 1, 1)).reshape(S, D, h, w)
         sparse = sparse + code.view(1, 1, C, 1, D)
 
@@ -368,7 +371,7 @@ def prompt_encoder(sd: SD, name: str, cfg: dict, image_embeddings: Tensor,
     norm = fe.sum(dim=1).unsqueeze(-1)
     norm = torch.where(norm == 0, torch.ones_like(norm), norm)
     class_emb = (emb * fe.unsqueeze(-1)).sum(dim=1) / norm  # prompt_encoder.py:738-745
-    return {"class_embs": class_emb, "class_examples_embeddings": emb, "flag_examples": flag_examples,
+    return {"class_embeddings": class_emb, "class_examples_embeddings": emb, "flag_examples": flag_examples,
             "class_examples_src": fused}
 
 
@@ -483,11 +486,11 @@ def lam_forward(sd: SD, cfg: dict, batch: dict, class_rows: Optional[Tensor] = N
     pe = prompt_encoder(sd, "prompt_encoder", cfg, support, pts, bxs, msk, flag_examples, class_rows)
     gauss = sd["prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"]
     gh, gw = cfg["image_embedding_size"]
-    low = mask_decoder(sd, "mask_decoder", cfg, query, dense_pe(gauss, gh, gw), pe["class_embs"])
+    low = mask_decoder(sd, "mask_decoder", cfg, query, dense_pe(gauss, gh, gw), pe["class_embeddings"])
     seg = postprocess_masks(low, batch["dims"], cfg["image_size"], cfg.get("custom_preprocess", True))
     if "flag_gts" in batch:
         seg[batch["flag_gts"].logical_not()] = float("-inf")  # lam.py:92-93
     out = {"logits": seg, "class_examples_embeddings": pe["class_examples_embeddings"]}
     if return_intermediates:
-        out.update(encoder_out=enc_out, features=feats, class_embs=pe["class_embs"], low_res_logits=low)
+        out.update(encoder_out=enc_out, features=feats, class_embs=pe["class_embeddings"], low_res_logits=low)
     return out

@@ -1,0 +1,261 @@
+"""Generate the committed golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference); the fixtures it writes are
+what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512]
+
+Every fixture stores: the oracle `cfg`, the inputs, the reference outputs and either the full state dict
+(tiny models) or the synthetic-weight seed (real-size models; weights are a pure function of
+(name, shape, seed), see labelanything_b200/synthetic.py).  Version info of the generating stack is recorded.
+"""
+from __future__ import annotations
+
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "oracle"))
+
+import torch
+
+import ref_import
+from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+GOLD = ROOT / "tests" / "golden"
+GOLD.mkdir(parents=True, exist_ok=True)
+
+
+def _meta():
+    import transformers
+
+    return {"torch": torch.__version__, "transformers": transformers.__version__,
+            "reference_commit": "6bb2c5a", "generator": "oracle/make_golden.py"}
+
+
+def _pin_rows(lam, rows):
+    ce = lam.prompt_encoder.class_encoder
+    if hasattr(ce, "sample_rows"):
+        ce.sample_rows = lambda C, device=None: rows[:C]
+
+
+def _tiny_episode(B, M, C, S, mask_hw, n_points, n_boxes, seed, with_points=True, with_boxes=True, dims=None):
+    g = torch.Generator().manual_seed(seed)
+    ep = {"images": torch.randn(B, M + 1, 3, S, S, generator=g),
+          "prompt_masks": (torch.rand(B, M, C, mask_hw, mask_hw, generator=g) > 0.5).float(),
+          "flag_masks": (torch.rand(B, M, C, generator=g) > 0.2).to(torch.uint8),
+          "flag_examples": (torch.rand(B, M, C, generator=g) > 0.3).to(torch.uint8)}
+    ep["flag_examples"][:, :, 0] = 1
+    if with_points:
+        ep["prompt_points"] = torch.rand(B, M, C, n_points, 2, generator=g) * S
+        ep["flag_points"] = torch.randint(-1, 2, (B, M, C, n_points), generator=g).float()
+        ep["flag_points"][0, 0, 0, 0] = 1
+    if with_boxes:
+        xy = torch.rand(B, M, C, n_boxes, 2, generator=g) * S / 2
+        ep["prompt_bboxes"] = torch.cat([xy, xy + S / 4], dim=-1)
+        ep["flag_bboxes"] = torch.randint(-1, 2, (B, M, C, n_boxes), generator=g).float()
+        ep["flag_bboxes"][0, 0, 0, 0] = 1
+    ep["dims"] = dims if dims is not None else torch.full((B, M + 1, 2), S, dtype=torch.int64)
+    return ep
+
+
+def tiny_sam(models):
+    """Tiny SAM-style Lam: windowed (pad 4->6) + global blocks with rel-pos, neck, all prompt types,
+    RandomMatrixEncoder with pinned rows, example_attention + class_attention + class_example_attention,
+    non-square original sizes with custom_preprocess."""
+    from label_anything.models.build_lam import build_mask_decoder
+    from label_anything.models.common import LayerNorm2d
+
+    torch.manual_seed(0)
+    S, D, Ce = 64, 32, 48
+    vit = models.ImageEncoderViT(img_size=S, patch_size=16, embed_dim=Ce, depth=3, num_heads=3, use_rel_pos=True,
+                                 window_size=3, global_attn_indexes=(1,), out_chans=D, project_last_hidden=False,
+                                 norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6))
+    neck = torch.nn.Sequential(torch.nn.Conv2d(Ce, D, 1, bias=False), LayerNorm2d(D),
+                               torch.nn.Conv2d(D, D, 3, padding=1, bias=False), LayerNorm2d(D))
+    pe = models.PromptImageEncoder(embed_dim=D, image_embedding_size=(4, 4), input_image_size=(S, S),
+                                   mask_in_chans=16, class_attention=True, example_attention=True,
+                                   example_class_attention=True,
+                                   transformer=models.TwoWayTransformer(depth=2, embedding_dim=D, mlp_dim=64,
+                                                                        num_heads=8),
+                                   class_encoder=models.RandomMatrixEncoder(bank_size=10, embed_dim=D))
+    dec = build_mask_decoder(embed_dim=D, decoder_attention_downsample_rate=2, spatial_convs=3)
+    lam = models.Lam(image_encoder=vit, prompt_encoder=pe, mask_decoder=dec, neck=neck, image_size=S,
+                     custom_preprocess=True).eval()
+    load_synth_weights(lam, seed=11)
+    rows = torch.tensor([0, 4, 2, 7])
+    _pin_rows(lam, rows)
+    B, M, C = 2, 2, 3
+    dims = torch.tensor([[[50, 64], [64, 64], [64, 64]], [[64, 40], [64, 64], [64, 64]]], dtype=torch.int64)
+    ep = _tiny_episode(B, M, C, S, 16, 2, 2, seed=5, dims=dims)
+    ep["flag_gts"] = torch.tensor([[True, True, False], [True, True, True]])
+    with torch.no_grad():
+        out = lam(ep)
+        enc = vit(ep["images"].flatten(0, 1))
+    cfg = {"image_size": S, "image_embedding_size": (4, 4), "has_neck": True, "spatial_convs": 3,
+           "class_attention": True, "example_attention": True, "example_class_attention": True,
+           "custom_preprocess": True,
+           "encoder": {"kind": "sam", "num_heads": 3, "depth": 3, "global_attn": [1], "window": 3}}
+    torch.save({"meta": _meta(), "cfg": cfg, "state_dict": lam.state_dict(), "episode": ep, "class_rows": rows,
+                "logits": out["logits"], "class_examples_embeddings": out["class_examples_embeddings"],
+                "encoder_out": enc}, GOLD / "tiny_sam_lam.pt")
+    print("tiny_sam_lam.pt", out["logits"].shape)
+
+    # variant: masks only (points/boxes flags all zero -> dropped), no class encoder, no custom preprocess
+    torch.manual_seed(1)
+    pe2 = models.PromptImageEncoder(embed_dim=D, image_embedding_size=(4, 4), input_image_size=(S, S),
+                                    mask_in_chans=16, class_attention=False, example_attention=False,
+                                    example_class_attention=True,
+                                    transformer=models.TwoWayTransformer(depth=2, embedding_dim=D, mlp_dim=64,
+                                                                         num_heads=8),
+                                    class_encoder=lambda x, y: (x, y))
+    lam2 = models.Lam(image_encoder=vit, prompt_encoder=pe2, mask_decoder=dec, neck=neck, image_size=S,
+                      custom_preprocess=False).eval()
+    load_synth_weights(lam2, seed=12)
+    ep2 = _tiny_episode(B, M, C, S, 16, 1, 1, seed=6)
+    ep2["flag_points"].zero_()
+    ep2["flag_bboxes"].zero_()
+    with torch.no_grad():
+        out2 = lam2(ep2)
+    cfg2 = dict(cfg, class_attention=False, example_attention=False, custom_preprocess=False)
+    torch.save({"meta": _meta(), "cfg": cfg2, "state_dict": lam2.state_dict(), "episode": ep2, "class_rows": None,
+                "logits": out2["logits"], "class_examples_embeddings": out2["class_examples_embeddings"]},
+               GOLD / "tiny_sam_lam_masks_only.pt")
+    print("tiny_sam_lam_masks_only.pt", out2["logits"].shape)
+
+
+def _hf_wrapper(hidden, layers, heads, inter, pretrain_size):
+    from label_anything.models.build_encoder import ViTModelWrapper
+    from transformers import ViTConfig
+
+    return ViTModelWrapper(ViTConfig(hidden_size=hidden, num_hidden_layers=layers, num_attention_heads=heads,
+                                     intermediate_size=inter, image_size=pretrain_size, patch_size=16))
+
+
+def tiny_mae(models):
+    """Tiny HF-ViT Lam: bicubic pos-emb resize (2x2 -> 3x3 grid), CLS dropped, 16x16 prompt masks -> 4x4 -> bilinear 3x3."""
+    from label_anything.models.build_lam import _build_lam
+
+    torch.manual_seed(0)
+    S, D, Ce = 48, 32, 48
+    lam = _build_lam(build_vit=lambda project_last_hidden: _hf_wrapper(Ce, 2, 3, 96, 32), image_embed_dim=Ce,
+                     embed_dim=D, image_size=S, spatial_convs=3, class_attention=False, example_attention=False,
+                     example_class_attention=True, custom_preprocess=False).eval()
+    load_synth_weights(lam, seed=21)
+    B, M, C = 2, 1, 2
+    ep = _tiny_episode(B, M, C, S, 16, 1, 1, seed=8, with_points=False, with_boxes=False)
+    with torch.no_grad():
+        out = lam(ep)
+        enc = lam.image_encoder(ep["images"].flatten(0, 1))
+    cfg = {"image_size": S, "image_embedding_size": (3, 3), "has_neck": True, "spatial_convs": 3,
+           "class_attention": False, "example_attention": False, "example_class_attention": True,
+           "custom_preprocess": False, "encoder": {"kind": "hf", "num_heads": 3, "depth": 2}}
+    torch.save({"meta": _meta(), "cfg": cfg, "state_dict": lam.state_dict(), "episode": ep, "class_rows": None,
+                "logits": out["logits"], "class_examples_embeddings": out["class_examples_embeddings"],
+                "encoder_out": enc}, GOLD / "tiny_mae_lam.pt")
+    print("tiny_mae_lam.pt", out["logits"].shape)
+
+
+MAE256_CFG = {"image_size": 480, "image_embedding_size": (30, 30), "has_neck": True, "spatial_convs": 3,
+              "class_attention": False, "example_attention": False, "example_class_attention": True,
+              "custom_preprocess": False, "encoder": {"kind": "hf", "num_heads": 12, "depth": 12}}
+
+
+def mae256(models):
+    """BASELINE config 1: MAE-256 (HF ViT-B, 480 px), 1-way 1-shot, B=1 — the reference's CPU-runnable case
+    (parameters/trainval/coco20i/mae_noembs.yaml:42-55).  Weights = synthetic seed 0; rows pinned."""
+    from label_anything.models.build_lam import _build_lam
+
+    lam = _build_lam(build_vit=lambda project_last_hidden: _hf_wrapper(768, 12, 12, 3072, 224),
+                     image_embed_dim=768, embed_dim=256, image_size=480, spatial_convs=3, class_attention=False,
+                     example_attention=False, example_class_attention=True,
+                     class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 256},
+                     custom_preprocess=False).eval()
+    load_synth_weights(lam, seed=0)
+    rows = torch.arange(2)
+    _pin_rows(lam, rows)
+    ep = make_episode(1, 1, 1, 480, seed=0)
+    t0 = time.time()
+    with torch.no_grad():
+        out = lam(ep)
+        enc = lam.image_encoder(ep["images"][0, :1])
+    print(f"mae256 reference forward {time.time() - t0:.1f}s")
+    torch.save({"meta": _meta(), "cfg": MAE256_CFG, "weights_seed": 0, "episode_args": dict(batch=1, n_ways=1, k_shots=1, image_size=480, seed=0),
+                "class_rows": rows, "logits_sub3": out["logits"][..., ::3, ::3].clone(),
+                "class_examples_embeddings": out["class_examples_embeddings"],
+                "encoder_out_sub": enc[0, ::16].clone(),
+                "shapes": {k: tuple(v.shape) for k, v in lam.state_dict().items()}}, GOLD / "mae256_1w1s.pt")
+    print("mae256_1w1s.pt", out["logits"].shape)
+
+
+SAM512_CFG = {"image_size": 1024, "image_embedding_size": (64, 64), "has_neck": True, "spatial_convs": 3,
+              "class_attention": False, "example_attention": True, "example_class_attention": False,
+              "custom_preprocess": True,
+              "encoder": {"kind": "sam", "num_heads": 12, "depth": 12, "global_attn": [2, 5, 8, 11], "window": 14}}
+
+
+def _sam512(models):
+    from label_anything.models.build_lam import _build_lam
+    from label_anything.models.build_encoder import build_vit_b
+
+    lam = _build_lam(build_vit=build_vit_b, image_embed_dim=768, embed_dim=512, image_size=1024,
+                     use_vit_sam_neck=False, spatial_convs=3, class_attention=False, example_attention=True,
+                     example_class_attention=False,
+                     class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 512},
+                     custom_preprocess=True).eval()
+    load_synth_weights(lam, seed=0)
+    return lam
+
+
+def samvit(models):
+    """SAM ViT-B (1024 px) encoder alone on one synthetic image, synthetic weights seed 0
+    (parameters/trainval/other/COCO_vit.yaml:47-63 encoder)."""
+    lam = _sam512(models)
+    ep = make_episode(1, 1, 1, 1024, seed=0)
+    img = ep["images"][0, :1]
+    t0 = time.time()
+    with torch.no_grad():
+        enc = lam.image_encoder(img)
+        feat = lam.neck(enc)
+    print(f"samvit reference forward {time.time() - t0:.1f}s")
+    torch.save({"meta": _meta(), "cfg": SAM512_CFG, "weights_seed": 0,
+                "episode_args": dict(batch=1, n_ways=1, k_shots=1, image_size=1024, seed=0),
+                "encoder_out_sub": enc[0, ::16].clone(), "neck_out_sub": feat[0, ::16].clone(),
+                "shapes": {k: tuple(v.shape) for k, v in lam.state_dict().items()}}, GOLD / "sam512_vit_1img.pt")
+    print("sam512_vit_1img.pt", enc.shape)
+
+
+def sam512(models):
+    """BASELINE config 3 shape at B=1: SAM-512 5-way 5-shot (26 images, 150 sequences).  Encoder fed 2 images
+    per call and the result handed over through the `embeddings` key (identical arithmetic, lam.py:139-146)."""
+    lam = _sam512(models)
+    rows = torch.arange(6)
+    _pin_rows(lam, rows)
+    ep = make_episode(1, 5, 5, 1024, seed=0)
+    imgs = ep.pop("images").flatten(0, 1)
+    t0 = time.time()
+    with torch.no_grad():
+        feats = torch.cat([lam.image_encoder(imgs[i:i + 2]) for i in range(0, imgs.shape[0], 2)])
+        ep["embeddings"] = feats.unsqueeze(0)
+        out = lam(ep)
+    print(f"sam512 5w5s reference forward {time.time() - t0:.1f}s")
+    torch.save({"meta": _meta(), "cfg": SAM512_CFG, "weights_seed": 0,
+                "episode_args": dict(batch=1, n_ways=5, k_shots=5, image_size=1024, seed=0), "class_rows": rows,
+                "logits_sub8": out["logits"][..., ::8, ::8].clone(),
+                "class_examples_embeddings": out["class_examples_embeddings"]}, GOLD / "sam512_5w5s.pt")
+    print("sam512_5w5s.pt", out["logits"].shape)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["tiny", "mae256", "samvit"]
+    models = ref_import.import_reference()
+    torch.set_num_threads(8)
+    if "tiny" in which:
+        tiny_sam(models)
+        tiny_mae(models)
+    if "mae256" in which:
+        mae256(models)
+    if "samvit" in which:
+        samvit(models)
+    if "sam512" in which:
+        sam512(models)
