@@ -52,20 +52,21 @@ int la_gemm_bf16(void* stream, const void* a, long long lda, const void* w, long
 
 /* ---- fused attention ----------------------------------------------------------------------------- */
 /* Multi-head self-attention, head_dim 64, over n_seq sequences of seq_len tokens stored as consecutive rows
- * of the packed projection matrix `qkv` [rows_total, ld_qkv] (bf16).  Head h reads q/k/v at columns
- * {q,k,v}_off + 64*h.  softmax(scale * q k^T + bias) v -> out [.., ld_out] bf16 at columns 64*h.
- * Optional decomposed relative-position bias (bias_h/bias_w != NULL): fp32 tables [n_heads][rows_total][ldb]
- * with table[h][row][grid_hw-1 - q_pos + k_pos] = q_row(h) . rel_pos[q_pos - k_pos + grid_hw-1], i.e. the
+ * of the projection matrices q [rows_total, ld_q] and kv [rows_total, ld_kv] (bf16; they may be the same
+ * packed qkv buffer).  Head h reads q at column q_off + 64*h and k / v at columns {k,v}_off + 64*h of kv.
+ * softmax(scale * q k^T + bias) v -> out [.., ld_out] bf16 at columns 64*h.
+ * Optional decomposed relative-position bias (bias_h/bias_w != NULL): fp32 tables [rows_total][n_heads][ldb]
+ * with table[row][h][grid_hw-1 - q_pos + k_pos] = q_row(h) . rel_pos[q_pos - k_pos + grid_hw-1], i.e. the
  * product of the head's q rows with the REVERSED rel_pos table (computed with la_gemm_bf16); grid_hw = 64
  * (global blocks, seq_len 4096) or 14 (windowed blocks, seq_len 196).
- * out_mode 0: out row = sequence*seq_len + token.  out_mode 1: window un-partition — sequence = image*nwin^2
+ * out_mode 0: out row = sequence*seq_len + token.  out_mode 1: window un-partition: sequence = image*nwin^2
  * + window, token (ty,tx) of window (wy,wx) goes to image row (wy*14+ty)*img_hw + wx*14+tx, padded
  * positions are dropped.
  *   label_anything/models/image_encoder.py:239-255,282-304,340-376; transformers modeling_vit.py:199-250 */
-int la_attention_bf16(void* stream, const void* qkv, long long ld_qkv, long long rows_total, int q_off, int k_off,
-                      int v_off, int n_seq, int seq_len, int n_heads, float scale, const float* bias_h,
-                      const float* bias_w, int ldb, int grid_hw, void* out, long long ld_out, int out_mode,
-                      int nwin, int img_hw);
+int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
+                      int k_off, int v_off, long long rows_total, int n_seq, int seq_len, int n_heads, float scale,
+                      const float* bias_h, const float* bias_w, int ldb, int grid_hw, void* out, long long ld_out,
+                      int out_mode, int nwin, int img_hw);
 
 /* ---- streaming row kernels ----------------------------------------------------------------------- */
 /* x = x_in[(row % x_mod) if x_mod > 0 else row] + delta[row]  (fp32 + bf16); optionally stored to x_out (may

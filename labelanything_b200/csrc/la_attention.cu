@@ -31,7 +31,7 @@ struct AttParams {
   int q_off, k_off, v_off;  // column (element) offsets of head 0 inside a qkv row
   long long rows_total;     // rows in the qkv matrix
   float scale_log2;         // softmax scale * log2(e)
-  // rel-pos bias tables: [n_heads][rows_total][ldb] fp32 (nullptr for ATT_BIAS_NONE)
+  // rel-pos bias tables: [rows_total][n_heads][ldb] fp32 (nullptr for ATT_BIAS_NONE)
   const float* bias_h;
   const float* bias_w;
   int ldb;
@@ -235,7 +235,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if constexpr (BIAS != ATT_BIAS_NONE) {
       const int tt = row_valid ? t : 0;
       const int qh = tt / GW, qw = tt % GW;
-      const long long brow = (static_cast<long long>(head) * p.rows_total + seq_row0 + tt) * p.ldb;
+      const long long brow = ((seq_row0 + tt) * p.n_heads + head) * p.ldb;
       const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
       bh_row = p.bias_h + brow + (GW - 1 - qh);
 #pragma unroll
@@ -432,14 +432,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 }
 
 template <int KV_TILE, int BIAS>
-static int launch_attention(cudaStream_t stream, const void* qkv, long long ld_qkv, const AttParams& p) {
+static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, const void* kv, long long ld_kv,
+                            const AttParams& p) {
   using S = AttSmem<KV_TILE>;
   CUtensorMap tm_q, tm_kv;
-  int rc = make_tensor_map_2d(&tm_q, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_qkv,
-                              (uint64_t)p.rows_total, (uint64_t)ld_qkv * 2, 64, 128, Swizzle::B128);
+  int rc = make_tensor_map_2d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_q, (uint64_t)p.rows_total,
+                              (uint64_t)ld_q * 2, 64, 128, Swizzle::B128);
   if (rc) return rc;
-  rc = make_tensor_map_2d(&tm_kv, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_qkv, (uint64_t)p.rows_total,
-                          (uint64_t)ld_qkv * 2, 64, KV_TILE, Swizzle::B128);
+  rc = make_tensor_map_2d(&tm_kv, kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_kv, (uint64_t)p.rows_total,
+                          (uint64_t)ld_kv * 2, 64, KV_TILE, Swizzle::B128);
   if (rc) return rc;
   auto kern = attention_fwd_kernel<KV_TILE, BIAS>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -451,15 +452,16 @@ static int launch_attention(cudaStream_t stream, const void* qkv, long long ld_q
 
 }  // namespace la
 
-extern "C" int la_attention_bf16(void* stream, const void* qkv, long long ld_qkv, long long rows_total, int q_off,
-                                 int k_off, int v_off, int n_seq, int seq_len, int n_heads, float scale,
-                                 const float* bias_h, const float* bias_w, int ldb, int grid_hw, void* out,
-                                 long long ld_out, int out_mode, int nwin, int img_hw) {
+extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv,
+                                 long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq,
+                                 int seq_len, int n_heads, float scale, const float* bias_h, const float* bias_w,
+                                 int ldb, int grid_hw, void* out, long long ld_out, int out_mode, int nwin,
+                                 int img_hw) {
   using namespace la;
-  LA_CHECK_ARG(qkv && out, "la_attention_bf16: null pointer");
+  LA_CHECK_ARG(q && kv && out, "la_attention_bf16: null pointer");
   LA_CHECK_ARG(n_seq > 0 && seq_len > 0 && n_heads > 0, "la_attention_bf16: empty problem");
   LA_CHECK_ARG(n_seq <= 65535 && n_heads <= 65535, "la_attention_bf16: n_seq/n_heads exceed the grid limits");
-  LA_CHECK_ARG(ld_qkv % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+  LA_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
                "la_attention_bf16: strides/offsets must be multiples of 8 elements");
   LA_CHECK_ARG(rows_total >= static_cast<long long>(n_seq) * seq_len, "la_attention_bf16: rows_total too small");
   LA_CHECK_ARG(rows_total < (1ll << 31), "la_attention_bf16: rows_total exceeds TMA coordinate range");
@@ -486,18 +488,18 @@ extern "C" int la_attention_bf16(void* stream, const void* qkv, long long ld_qkv
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!has_bias) {
     LA_CHECK_ARG(out_mode == 0, "la_attention_bf16: window output mapping needs the window bias mode");
-    return launch_attention<128, ATT_BIAS_NONE>(st, qkv, ld_qkv, p);
+    return launch_attention<128, ATT_BIAS_NONE>(st, q, ld_q, kv, ld_kv, p);
   }
   if (grid_hw == 64) {
     LA_CHECK_ARG(seq_len == 4096 && ldb >= 127 && out_mode == 0,
                  "la_attention_bf16: 64x64 rel-pos mode expects seq_len 4096, ldb >= 127");
-    return launch_attention<128, ATT_BIAS_GLOBAL64>(st, qkv, ld_qkv, p);
+    return launch_attention<128, ATT_BIAS_GLOBAL64>(st, q, ld_q, kv, ld_kv, p);
   }
   if (grid_hw == 14) {
     LA_CHECK_ARG(seq_len == 196 && ldb >= 27, "la_attention_bf16: 14x14 rel-pos mode expects seq_len 196, ldb >= 27");
     LA_CHECK_ARG(out_mode == 0 || (nwin > 0 && img_hw > 0 && n_seq % (nwin * nwin) == 0),
                  "la_attention_bf16: bad window-unpartition parameters");
-    return launch_attention<112, ATT_BIAS_WINDOW14>(st, qkv, ld_qkv, p);
+    return launch_attention<112, ATT_BIAS_WINDOW14>(st, q, ld_q, kv, ld_kv, p);
   }
   set_last_error("la_attention_bf16: unsupported rel-pos grid %d (built for 64 and 14)", grid_hw);
   return LA_ERR_UNSUPPORTED;

@@ -1,0 +1,168 @@
+"""SAM / ViTDet image encoder with the reference's module surface, running on the native kernels.
+
+Mirror of label_anything/models/image_encoder.py: `ImageEncoderViT` (:19-131), `Block` (:134-197),
+`Attention` (:200-255), `PatchEmbed` (:379-410).  Attribute names and state-dict keys are identical
+(`patch_embed.proj`, `pos_embed`, `blocks.N.{norm1,attn.{qkv,proj,rel_pos_h,rel_pos_w},norm2,mlp.{lin1,lin2}}`,
+`neck.{0..3}`), so SAM checkpoints and reference checkpoints load unchanged.  The arithmetic is
+`vit_engine.run_vit` (tcgen05 GEMMs, fused attention with decomposed rel-pos bias, add+LayerNorm kernels).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Type
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .common import LayerNorm2d, MLPBlock, NativeModule, bf16_weight, f32
+from .vit_engine import BlockWeights, VitSpec, pack_neck, reversed_rel_table, run_neck, run_vit, tokens_to_nchw
+
+LAST_HIDDEN_STATE = "last_hidden_state"  # label_anything/utils/utils.py:356-364 (ResultDict)
+LAST_BLOCK_STATE = "last_block_state"
+
+
+class PatchEmbed(NativeModule):
+    def __init__(self, kernel_size=(16, 16), stride=(16, 16), padding=(0, 0), in_chans: int = 3,
+                 embed_dim: int = 768) -> None:
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=kernel_size, stride=stride, padding=padding)
+
+
+class Attention(NativeModule):
+    """Multi-head attention block with decomposed relative position embeddings (image_encoder.py:200-237)."""
+
+    def __init__(self, dim: int, num_heads: int = 8, qkv_bias: bool = True, use_rel_pos: bool = False,
+                 rel_pos_zero_init: bool = True, input_size: Optional[Tuple[int, int]] = None) -> None:
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.use_rel_pos = use_rel_pos
+        if self.use_rel_pos:
+            assert input_size is not None, "Input size must be provided if using relative positional encoding."
+            self.rel_pos_h = nn.Parameter(torch.zeros(2 * input_size[0] - 1, head_dim))
+            self.rel_pos_w = nn.Parameter(torch.zeros(2 * input_size[1] - 1, head_dim))
+
+
+class Block(NativeModule):
+    def __init__(self, dim: int, num_heads: int, mlp_ratio: float = 4.0, qkv_bias: bool = True,
+                 norm_layer: Type[nn.Module] = nn.LayerNorm, act_layer: Type[nn.Module] = nn.GELU,
+                 use_rel_pos: bool = False, rel_pos_zero_init: bool = True, window_size: int = 0,
+                 input_size: Optional[Tuple[int, int]] = None) -> None:
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, use_rel_pos=use_rel_pos,
+                              rel_pos_zero_init=rel_pos_zero_init,
+                              input_size=input_size if window_size == 0 else (window_size, window_size))
+        self.norm2 = norm_layer(dim)
+        self.mlp = MLPBlock(embedding_dim=dim, mlp_dim=int(dim * mlp_ratio), act=act_layer)
+        self.window_size = window_size
+
+
+class ImageEncoderViT(NativeModule):
+    def __init__(self, img_size: int = 1024, patch_size: int = 16, in_chans: int = 3, embed_dim: int = 768,
+                 depth: int = 12, num_heads: int = 12, mlp_ratio: float = 4.0, out_chans: int = 256,
+                 qkv_bias: bool = True, norm_layer: Type[nn.Module] = nn.LayerNorm,
+                 act_layer: Type[nn.Module] = nn.GELU, use_abs_pos: bool = True, use_rel_pos: bool = False,
+                 rel_pos_zero_init: bool = True, window_size: int = 0, global_attn_indexes: Tuple[int, ...] = (),
+                 project_last_hidden: bool = True) -> None:
+        super().__init__()
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.project_last_hidden = project_last_hidden
+        self.patch_embed = PatchEmbed(kernel_size=(patch_size, patch_size), stride=(patch_size, patch_size),
+                                      in_chans=in_chans, embed_dim=embed_dim)
+        self.pos_embed: Optional[nn.Parameter] = None
+        if use_abs_pos:
+            self.pos_embed = nn.Parameter(torch.zeros(1, img_size // patch_size, img_size // patch_size, embed_dim))
+        self.blocks = nn.ModuleList()
+        for i in range(depth):
+            self.blocks.append(Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                                     norm_layer=norm_layer, act_layer=act_layer, use_rel_pos=use_rel_pos,
+                                     rel_pos_zero_init=rel_pos_zero_init,
+                                     window_size=window_size if i not in global_attn_indexes else 0,
+                                     input_size=(img_size // patch_size, img_size // patch_size)))
+        self.neck = nn.Sequential(
+            nn.Conv2d(embed_dim, out_chans, kernel_size=1, bias=False), LayerNorm2d(out_chans),
+            nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False), LayerNorm2d(out_chans))
+        #: images per launch group; bounds the workspace (~125 MB per 1024-px image)
+        self.max_images_per_chunk = 32
+
+    # ------------------------------------------------------------------ weight packing
+    def _spec(self, grid: int) -> VitSpec:
+        d = self.embed_dim
+        blocks = []
+        for i, blk in enumerate(self.blocks):
+            a = blk.attn
+            wqkv = bf16_weight(self, f"b{i}.qkv", a.qkv.weight)
+            bqkv = f32(self, f"b{i}.qkv.b", a.qkv.bias)
+            rel, pad = None, 0
+            if a.use_rel_pos:
+                size = blk.window_size if blk.window_size > 0 else grid
+                pad = 128 if size > 32 else 64
+                assert 2 * size - 1 <= pad and a.rel_pos_h.shape[1] == 64
+                rel = self.packed(
+                    f"b{i}.rel:{size}",
+                    lambda a=a, size=size, pad=pad: torch.cat(
+                        [reversed_rel_table(a.rel_pos_h, size, pad), reversed_rel_table(a.rel_pos_w, size, pad)])
+                    .to(torch.bfloat16).contiguous(), a.rel_pos_h, a.rel_pos_w)
+            eps = blk.norm1.eps
+            blocks.append(BlockWeights(
+                f32(self, f"b{i}.n1w", blk.norm1.weight), f32(self, f"b{i}.n1b", blk.norm1.bias),
+                wqkv[:d], None if bqkv is None else bqkv[:d], wqkv[d:], None if bqkv is None else bqkv[d:],
+                bf16_weight(self, f"b{i}.proj", a.proj.weight), f32(self, f"b{i}.proj.b", a.proj.bias),
+                f32(self, f"b{i}.n2w", blk.norm2.weight), f32(self, f"b{i}.n2b", blk.norm2.bias),
+                bf16_weight(self, f"b{i}.lin1", blk.mlp.lin1.weight), f32(self, f"b{i}.lin1.b", blk.mlp.lin1.bias),
+                bf16_weight(self, f"b{i}.lin2", blk.mlp.lin2.weight), f32(self, f"b{i}.lin2.b", blk.mlp.lin2.bias),
+                window=blk.window_size, rel_table=rel, rel_pad=pad))
+        return VitSpec(d=d, heads=self.num_heads, eps=eps, blocks=blocks, grid=grid)
+
+    # ------------------------------------------------------------------ forward
+    def encode_tokens(self, images: torch.Tensor, out_dtype: torch.dtype = torch.float32,
+                      want_last_block: bool = False):
+        """images [I, 3, S, S] fp32 CUDA -> token-major features [I*g*g, C] (+ optionally the pre-neck state)."""
+        ops._require_cuda(images)
+        I, C, S, S2 = images.shape
+        assert S == S2 and self.patch_size == 16, "native patch embedding is built for 16x16 patches"
+        g = S // 16
+        if self.pos_embed is not None:
+            assert self.pos_embed.shape[1] == g, "pos_embed grid must match the input resolution"
+        images = images.float().contiguous()
+        spec = self._spec(g)
+        w_pe = bf16_weight(self, "patch", self.patch_embed.proj.weight)
+        b_pe = f32(self, "patch.b", self.patch_embed.proj.bias)
+        pos = f32(self, "pos", self.pos_embed).view(g * g, -1) if self.pos_embed is not None else None
+        nw = pack_neck(self, self.neck) if self.project_last_hidden else None
+        outs, lasts = [], []
+        for s in range(0, I, self.max_images_per_chunk):
+            n = min(self.max_images_per_chunk, I - s)
+            cols = ops.im2col_patch16(images[s:s + n])
+            patch = ops.gemm(cols, w_pe, b_pe)
+            del cols
+            x = torch.empty((n * g * g, self.embed_dim), dtype=torch.float32, device=images.device)
+            ops.embed_tokens(patch, None, pos, x, n, g * g, 0, self.embed_dim)
+            del patch
+            need_bf16 = self.project_last_hidden and not want_last_block
+            t = run_vit(spec, x, n, torch.bfloat16 if need_bf16 else (out_dtype if nw is None else torch.float32))
+            if want_last_block:
+                lasts.append(t)
+            if nw is not None:
+                t = run_neck(nw, t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16), n, g, out_dtype)
+            outs.append(t)
+        feats = outs[0] if len(outs) == 1 else torch.cat(outs)
+        if want_last_block:
+            return feats, (lasts[0] if len(lasts) == 1 else torch.cat(lasts)), g
+        return feats, g
+
+    def forward(self, x: torch.Tensor, return_last_block_state: bool = False):
+        """Reference-compatible output: [I, C, h, w] fp32 (image_encoder.py:110-131)."""
+        I = x.shape[0]
+        if return_last_block_state and self.project_last_hidden:
+            feats, last, g = self.encode_tokens(x, torch.float32, want_last_block=True)
+            return {LAST_HIDDEN_STATE: tokens_to_nchw(feats, I, g), LAST_BLOCK_STATE: tokens_to_nchw(last, I, g)}
+        feats, g = self.encode_tokens(x, torch.float32)
+        return tokens_to_nchw(feats, I, g)

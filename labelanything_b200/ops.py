@@ -52,24 +52,27 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
-def attention(qkv: torch.Tensor, n_seq: int, seq_len: int, n_heads: int, scale: float, out: torch.Tensor,
-              q_off: int, k_off: int, v_off: int, bias_h: torch.Tensor | None = None,
+def attention(q: torch.Tensor, kv: torch.Tensor, n_seq: int, seq_len: int, n_heads: int, scale: float,
+              out: torch.Tensor, q_off: int, k_off: int, v_off: int, bias_h: torch.Tensor | None = None,
               bias_w: torch.Tensor | None = None, grid_hw: int = 0, out_mode: int = 0, nwin: int = 0,
               img_hw: int = 0) -> torch.Tensor:
-    """Fused MHSA (head_dim 64) over the packed projection matrix `qkv` [rows, ld] bf16; see the C header."""
-    _require_cuda(qkv, out, bias_h, bias_w)
-    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1
-    assert out.dtype == torch.bfloat16 and out.dim() == 2 and out.stride(1) == 1
+    """Fused MHSA (head_dim 64); q [rows, ld_q], kv [rows, ld_kv] bf16 (may be one packed buffer).
+    bias_h / bias_w: fp32 views [rows, heads, >=2g-1] sharing one row stride (see the C header)."""
+    _require_cuda(q, kv, out, bias_h, bias_w)
+    for t in (q, kv, out):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    assert q.shape[0] == kv.shape[0]
     ldb = 0
     if bias_h is not None:
         assert bias_h.dtype == torch.float32 and bias_w.dtype == torch.float32
-        assert bias_h.is_contiguous() and bias_w.is_contiguous() and bias_h.shape == bias_w.shape
-        assert bias_h.shape[0] == n_heads and bias_h.shape[1] == qkv.shape[0]
-        ldb = bias_h.shape[2]
+        assert bias_h.dim() == 3 and bias_h.shape[:2] == (q.shape[0], n_heads) and bias_w.shape[:2] == bias_h.shape[:2]
+        assert bias_h.stride(2) == 1 and bias_w.stride(2) == 1 and bias_h.stride() == bias_w.stride()
+        ldb = bias_h.stride(1)
+        assert bias_h.stride(0) == ldb * n_heads
     rc = _native.lib().la_attention_bf16(
-        _stream(qkv), qkv.data_ptr(), qkv.stride(0), qkv.shape[0], q_off, k_off, v_off, n_seq, seq_len, n_heads,
-        float(scale), _ptr(bias_h), _ptr(bias_w), ldb, grid_hw, out.data_ptr(), out.stride(0), out_mode, nwin,
-        img_hw)
+        _stream(q), q.data_ptr(), q.stride(0), q_off, kv.data_ptr(), kv.stride(0), k_off, v_off, q.shape[0], n_seq,
+        seq_len, n_heads, float(scale), _ptr(bias_h), _ptr(bias_w), ldb, grid_hw, out.data_ptr(), out.stride(0),
+        out_mode, nwin, img_hw)
     _native.check(rc, "attention")
     return out
 
