@@ -70,17 +70,28 @@ int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, co
 
 /* ---- streaming row kernels ----------------------------------------------------------------------- */
 /* x = x_in[(row % x_mod) if x_mod > 0 else row] + delta[row]  (fp32 + bf16); optionally stored to x_out (may
- * alias x_in); y = LayerNorm(x) * gamma + beta (biased variance, `eps`), or a plain cast when gamma == NULL;
- * y stored as bf16 / fp32 (y_dtype) with a row remapping:
+ * alias x_in); y = act(LayerNorm(x) * gamma + beta) (biased variance, `eps`), or a plain cast when
+ * gamma == NULL.  Outputs (each optional): y_out as bf16 / fp32 (y_dtype), y2_out = y in fp32,
+ * ype_out = bf16(y + pe[row % pe_mod]) (positional table folded in for the next projection).  Row remapping:
  *   map_mode 0: identity.
  *   map_mode 1: `rows` counts OUTPUT rows in window-partitioned order (image, wy, wx, ty, tx) for win x win
  *               windows, nwin per side, over an hw x hw grid; rows that fall in the zero padding are written
  *               as zeros (F.pad happens after norm1).  image_encoder.py:183-187,258-279
  *   map_mode 2: drop token 0 (CLS) of every seq_len-token sequence.  build_encoder.py:98
- *   image_encoder.py:181-197; common.py:42-54; transformers modeling_vit.py:325-346,416 */
+ *   image_encoder.py:181-197; common.py:42-54,183-184; transformer.py:308-327; mask_decoder.py:214-215,250-254;
+ *   transformers modeling_vit.py:325-346,416 */
 int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const void* delta, float* x_out,
-                     const float* gamma, const float* beta, float eps, void* y_out, int y_dtype, long long rows,
-                     int d, int map_mode, int seq_len, int win, int nwin, int hw);
+                     const float* gamma, const float* beta, float eps, int act, void* y_out, int y_dtype,
+                     float* y2_out, const float* pe, long long pe_mod, void* ype_out, long long rows, int d,
+                     int map_mode, int seq_len, int win, int nwin, int hw);
+
+/* out[s, :] = mean over the rows_per_seq rows of sequence s of LayerNorm(x_in + delta): the last
+ * image-token LayerNorm of the prompt encoder's two-way transformer fused with the spatial average pooling
+ * (the normalised tokens are never written).  partial_ws: fp32 scratch [n_seq * slices * d]; deterministic.
+ *   label_anything/models/transformer.py:326-327 + prompt_encoder.py:733-735 */
+int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta, const float* gamma,
+                              const float* beta, float eps, long long n_seq, int rows_per_seq, int d,
+                              float* partial_ws, int slices, float* out);
 
 /* x[img, tok, :] = (tok < n_cls ? cls : patch[img, tok - n_cls, :]) + pos[tok, :]; patch bf16, x fp32.
  *   image_encoder.py:112-114; transformers modeling_vit.py:109-125 */

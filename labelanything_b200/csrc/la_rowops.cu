@@ -29,6 +29,14 @@ struct AddLnParams {
   float eps;
   void* y_out;                  // nullptr -> skip
   int y_f32;                    // 0 bf16, 1 fp32
+  float* y2_out;                // optional second copy of y in fp32 (same row mapping)
+  const float* pe;              // optional [pe_mod, d] table: ype = y + pe[dst_row % pe_mod]
+  long long pe_mod;
+  __nv_bfloat16* ype_out;       // optional bf16 (y + pe)
+  int act;                      // LA_ACT_* applied to y after the affine
+  float* pool_out;              // pooling variant: [n_seq, pool_slices, d] partial sums of y
+  int pool_rows;                // rows per sequence (pooling variant)
+  int pool_slices;
   long long rows;               // source rows (map 0, 2) ; output rows (map 1)
   int d;
   int map_mode;                 // 0 identity, 1 window partition with zero pad, 2 drop first token per sequence
@@ -38,14 +46,34 @@ struct AddLnParams {
 
 __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p) {
   const int lane = threadIdx.x & 31;
-  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  const int nv = p.d >> 7;           // full float4 groups per lane
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int nv = p.d >> 7;            // full float4 groups per lane
   const int tail = (p.d & 127) >> 2;  // leftover float4s (< 32)
 
-  for (long long row = warp_global; row < p.rows; row += n_warps) {
+  long long row_begin, row_end, row_step;
+  if (p.pool_out) {
+    // pooling variant: CTA = (sequence, slice); its 8 warps stride over the slice's rows
+    const long long seq = blockIdx.x / p.pool_slices;
+    const int sl = blockIdx.x % p.pool_slices;
+    const int per = (p.pool_rows + p.pool_slices - 1) / p.pool_slices;
+    row_begin = seq * p.pool_rows + static_cast<long long>(sl) * per + warp_in_cta;
+    long long e = seq * p.pool_rows + static_cast<long long>(sl + 1) * per;
+    const long long seq_end = (seq + 1) * p.pool_rows;
+    row_end = e < seq_end ? e : seq_end;
+    row_step = blockDim.x >> 5;
+  } else {
+    row_begin = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    row_end = p.rows;
+    row_step = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  }
+  const bool any_y = p.y_out || p.y2_out || p.ype_out || p.pool_out;
+  float4 acc[ROW_MAXV + 1];
+#pragma unroll
+  for (int i = 0; i <= ROW_MAXV; ++i) acc[i] = make_float4(0, 0, 0, 0);
+
+  for (long long row = row_begin; row < row_end; row += row_step) {
     long long src = row, dst = row;
-    bool pad = false, write_y = p.y_out != nullptr;
+    bool pad = false, write_y = any_y;
     if (p.map_mode == 1) {
       const int w2 = p.win * p.win;
       const long long widx = row / w2;
@@ -67,10 +95,12 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
     uint8_t* yrow = static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(dst) * p.d * ebytes;
     if (pad) {
       // zero row (padding token of a window): F.pad after norm1, image_encoder.py:271-275
-      if (p.y_f32) {
-        for (int i = lane; i < p.d / 4; i += 32) reinterpret_cast<float4*>(yrow)[i] = make_float4(0, 0, 0, 0);
-      } else {
-        for (int i = lane; i < p.d / 8; i += 32) reinterpret_cast<uint4*>(yrow)[i] = make_uint4(0, 0, 0, 0);
+      if (p.y_out) {
+        if (p.y_f32) {
+          for (int i = lane; i < p.d / 4; i += 32) reinterpret_cast<float4*>(yrow)[i] = make_float4(0, 0, 0, 0);
+        } else {
+          for (int i = lane; i < p.d / 8; i += 32) reinterpret_cast<uint4*>(yrow)[i] = make_uint4(0, 0, 0, 0);
+        }
       }
       continue;
     }
@@ -133,16 +163,81 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
           o.z = (o.z - mean) * rstd * g.z + b.z;
           o.w = (o.w - mean) * rstd * g.w + b.w;
         }
-        if (p.y_f32) {
-          reinterpret_cast<float4*>(yrow)[idx] = o;
-        } else {
-          uint2 pk;
-          pk.x = pack_bf16(o.x, o.y);
-          pk.y = pack_bf16(o.z, o.w);
-          reinterpret_cast<uint2*>(yrow)[idx] = pk;
+        if (p.act == LA_ACT_GELU) {
+          o.x = gelu_erf(o.x);
+          o.y = gelu_erf(o.y);
+          o.z = gelu_erf(o.z);
+          o.w = gelu_erf(o.w);
+        } else if (p.act == LA_ACT_RELU) {
+          o.x = fmaxf(o.x, 0.f);
+          o.y = fmaxf(o.y, 0.f);
+          o.z = fmaxf(o.z, 0.f);
+          o.w = fmaxf(o.w, 0.f);
         }
+        if (p.y_out) {
+          if (p.y_f32) {
+            reinterpret_cast<float4*>(yrow)[idx] = o;
+          } else {
+            uint2 pk;
+            pk.x = pack_bf16(o.x, o.y);
+            pk.y = pack_bf16(o.z, o.w);
+            reinterpret_cast<uint2*>(yrow)[idx] = pk;
+          }
+        }
+        if (p.y2_out) reinterpret_cast<float4*>(p.y2_out + dst * p.d)[idx] = o;
+        if (p.ype_out) {
+          const float4 e = __ldg(reinterpret_cast<const float4*>(p.pe + (dst % p.pe_mod) * p.d) + idx);
+          uint2 pk;
+          pk.x = pack_bf16(o.x + e.x, o.y + e.y);
+          pk.y = pack_bf16(o.z + e.z, o.w + e.w);
+          reinterpret_cast<uint2*>(p.ype_out + dst * p.d)[idx] = pk;
+        }
+        acc[i].x += o.x;
+        acc[i].y += o.y;
+        acc[i].z += o.z;
+        acc[i].w += o.w;
       }
     }
+  }
+  if (p.pool_out) {
+    // deterministic reduction: lanes own disjoint channels; the CTA's warps are summed in a fixed order
+    // through shared memory; one partial row per (sequence, slice).
+    extern __shared__ float4 red[];  // [warps][d/4]
+    const int dv = p.d >> 2;
+#pragma unroll
+    for (int i = 0; i <= ROW_MAXV; ++i) {
+      const bool on = (i < nv) || (i == nv && lane < tail);
+      if (on) red[warp_in_cta * dv + i * 32 + lane] = acc[i];
+    }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    float4* dstp = reinterpret_cast<float4*>(p.pool_out + static_cast<long long>(blockIdx.x) * p.d);
+    for (int c = threadIdx.x; c < dv; c += blockDim.x) {
+      float4 t = red[c];
+      for (int w = 1; w < nw; ++w) {
+        const float4 u = red[w * dv + c];
+        t.x += u.x;
+        t.y += u.y;
+        t.z += u.z;
+        t.w += u.w;
+      }
+      dstp[c] = t;
+    }
+  }
+}
+
+// out[s, :] = scale * sum_p partial[s, p, :]
+__global__ void __launch_bounds__(256)
+pool_finish_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n_seq, int slices, int d,
+                   float scale) {
+  const long long total = n_seq * d;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long s = i / d;
+    const int c = static_cast<int>(i % d);
+    float t = 0.f;
+    for (int q = 0; q < slices; ++q) t += partial[(s * slices + q) * d + c];
+    out[i] = t * scale;
   }
 }
 
@@ -243,8 +338,9 @@ static int grid_for(long long work_items, int block, int per_sm) {
 extern "C" {
 
 int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const void* delta, float* x_out,
-                     const float* gamma, const float* beta, float eps, void* y_out, int y_dtype, long long rows,
-                     int d, int map_mode, int seq_len, int win, int nwin, int hw) {
+                     const float* gamma, const float* beta, float eps, int act, void* y_out, int y_dtype,
+                     float* y2_out, const float* pe, long long pe_mod, void* ype_out, long long rows, int d,
+                     int map_mode, int seq_len, int win, int nwin, int hw) {
   using namespace la;
   LA_CHECK_ARG(rows > 0 && d > 0, "la_add_layernorm: empty problem");
   LA_CHECK_ARG(d % 8 == 0 && d <= 128 * ROW_MAXV + 124, "la_add_layernorm: d=%d unsupported (multiple of 8, <= 1404)", d);
@@ -254,7 +350,9 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   LA_CHECK_ARG(map_mode != 1 || (win > 0 && nwin > 0 && hw > 0 && rows % (static_cast<long long>(win) * win * nwin * nwin) == 0),
                "la_add_layernorm: bad window parameters");
   LA_CHECK_ARG(map_mode != 2 || (seq_len > 1 && rows % seq_len == 0), "la_add_layernorm: bad seq_len");
-  AddLnParams p;
+  LA_CHECK_ARG(!ype_out || (pe && pe_mod > 0), "la_add_layernorm: ype_out needs the pe table");
+  LA_CHECK_ARG(act >= LA_ACT_NONE && act <= LA_ACT_RELU, "la_add_layernorm: bad act");
+  AddLnParams p = {};
   p.x_in = x_in;
   p.x_mod = x_mod;
   p.delta = static_cast<const __nv_bfloat16*>(delta);
@@ -264,6 +362,11 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   p.eps = eps;
   p.y_out = y_out;
   p.y_f32 = y_dtype == LA_DTYPE_F32;
+  p.y2_out = y2_out;
+  p.pe = pe;
+  p.pe_mod = pe_mod;
+  p.ype_out = static_cast<__nv_bfloat16*>(ype_out);
+  p.act = act;
   p.rows = rows;
   p.d = d;
   p.map_mode = map_mode;
@@ -273,6 +376,37 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   p.hw = hw;
   const int grid = grid_for(rows * 32, 256, 8);
   add_layernorm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta, const float* gamma,
+                              const float* beta, float eps, long long n_seq, int rows_per_seq, int d,
+                              float* partial_ws, int slices, float* out) {
+  using namespace la;
+  LA_CHECK_ARG(n_seq > 0 && rows_per_seq > 0 && d > 0 && slices > 0, "la_add_layernorm_meanpool: empty problem");
+  LA_CHECK_ARG(d % 8 == 0 && d <= 128 * ROW_MAXV + 124, "la_add_layernorm_meanpool: d=%d unsupported", d);
+  LA_CHECK_ARG((x_in || delta) && gamma && beta && partial_ws && out, "la_add_layernorm_meanpool: null pointer");
+  LA_CHECK_ARG(n_seq * slices < (1ll << 31), "la_add_layernorm_meanpool: grid too large");
+  AddLnParams p = {};
+  p.x_in = x_in;
+  p.delta = static_cast<const __nv_bfloat16*>(delta);
+  p.gamma = gamma;
+  p.beta = beta;
+  p.eps = eps;
+  p.pool_out = partial_ws;
+  p.pool_rows = rows_per_seq;
+  p.pool_slices = slices;
+  p.rows = n_seq * rows_per_seq;
+  p.d = d;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = 8 * static_cast<size_t>(d) * sizeof(float);
+  if (smem > 48 * 1024)
+    LA_CHECK_CUDA(cudaFuncSetAttribute(add_layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  add_layernorm_kernel<<<static_cast<int>(n_seq * slices), 256, smem, st>>>(p);
+  LA_CHECK_CUDA(cudaGetLastError());
+  pool_finish_kernel<<<grid_for(n_seq * d, 256, 8), 256, 0, st>>>(partial_ws, out, n_seq, slices, d,
+                                                                 1.0f / rows_per_seq);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }

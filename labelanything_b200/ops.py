@@ -79,20 +79,44 @@ def attention(q: torch.Tensor, kv: torch.Tensor, n_seq: int, seq_len: int, n_hea
 
 def add_layernorm(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: torch.Tensor | None,
                   beta: torch.Tensor | None, eps: float, *, rows: int, d: int, x_out: torch.Tensor | None = None,
-                  y_out: torch.Tensor | None = None, x_mod: int = 0, map_mode: int = 0, seq_len: int = 0,
-                  win: int = 0, nwin: int = 0, hw: int = 0) -> None:
-    """x = x_in + delta (-> x_out); y = LN(x) (-> y_out, bf16 or fp32) with optional row remapping."""
-    _require_cuda(x_in, delta, gamma, beta, x_out, y_out)
+                  y_out: torch.Tensor | None = None, y2_out: torch.Tensor | None = None,
+                  pe: torch.Tensor | None = None, ype_out: torch.Tensor | None = None, act: int = ACT_NONE,
+                  x_mod: int = 0, map_mode: int = 0, seq_len: int = 0, win: int = 0, nwin: int = 0,
+                  hw: int = 0) -> None:
+    """x = x_in + delta (-> x_out); y = act(LN(x)) -> y_out (bf16/fp32), y2_out (fp32), ype_out (bf16, y + pe)."""
+    _require_cuda(x_in, delta, gamma, beta, x_out, y_out, y2_out, pe, ype_out)
     ref = x_in if x_in is not None else delta
-    for t in (x_in, x_out, gamma, beta):
+    for t in (x_in, x_out, gamma, beta, y2_out, pe):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
-    assert delta is None or (delta.dtype == torch.bfloat16 and delta.is_contiguous())
+    for t in (delta, ype_out):
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous())
     assert y_out is None or (y_out.is_contiguous() and y_out.dtype in (torch.bfloat16, torch.float32))
+    pe_mod = 0
+    if ype_out is not None:
+        assert pe is not None and pe.shape[-1] == d
+        pe_mod = pe.numel() // d
     rc = _native.lib().la_add_layernorm(
-        _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(x_out), _ptr(gamma), _ptr(beta), float(eps),
-        _ptr(y_out), DT_F32 if (y_out is not None and y_out.dtype == torch.float32) else DT_BF16, rows, d,
-        map_mode, seq_len, win, nwin, hw)
+        _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(x_out), _ptr(gamma), _ptr(beta), float(eps), act,
+        _ptr(y_out), DT_F32 if (y_out is not None and y_out.dtype == torch.float32) else DT_BF16, _ptr(y2_out),
+        _ptr(pe), pe_mod, _ptr(ype_out), rows, d, map_mode, seq_len, win, nwin, hw)
     _native.check(rc, "add_layernorm")
+
+
+def add_layernorm_meanpool(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: torch.Tensor,
+                           beta: torch.Tensor, eps: float, n_seq: int, rows_per_seq: int, d: int,
+                           slices: int = 8) -> torch.Tensor:
+    """mean over each sequence's rows of LN(x_in + delta) -> fp32 [n_seq, d]."""
+    _require_cuda(x_in, delta, gamma, beta)
+    ref = x_in if x_in is not None else delta
+    assert x_in is None or (x_in.dtype == torch.float32 and x_in.is_contiguous())
+    assert delta is None or (delta.dtype == torch.bfloat16 and delta.is_contiguous())
+    ws = torch.empty((n_seq * slices, d), dtype=torch.float32, device=ref.device)
+    out = torch.empty((n_seq, d), dtype=torch.float32, device=ref.device)
+    rc = _native.lib().la_add_layernorm_meanpool(_stream(ref), _ptr(x_in), _ptr(delta), gamma.data_ptr(),
+                                                 beta.data_ptr(), float(eps), n_seq, rows_per_seq, d,
+                                                 ws.data_ptr(), slices, out.data_ptr())
+    _native.check(rc, "add_layernorm_meanpool")
+    return out
 
 
 def embed_tokens(patch: torch.Tensor, cls: torch.Tensor | None, pos: torch.Tensor | None, x: torch.Tensor,
