@@ -70,7 +70,8 @@ int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, co
 
 /* ---- streaming row kernels ----------------------------------------------------------------------- */
 /* x = x_in[(row % x_mod) if x_mod > 0 else row] + delta[row]  (fp32 + bf16); optionally stored to x_out (may
- * alias x_in); y = act(LayerNorm(x) * gamma + beta) (biased variance, `eps`), or a plain cast when
+ * alias x_in), plus the optional addends delta2[row] (bf16) and seq_add[row / seq_rows] (fp32, one vector per
+ * sequence); y = act(LayerNorm(x) * gamma + beta) (biased variance, `eps`), or a plain cast when
  * gamma == NULL.  Outputs (each optional): y_out as bf16 / fp32 (y_dtype), y2_out = y in fp32,
  * ype_out = bf16(y + pe[row % pe_mod]) (positional table folded in for the next projection).  Row remapping:
  *   map_mode 0: identity.
@@ -78,20 +79,22 @@ int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, co
  *               windows, nwin per side, over an hw x hw grid; rows that fall in the zero padding are written
  *               as zeros (F.pad happens after norm1).  image_encoder.py:183-187,258-279
  *   map_mode 2: drop token 0 (CLS) of every seq_len-token sequence.  build_encoder.py:98
+ *   map_mode 3: pixel shuffle of a stride-2 ConvTranspose2d computed as a GEMM: source row (img, y, x, ky, kx) over an
+ *               hw x hw grid -> destination row (img, 2y+ky, 2x+kx).  mask_decoder.py:206-222
  *   image_encoder.py:181-197; common.py:42-54,183-184; transformer.py:308-327; mask_decoder.py:214-215,250-254;
  *   transformers modeling_vit.py:325-346,416 */
-int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const void* delta, float* x_out,
-                     const float* gamma, const float* beta, float eps, int act, void* y_out, int y_dtype,
-                     float* y2_out, const float* pe, long long pe_mod, void* ype_out, long long rows, int d,
-                     int map_mode, int seq_len, int win, int nwin, int hw);
+int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const void* delta, const void* delta2,
+                     const float* seq_add, long long seq_rows, float* x_out, const float* gamma, const float* beta,
+                     float eps, int act, void* y_out, int y_dtype, float* y2_out, const float* pe, long long pe_mod,
+                     void* ype_out, long long rows, int d, int map_mode, int seq_len, int win, int nwin, int hw);
 
-/* out[s, :] = mean over the rows_per_seq rows of sequence s of LayerNorm(x_in + delta): the last
- * image-token LayerNorm of the prompt encoder's two-way transformer fused with the spatial average pooling
- * (the normalised tokens are never written).  partial_ws: fp32 scratch [n_seq * slices * d]; deterministic.
- *   label_anything/models/transformer.py:326-327 + prompt_encoder.py:733-735 */
-int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta, const float* gamma,
-                              const float* beta, float eps, long long n_seq, int rows_per_seq, int d,
-                              float* partial_ws, int slices, float* out);
+/* out[s, :] = mean over the rows_per_seq rows of sequence s of LayerNorm(x_in + delta + delta2 + seq_add[s]): the
+ * last image-token LayerNorm of the prompt encoder's two-way transformer fused with the spatial average
+ * pooling (the normalised tokens are never written).  partial_ws: fp32 scratch [n_seq * slices * d];
+ * deterministic.   label_anything/models/transformer.py:326-327 + prompt_encoder.py:733-735 */
+int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta, const void* delta2,
+                              const float* seq_add, const float* gamma, const float* beta, float eps,
+                              long long n_seq, int rows_per_seq, int d, float* partial_ws, int slices, float* out);
 
 /* x[img, tok, :] = (tok < n_cls ? cls : patch[img, tok - n_cls, :]) + pos[tok, :]; patch bf16, x fp32.
  *   image_encoder.py:112-114; transformers modeling_vit.py:109-125 */
@@ -105,6 +108,69 @@ int la_im2col_patch16(void* stream, const float* images, void* out, long long n_
 /* token-major bf16 map [n_img, height, width, channels] -> [n_img*height*width, 9*channels] bf16 rows,
  * column = (ky*3+kx)*channels + c, zero padding 1.  build_lam.py:162-168; mask_decoder.py:241-247 */
 int la_im2col_3x3(void* stream, const void* in, void* out, long long n_img, int height, int width, int channels);
+
+/* ---- token <-> image attention of the two-way transformer -------------------------------------------- */
+/* Multi-head attention softmax(scale * (q + q_add)(k + k_add)^T) v for n_seq sequences of nq queries and nk keys;
+ * q [n_seq*nq, ld_q], k [n_seq*nk, ld_k], v [n_seq*nk, ld_v], out [n_seq*nq, ld_out], all bf16 with head h at
+ * columns [h*head_dim, (h+1)*head_dim) of the given base pointers (pass base + column offset for packed buffers).
+ * q_add [nq, ld_qadd] / k_add [nk, ld_kadd]: optional fp32 tables shared by all sequences (the projected image
+ * positional encoding), indexed by the query / key position.  head_dim in {8, 16, 32, 64}.  No masks: the
+ * reference's key_mask / query_mask are no-ops (common.py:117-139).  Few queries against many keys run
+ * key-parallel and may need `workspace` (la_attention_tokens_workspace_bytes; 0 = none).
+ *   label_anything/models/common.py:97-148; transformer.py:245-250,300-327 */
+int la_attention_tokens_splits(long long n_seq, int nq, int nk);
+long long la_attention_tokens_workspace_bytes(long long n_seq, int nq, int nk, int n_heads, int head_dim);
+int la_attention_tokens(void* stream, const void* q, long long ld_q, const void* k, long long ld_k, const void* v,
+                        long long ld_v, const float* q_add, long long ld_qadd, const float* k_add,
+                        long long ld_kadd, void* out, long long ld_out, long long n_seq, int nq, int nk, int n_heads,
+                        int head_dim, float scale, void* workspace);
+
+/* ---- prompt encoder ------------------------------------------------------------------------------------ */
+/* masks [n_seq, height, width] fp32 -> out [n_seq, height/4, width/4, 16] fp32:
+ * Conv2d(1,4,2,2) -> LayerNorm2d -> GELU -> Conv2d(4,16,2,2) -> LayerNorm2d -> GELU.  The 10 weight arrays are HOST
+ * pointers (352 floats, passed by value to the kernel): w0 [4,1,2,2], w3 [16,4,2,2] in PyTorch layout.
+ *   label_anything/models/prompt_encoder.py:61-67,516-531 */
+int la_mask_downscale(void* stream, const float* masks, float* out, long long n_seq, int height, int width,
+                      const float* w0, const float* b0, const float* ln1_w, const float* ln1_b, float eps1,
+                      const float* w3, const float* b3, const float* ln2_w, const float* ln2_b, float eps2);
+
+/* token-major fp32 [n, in_h, in_w, channels] -> [n, out_h, out_w, channels], bilinear, align_corners=False
+ * (F.interpolate semantics).  prompt_encoder.py:787-793 */
+int la_resize_bilinear(void* stream, const float* in, float* out, long long n, int in_h, int in_w, int out_h,
+                       int out_w, int channels);
+
+/* src[s, t, :] = feat[s / n_classes, t, :] + dense(s, t) + code[s % n_classes]  -> bf16 [n_seq*tokens, d], with
+ * dense(s, t) = w6 . m16[s, t, :] + b6 (mask_downscaling[6]), or not_a_mask when mask_flags[s] == 0, or no_mask when
+ * m16 == NULL (no mask prompts).  feat fp32 [n_seq/n_classes * tokens, d]; m16 fp32 [n_seq, tokens, 16]; w6 [d, 16];
+ * code [n_classes, d] or NULL.   prompt_encoder.py:68,532-539,637-646,795-805,250-264 */
+int la_build_src(void* stream, const float* feat, const float* m16, const unsigned char* mask_flags,
+                 const float* w6, const float* b6, const float* not_a_mask, const float* no_mask, const float* code,
+                 void* out, long long n_seq, int tokens, int d, int n_classes);
+
+/* Sparse prompt tokens [n_seq, n, d] fp32, n = (n_points + (boxes ? 0 : 1)) + 2*n_boxes: random-Fourier positional
+ * encoding of point / box-corner coordinates (+0.5, normalised by the image size) plus the label dependent
+ * embeddings; pe_table [4, d] = point_embeddings[0..3].   prompt_encoder.py:83-114,201-211,226-233,648-669 */
+int la_embed_sparse(void* stream, const float* points, const float* point_labels, int n_points, const float* boxes,
+                    const float* box_flags, int n_boxes, const float* gauss, const float* not_a_point,
+                    const float* pe_table, float* out, long long n_seq, int d, int image_w, int image_h);
+
+/* out[b, c, :] = sum_m flags[b,m,c] * emb[b,m,c,:] / max(sum_m flags[b,m,c], 1).   prompt_encoder.py:738-745 */
+int la_masked_mean(void* stream, const float* emb, const unsigned char* flags, float* out, int batch, int examples,
+                   int classes, int d);
+
+/* ---- mask decoder / post-processing ---------------------------------------------------------------------- */
+/* out[b, c, p] = sum_k cls[b, c, k] * x[b, p, k];  x bf16 [batch*pixels, dk], cls fp32 [batch, classes, dk],
+ * out fp32 [batch, classes, pixels].   label_anything/models/mask_decoder.py:299-314 */
+int la_classify(void* stream, const void* x, const float* cls, float* out, int batch, long long pixels, int classes,
+                int dk);
+
+/* logits [batch, classes, low_h, low_w] fp32 -> out [batch, classes, out_h, out_w] fp32: bilinear to
+ * image_size x image_size, crop [0:ih, 0:iw], bilinear to (oh, ow), pad with -inf (class 0: 0); classes with
+ * flag_gts[b, c] == 0 become -inf.  sizes int32 [batch, 4] = (oh, ow, ih, iw) (device memory).
+ *   label_anything/models/lam.py:383-453,92-93 */
+int la_postprocess_masks(void* stream, const float* logits, float* out, const int* sizes,
+                         const unsigned char* flag_gts, int batch, int classes, int low_h, int low_w, int image_size,
+                         int out_h, int out_w);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,7 @@ def declared_functions(header: Path = HEADER_PATH) -> dict[str, tuple[str, list[
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     text = re.sub(r"//[^\n]*", " ", text)
     out: dict[str, tuple[str, list[str]]] = {}
-    for m in re.finditer(r"\b(int|const char\*)\s+(la_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"\b(int|long long|const char\*)\s+(la_\w+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
         types: list[str] = []
         if args and args != "void":
@@ -65,7 +65,7 @@ def lib() -> ctypes.CDLL:
     cdll = ctypes.CDLL(str(LIB_PATH))
     for name, (ret, types) in declared_functions().items():
         fn = getattr(cdll, name)  # AttributeError if the header and the library disagree
-        fn.restype = ctypes.c_char_p if ret == "const char*" else ctypes.c_int
+        fn.restype = {"const char*": ctypes.c_char_p, "long long": ctypes.c_longlong}.get(ret, ctypes.c_int)
         fn.argtypes = [_CTYPE[t] for t in types]
     _lib = cdll
     return _lib

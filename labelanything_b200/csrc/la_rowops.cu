@@ -23,6 +23,9 @@ struct AddLnParams {
   const float* x_in;            // [x_rows, d] fp32 or nullptr
   long long x_mod;              // >0: x_in row = src_row % x_mod (broadcast table)
   const __nv_bfloat16* delta;   // [rows, d] or nullptr
+  const __nv_bfloat16* delta2;  // [rows, d] or nullptr (second bf16 addend)
+  const float* seq_add;         // [rows / seq_rows, d] or nullptr: per-sequence vector added to every row
+  long long seq_rows;
   float* x_out;                 // [rows, d] or nullptr
   const float* gamma;           // nullptr -> no normalisation (plain cast)
   const float* beta;
@@ -39,7 +42,8 @@ struct AddLnParams {
   int pool_slices;
   long long rows;               // source rows (map 0, 2) ; output rows (map 1)
   int d;
-  int map_mode;                 // 0 identity, 1 window partition with zero pad, 2 drop first token per sequence
+  int map_mode;                 // 0 identity, 1 window partition with zero pad, 2 drop first token per sequence,
+                                // 3 pixel shuffle: src row = (img, y, x, ky, kx) -> dst row (img, 2y+ky, 2x+kx)
   int seq_len;                  // map 2
   int win, nwin, hw;            // map 1
 };
@@ -90,6 +94,15 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
       const int tin = static_cast<int>(row % p.seq_len);
       write_y = write_y && tin > 0;
       dst = row - s - 1;
+    } else if (p.map_mode == 3) {
+      // hw = input grid side (square), rows enumerate (img, y, x, ky, kx)
+      const int g4 = static_cast<int>(row & 3);
+      const long long pix = row >> 2;
+      const int x = static_cast<int>(pix % p.hw);
+      const long long r2 = pix / p.hw;
+      const int y = static_cast<int>(r2 % p.hw);
+      const long long img = r2 / p.hw;
+      dst = (img * (2 * p.hw) + 2 * y + (g4 >> 1)) * (2 * p.hw) + 2 * x + (g4 & 1);
     }
     const size_t ebytes = p.y_f32 ? 4 : 2;
     uint8_t* yrow = static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(dst) * p.d * ebytes;
@@ -108,6 +121,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
     const long long xrow = p.x_mod > 0 ? src % p.x_mod : src;
     const float4* xin = p.x_in ? reinterpret_cast<const float4*>(p.x_in + xrow * p.d) : nullptr;
     const uint2* din = p.delta ? reinterpret_cast<const uint2*>(p.delta + src * p.d) : nullptr;
+    const uint2* din2 = p.delta2 ? reinterpret_cast<const uint2*>(p.delta2 + src * p.d) : nullptr;
+    const float4* sadd = p.seq_add ? reinterpret_cast<const float4*>(p.seq_add + (src / p.seq_rows) * p.d) : nullptr;
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i <= ROW_MAXV; ++i) {
@@ -124,6 +139,22 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
           a.y += __high2float(d01);
           a.z += __low2float(d23);
           a.w += __high2float(d23);
+        }
+        if (din2) {
+          const uint2 dv = din2[idx];
+          const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
+          const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
+          a.x += __low2float(d01);
+          a.y += __high2float(d01);
+          a.z += __low2float(d23);
+          a.w += __high2float(d23);
+        }
+        if (sadd) {
+          const float4 e = __ldg(sadd + idx);
+          a.x += e.x;
+          a.y += e.y;
+          a.z += e.z;
+          a.w += e.w;
         }
         if (p.x_out) reinterpret_cast<float4*>(p.x_out + src * p.d)[idx] = a;
       }
@@ -337,16 +368,18 @@ static int grid_for(long long work_items, int block, int per_sm) {
 
 extern "C" {
 
-int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const void* delta, float* x_out,
-                     const float* gamma, const float* beta, float eps, int act, void* y_out, int y_dtype,
-                     float* y2_out, const float* pe, long long pe_mod, void* ype_out, long long rows, int d,
-                     int map_mode, int seq_len, int win, int nwin, int hw) {
+int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const void* delta, const void* delta2,
+                     const float* seq_add, long long seq_rows, float* x_out, const float* gamma, const float* beta,
+                     float eps, int act, void* y_out, int y_dtype, float* y2_out, const float* pe, long long pe_mod,
+                     void* ype_out, long long rows, int d, int map_mode, int seq_len, int win, int nwin, int hw) {
   using namespace la;
   LA_CHECK_ARG(rows > 0 && d > 0, "la_add_layernorm: empty problem");
   LA_CHECK_ARG(d % 8 == 0 && d <= 128 * ROW_MAXV + 124, "la_add_layernorm: d=%d unsupported (multiple of 8, <= 1404)", d);
   LA_CHECK_ARG(x_in || delta, "la_add_layernorm: need x_in and/or delta");
+  LA_CHECK_ARG(!seq_add || seq_rows > 0, "la_add_layernorm: seq_add needs seq_rows");
   LA_CHECK_ARG((gamma == nullptr) == (beta == nullptr), "la_add_layernorm: gamma/beta must come together");
-  LA_CHECK_ARG(map_mode >= 0 && map_mode <= 2, "la_add_layernorm: bad map_mode");
+  LA_CHECK_ARG(map_mode >= 0 && map_mode <= 3, "la_add_layernorm: bad map_mode");
+  LA_CHECK_ARG(map_mode != 3 || (hw > 0 && rows % (4ll * hw * hw) == 0), "la_add_layernorm: bad pixel-shuffle grid");
   LA_CHECK_ARG(map_mode != 1 || (win > 0 && nwin > 0 && hw > 0 && rows % (static_cast<long long>(win) * win * nwin * nwin) == 0),
                "la_add_layernorm: bad window parameters");
   LA_CHECK_ARG(map_mode != 2 || (seq_len > 1 && rows % seq_len == 0), "la_add_layernorm: bad seq_len");
@@ -356,6 +389,9 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   p.x_in = x_in;
   p.x_mod = x_mod;
   p.delta = static_cast<const __nv_bfloat16*>(delta);
+  p.delta2 = static_cast<const __nv_bfloat16*>(delta2);
+  p.seq_add = seq_add;
+  p.seq_rows = seq_rows;
   p.x_out = x_out;
   p.gamma = gamma;
   p.beta = beta;
@@ -380,9 +416,9 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   return LA_OK;
 }
 
-int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta, const float* gamma,
-                              const float* beta, float eps, long long n_seq, int rows_per_seq, int d,
-                              float* partial_ws, int slices, float* out) {
+int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta, const void* delta2,
+                              const float* seq_add, const float* gamma, const float* beta, float eps,
+                              long long n_seq, int rows_per_seq, int d, float* partial_ws, int slices, float* out) {
   using namespace la;
   LA_CHECK_ARG(n_seq > 0 && rows_per_seq > 0 && d > 0 && slices > 0, "la_add_layernorm_meanpool: empty problem");
   LA_CHECK_ARG(d % 8 == 0 && d <= 128 * ROW_MAXV + 124, "la_add_layernorm_meanpool: d=%d unsupported", d);
@@ -391,6 +427,9 @@ int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta
   AddLnParams p = {};
   p.x_in = x_in;
   p.delta = static_cast<const __nv_bfloat16*>(delta);
+  p.delta2 = static_cast<const __nv_bfloat16*>(delta2);
+  p.seq_add = seq_add;
+  p.seq_rows = rows_per_seq;
   p.gamma = gamma;
   p.beta = beta;
   p.eps = eps;

@@ -1,0 +1,379 @@
+// labelanything_b200 — multi-head attention for the token <-> image attentions of the two-way transformer and the
+// small token-set attentions of the prompt encoder (sm_100a, CUDA cores).
+//
+// These attentions have one tiny side: n = 1..~60 prompt/class tokens against T = 900..4096 image tokens with
+// head_dim 8..64 (hard part H6).  They are HBM/L2-bound streaming reductions, not
+// tensor-core shaped contractions, so they run as vectorised CUDA-core kernels:
+//
+//   la_attention_tokens, mode chosen from the shape:
+//     * key-parallel   (few queries, many keys — tokens -> image, transformer.py:311-316,245-250):
+//         one warp per (sequence, head, key split); lanes split each key's head slice in 16-byte pieces and walk
+//         the keys with an online softmax for up to 4 queries at a time; partial (m, l, acc) of the key groups
+//         are merged by shuffles, of the key splits by a second tiny kernel.
+//     * query-parallel (many queries or few keys — image -> tokens, transformer.py:322-327; token
+//         self-attention, :300-306; AttentionMLPBlock, common.py:151-184): head_dim/8 lanes per (query, head),
+//         sequential online softmax over the keys (which stay L1/L2 resident).
+//   Projected positional tables can be added on the fly: q' = q + q_add[query index], k' = k + k_add[key index]
+//   (the image positional encoding pushed through the projection once per model: Wk·pe + bk), so the image
+//   tokens need only ONE projection GEMM with concatenated weights.
+//   Masks: the reference's key_mask / query_mask are no-ops (common.py:117-139) -> none here.
+#include "la_common.cuh"
+
+namespace la {
+
+struct TokAttParams {
+  const __nv_bfloat16* q;
+  long long ld_q;
+  const __nv_bfloat16* k;
+  long long ld_k;
+  const __nv_bfloat16* v;
+  long long ld_v;
+  const float* q_add;  // [nq, ld_qadd] or nullptr (column = head*DH + d)
+  long long ld_qadd;
+  const float* k_add;  // [nk, ld_kadd] or nullptr
+  long long ld_kadd;
+  __nv_bfloat16* out;
+  long long ld_out;
+  float* ws;  // key-parallel partials: [n_seq][splits][heads][nq][DH + 2]
+  int n_seq, nq, nk, n_heads, splits;
+  float scale_log2;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __low2float(h[i]);
+    f[2 * i + 1] = __high2float(h[i]);
+  }
+}
+__device__ __forceinline__ void add8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
+  f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8], float s) {
+  uint4 u;
+  u.x = pack_bf16(f[0] * s, f[1] * s);
+  u.y = pack_bf16(f[2] * s, f[3] * s);
+  u.z = pack_bf16(f[4] * s, f[5] * s);
+  u.w = pack_bf16(f[6] * s, f[7] * s);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// query-parallel: G = DH/8 lanes per (sequence, query, head)
+// ------------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256) attn_query_parallel_kernel(const TokAttParams p) {
+  constexpr int G = DH / 8;
+  const long long gid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+  const int sub = threadIdx.x % G;
+  const long long total = static_cast<long long>(p.n_seq) * p.nq * p.n_heads;
+  const bool live = gid < total;
+  const long long g = live ? gid : total - 1;  // dead lanes shadow the last unit so shuffles stay converged
+  const int h = static_cast<int>(g % p.n_heads);
+  const long long sq = g / p.n_heads;  // seq * nq + query
+  const int qi = static_cast<int>(sq % p.nq);
+  const long long seq = sq / p.nq;
+  const int col = h * DH + sub * 8;
+
+  float q[8];
+  load8(p.q + sq * p.ld_q + col, q);
+  if (p.q_add) add8(p.q_add + static_cast<long long>(qi) * p.ld_qadd + col, q);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] *= p.scale_log2;
+
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const __nv_bfloat16* kp = p.k + seq * p.nk * p.ld_k + col;
+  const __nv_bfloat16* vp = p.v + seq * p.nk * p.ld_v + col;
+
+  int j = 0;
+  for (; j + 2 <= p.nk; j += 2) {
+    float k0[8], k1[8], v0[8], v1[8];
+    load8(kp + static_cast<long long>(j) * p.ld_k, k0);
+    load8(kp + static_cast<long long>(j + 1) * p.ld_k, k1);
+    load8(vp + static_cast<long long>(j) * p.ld_v, v0);
+    load8(vp + static_cast<long long>(j + 1) * p.ld_v, v1);
+    if (p.k_add) {
+      add8(p.k_add + static_cast<long long>(j) * p.ld_kadd + col, k0);
+      add8(p.k_add + static_cast<long long>(j + 1) * p.ld_kadd + col, k1);
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s0 = fmaf(q[i], k0[i], s0);
+      s1 = fmaf(q[i], k1[i], s1);
+    }
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    const float mn = fmaxf(m, fmaxf(s0, s1));
+    const float c = ex2f(m - mn), p0 = ex2f(s0 - mn), p1 = ex2f(s1 - mn);
+    l = fmaf(l, c, p0 + p1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(acc[i], c, fmaf(p0, v0[i], p1 * v1[i]));
+    m = mn;
+  }
+  if (j < p.nk) {
+    float k0[8], v0[8];
+    load8(kp + static_cast<long long>(j) * p.ld_k, k0);
+    load8(vp + static_cast<long long>(j) * p.ld_v, v0);
+    if (p.k_add) add8(p.k_add + static_cast<long long>(j) * p.ld_kadd + col, k0);
+    float s0 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s0 = fmaf(q[i], k0[i], s0);
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    const float mn = fmaxf(m, s0);
+    const float c = ex2f(m - mn), p0 = ex2f(s0 - mn);
+    l = fmaf(l, c, p0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(acc[i], c, p0 * v0[i]);
+    m = mn;
+  }
+  if (live) store8(p.out + sq * p.ld_out + col, acc, 1.0f / l);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// key-parallel: one warp per (sequence, split, head); QB queries per pass
+// ------------------------------------------------------------------------------------------------------
+constexpr int KP_QB = 4;
+
+template <int DH>
+__global__ void __launch_bounds__(256) attn_key_parallel_kernel(const TokAttParams p) {
+  constexpr int G = DH / 8;
+  constexpr int KG = 32 / G;  // keys per warp iteration
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int sub = lane % G, kg = lane / G;
+  const long long seq = blockIdx.x / p.splits;
+  const int split = blockIdx.x % p.splits;
+  const int per = (p.nk + p.splits - 1) / p.splits;
+  const int k_begin = split * per;
+  const int k_end = min(p.nk, k_begin + per);
+
+  for (int h = warp; h < p.n_heads; h += nwarps) {
+    const int col = h * DH + sub * 8;
+    const __nv_bfloat16* kp = p.k + seq * p.nk * p.ld_k + col;
+    const __nv_bfloat16* vp = p.v + seq * p.nk * p.ld_v + col;
+    for (int q0 = 0; q0 < p.nq; q0 += KP_QB) {
+      float q[KP_QB][8], m[KP_QB], l[KP_QB], acc[KP_QB][8];
+#pragma unroll
+      for (int a = 0; a < KP_QB; ++a) {
+        const int qi = min(q0 + a, p.nq - 1);
+        load8(p.q + (seq * p.nq + qi) * p.ld_q + col, q[a]);
+        if (p.q_add) add8(p.q_add + static_cast<long long>(qi) * p.ld_qadd + col, q[a]);
+        m[a] = -INFINITY;
+        l[a] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          q[a][i] *= p.scale_log2;
+          acc[a][i] = 0.f;
+        }
+      }
+      for (int j0 = k_begin; j0 < k_end; j0 += KG) {
+        const int j = j0 + kg;
+        const bool on = j < k_end;
+        const int jj = on ? j : k_end - 1;
+        float kk[8], vv[8];
+        load8(kp + static_cast<long long>(jj) * p.ld_k, kk);
+        load8(vp + static_cast<long long>(jj) * p.ld_v, vv);
+        if (p.k_add) add8(p.k_add + static_cast<long long>(jj) * p.ld_kadd + col, kk);
+#pragma unroll
+        for (int a = 0; a < KP_QB; ++a) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s = fmaf(q[a][i], kk[i], s);
+#pragma unroll
+          for (int o = 1; o < G; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (!on) s = -INFINITY;
+          const float mn = fmaxf(m[a], s);
+          // mn == -inf only while this key group has seen no key at all: keep the state untouched
+          const float c = (mn == -INFINITY) ? 1.f : ex2f(m[a] - mn);
+          const float pw = (mn == -INFINITY) ? 0.f : ex2f(s - mn);
+          l[a] = fmaf(l[a], c, pw);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[a][i] = fmaf(acc[a][i], c, pw * vv[i]);
+          m[a] = mn;
+        }
+      }
+      // merge the KG key groups of the warp
+#pragma unroll
+      for (int a = 0; a < KP_QB; ++a) {
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1) {
+          const float mo = __shfl_xor_sync(0xffffffffu, m[a], o);
+          const float lo = __shfl_xor_sync(0xffffffffu, l[a], o);
+          const float mn = fmaxf(m[a], mo);
+          const float c0 = (mn == -INFINITY) ? 1.f : ex2f(m[a] - mn);
+          const float c1 = (mn == -INFINITY) ? 0.f : ex2f(mo - mn);
+          l[a] = l[a] * c0 + lo * c1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float ao = __shfl_xor_sync(0xffffffffu, acc[a][i], o);
+            acc[a][i] = acc[a][i] * c0 + ao * c1;
+          }
+          m[a] = mn;
+        }
+      }
+      if (kg == 0) {
+#pragma unroll
+        for (int a = 0; a < KP_QB; ++a) {
+          const int qi = q0 + a;
+          if (qi < p.nq) {
+            if (p.splits == 1) {
+              store8(p.out + (seq * p.nq + qi) * p.ld_out + col, acc[a], 1.0f / l[a]);
+            } else {
+              float* w = p.ws + ((((seq * p.splits + split) * p.n_heads + h) * p.nq) + qi) * (DH + 2);
+              if (sub == 0) {
+                w[0] = m[a];
+                w[1] = l[a];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w[2 + sub * 8 + i] = acc[a][i];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// merge the key splits: one thread per (sequence, head, query, d)
+template <int DH>
+__global__ void __launch_bounds__(256) attn_merge_splits_kernel(const TokAttParams p) {
+  const long long total = static_cast<long long>(p.n_seq) * p.n_heads * p.nq * DH;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(i % DH);
+    long long r = i / DH;
+    const int qi = static_cast<int>(r % p.nq);
+    r /= p.nq;
+    const int h = static_cast<int>(r % p.n_heads);
+    const long long seq = r / p.n_heads;
+    float mx = -INFINITY;
+    for (int s = 0; s < p.splits; ++s)
+      mx = fmaxf(mx, p.ws[((((seq * p.splits + s) * p.n_heads + h) * p.nq) + qi) * (DH + 2)]);
+    float l = 0.f, a = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+      const float* w = p.ws + ((((seq * p.splits + s) * p.n_heads + h) * p.nq) + qi) * (DH + 2);
+      const float c = (w[0] == -INFINITY) ? 0.f : ex2f(w[0] - mx);
+      l = fmaf(w[1], c, l);
+      a = fmaf(w[2 + d], c, a);
+    }
+    p.out[(seq * p.nq + qi) * p.ld_out + h * DH + d] = __float2bfloat16_rn(a / l);
+  }
+}
+
+template <int DH>
+static int launch_tokens(cudaStream_t st, const TokAttParams& p, bool key_parallel) {
+  if (key_parallel) {
+    const long long grid = static_cast<long long>(p.n_seq) * p.splits;
+    const int threads = 32 * (p.n_heads < 8 ? p.n_heads : 8);
+    attn_key_parallel_kernel<DH><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
+    LA_CHECK_CUDA(cudaGetLastError());
+    if (p.splits > 1) {
+      const long long total = static_cast<long long>(p.n_seq) * p.n_heads * p.nq * DH;
+      long long blocks = (total + 255) / 256;
+      const long long cap = static_cast<long long>(sm_count()) * 8;
+      if (blocks > cap) blocks = cap;
+      attn_merge_splits_kernel<DH><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
+      LA_CHECK_CUDA(cudaGetLastError());
+    }
+  } else {
+    constexpr int G = DH / 8;
+    const long long units = static_cast<long long>(p.n_seq) * p.nq * p.n_heads;
+    const long long blocks = (units * G + 255) / 256;
+    attn_query_parallel_kernel<DH><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
+    LA_CHECK_CUDA(cudaGetLastError());
+  }
+  return LA_OK;
+}
+
+}  // namespace la
+
+extern "C" {
+
+int la_attention_tokens_splits(long long n_seq, int nq, int nk) {
+  // key-parallel only when the queries are few and the keys many
+  if (!(nq <= 64 && nk >= 256 && nk >= 8 * nq)) return 0;
+  const long long target = 2ll * la::sm_count();
+  long long s = (target + n_seq - 1) / n_seq;
+  const long long max_s = nk / 128;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  return static_cast<int>(s);
+}
+
+long long la_attention_tokens_workspace_bytes(long long n_seq, int nq, int nk, int n_heads, int head_dim) {
+  const int s = la_attention_tokens_splits(n_seq, nq, nk);
+  if (s <= 1) return 0;
+  return n_seq * s * n_heads * nq * static_cast<long long>(head_dim + 2) * 4;
+}
+
+int la_attention_tokens(void* stream, const void* q, long long ld_q, const void* k, long long ld_k, const void* v,
+                        long long ld_v, const float* q_add, long long ld_qadd, const float* k_add,
+                        long long ld_kadd, void* out, long long ld_out, long long n_seq, int nq, int nk, int n_heads,
+                        int head_dim, float scale, void* workspace) {
+  using namespace la;
+  LA_CHECK_ARG(q && k && v && out, "la_attention_tokens: null pointer");
+  LA_CHECK_ARG(n_seq > 0 && nq > 0 && nk > 0 && n_heads > 0, "la_attention_tokens: empty problem");
+  LA_CHECK_ARG(head_dim == 8 || head_dim == 16 || head_dim == 32 || head_dim == 64,
+               "la_attention_tokens: head_dim %d unsupported (8, 16, 32, 64)", head_dim);
+  LA_CHECK_ARG(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_out % 8 == 0,
+               "la_attention_tokens: row strides must be multiples of 8 elements");
+  LA_CHECK_ARG((!q_add || ld_qadd % 4 == 0) && (!k_add || ld_kadd % 4 == 0),
+               "la_attention_tokens: table strides must be multiples of 4");
+  LA_CHECK_ARG(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                 reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(q_add) |
+                 reinterpret_cast<uintptr_t>(k_add)) & 15) == 0,
+               "la_attention_tokens: pointers must be 16-byte aligned");
+  LA_CHECK_ARG(n_seq * static_cast<long long>(nq) * n_heads * (head_dim / 8) < (1ll << 38),
+               "la_attention_tokens: problem too large");
+  TokAttParams p;
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.ld_q = ld_q;
+  p.k = static_cast<const __nv_bfloat16*>(k);
+  p.ld_k = ld_k;
+  p.v = static_cast<const __nv_bfloat16*>(v);
+  p.ld_v = ld_v;
+  p.q_add = q_add;
+  p.ld_qadd = ld_qadd;
+  p.k_add = k_add;
+  p.ld_kadd = ld_kadd;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out;
+  p.ws = static_cast<float*>(workspace);
+  p.n_seq = static_cast<int>(n_seq);
+  p.nq = nq;
+  p.nk = nk;
+  p.n_heads = n_heads;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.splits = la_attention_tokens_splits(n_seq, nq, nk);
+  const bool key_parallel = p.splits >= 1;
+  LA_CHECK_ARG(n_seq < (1ll << 31) / (p.splits > 0 ? p.splits : 1), "la_attention_tokens: too many sequences");
+  LA_CHECK_ARG(p.splits <= 1 || workspace, "la_attention_tokens: workspace required (%d key splits)", p.splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (head_dim) {
+    case 8: return launch_tokens<8>(st, p, key_parallel);
+    case 16: return launch_tokens<16>(st, p, key_parallel);
+    case 32: return launch_tokens<32>(st, p, key_parallel);
+    default: return launch_tokens<64>(st, p, key_parallel);
+  }
+}
+
+}  // extern "C"

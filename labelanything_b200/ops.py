@@ -81,14 +81,16 @@ def add_layernorm(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: 
                   beta: torch.Tensor | None, eps: float, *, rows: int, d: int, x_out: torch.Tensor | None = None,
                   y_out: torch.Tensor | None = None, y2_out: torch.Tensor | None = None,
                   pe: torch.Tensor | None = None, ype_out: torch.Tensor | None = None, act: int = ACT_NONE,
+                  delta2: torch.Tensor | None = None, seq_add: torch.Tensor | None = None, seq_rows: int = 0,
                   x_mod: int = 0, map_mode: int = 0, seq_len: int = 0, win: int = 0, nwin: int = 0,
                   hw: int = 0) -> None:
-    """x = x_in + delta (-> x_out); y = act(LN(x)) -> y_out (bf16/fp32), y2_out (fp32), ype_out (bf16, y + pe)."""
-    _require_cuda(x_in, delta, gamma, beta, x_out, y_out, y2_out, pe, ype_out)
+    """x = x_in + delta + delta2 + seq_add[row // seq_rows] (-> x_out); y = act(LN(x)) -> y_out (bf16/fp32),
+    y2_out (fp32), ype_out (bf16, y + pe)."""
+    _require_cuda(x_in, delta, delta2, seq_add, gamma, beta, x_out, y_out, y2_out, pe, ype_out)
     ref = x_in if x_in is not None else delta
-    for t in (x_in, x_out, gamma, beta, y2_out, pe):
+    for t in (x_in, x_out, gamma, beta, y2_out, pe, seq_add):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
-    for t in (delta, ype_out):
+    for t in (delta, delta2, ype_out):
         assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous())
     assert y_out is None or (y_out.is_contiguous() and y_out.dtype in (torch.bfloat16, torch.float32))
     pe_mod = 0
@@ -96,25 +98,29 @@ def add_layernorm(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: 
         assert pe is not None and pe.shape[-1] == d
         pe_mod = pe.numel() // d
     rc = _native.lib().la_add_layernorm(
-        _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(x_out), _ptr(gamma), _ptr(beta), float(eps), act,
-        _ptr(y_out), DT_F32 if (y_out is not None and y_out.dtype == torch.float32) else DT_BF16, _ptr(y2_out),
-        _ptr(pe), pe_mod, _ptr(ype_out), rows, d, map_mode, seq_len, win, nwin, hw)
+        _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(delta2), _ptr(seq_add), seq_rows, _ptr(x_out),
+        _ptr(gamma), _ptr(beta), float(eps), act, _ptr(y_out),
+        DT_F32 if (y_out is not None and y_out.dtype == torch.float32) else DT_BF16, _ptr(y2_out), _ptr(pe), pe_mod,
+        _ptr(ype_out), rows, d, map_mode, seq_len, win, nwin, hw)
     _native.check(rc, "add_layernorm")
 
 
 def add_layernorm_meanpool(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: torch.Tensor,
                            beta: torch.Tensor, eps: float, n_seq: int, rows_per_seq: int, d: int,
+                           delta2: torch.Tensor | None = None, seq_add: torch.Tensor | None = None,
                            slices: int = 8) -> torch.Tensor:
-    """mean over each sequence's rows of LN(x_in + delta) -> fp32 [n_seq, d]."""
-    _require_cuda(x_in, delta, gamma, beta)
+    """mean over each sequence's rows of LN(x_in + delta + delta2 + seq_add[seq]) -> fp32 [n_seq, d]."""
+    _require_cuda(x_in, delta, delta2, seq_add, gamma, beta)
     ref = x_in if x_in is not None else delta
     assert x_in is None or (x_in.dtype == torch.float32 and x_in.is_contiguous())
-    assert delta is None or (delta.dtype == torch.bfloat16 and delta.is_contiguous())
+    for t in (delta, delta2):
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous())
+    assert seq_add is None or (seq_add.dtype == torch.float32 and seq_add.is_contiguous())
     ws = torch.empty((n_seq * slices, d), dtype=torch.float32, device=ref.device)
     out = torch.empty((n_seq, d), dtype=torch.float32, device=ref.device)
-    rc = _native.lib().la_add_layernorm_meanpool(_stream(ref), _ptr(x_in), _ptr(delta), gamma.data_ptr(),
-                                                 beta.data_ptr(), float(eps), n_seq, rows_per_seq, d,
-                                                 ws.data_ptr(), slices, out.data_ptr())
+    rc = _native.lib().la_add_layernorm_meanpool(_stream(ref), _ptr(x_in), _ptr(delta), _ptr(delta2), _ptr(seq_add),
+                                                 gamma.data_ptr(), beta.data_ptr(), float(eps), n_seq, rows_per_seq,
+                                                 d, ws.data_ptr(), slices, out.data_ptr())
     _native.check(rc, "add_layernorm_meanpool")
     return out
 
@@ -150,4 +156,130 @@ def im2col_3x3(x: torch.Tensor, n_img: int, h: int, w: int, c: int, out: torch.T
         out = torch.empty((n_img * h * w, 9 * c), dtype=torch.bfloat16, device=x.device)
     rc = _native.lib().la_im2col_3x3(_stream(x), x.data_ptr(), out.data_ptr(), n_img, h, w, c)
     _native.check(rc, "im2col_3x3")
+    return out
+
+
+def attention_tokens(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int, nq: int, nk: int, n_heads: int,
+                     head_dim: int, q_add: torch.Tensor | None = None, k_add: torch.Tensor | None = None,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
+    """softmax((q + q_add)(k + k_add)^T / sqrt(head_dim)) v per (sequence, head).  q/k/v: bf16 2-D views (column
+    slices of packed projection buffers are fine) with n_heads*head_dim columns; *_add: fp32 [nq|nk, heads*dh]."""
+    _require_cuda(q, k, v, q_add, k_add, out)
+    w = n_heads * head_dim
+    for t, rows in ((q, n_seq * nq), (k, n_seq * nk), (v, n_seq * nk)):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.shape == (rows, w) and t.stride(1) == 1, (t.shape, rows, w)
+    for t, rows in ((q_add, nq), (k_add, nk)):
+        assert t is None or (t.dtype == torch.float32 and t.shape == (rows, w) and t.stride(1) == 1)
+    if out is None:
+        out = torch.empty((n_seq * nq, w), dtype=torch.bfloat16, device=q.device)
+    assert out.dtype == torch.bfloat16 and out.shape == (n_seq * nq, w) and out.stride(1) == 1
+    lib = _native.lib()
+    ws_bytes = lib.la_attention_tokens_workspace_bytes(n_seq, nq, nk, n_heads, head_dim)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes > 0 else None
+    rc = lib.la_attention_tokens(
+        _stream(q), q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _ptr(q_add),
+        q_add.stride(0) if q_add is not None else 0, _ptr(k_add), k_add.stride(0) if k_add is not None else 0,
+        out.data_ptr(), out.stride(0), n_seq, nq, nk, n_heads, head_dim, head_dim ** -0.5, _ptr(ws))
+    _native.check(rc, "attention_tokens")
+    return out
+
+
+def mask_downscale(masks: torch.Tensor, host_weights: dict) -> torch.Tensor:
+    """masks fp32 [S, H, W] -> fp32 [S, H/4, W/4, 16].  host_weights: CPU fp32 tensors w0,b0,g1,be1,w3,b3,g2,be2 + eps."""
+    _require_cuda(masks)
+    assert masks.dtype == torch.float32 and masks.is_contiguous() and masks.dim() == 3
+    S, H, W = masks.shape
+    out = torch.empty((S, H // 4, W // 4, 16), dtype=torch.float32, device=masks.device)
+    hw = host_weights
+    for k in ("w0", "b0", "g1", "be1", "w3", "b3", "g2", "be2"):
+        assert hw[k].device.type == "cpu" and hw[k].dtype == torch.float32 and hw[k].is_contiguous()
+    assert hw["w0"].numel() == 16 and hw["w3"].numel() == 256, "mask_downscaling is built for mask_in_chans = 16"
+    rc = _native.lib().la_mask_downscale(
+        _stream(masks), masks.data_ptr(), out.data_ptr(), S, H, W, hw["w0"].data_ptr(), hw["b0"].data_ptr(),
+        hw["g1"].data_ptr(), hw["be1"].data_ptr(), float(hw["eps1"]), hw["w3"].data_ptr(), hw["b3"].data_ptr(),
+        hw["g2"].data_ptr(), hw["be2"].data_ptr(), float(hw["eps2"]))
+    _native.check(rc, "mask_downscale")
+    return out
+
+
+def resize_bilinear(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """token-major fp32 [n, h, w, c] -> [n, out_h, out_w, c] (F.interpolate bilinear, align_corners=False)."""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, h, w, c = x.shape
+    out = torch.empty((n, out_h, out_w, c), dtype=torch.float32, device=x.device)
+    rc = _native.lib().la_resize_bilinear(_stream(x), x.data_ptr(), out.data_ptr(), n, h, w, out_h, out_w, c)
+    _native.check(rc, "resize_bilinear")
+    return out
+
+
+def build_src(feat: torch.Tensor, m16: torch.Tensor | None, mask_flags: torch.Tensor | None, w6, b6, not_a_mask,
+              no_mask, code: torch.Tensor | None, n_seq: int, tokens: int, d: int, n_classes: int) -> torch.Tensor:
+    _require_cuda(feat, m16, mask_flags, w6, b6, not_a_mask, no_mask, code)
+    assert feat.dtype == torch.float32 and feat.is_contiguous() and feat.numel() == (n_seq // n_classes) * tokens * d
+    assert m16 is None or (m16.dtype == torch.float32 and m16.is_contiguous() and m16.numel() == n_seq * tokens * 16)
+    assert mask_flags is None or (mask_flags.dtype == torch.uint8 and mask_flags.is_contiguous() and mask_flags.numel() == n_seq)
+    for t in (w6, b6, not_a_mask, no_mask, code):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    out = torch.empty((n_seq * tokens, d), dtype=torch.bfloat16, device=feat.device)
+    rc = _native.lib().la_build_src(_stream(feat), feat.data_ptr(), _ptr(m16), _ptr(mask_flags), _ptr(w6), _ptr(b6),
+                                    _ptr(not_a_mask), _ptr(no_mask), _ptr(code), out.data_ptr(), n_seq, tokens, d,
+                                    n_classes)
+    _native.check(rc, "build_src")
+    return out
+
+
+def embed_sparse(points, point_labels, boxes, box_flags, gauss, not_a_point, pe_table, n_seq: int, d: int,
+                 image_w: int, image_h: int) -> torch.Tensor:
+    """-> fp32 [n_seq, n, d];  points [S,P,2], point_labels [S,P], boxes [S,Bx,4], box_flags [S,Bx] (fp32) or None."""
+    _require_cuda(points, point_labels, boxes, box_flags, gauss, not_a_point, pe_table)
+    for t in (points, point_labels, boxes, box_flags, gauss, not_a_point, pe_table):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    P = points.shape[1] if points is not None else 0
+    Bx = boxes.shape[1] if boxes is not None else 0
+    n = (P + (0 if boxes is not None else 1) if points is not None else 0) + 2 * Bx
+    out = torch.empty((n_seq, n, d), dtype=torch.float32, device=gauss.device)
+    rc = _native.lib().la_embed_sparse(_stream(gauss), _ptr(points), _ptr(point_labels), P, _ptr(boxes),
+                                       _ptr(box_flags), Bx, gauss.data_ptr(), not_a_point.data_ptr(),
+                                       pe_table.data_ptr(), out.data_ptr(), n_seq, d, image_w, image_h)
+    _native.check(rc, "embed_sparse")
+    return out
+
+
+def masked_mean(emb: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
+    """emb fp32 [B,M,C,D], flags uint8 [B,M,C] -> fp32 [B,C,D]."""
+    _require_cuda(emb, flags)
+    assert emb.dtype == torch.float32 and emb.is_contiguous() and flags.dtype == torch.uint8 and flags.is_contiguous()
+    B, M, C, D = emb.shape
+    assert flags.shape == (B, M, C)
+    out = torch.empty((B, C, D), dtype=torch.float32, device=emb.device)
+    rc = _native.lib().la_masked_mean(_stream(emb), emb.data_ptr(), flags.data_ptr(), out.data_ptr(), B, M, C, D)
+    _native.check(rc, "masked_mean")
+    return out
+
+
+def classify(x: torch.Tensor, cls: torch.Tensor, batch: int, pixels: int) -> torch.Tensor:
+    """x bf16 [batch*pixels, dk], cls fp32 [batch, C, dk] -> fp32 [batch, C, pixels]."""
+    _require_cuda(x, cls)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and cls.dtype == torch.float32 and cls.is_contiguous()
+    C, dk = cls.shape[1], cls.shape[2]
+    assert x.shape == (batch * pixels, dk) and cls.shape[0] == batch
+    out = torch.empty((batch, C, pixels), dtype=torch.float32, device=x.device)
+    rc = _native.lib().la_classify(_stream(x), x.data_ptr(), cls.data_ptr(), out.data_ptr(), batch, pixels, C, dk)
+    _native.check(rc, "classify")
+    return out
+
+
+def postprocess_masks(logits: torch.Tensor, sizes: torch.Tensor, flag_gts: torch.Tensor | None, image_size: int,
+                      out_h: int, out_w: int) -> torch.Tensor:
+    """logits fp32 [B,C,lh,lw]; sizes int32 [B,4] = (oh, ow, ih, iw) on device -> fp32 [B,C,out_h,out_w]."""
+    _require_cuda(logits, sizes, flag_gts)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 4
+    assert sizes.dtype == torch.int32 and sizes.is_contiguous() and sizes.shape == (logits.shape[0], 4)
+    assert flag_gts is None or (flag_gts.dtype == torch.uint8 and flag_gts.is_contiguous())
+    B, C, lh, lw = logits.shape
+    out = torch.empty((B, C, out_h, out_w), dtype=torch.float32, device=logits.device)
+    rc = _native.lib().la_postprocess_masks(_stream(logits), logits.data_ptr(), out.data_ptr(), sizes.data_ptr(),
+                                            _ptr(flag_gts), B, C, lh, lw, image_size, out_h, out_w)
+    _native.check(rc, "postprocess_masks")
     return out
