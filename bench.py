@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the LabelAnything hot path on B200 (BASELINE.json metric: episodes/s, query+support forward,
+SAM ViT-B 1024 px, 5-way 5-shot).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--batch B]
+
+One step = `Lam.forward` over a batch of B synthetic episodes per GPU (each: 1 query + 25 support images at
+1024 px, 150 mask prompts) through the `images` key, SAM-512 model (parameters/trainval/other/COCO_vit.yaml:47-63 of
+the reference), random-init synthetic weights.  For N > 1 launch with torchrun (one rank per GPU); episodes are
+sharded across ranks with no data-path collective (weak scaling), timing is the max over ranks.
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: the same step with the batch in pinned host
+memory, H2D copies and the D2H read of the logits inside the timed region.  `roofline`: the kernel family with the
+largest share of the step, timed live with CUDA events around every launch.  `cpu_baseline`: the CPU oracle (a
+port of the reference's PyTorch forward) timed on this box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_WAYS, K_SHOTS, IMAGE_SIZE, EMBED_DIM = 5, 5, 1024, 512
+METRIC = "episodes/sec (query+support fwd) ViT-B 1024 5-way 5-shot"
+SAM512 = dict(image_embed_dim=768, embed_dim=EMBED_DIM, image_size=IMAGE_SIZE, use_vit_sam_neck=False, spatial_convs=3,
+              class_attention=False, example_attention=True, example_class_attention=False,
+              class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": EMBED_DIM},
+              custom_preprocess=True)
+# algorithmic FLOPs of one episode (26 images x (965.64 + 22.55) + 150 x 10.855 + 28.7 GFLOP)
+EPISODE_GFLOP = 26 * (965.64 + 22.55) + 150 * 10.855 + 28.7
+
+
+def _peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        d["_source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.lines: list[str] = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self) -> None:
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def _build_model():
+    from labelanything_b200.build_lam import build_lam_vit_b
+    from labelanything_b200.synthetic import load_synth_weights
+
+    lam = build_lam_vit_b(**SAM512)
+    load_synth_weights(lam, seed=0)
+    return lam
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (port of the reference forward) on a bounded sample of the workload
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(sd, seed: int = 0, threads: int | None = None) -> dict:
+    """Time 1 image through the SAM ViT-B encoder + neck, the prompt encoder on the 6 prompt sequences of one
+    support image, and the mask decoder + postprocess of one query — all with the CPU oracle — and extrapolate
+    to one 5-way 5-shot episode: 26 images, 150 sequences, 1 decode."""
+    import torch
+
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import lam_oracle as O  # the timed CPU baseline (bench.py's cpu_baseline / --impl reference legs only)
+
+    from labelanything_b200.synthetic import make_episode
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = {"image_size": IMAGE_SIZE, "image_embedding_size": (64, 64), "has_neck": True, "spatial_convs": 3,
+           "class_attention": False, "example_attention": True, "example_class_attention": False,
+           "custom_preprocess": True,
+           "encoder": {"kind": "sam", "num_heads": 12, "depth": 12, "global_attn": [2, 5, 8, 11], "window": 14}}
+    ep = make_episode(1, N_WAYS, 1, IMAGE_SIZE, seed=seed)   # M = 5 support images generated, 1 used
+    C = N_WAYS + 1
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        enc = O.encode_images(sd, cfg, ep["images"][0, :1], chunk=1)
+        feat = O.neck(sd, "neck", enc)
+        t_img = time.perf_counter() - t0
+        support = feat.unsqueeze(0)                           # [1, 1, D, 64, 64]
+        masks = (ep["prompt_masks"][:, :1], ep["flag_masks"][:, :1])
+        t0 = time.perf_counter()
+        pe = O.prompt_encoder(sd, "prompt_encoder", cfg, support, None, None, masks, ep["flag_examples"][:, :1],
+                              class_rows=torch.arange(C))
+        t_seq = (time.perf_counter() - t0) / C
+        gauss = sd["prompt_encoder.pe_layer.positional_encoding_gaussian_matrix"]
+        t0 = time.perf_counter()
+        low = O.mask_decoder(sd, "mask_decoder", cfg, feat, O.dense_pe(gauss, 64, 64), pe["class_embeddings"])
+        O.postprocess_masks(low, ep["dims"][:, :2], IMAGE_SIZE, True)
+        t_dec = time.perf_counter() - t0
+    M = N_WAYS * K_SHOTS
+    t_episode = (M + 1) * t_img + M * C * t_seq + t_dec
+    return {"value": 1.0 / t_episode, "unit": "episodes/s", "cores": cores, "kind": "port",
+            "sample": (f"CPU oracle (port of the reference PyTorch forward, fp32): 1 image encoder+neck {t_img:.2f}s, "
+                       f"{C} prompt sequences {t_seq * C:.2f}s, 1 decode+postprocess {t_dec:.2f}s; extrapolated to "
+                       f"26 images + 150 sequences + 1 decode = {t_episode:.1f}s/episode"),
+            "seconds_per_episode": t_episode}
+
+
+def run_reference(args) -> None:
+    rank, _, world = _dist_env()
+    if rank != 0:
+        return
+    lam = _build_model()
+    sd = {k: v.clone() for k, v in lam.state_dict().items()}
+    del lam
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_sample(sd, seed=i)
+        if i >= args.warmup:
+            vals.append(r)
+    t_ep = statistics.mean(v["seconds_per_episode"] for v in vals)
+    last = vals[-1]
+    value = 1.0 / t_ep
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "episodes/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_ep, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SAM ViT-B 1024px 5-way 5-shot (SAM-512 model), CPU forward, bounded sample "
+                                   "extrapolated per episode", "sample": last["sample"]},
+            "cpu_baseline": {"value": value, "unit": "episodes/s", "cores": last["cores"], "kind": "port",
+                             "sample": last["sample"]},
+            "e2e": {"value": value, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------------------
+def run_native(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from labelanything_b200 import _native, ops
+    from labelanything_b200.synthetic import make_episode
+
+    rank, local, world = _dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    _native.check(_native.lib().la_device_check(), "device_check")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    lam = _build_model()
+    sd_cpu = {k: v.clone() for k, v in lam.state_dict().items()} if (rank == 0 and world == 1 and not args.no_cpu) else None
+    lam.prompt_encoder.class_encoder.fixed_rows = torch.arange(N_WAYS + 1)
+    lam = lam.cuda()
+
+    host = make_episode(B, N_WAYS, K_SHOTS, IMAGE_SIZE, seed=100 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            return lam(dev)["logits"]
+
+    def step_e2e():
+        nonlocal out_host
+        with torch.no_grad():
+            d = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+            logits = lam(d)["logits"]
+            if out_host is None:
+                out_host = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
+            out_host.copy_(logits, non_blocking=True)
+        return logits
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM, every launch bracketed by CUDA events ----------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ops.profile() as prof:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step_resident()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    fam = prof.summary()
+    launches = prof.launches
+    clocks = sampler.stop() if sampler else None
+
+    # ---- timed region 2: end to end from pinned host memory ---------------------------------------------------
+    step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    d2h_bytes = out_host.numel() * out_host.element_size()
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    episodes = B * world * args.steps
+    value = episodes / (ms / 1000.0)
+    e2e = episodes / (ms_e2e / 1000.0)
+
+    if rank == 0:
+        peaks = _peaks()
+        kernel_ms = sum(f["ms"] for f in fam.values())
+        top = max(fam, key=lambda k: fam[k]["ms"])
+        f = fam[top]
+        tensor_bound = f["flops"] > 0 and top in ("gemm", "attention")
+        if tensor_bound:
+            achieved, peak, unit = f["flops"] / f["ms"] / 1e9, peaks["bf16_tflops_sustained"], "TFLOP/s"
+        else:
+            achieved, peak, unit = f["bytes"] / f["ms"] / 1e6, peaks["hbm_gbs"], "GB/s"
+        roofline = {"kernel": top, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
+                    "unit": unit, "frac": achieved / peak, "traffic": None, "peak_source": peaks["_source"],
+                    "avg_launch_ms": f["ms"] / f["launches"], "share_of_kernel_time": f["ms"] / kernel_ms,
+                    "whole_step": {"achieved": EPISODE_GFLOP * episodes / ms / 1e3, "unit": "TFLOP/s",
+                                   "frac": EPISODE_GFLOP * episodes / ms / 1e3 / peaks["bf16_tflops_sustained"]},
+                    "families": {k: {"launches": v["launches"] // args.steps, "ms_per_step": v["ms"] / args.steps,
+                                     "tflops": (v["flops"] / v["ms"] / 1e9) if v["flops"] else None,
+                                     "gbs": (v["bytes"] / v["ms"] / 1e6) if v["bytes"] else None}
+                                 for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
+        cpu = None
+        if sd_cpu is not None:
+            cpu = cpu_reference_sample(sd_cpu)
+            cpu.pop("seconds_per_episode", None)
+        line = {"metric": METRIC, "value": value, "unit": "episodes/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"SAM ViT-B 1024px 5-way 5-shot inference, batch={B} episodes per GPU "
+                                       f"(SAM-512: embed_dim 512, Lam.forward(images): 26 images + 150 mask-prompt "
+                                       f"sequences per episode)", "mode": "A (images)", "episodes_per_step_per_gpu": B,
+                           "l2": "inputs larger than L2 (images 12.6 MB each, > 2 GB per step)",
+                           "parallelism": f"episode-sharded x{world}, no data-path collective"},
+                "e2e": {"value": e2e, "unit": "episodes/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="episodes per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

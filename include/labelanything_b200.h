@@ -139,13 +139,15 @@ int la_mask_downscale(void* stream, const float* masks, float* out, long long n_
 int la_resize_bilinear(void* stream, const float* in, float* out, long long n, int in_h, int in_w, int out_h,
                        int out_w, int channels);
 
-/* src[s, t, :] = feat[s / n_classes, t, :] + dense(s, t) + code[s % n_classes]  -> bf16 [n_seq*tokens, d], with
+/* src[s, t, :] = feat[img(s), t, :] + dense(s, t) + code[s % n_classes]  -> bf16 [n_seq*tokens, d], with
  * dense(s, t) = w6 . m16[s, t, :] + b6 (mask_downscaling[6]), or not_a_mask when mask_flags[s] == 0, or no_mask when
- * m16 == NULL (no mask prompts).  feat fp32 [n_seq/n_classes * tokens, d]; m16 fp32 [n_seq, tokens, 16]; w6 [d, 16];
- * code [n_classes, d] or NULL.   prompt_encoder.py:68,532-539,637-646,795-805,250-264 */
+ * m16 == NULL (no mask prompts).  Sequence s = ((b * examples) + m) * n_classes + c reads the features of image
+ * img(s) = b * (examples + feat_lead) + feat_lead + m of feat fp32 [n_img * tokens, d] (feat_lead = 1 skips the query
+ * image stored in front of every episode's support images, lam.py:167-168); m16 fp32 [n_seq, tokens, 16];
+ * w6 [d, 16]; code [n_classes, d] or NULL.   prompt_encoder.py:68,532-539,637-646,795-805,250-264 */
 int la_build_src(void* stream, const float* feat, const float* m16, const unsigned char* mask_flags,
                  const float* w6, const float* b6, const float* not_a_mask, const float* no_mask, const float* code,
-                 void* out, long long n_seq, int tokens, int d, int n_classes);
+                 void* out, long long n_seq, int tokens, int d, int n_classes, int examples, int feat_lead);
 
 /* Sparse prompt tokens [n_seq, n, d] fp32, n = (n_points + (boxes ? 0 : 1)) + 2*n_boxes: random-Fourier positional
  * encoding of point / box-corner coordinates (+0.5, normalised by the image size) plus the label dependent
@@ -157,6 +159,26 @@ int la_embed_sparse(void* stream, const float* points, const float* point_labels
 /* out[b, c, :] = sum_m flags[b,m,c] * emb[b,m,c,:] / max(sum_m flags[b,m,c], 1).   prompt_encoder.py:738-745 */
 int la_masked_mean(void* stream, const float* emb, const unsigned char* flags, float* out, int batch, int examples,
                    int classes, int d);
+
+/* ---- layout conversion at the module boundary ---------------------------------------------------------------- */
+/* [n, channels, pixels] fp32 (NCHW) -> [n, pixels, channels] fp32 and/or bf16 (either output may be NULL).
+ *   label_anything/models/lam.py:139-146 (precomputed `embeddings` input) */
+int la_nchw_to_tokens(void* stream, const float* in, float* out_f32, void* out_bf16, long long n, int channels,
+                      int pixels);
+/* [n, pixels, channels] fp32 -> [n, channels, pixels] fp32.   image_encoder.py:119-131 (x.permute(0, 3, 1, 2)) */
+int la_tokens_to_nchw(void* stream, const float* in, float* out, long long n, int channels, int pixels);
+/* out[s, r, :] = in[s * in_stride_rows + in_offset_rows + r, :] for r < slab_rows: gathers equally spaced row slabs
+ * (the query image of every episode, lam.py:167 `embeddings[:, 0]`) as fp32 and/or bf16. */
+int la_copy_slabs(void* stream, const float* in, long long in_stride_rows, long long in_offset_rows, float* out_f32,
+                  void* out_bf16, long long n_slabs, long long slab_rows, int d);
+
+/* out[r, :] = a[r, :] + b[(r / row_div) % b_mod, :], fp32 rows of d channels: the RandomMatrixEncoder class code added
+ * to every sparse token of its class.   prompt_encoder.py:250-256 */
+int la_add_bcast(void* stream, const float* a, const float* b, float* out, long long rows, int d, long long row_div,
+                 long long b_mod);
+/* out[o, j, i, :] = in[o, i, j, :] for i < na, j < nb (fp32 rows): "b m c d -> b c m d" around example_attention.
+ *   prompt_encoder.py:706-710 */
+int la_permute_rows(void* stream, const float* in, float* out, long long outer, int na, int nb, int d);
 
 /* ---- mask decoder / post-processing ---------------------------------------------------------------------- */
 /* out[b, c, p] = sum_k cls[b, c, k] * x[b, p, k];  x bf16 [batch*pixels, dk], cls fp32 [batch, classes, dk],

@@ -166,6 +166,7 @@ struct BuildSrcParams {
   __nv_bfloat16* out;          // [S * T, D]
   long long n_seq;
   int T, D, C;
+  int M, lead;                 // feature image of sequence s: (bm / M) * (M + lead) + lead + bm % M, bm = s / C
 };
 
 // One thread owns 4 channels and keeps its 4x16 slice of W6 in registers; a CTA walks the rows of one sequence.
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(256) build_src_kernel(const BuildSrcParams p) 
   const int t_begin = chunk * per;
   const int t_end = min(p.T, t_begin + per);
   const int c = static_cast<int>(s % p.C);
-  const long long bm = s / p.C;
+  const long long bm_seq = s / p.C;
+  const long long bm = (bm_seq / p.M) * (p.M + p.lead) + p.lead + bm_seq % p.M;
 
   const bool has_map = p.m16 != nullptr && (p.mflag == nullptr || p.mflag[s] != 0);
   float base[4];
@@ -466,9 +468,10 @@ int la_resize_bilinear(void* stream, const float* in, float* out, long long n, i
 
 int la_build_src(void* stream, const float* feat, const float* m16, const unsigned char* mask_flags,
                  const float* w6, const float* b6, const float* not_a_mask, const float* no_mask, const float* code,
-                 void* out, long long n_seq, int tokens, int d, int n_classes) {
+                 void* out, long long n_seq, int tokens, int d, int n_classes, int examples, int feat_lead) {
   using namespace la;
   LA_CHECK_ARG(feat && out && n_seq > 0 && tokens > 0 && n_classes > 0, "la_build_src: bad arguments");
+  LA_CHECK_ARG(examples > 0 && feat_lead >= 0, "la_build_src: bad examples / feat_lead");
   LA_CHECK_ARG(d % 4 == 0 && d >= 32 && d <= 1024, "la_build_src: d=%d unsupported (multiple of 4 in [32, 1024])", d);
   LA_CHECK_ARG(m16 ? (w6 && b6 && not_a_mask) : (no_mask != nullptr), "la_build_src: missing dense-embedding weights");
   LA_CHECK_ARG(n_seq <= 65535ll * 65535ll, "la_build_src: too many sequences");
@@ -486,6 +489,8 @@ int la_build_src(void* stream, const float* feat, const float* m16, const unsign
   p.T = tokens;
   p.D = d;
   p.C = n_classes;
+  p.M = examples;
+  p.lead = feat_lead;
   const int tpr = d / 4;
   int threads = tpr >= 256 ? tpr : (256 / tpr) * tpr;
   // row chunks per sequence: enough CTAs to fill the machine even for few sequences

@@ -17,6 +17,67 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+class OpProfiler:
+    """Per-launch CUDA-event timing of the native ops on the launching (= torch's current) stream.
+
+    bench.py installs one over the timed region (`with ops.profile() as prof`) to get each kernel family's share of
+    the step and its achieved FLOP/s / GB/s from ALGORITHMIC work (the `cost` the wrappers declare), which is
+    what the roofline block of the bench line reports.  Off by default; costs two event records per launch."""
+
+    def __init__(self) -> None:
+        self.records: list = []   # (family, flops, bytes, start_event, end_event)
+        self.launches = 0
+
+    def summary(self) -> dict:
+        fam: dict = {}
+        for name, flops, nbytes, e0, e1 in self.records:
+            f = fam.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            f["launches"] += 1
+            f["ms"] += e0.elapsed_time(e1)
+            f["flops"] += flops
+            f["bytes"] += nbytes
+        return fam
+
+
+_PROF: OpProfiler | None = None
+_COST = (0.0, 0.0)  # (flops, bytes) of the next native call, declared by the wrapper
+
+
+class profile:
+    def __enter__(self) -> OpProfiler:
+        global _PROF
+        self.prev = _PROF
+        _PROF = OpProfiler()
+        return _PROF
+
+    def __exit__(self, *exc) -> None:
+        global _PROF
+        _PROF = self.prev
+
+
+def _cost(flops: float = 0.0, nbytes: float = 0.0) -> None:
+    global _COST
+    _COST = (float(flops), float(nbytes))
+
+
+def _call(what: str, fn: str, *args) -> None:
+    """Invoke one C-ABI entry point; raise RuntimeError with the library's message on failure."""
+    global _COST
+    f = getattr(_native.lib(), fn)
+    prof = _PROF
+    if prof is None:
+        rc = f(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = f(*args)
+        e1.record()
+        prof.records.append((what, _COST[0], _COST[1], e0, e1))
+        prof.launches += 1
+    _COST = (0.0, 0.0)
+    _native.check(rc, what)
+
+
 def _require_cuda(*ts: torch.Tensor) -> None:
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -40,11 +101,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act
     assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
-    rc = _native.lib().la_gemm_bf16(
-        _stream(a), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
+    _cost(2.0 * M * N * K, 2.0 * (M * K + N * K) + M * N * out.element_size())
+    _call("gemm", "la_gemm_bf16", _stream(a), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
         bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0),
         DT_BF16 if out.dtype == torch.bfloat16 else DT_F32, M, N, K, act)
-    _native.check(rc, "gemm")
     return out
 
 
@@ -69,11 +129,10 @@ def attention(q: torch.Tensor, kv: torch.Tensor, n_seq: int, seq_len: int, n_hea
         assert bias_h.stride(2) == 1 and bias_w.stride(2) == 1 and bias_h.stride() == bias_w.stride()
         ldb = bias_h.stride(1)
         assert bias_h.stride(0) == ldb * n_heads
-    rc = _native.lib().la_attention_bf16(
-        _stream(q), q.data_ptr(), q.stride(0), q_off, kv.data_ptr(), kv.stride(0), k_off, v_off, q.shape[0], n_seq,
+    _cost(4.0 * n_seq * n_heads * seq_len * seq_len * 64, 2.0 * 4 * n_seq * seq_len * n_heads * 64)
+    _call("attention", "la_attention_bf16", _stream(q), q.data_ptr(), q.stride(0), q_off, kv.data_ptr(), kv.stride(0), k_off, v_off, q.shape[0], n_seq,
         seq_len, n_heads, float(scale), _ptr(bias_h), _ptr(bias_w), ldb, grid_hw, out.data_ptr(), out.stride(0),
         out_mode, nwin, img_hw)
-    _native.check(rc, "attention")
     return out
 
 
@@ -97,12 +156,13 @@ def add_layernorm(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: 
     if ype_out is not None:
         assert pe is not None and pe.shape[-1] == d
         pe_mod = pe.numel() // d
-    rc = _native.lib().la_add_layernorm(
-        _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(delta2), _ptr(seq_add), seq_rows, _ptr(x_out),
+    _cost(0.0, float(rows) * d * sum(sz for t, sz in ((x_in, 4 if x_mod == 0 else 0), (delta, 2), (delta2, 2), (x_out, 4),
+                                                        (y_out, y_out.element_size() if y_out is not None else 0),
+                                                        (y2_out, 4), (ype_out, 2)) if t is not None))
+    _call("add_layernorm", "la_add_layernorm", _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(delta2), _ptr(seq_add), seq_rows, _ptr(x_out),
         _ptr(gamma), _ptr(beta), float(eps), act, _ptr(y_out),
         DT_F32 if (y_out is not None and y_out.dtype == torch.float32) else DT_BF16, _ptr(y2_out), _ptr(pe), pe_mod,
         _ptr(ype_out), rows, d, map_mode, seq_len, win, nwin, hw)
-    _native.check(rc, "add_layernorm")
 
 
 def add_layernorm_meanpool(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: torch.Tensor,
@@ -118,10 +178,11 @@ def add_layernorm_meanpool(x_in: torch.Tensor | None, delta: torch.Tensor | None
     assert seq_add is None or (seq_add.dtype == torch.float32 and seq_add.is_contiguous())
     ws = torch.empty((n_seq * slices, d), dtype=torch.float32, device=ref.device)
     out = torch.empty((n_seq, d), dtype=torch.float32, device=ref.device)
-    rc = _native.lib().la_add_layernorm_meanpool(_stream(ref), _ptr(x_in), _ptr(delta), _ptr(delta2), _ptr(seq_add),
+    _cost(0.0, float(n_seq) * rows_per_seq * d * ((4 if x_in is not None else 0) + (2 if delta is not None else 0) +
+                                                    (2 if delta2 is not None else 0)))
+    _call("add_layernorm_meanpool", "la_add_layernorm_meanpool", _stream(ref), _ptr(x_in), _ptr(delta), _ptr(delta2), _ptr(seq_add),
                                                  gamma.data_ptr(), beta.data_ptr(), float(eps), n_seq, rows_per_seq,
                                                  d, ws.data_ptr(), slices, out.data_ptr())
-    _native.check(rc, "add_layernorm_meanpool")
     return out
 
 
@@ -129,9 +190,8 @@ def embed_tokens(patch: torch.Tensor, cls: torch.Tensor | None, pos: torch.Tenso
                  n_img: int, tokens_per_img: int, n_cls: int, d: int) -> torch.Tensor:
     _require_cuda(patch, cls, pos, x)
     assert patch.dtype == torch.bfloat16 and patch.is_contiguous() and x.dtype == torch.float32 and x.is_contiguous()
-    rc = _native.lib().la_embed_tokens(_stream(x), patch.data_ptr(), _ptr(cls), _ptr(pos), x.data_ptr(), n_img,
+    _call("embed_tokens", "la_embed_tokens", _stream(x), patch.data_ptr(), _ptr(cls), _ptr(pos), x.data_ptr(), n_img,
                                        tokens_per_img, n_cls, d)
-    _native.check(rc, "embed_tokens")
     return x
 
 
@@ -143,8 +203,8 @@ def im2col_patch16(images: torch.Tensor, out: torch.Tensor | None = None) -> tor
     assert S == S2 and S % 16 == 0
     if out is None:
         out = torch.empty((I * (S // 16) ** 2, C * 256), dtype=torch.bfloat16, device=images.device)
-    rc = _native.lib().la_im2col_patch16(_stream(images), images.data_ptr(), out.data_ptr(), I, C, S)
-    _native.check(rc, "im2col_patch16")
+    _cost(0.0, float(I) * C * S * S * 6)
+    _call("im2col_patch16", "la_im2col_patch16", _stream(images), images.data_ptr(), out.data_ptr(), I, C, S)
     return out
 
 
@@ -154,8 +214,8 @@ def im2col_3x3(x: torch.Tensor, n_img: int, h: int, w: int, c: int, out: torch.T
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == n_img * h * w * c
     if out is None:
         out = torch.empty((n_img * h * w, 9 * c), dtype=torch.bfloat16, device=x.device)
-    rc = _native.lib().la_im2col_3x3(_stream(x), x.data_ptr(), out.data_ptr(), n_img, h, w, c)
-    _native.check(rc, "im2col_3x3")
+    _cost(0.0, float(n_img) * h * w * c * 2 * 10)
+    _call("im2col_3x3", "la_im2col_3x3", _stream(x), x.data_ptr(), out.data_ptr(), n_img, h, w, c)
     return out
 
 
@@ -176,11 +236,10 @@ def attention_tokens(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: i
     lib = _native.lib()
     ws_bytes = lib.la_attention_tokens_workspace_bytes(n_seq, nq, nk, n_heads, head_dim)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes > 0 else None
-    rc = lib.la_attention_tokens(
-        _stream(q), q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _ptr(q_add),
+    _cost(4.0 * n_seq * nq * nk * w, 2.0 * n_seq * (2 * nq + 2 * nk) * w)
+    _call("attention_tokens", "la_attention_tokens", _stream(q), q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _ptr(q_add),
         q_add.stride(0) if q_add is not None else 0, _ptr(k_add), k_add.stride(0) if k_add is not None else 0,
         out.data_ptr(), out.stride(0), n_seq, nq, nk, n_heads, head_dim, head_dim ** -0.5, _ptr(ws))
-    _native.check(rc, "attention_tokens")
     return out
 
 
@@ -194,11 +253,10 @@ def mask_downscale(masks: torch.Tensor, host_weights: dict) -> torch.Tensor:
     for k in ("w0", "b0", "g1", "be1", "w3", "b3", "g2", "be2"):
         assert hw[k].device.type == "cpu" and hw[k].dtype == torch.float32 and hw[k].is_contiguous()
     assert hw["w0"].numel() == 16 and hw["w3"].numel() == 256, "mask_downscaling is built for mask_in_chans = 16"
-    rc = _native.lib().la_mask_downscale(
-        _stream(masks), masks.data_ptr(), out.data_ptr(), S, H, W, hw["w0"].data_ptr(), hw["b0"].data_ptr(),
+    _cost(0.0, float(S) * H * W * 4 * 2)
+    _call("mask_downscale", "la_mask_downscale", _stream(masks), masks.data_ptr(), out.data_ptr(), S, H, W, hw["w0"].data_ptr(), hw["b0"].data_ptr(),
         hw["g1"].data_ptr(), hw["be1"].data_ptr(), float(hw["eps1"]), hw["w3"].data_ptr(), hw["b3"].data_ptr(),
         hw["g2"].data_ptr(), hw["be2"].data_ptr(), float(hw["eps2"]))
-    _native.check(rc, "mask_downscale")
     return out
 
 
@@ -208,24 +266,31 @@ def resize_bilinear(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
     n, h, w, c = x.shape
     out = torch.empty((n, out_h, out_w, c), dtype=torch.float32, device=x.device)
-    rc = _native.lib().la_resize_bilinear(_stream(x), x.data_ptr(), out.data_ptr(), n, h, w, out_h, out_w, c)
-    _native.check(rc, "resize_bilinear")
+    _call("resize_bilinear", "la_resize_bilinear", _stream(x), x.data_ptr(), out.data_ptr(), n, h, w, out_h, out_w, c)
     return out
 
 
 def build_src(feat: torch.Tensor, m16: torch.Tensor | None, mask_flags: torch.Tensor | None, w6, b6, not_a_mask,
-              no_mask, code: torch.Tensor | None, n_seq: int, tokens: int, d: int, n_classes: int) -> torch.Tensor:
+              no_mask, code: torch.Tensor | None, n_seq: int, tokens: int, d: int, n_classes: int, examples: int,
+              feat_lead: int = 0, seq_offset: int = 0) -> torch.Tensor:
+    """src rows (bf16 [n_seq*tokens, d]) of sequences [seq_offset, seq_offset + n_seq); seq_offset must be a multiple
+    of examples * n_classes (whole episodes), m16 / mask_flags cover exactly these sequences."""
     _require_cuda(feat, m16, mask_flags, w6, b6, not_a_mask, no_mask, code)
-    assert feat.dtype == torch.float32 and feat.is_contiguous() and feat.numel() == (n_seq // n_classes) * tokens * d
+    assert feat.dtype == torch.float32 and feat.is_contiguous()
+    assert seq_offset % (examples * n_classes) == 0 and n_seq % n_classes == 0
+    ep0 = seq_offset // (examples * n_classes)
+    n_img_needed = (ep0 + -(-n_seq // (examples * n_classes))) * (examples + feat_lead)
+    assert feat.numel() >= min(n_img_needed, feat.numel() // (tokens * d)) * tokens * d
+    feat = feat.view(-1, d)[ep0 * (examples + feat_lead) * tokens:]
     assert m16 is None or (m16.dtype == torch.float32 and m16.is_contiguous() and m16.numel() == n_seq * tokens * 16)
     assert mask_flags is None or (mask_flags.dtype == torch.uint8 and mask_flags.is_contiguous() and mask_flags.numel() == n_seq)
     for t in (w6, b6, not_a_mask, no_mask, code):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
     out = torch.empty((n_seq * tokens, d), dtype=torch.bfloat16, device=feat.device)
-    rc = _native.lib().la_build_src(_stream(feat), feat.data_ptr(), _ptr(m16), _ptr(mask_flags), _ptr(w6), _ptr(b6),
+    _cost(0.0, float(n_seq) * tokens * (d * 2 + (64 if m16 is not None else 0)) + float(n_seq // n_classes) * tokens * d * 4)
+    _call("build_src", "la_build_src", _stream(feat), feat.data_ptr(), _ptr(m16), _ptr(mask_flags), _ptr(w6), _ptr(b6),
                                     _ptr(not_a_mask), _ptr(no_mask), _ptr(code), out.data_ptr(), n_seq, tokens, d,
-                                    n_classes)
-    _native.check(rc, "build_src")
+                                    n_classes, examples, feat_lead)
     return out
 
 
@@ -239,10 +304,9 @@ def embed_sparse(points, point_labels, boxes, box_flags, gauss, not_a_point, pe_
     Bx = boxes.shape[1] if boxes is not None else 0
     n = (P + (0 if boxes is not None else 1) if points is not None else 0) + 2 * Bx
     out = torch.empty((n_seq, n, d), dtype=torch.float32, device=gauss.device)
-    rc = _native.lib().la_embed_sparse(_stream(gauss), _ptr(points), _ptr(point_labels), P, _ptr(boxes),
+    _call("embed_sparse", "la_embed_sparse", _stream(gauss), _ptr(points), _ptr(point_labels), P, _ptr(boxes),
                                        _ptr(box_flags), Bx, gauss.data_ptr(), not_a_point.data_ptr(),
                                        pe_table.data_ptr(), out.data_ptr(), n_seq, d, image_w, image_h)
-    _native.check(rc, "embed_sparse")
     return out
 
 
@@ -253,8 +317,7 @@ def masked_mean(emb: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
     B, M, C, D = emb.shape
     assert flags.shape == (B, M, C)
     out = torch.empty((B, C, D), dtype=torch.float32, device=emb.device)
-    rc = _native.lib().la_masked_mean(_stream(emb), emb.data_ptr(), flags.data_ptr(), out.data_ptr(), B, M, C, D)
-    _native.check(rc, "masked_mean")
+    _call("masked_mean", "la_masked_mean", _stream(emb), emb.data_ptr(), flags.data_ptr(), out.data_ptr(), B, M, C, D)
     return out
 
 
@@ -265,8 +328,8 @@ def classify(x: torch.Tensor, cls: torch.Tensor, batch: int, pixels: int) -> tor
     C, dk = cls.shape[1], cls.shape[2]
     assert x.shape == (batch * pixels, dk) and cls.shape[0] == batch
     out = torch.empty((batch, C, pixels), dtype=torch.float32, device=x.device)
-    rc = _native.lib().la_classify(_stream(x), x.data_ptr(), cls.data_ptr(), out.data_ptr(), batch, pixels, C, dk)
-    _native.check(rc, "classify")
+    _cost(2.0 * batch * pixels * C * dk, float(batch) * pixels * (dk * 2 + C * 4))
+    _call("classify", "la_classify", _stream(x), x.data_ptr(), cls.data_ptr(), out.data_ptr(), batch, pixels, C, dk)
     return out
 
 
@@ -279,7 +342,68 @@ def postprocess_masks(logits: torch.Tensor, sizes: torch.Tensor, flag_gts: torch
     assert flag_gts is None or (flag_gts.dtype == torch.uint8 and flag_gts.is_contiguous())
     B, C, lh, lw = logits.shape
     out = torch.empty((B, C, out_h, out_w), dtype=torch.float32, device=logits.device)
-    rc = _native.lib().la_postprocess_masks(_stream(logits), logits.data_ptr(), out.data_ptr(), sizes.data_ptr(),
+    _cost(0.0, float(B) * C * (out_h * out_w + lh * lw) * 4)
+    _call("postprocess_masks", "la_postprocess_masks", _stream(logits), logits.data_ptr(), out.data_ptr(), sizes.data_ptr(),
                                             _ptr(flag_gts), B, C, lh, lw, image_size, out_h, out_w)
-    _native.check(rc, "postprocess_masks")
+    return out
+
+
+def nchw_to_tokens(x: torch.Tensor, want_f32: bool = True, want_bf16: bool = False):
+    """[n, C, h, w] fp32 -> token-major [n*h*w, C] fp32 and/or bf16."""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, C, h, w = x.shape
+    o32 = torch.empty((n * h * w, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    o16 = torch.empty((n * h * w, C), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    for s in range(0, n, 32768):
+        m = min(32768, n - s)
+        _call("nchw_to_tokens", "la_nchw_to_tokens", _stream(x), x[s:].data_ptr(),
+                                             o32[s * h * w:].data_ptr() if want_f32 else None,
+                                             o16[s * h * w:].data_ptr() if want_bf16 else None, m, C, h * w)
+    return o32, o16
+
+
+def tokens_to_nchw(x: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    """token-major fp32 [n*h*w, C] -> [n, C, h, w] fp32."""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.shape[0] == n * h * w
+    C = x.shape[1]
+    out = torch.empty((n, C, h, w), dtype=torch.float32, device=x.device)
+    for s in range(0, n, 32768):
+        m = min(32768, n - s)
+        _call("tokens_to_nchw", "la_tokens_to_nchw", _stream(x), x[s * h * w:].data_ptr(), out[s:].data_ptr(), m, C, h * w)
+    return out
+
+
+def copy_slabs(x: torch.Tensor, n_slabs: int, slab_rows: int, stride_rows: int, offset_rows: int = 0,
+               want_f32: bool = True, want_bf16: bool = False):
+    """out[s, r] = x[s*stride_rows + offset_rows + r] for r < slab_rows (fp32 in; fp32 and/or bf16 out)."""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    d = x.shape[1]
+    assert (n_slabs - 1) * stride_rows + offset_rows + slab_rows <= x.shape[0]
+    o32 = torch.empty((n_slabs * slab_rows, d), dtype=torch.float32, device=x.device) if want_f32 else None
+    o16 = torch.empty((n_slabs * slab_rows, d), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    _call("copy_slabs", "la_copy_slabs", _stream(x), x.data_ptr(), stride_rows, offset_rows, _ptr(o32), _ptr(o16),
+                                     n_slabs, slab_rows, d)
+    return o32, o16
+
+
+def add_bcast(a: torch.Tensor, b: torch.Tensor, row_div: int, b_mod: int) -> torch.Tensor:
+    """out[r] = a[r] + b[(r // row_div) % b_mod]; fp32 [rows, d]."""
+    _require_cuda(a, b)
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1] and b.shape[0] >= b_mod
+    out = torch.empty_like(a)
+    _call("add_bcast", "la_add_bcast", _stream(a), a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], a.shape[1],
+                                    row_div, b_mod)
+    return out
+
+
+def permute_rows(x: torch.Tensor, outer: int, na: int, nb: int) -> torch.Tensor:
+    """fp32 [outer*na*nb, d] -> rows reordered (o, i, j) -> (o, j, i)."""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.shape[0] == outer * na * nb
+    out = torch.empty_like(x)
+    _call("permute_rows", "la_permute_rows", _stream(x), x.data_ptr(), out.data_ptr(), outer, na, nb, x.shape[1])
     return out

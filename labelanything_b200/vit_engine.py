@@ -166,4 +166,4 @@ def run_neck(nw: NeckWeights, tokens: torch.Tensor, n_img: int, g: int, out_dtyp
 
 def tokens_to_nchw(tokens: torch.Tensor, n_img: int, g: int) -> torch.Tensor:
     """[n_img*g*g, C] -> [n_img, C, g, g] (layout change for callers that expect the reference's NCHW output)."""
-    return tokens.view(n_img, g, g, -1).permute(0, 3, 1, 2).contiguous()
+    return ops.tokens_to_nchw(tokens if tokens.dtype == torch.float32 else tokens.float(), n_img, g, g)

@@ -1,0 +1,186 @@
+"""GPU parity of the native `Lam` (prompt encoder + mask decoder + postprocess, with and without the image
+encoder) against (a) golden tensors produced by the UNMODIFIED reference and (b) the CPU oracle run on the same
+seeded inputs.  The native path computes with bf16 operands / fp32 accumulation; the references are fp32, so the
+tolerances below are bf16 end-to-end drift bounds, stated per comparison."""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import lam_oracle
+
+    return lam_oracle
+
+
+def _report(name, a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    fin = torch.isfinite(b)
+    assert torch.equal(torch.isfinite(a), fin), f"{name}: -inf pattern differs"
+    assert torch.equal(a[~fin], b[~fin]), f"{name}: non-finite values differ"
+    err = (a[fin] - b[fin]).abs()
+    mx, mean, mag = err.max().item(), err.mean().item(), b[fin].abs().mean().item()
+    print(f"{name}: max_abs_err={mx:.5f} mean_abs_err={mean:.6f} ref_mean_abs={mag:.4f} ref_std={b[fin].std().item():.4f}")
+    return mx, mean, mag
+
+
+def _to_cuda(ep):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ep.items()}
+
+
+def test_mae256_1w1s_matches_reference_golden():
+    """BASELINE config 1/2 model (MAE-256: HF ViT-B 480 px, D=256), 1-way 1-shot."""
+    from labelanything_b200.build_encoder import build_vit_from_config
+    from labelanything_b200.build_lam import build_lam
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    g = torch.load(GOLD / "mae256_1w1s.pt", weights_only=False)
+    lam = build_lam(build_vit=lambda project_last_hidden: build_vit_from_config(), image_embed_dim=768,
+                    embed_dim=256, image_size=480, spatial_convs=3, class_attention=False, example_attention=False,
+                    example_class_attention=True,
+                    class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 256},
+                    custom_preprocess=False)
+    assert {k: tuple(v.shape) for k, v in lam.state_dict().items()} == g["shapes"]
+    load_synth_weights(lam, seed=g["weights_seed"])
+    lam.prompt_encoder.class_encoder.fixed_rows = g["class_rows"]
+    lam = lam.cuda()
+    ep = _to_cuda(make_episode(**g["episode_args"]))
+    with torch.no_grad():
+        out = lam(ep)
+    assert out["logits"].shape == (1, 2, 480, 480) and out["logits"].dtype == torch.float32
+    mx, mean, mag = _report("mae256 class_examples_embeddings", out["class_examples_embeddings"],
+                            g["class_examples_embeddings"])
+    assert mx < 0.08 and mean < 0.01
+    mx, mean, mag = _report("mae256 logits", out["logits"][..., ::3, ::3], g["logits_sub3"])
+    assert mx < 0.06 and mean < 0.01
+
+
+def test_sam512_5w5s_matches_reference_golden():
+    """BASELINE config 3 model (SAM ViT-B 1024 px, D=512), 5-way 5-shot, one episode through the `images` path."""
+    from labelanything_b200.build_lam import build_lam_vit_b
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    p = GOLD / "sam512_5w5s.pt"
+    if not p.exists():
+        pytest.skip("sam512_5w5s.pt not generated")
+    g = torch.load(p, weights_only=False)
+    lam = build_lam_vit_b(image_embed_dim=768, embed_dim=512, image_size=1024, use_vit_sam_neck=False,
+                          spatial_convs=3, class_attention=False, example_attention=True,
+                          example_class_attention=False,
+                          class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 512},
+                          custom_preprocess=True)
+    load_synth_weights(lam, seed=g["weights_seed"])
+    lam.prompt_encoder.class_encoder.fixed_rows = g["class_rows"]
+    lam = lam.cuda()
+    ep = _to_cuda(make_episode(**g["episode_args"]))
+    with torch.no_grad():
+        out = lam(ep)
+    assert out["logits"].shape == (1, 6, 1024, 1024)
+    mx, mean, mag = _report("sam512 class_examples_embeddings", out["class_examples_embeddings"],
+                            g["class_examples_embeddings"])
+    assert mx < 0.15 and mean < 0.015
+    mx, mean, mag = _report("sam512 logits", out["logits"][..., ::8, ::8], g["logits_sub8"])
+    assert mx < 0.08 and mean < 0.01
+
+
+@pytest.mark.parametrize("variant", ["mixed_all_attn", "masks_only", "points_only"])
+def test_lam_no_vit_matches_oracle(variant):
+    """Prompt encoder + decoder + postprocess on precomputed `embeddings` against the CPU oracle: mixed prompts
+    (n = 9 tokens), null prompts, padded examples, all three merge attentions, non-square originals with
+    custom_preprocess, flag_gts."""
+    from labelanything_b200.build_lam import build_lam_no_vit
+    from labelanything_b200.synthetic import load_synth_weights
+
+    O = _oracle()
+    torch.manual_seed(0)
+    B, M, C, S, D, Ce = 2, 3, 3, 256, 256, 384
+    g = torch.Generator().manual_seed(7)
+    h = S // 16
+    kw = dict(image_embed_dim=Ce, embed_dim=D, image_size=S, spatial_convs=3)
+    ep = {"embeddings": torch.randn(B, M + 1, Ce, h, h, generator=g),
+          "flag_examples": (torch.rand(B, M, C, generator=g) > 0.3).to(torch.uint8)}
+    ep["flag_examples"][:, :, 0] = 1
+    dims = torch.full((B, M + 1, 2), S, dtype=torch.int64)
+    rows = None
+    if variant == "mixed_all_attn":
+        kw.update(class_attention=True, example_attention=True, example_class_attention=True,
+                  class_encoder={"name": "RandomMatrixEncoder", "bank_size": 10, "embed_dim": D},
+                  custom_preprocess=True)
+        rows = torch.tensor([0, 4, 2, 7])
+        ep["prompt_masks"] = (torch.rand(B, M, C, 256, 256, generator=g) > 0.5).float()
+        ep["flag_masks"] = (torch.rand(B, M, C, generator=g) > 0.2).to(torch.uint8)
+        ep["prompt_points"] = torch.rand(B, M, C, 5, 2, generator=g) * S
+        ep["flag_points"] = torch.randint(-1, 2, (B, M, C, 5), generator=g).float()
+        xy = torch.rand(B, M, C, 2, 2, generator=g) * S / 2
+        ep["prompt_bboxes"] = torch.cat([xy, xy + S / 4], dim=-1)
+        ep["flag_bboxes"] = torch.randint(-1, 2, (B, M, C, 2), generator=g).float()
+        ep["flag_points"][0, 0, 0, 0] = 1
+        ep["flag_bboxes"][0, 0, 0, 0] = 1
+        dims[0, 0] = torch.tensor([200, 256])
+        dims[1, 0] = torch.tensor([256, 160])
+        ep["flag_gts"] = torch.tensor([[True, True, False], [True, True, True]])
+    elif variant == "masks_only":
+        kw.update(custom_preprocess=False)
+        ep["prompt_masks"] = (torch.rand(B, M, C, 256, 256, generator=g) > 0.5).float()
+        ep["flag_masks"] = torch.ones(B, M, C, dtype=torch.uint8)
+        ep["prompt_points"] = torch.zeros(B, M, C, 1, 2)
+        ep["flag_points"] = torch.zeros(B, M, C, 1)
+    else:
+        kw.update(custom_preprocess=False, example_class_attention=False)
+        ep["prompt_points"] = torch.rand(B, M, C, 3, 2, generator=g) * S
+        ep["flag_points"] = torch.randint(-1, 2, (B, M, C, 3), generator=g).float()
+        ep["flag_points"][0, 0, 0, 0] = 1
+    ep["dims"] = dims
+    lam = build_lam_no_vit(**kw)
+    load_synth_weights(lam, seed=3)
+    if rows is not None:
+        lam.prompt_encoder.class_encoder.fixed_rows = rows
+    sd = {k: v.clone() for k, v in lam.state_dict().items()}
+    cfg = {"image_size": S, "image_embedding_size": (h, h), "has_neck": True, "spatial_convs": 3,
+           "class_attention": kw.get("class_attention", False), "example_attention": kw.get("example_attention", False),
+           "example_class_attention": kw.get("example_class_attention", True),
+           "custom_preprocess": kw["custom_preprocess"]}
+    with torch.no_grad():
+        ref = O.lam_forward(sd, cfg, dict(ep), class_rows=rows)
+        out = lam.cuda()(_to_cuda(ep))
+    assert out["logits"].shape == ref["logits"].shape
+    mx, mean, mag = _report(f"{variant} class_examples_embeddings", out["class_examples_embeddings"],
+                            ref["class_examples_embeddings"])
+    assert mx < 0.1 and mean < 0.012
+    mx, mean, mag = _report(f"{variant} logits", out["logits"], ref["logits"])
+    assert mx < 0.08 and mean < 0.008
+
+
+def test_generate_class_embeddings_then_predict_equals_forward():
+    """lam.py:349-381: the cached-support split must reproduce the one-shot forward (same kernels, same inputs)."""
+    from labelanything_b200.build_lam import build_lam_no_vit
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    lam = build_lam_no_vit(image_embed_dim=384, embed_dim=256, image_size=256, spatial_convs=3,
+                           custom_preprocess=False)
+    load_synth_weights(lam, seed=5)
+    lam = lam.cuda()
+    ep = _to_cuda(make_episode(2, 2, 1, 256, seed=1, embeddings=(384, 16)))
+    with torch.no_grad():
+        full = lam(ep)["logits"]
+        support = {k: (v[:, 1:] if k in ("embeddings", "dims") else v) for k, v in ep.items()}
+        ce = lam.generate_class_embeddings(support)
+        query = {"embeddings": ep["embeddings"][:, :1], "dims": ep["dims"][:, 0]}
+        pred = lam.predict(query, ce)
+    assert torch.equal(full, pred)
+
+
+def test_cpu_inputs_fail_loudly():
+    from labelanything_b200.build_lam import build_lam_no_vit
+    from labelanything_b200.synthetic import make_episode
+
+    lam = build_lam_no_vit(image_embed_dim=384, embed_dim=256, image_size=256, spatial_convs=3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lam(make_episode(1, 1, 1, 256, embeddings=(384, 16)))
