@@ -289,8 +289,8 @@ def run_native(args) -> None:
         roofline = {"kernel": top, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
                     "unit": unit, "frac": achieved / peak, "traffic": None, "peak_source": peaks["_source"],
                     "avg_launch_ms": f["ms"] / f["launches"], "share_of_kernel_time": f["ms"] / kernel_ms,
-                    "whole_step": {"achieved": EPISODE_GFLOP * episodes / ms / 1e3, "unit": "TFLOP/s",
-                                   "frac": EPISODE_GFLOP * episodes / ms / 1e3 / peaks["bf16_tflops_sustained"]},
+                    "whole_step": {"achieved": EPISODE_GFLOP * episodes / ms, "unit": "TFLOP/s",
+                                   "frac": EPISODE_GFLOP * episodes / ms / peaks["bf16_tflops_sustained"]},
                     "families": {k: {"launches": v["launches"] // args.steps, "ms_per_step": v["ms"] / args.steps,
                                      "tflops": (v["flops"] / v["ms"] / 1e9) if v["flops"] else None,
                                      "gbs": (v["bytes"] / v["ms"] / 1e6) if v["bytes"] else None}
