@@ -10,9 +10,11 @@
 // ping-pong on the tensor core while their softmax warpgroups run on the CUDA cores (FlashAttention-style
 // online softmax, accumulator O kept in TMEM and rescaled only when the running max grows by > 2^8).
 //   warp 0      : TMA producer (Q once; K and V tiles through two independent smem rings)
-//   warp 1      : MMA issuer   (S = Q K^T into TMEM;  O += P V with P staged in smem, V as MN-major operand)
+//   warp 1      : MMA issuer   (S = Q K^T into TMEM;  O += P V with P read from TMEM -- it overlays the scores it
+//                 was computed from -- and V as MN-major smem operand)
 //   warp 2      : TMEM allocator
-//   warps 4-7   : softmax + epilogue for Q tile A     warps 8-11: same for Q tile B
+//   warps 4-7   : softmax + epilogue for Q tile A     warps 8-11: same for Q tile B   (one thread per query row,
+//                 the whole 128-column score row held in registers: setmaxnreg gives these warps 224 registers)
 // The decomposed relative-position bias  rel_h[q, kh] + rel_w[q, kw]  is read from fp32 tables produced
 // by la_gemm_bf16 (q_head @ reversed_table^T), already shifted so that entry (gh-1 - qh + kh) is the bias
 // of key row kh for a query in grid row qh.
@@ -22,7 +24,11 @@ namespace la {
 
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_D = 64;
-constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_RW_STRIDE = 272;      // bytes per row of the rel_w staging area (68 floats: conflict-free LDS.128)
+constexpr int ATT_REGS_SOFTMAX = 216;  // setmaxnreg budget: 256 x 216 + 128 x 72 = 64512 = 384 threads x 168 (launch allocation)
+constexpr int ATT_REGS_CONTROL = 72;
+static_assert(256 * ATT_REGS_SOFTMAX + 128 * ATT_REGS_CONTROL <= ATT_THREADS * 168,
+              "setmaxnreg.inc can only hand out what the CTA was launched with (168 registers x 384 threads)");
 
 enum AttBias : int { ATT_BIAS_NONE = 0, ATT_BIAS_GLOBAL64 = 1, ATT_BIAS_WINDOW14 = 2 };
 
@@ -42,16 +48,17 @@ struct AttParams {
   int win, nwin, img_hw;  // out_mode 1: window size, windows per side, un-padded grid side
 };
 
-template <int KV_TILE>
+template <int KV_TILE, int BIAS>
 struct AttSmem {
+  static constexpr int STAGES = BIAS == 1 ? 3 : 4;          // K / V ring depth (the 64x64 bias variant needs room for rel_w)
   static constexpr int Q_BYTES = 2 * 128 * 128;             // two Q tiles, 128 rows x 128 B
   static constexpr int KV_BYTES = KV_TILE * 128;            // one K or V tile
   static constexpr int KV_SLOT = ((KV_BYTES + 1023) / 1024) * 1024;
-  static constexpr int P_BYTES = 2 * 16384;                 // per Q tile: two K-blocks of 128 rows x 128 B
   static constexpr int OFF_K = Q_BYTES;
-  static constexpr int OFF_V = OFF_K + ATT_KV_STAGES * KV_SLOT;
-  static constexpr int OFF_P = OFF_V + ATT_KV_STAGES * KV_SLOT;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int OFF_V = OFF_K + STAGES * KV_SLOT;
+  static constexpr int OFF_RW = OFF_V + STAGES * KV_SLOT;   // [256 rows][68] fp32 rel_w terms (64x64 bias variant)
+  static constexpr int RW_BYTES = BIAS == 1 ? 256 * ATT_RW_STRIDE : 0;
+  static constexpr int OFF_BAR = OFF_RW + RW_BYTES;
   static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
@@ -65,9 +72,12 @@ template <int KV_TILE, int BIAS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const AttParams p) {
-  using S = AttSmem<KV_TILE>;
-  constexpr int GW = BIAS == ATT_BIAS_GLOBAL64 ? 64 : (BIAS == ATT_BIAS_WINDOW14 ? 14 : 1);
-  constexpr int NCH = (KV_TILE + 31) / 32;  // 32-column chunks per S row (last one may be 16 wide)
+  using S = AttSmem<KV_TILE, BIAS>;
+  constexpr int ATT_KV_STAGES = S::STAGES;
+  // bias(q, k) = rel_w[q][k % GW] + rel_h[q][k / GW]: a KV tile holds NG key-grid rows of GW keys
+  constexpr int GW = BIAS == ATT_BIAS_GLOBAL64 ? 64 : (BIAS == ATT_BIAS_WINDOW14 ? 14 : KV_TILE);
+  constexpr int NG = KV_TILE / GW;
+  static_assert(NG * GW == KV_TILE && KV_TILE % 16 == 0 && KV_TILE <= 128, "tile must hold whole key-grid rows");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -117,105 +127,109 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384)
+  // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384); P (bf16) overlays the first KV_TILE/2
+  // columns of its S tile once the scores have been read.
   const uint32_t TM_S = 0, TM_O = 256;
 
-  if (warp == 0) {
-    // ------------------------------------ TMA producer ------------------------------------
-    if (lane == 0) {
-      const int q_row = static_cast<int>(seq_row0) + qpair * 256;
-      mbar_arrive_expect_tx(bar_q, S::Q_BYTES);
-      tma_load_2d(smem, &tm_q, bar_q, p.q_off + head * ATT_D, q_row);
-      tma_load_2d(smem + 16384, &tm_q, bar_q, p.q_off + head * ATT_D, q_row + 128);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < NT; ++j) {
-        const int kv_row = static_cast<int>(seq_row0) + j * KV_TILE;
-        mbar_wait(&empty_k[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_k[stage], S::KV_BYTES);
-        tma_load_2d(smem + S::OFF_K + stage * S::KV_SLOT, &tm_kv, &full_k[stage], p.k_off + head * ATT_D, kv_row);
-        mbar_wait(&empty_v[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_v[stage], S::KV_BYTES);
-        tma_load_2d(smem + S::OFF_V + stage * S::KV_SLOT, &tm_kv, &full_v[stage], p.v_off + head * ATT_D, kv_row);
-        if (++stage == ATT_KV_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------ MMA issuer --------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, KV_TILE, 0, 0);  // S = Q K^T   (both K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (V is MN-major)
-      const uint32_t q_base = smem_u32(smem);
-      const uint32_t p_base = smem_u32(smem + S::OFF_P);
-
-      auto issue_s = [&](int x, int kstage) {
-        const uint32_t k_base = smem_u32(smem + S::OFF_K + kstage * S::KV_SLOT);
-#pragma unroll
-        for (int ks = 0; ks < ATT_D / 16; ++ks) {
-          umma_bf16_ss(tmem_base + TM_S + x * 128, umma_smem_desc_sw128(q_base + x * 16384 + ks * 32),
-                       umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
-        }
-      };
-      auto issue_pv = [&](int x, int vstage, bool acc) {
-        const uint32_t v_base = smem_u32(smem + S::OFF_V + vstage * S::KV_SLOT);
-#pragma unroll
-        for (int ks = 0; ks < KV_TILE / 16; ++ks) {
-          const uint32_t a_addr = p_base + x * S::P_BYTES + (ks >> 2) * 16384 + (ks & 3) * 32;
-          umma_bf16_ss(tmem_base + TM_O + x * 64, umma_smem_desc_sw128(a_addr),
-                       umma_smem_desc_sw128(v_base + ks * 2048), idesc_o, (acc || ks > 0) ? 1u : 0u);
-        }
-      };
-
-      mbar_wait(bar_q, 0);
-      mbar_wait(&full_k[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      umma_commit(&bar_s[0]);
-      issue_s(1, 0);
-      umma_commit(&bar_s[1]);
-      umma_commit(&empty_k[0]);
-
-      int kstage = 0, vstage = 0;
-      uint32_t kphase = 0, vphase = 0;
-      for (int j = 0; j < NT; ++j) {
-        int kstage_next = kstage + 1;
-        uint32_t kphase_next = kphase;
-        if (kstage_next == ATT_KV_STAGES) {
-          kstage_next = 0;
-          kphase_next ^= 1;
-        }
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          mbar_wait(&bar_p[x], j & 1);
-          if (x == 0) mbar_wait(&full_v[vstage], vphase);
-          tc_fence_after();
-          issue_pv(x, vstage, j > 0);
-          if (x == 1) umma_commit(&empty_v[vstage]);
-          if (j + 1 < NT) {
-            if (x == 0) {
-              mbar_wait(&full_k[kstage_next], kphase_next);
-              tc_fence_after();
-            }
-            issue_s(x, kstage_next);
-            umma_commit(&bar_s[x]);
-            if (x == 1) umma_commit(&empty_k[kstage_next]);
-          } else {
-            umma_commit(&bar_o[x]);
+  if (warp < 4) {
+    // ===================================== control warpgroup =====================================
+    setmaxnreg_dec<ATT_REGS_CONTROL>();
+    if (warp == 0) {
+      // ------------------------------------ TMA producer ------------------------------------
+      if (lane == 0) {
+        const int q_row = static_cast<int>(seq_row0) + qpair * 256;
+        mbar_arrive_expect_tx(bar_q, S::Q_BYTES);
+        tma_load_2d(smem, &tm_q, bar_q, p.q_off + head * ATT_D, q_row);
+        tma_load_2d(smem + 16384, &tm_q, bar_q, p.q_off + head * ATT_D, q_row + 128);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < NT; ++j) {
+          const int kv_row = static_cast<int>(seq_row0) + j * KV_TILE;
+          mbar_wait(&empty_k[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_k[stage], S::KV_BYTES);
+          tma_load_2d(smem + S::OFF_K + stage * S::KV_SLOT, &tm_kv, &full_k[stage], p.k_off + head * ATT_D, kv_row);
+          mbar_wait(&empty_v[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_v[stage], S::KV_BYTES);
+          tma_load_2d(smem + S::OFF_V + stage * S::KV_SLOT, &tm_kv, &full_v[stage], p.v_off + head * ATT_D, kv_row);
+          if (++stage == ATT_KV_STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
-        kstage = kstage_next;
-        kphase = kphase_next;
-        if (++vstage == ATT_KV_STAGES) {
-          vstage = 0;
-          vphase ^= 1;
+      }
+    } else if (warp == 1) {
+      // ------------------------------------ MMA issuer --------------------------------------
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, KV_TILE, 0, 0);  // S = Q K^T   (both K-major, smem)
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (P in TMEM, V MN-major)
+        const uint32_t q_base = smem_u32(smem);
+
+        auto issue_s = [&](int x, int kstage) {
+          const uint32_t k_base = smem_u32(smem + S::OFF_K + kstage * S::KV_SLOT);
+#pragma unroll
+          for (int ks = 0; ks < ATT_D / 16; ++ks) {
+            umma_bf16_ss(tmem_base + TM_S + x * 128, umma_smem_desc_sw128(q_base + x * 16384 + ks * 32),
+                         umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
+          }
+        };
+        auto issue_pv = [&](int x, int vstage, bool acc) {
+          const uint32_t v_base = smem_u32(smem + S::OFF_V + vstage * S::KV_SLOT);
+#pragma unroll
+          for (int ks = 0; ks < KV_TILE / 16; ++ks) {
+            umma_bf16_ts(tmem_base + TM_O + x * 64, tmem_base + TM_S + x * 128 + ks * 8,
+                         umma_smem_desc_sw128(v_base + ks * 2048), idesc_o, (acc || ks > 0) ? 1u : 0u);
+          }
+        };
+
+        mbar_wait(bar_q, 0);
+        mbar_wait(&full_k[0], 0);
+        tc_fence_after();
+        issue_s(0, 0);
+        umma_commit(&bar_s[0]);
+        issue_s(1, 0);
+        umma_commit(&bar_s[1]);
+        umma_commit(&empty_k[0]);
+
+        int kstage = 0, vstage = 0;
+        uint32_t kphase = 0, vphase = 0;
+        for (int j = 0; j < NT; ++j) {
+          int kstage_next = kstage + 1;
+          uint32_t kphase_next = kphase;
+          if (kstage_next == ATT_KV_STAGES) {
+            kstage_next = 0;
+            kphase_next ^= 1;
+          }
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            mbar_wait(&bar_p[x], j & 1);
+            if (x == 0) mbar_wait(&full_v[vstage], vphase);
+            tc_fence_after();
+            issue_pv(x, vstage, j > 0);
+            if (x == 1) umma_commit(&empty_v[vstage]);
+            if (j + 1 < NT) {
+              if (x == 0) {
+                mbar_wait(&full_k[kstage_next], kphase_next);
+                tc_fence_after();
+              }
+              issue_s(x, kstage_next);   // overwrites P(j) of this Q tile: ordered behind PV(j) in the MMA pipe
+              umma_commit(&bar_s[x]);
+              if (x == 1) umma_commit(&empty_k[kstage_next]);
+            } else {
+              umma_commit(&bar_o[x]);
+            }
+          }
+          kstage = kstage_next;
+          kphase = kphase_next;
+          if (++vstage == ATT_KV_STAGES) {
+            vstage = 0;
+            vphase ^= 1;
+          }
         }
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------ softmax + epilogue ------------------------------
+  } else {
+    // ===================================== softmax warpgroups =====================================
+    setmaxnreg_inc<ATT_REGS_SOFTMAX>();
     const int x = (warp - 4) >> 2;     // Q tile: 0 = A, 1 = B
     const int quarter = warp & 3;      // TMEM lane quarter
     const int r = quarter * 32 + lane;  // row inside the Q tile
@@ -224,29 +238,39 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t t_s = tmem_base + lane_addr + TM_S + x * 128;
     const uint32_t t_o = tmem_base + lane_addr + TM_O + x * 64;
-    uint8_t* p_row = smem + S::OFF_P + x * S::P_BYTES + r * 128;
     const float sl2 = p.scale_log2;
     constexpr float LOG2E = 1.4426950408889634f;
 
-    // ---- rel-pos bias prologue: per-row tables in registers (already in log2 units) ----
-    float rw2[GW];
-    float rh2w[BIAS == ATT_BIAS_WINDOW14 ? 16 : 1];
+    // ---- rel-pos bias prologue (log2 units): rel_w terms of this query row.  14x14 windows: 14 registers;
+    //      64x64 grid: 64 floats staged in shared memory (own row, read back with LDS.128 in pass 1) ----
+    float rw2[BIAS == ATT_BIAS_WINDOW14 ? GW : 1];
     const float* bh_row = nullptr;
+    [[maybe_unused]] const float4* rw_s =
+        reinterpret_cast<const float4*>(smem + S::OFF_RW + (x * 128 + r) * ATT_RW_STRIDE);
     if constexpr (BIAS != ATT_BIAS_NONE) {
       const int tt = row_valid ? t : 0;
       const int qh = tt / GW, qw = tt % GW;
       const long long brow = ((seq_row0 + tt) * p.n_heads + head) * p.ldb;
       const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
       bh_row = p.bias_h + brow + (GW - 1 - qh);
-#pragma unroll
-      for (int i = 0; i < GW; ++i) rw2[i] = __ldg(bw_row + i) * LOG2E;
       if constexpr (BIAS == ATT_BIAS_WINDOW14) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) rh2w[i] = i < 14 ? __ldg(bh_row + i) * LOG2E : 0.0f;
+        for (int i = 0; i < GW; ++i) rw2[i] = __ldg(bw_row + i) * LOG2E;
+      } else {
+        float4* dst = reinterpret_cast<float4*>(smem + S::OFF_RW + (x * 128 + r) * ATT_RW_STRIDE);
+#pragma unroll
+        for (int i = 0; i < GW / 4; ++i) {
+          float4 w;
+          w.x = __ldg(bw_row + 4 * i) * LOG2E;
+          w.y = __ldg(bw_row + 4 * i + 1) * LOG2E;
+          w.z = __ldg(bw_row + 4 * i + 2) * LOG2E;
+          w.w = __ldg(bw_row + 4 * i + 3) * LOG2E;
+          dst[i] = w;   // only this thread reads it back: no barrier needed
+        }
+        rw2[0] = 0.0f;
       }
     } else {
       rw2[0] = 0.0f;
-      rh2w[0] = 0.0f;
     }
 
     float m_used = -INFINITY;
@@ -254,15 +278,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
     for (int j = 0; j < NT; ++j) {
       const int valid = p.seq_len - j * KV_TILE;  // keys of this tile that exist (may exceed KV_TILE)
-      const bool partial = valid < KV_TILE;
-      // per-tile rel_h terms
-      float rh2[BIAS == ATT_BIAS_GLOBAL64 ? 2 : (BIAS == ATT_BIAS_WINDOW14 ? 8 : 1)];
+      // rel_h terms of the NG key-grid rows of this tile
+      float rh2[NG];
       if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
         rh2[0] = __ldg(bh_row + 2 * j) * LOG2E;
         rh2[1] = __ldg(bh_row + 2 * j + 1) * LOG2E;
       } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rh2[i] = (j == 0) ? rh2w[i] : rh2w[8 + i];
+        for (int i = 0; i < NG; ++i) rh2[i] = (j * NG + i < GW) ? __ldg(bh_row + j * NG + i) * LOG2E : 0.0f;
       } else {
         rh2[0] = 0.0f;
       }
@@ -270,37 +293,61 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_wait(&bar_s[x], j & 1);
       tc_fence_after();
 
-      // ---- pass 1: row max of the biased, scaled scores ----
+      // ---- the whole score row into registers: ONE pass over TMEM ----
+      uint32_t sv[KV_TILE];
+#pragma unroll
+      for (int c = 0; c + 32 <= KV_TILE; c += 32) tmem_ld_x32(t_s + c, sv + c);
+      if constexpr (KV_TILE % 32 != 0) tmem_ld_x16(t_s + (KV_TILE / 32) * 32, sv + (KV_TILE / 32) * 32);
+      tmem_ld_wait();
+      if (valid < KV_TILE) {   // ragged last tile: keys beyond the sequence get -inf
+#pragma unroll
+        for (int i = 0; i < KV_TILE; ++i)
+          if (i >= valid) sv[i] = 0xff800000u;
+      }
+
+      // ---- pass 1: t = s * scale + rel_w (kept in place), tile max incl. rel_h ----
       float mx = -INFINITY;
+      if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
+        float ma0 = -INFINITY, ma1 = -INFINITY, mb0 = -INFINITY, mb1 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        constexpr int W32 = 32;
-        const int width = (c * 32 + 32 <= KV_TILE) ? 32 : 16;
-        uint32_t sv[W32];
-        if (c * 32 + 32 <= KV_TILE) {
-          tmem_ld_32x32b_x32(t_s + c * 32, sv);
-        } else {
-          uint32_t s16[16];
-          tmem_ld_32x32b_x16(t_s + c * 32, s16);
+        for (int i4 = 0; i4 < GW / 4; ++i4) {
+          const float4 w = rw_s[i4];
+          const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-          for (int i = 0; i < 16; ++i) sv[i] = s16[i];
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < W32; ++i) {
-          if (i < width) {
-            const int col = c * 32 + i;
-            float tv;
-            if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
-              tv = fmaf(__uint_as_float(sv[i]), sl2, rw2[col % 64] + rh2[col / 64]);
-            } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
-              tv = fmaf(__uint_as_float(sv[i]), sl2, rw2[col % 14] + rh2[col / 14]);
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * i4 + k;
+            const float ta = fmaf(__uint_as_float(sv[i]), sl2, wv[k]);
+            const float tb = fmaf(__uint_as_float(sv[GW + i]), sl2, wv[k]);
+            sv[i] = __float_as_uint(ta);
+            sv[GW + i] = __float_as_uint(tb);
+            if (k & 1) {
+              ma1 = fmaxf(ma1, ta);
+              mb1 = fmaxf(mb1, tb);
             } else {
-              tv = __uint_as_float(sv[i]) * sl2;
+              ma0 = fmaxf(ma0, ta);
+              mb0 = fmaxf(mb0, tb);
             }
-            if (partial && col >= valid) tv = -INFINITY;
-            mx = fmaxf(mx, tv);
           }
+        }
+        mx = fmaxf(fmaxf(ma0, ma1) + rh2[0], fmaxf(mb0, mb1) + rh2[1]);
+      } else {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < GW; ++i) {
+            const int col = g * GW + i;
+            float tv;
+            if constexpr (BIAS == ATT_BIAS_NONE) {
+              tv = __uint_as_float(sv[col]) * sl2;
+            } else {
+              tv = fmaf(__uint_as_float(sv[col]), sl2, rw2[i]);
+            }
+            sv[col] = __float_as_uint(tv);
+            if (i & 1) m1 = fmaxf(m1, tv);
+            else m0 = fmaxf(m0, tv);
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1) + rh2[g]);
         }
       }
 
@@ -319,69 +366,46 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
         for (int hseg = 0; hseg < 2; ++hseg) {
           uint32_t ov[32];
-          tmem_ld_32x32b_x32(t_o + hseg * 32, ov);
+          tmem_ld_x32(t_o + hseg * 32, ov);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-          tmem_st_32x32b_x32(t_o + hseg * 32, ov);
+          tmem_st_x32(t_o + hseg * 32, ov);
         }
-        tmem_st_wait();
         l_sum *= alpha;
       }
 
-      // ---- pass 2: P = exp2(t - m_used) -> bf16 -> swizzled smem (A operand of the PV MMA) ----
-      const float neg_m = -m_used;
+      // ---- pass 2: P = exp2(t + rel_h - m) -> bf16 pairs -> TMEM (A operand of the PV MMA) over the score columns
+      //      just consumed, 32 columns (16 words) at a time so that the stores overlap the remaining exponentials ----
+      float offg[NG];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        constexpr int W32 = 32;
-        const int width = (c * 32 + 32 <= KV_TILE) ? 32 : 16;
-        uint32_t sv[W32];
-        if (c * 32 + 32 <= KV_TILE) {
-          tmem_ld_32x32b_x32(t_s + c * 32, sv);
-        } else {
-          uint32_t s16[16];
-          tmem_ld_32x32b_x16(t_s + c * 32, s16);
+      for (int g = 0; g < NG; ++g) offg[g] = rh2[g] - m_used;
+      float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) sv[i] = s16[i];
-        }
-        tmem_ld_wait();
-        float pv[W32];
+      for (int c0 = 0; c0 < KV_TILE; c0 += 32) {
+        const int width = (KV_TILE - c0 >= 32) ? 32 : 16;
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < W32; ++i) {
+        for (int i = 0; i < 32; i += 2) {
           if (i < width) {
-            const int col = c * 32 + i;
-            float tv;
-            if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
-              tv = fmaf(__uint_as_float(sv[i]), sl2, rw2[col % 64] + (rh2[col / 64] + neg_m));
-            } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
-              tv = fmaf(__uint_as_float(sv[i]), sl2, rw2[col % 14] + (rh2[col / 14] + neg_m));
+            const int col = c0 + i;
+            const float e0 = ex2_approx(__uint_as_float(sv[col]) + offg[col / GW]);
+            const float e1 = ex2_approx(__uint_as_float(sv[col + 1]) + offg[(col + 1) / GW]);
+            if ((i & 2) == 0) {
+              l0 += e0;
+              l1 += e1;
             } else {
-              tv = fmaf(__uint_as_float(sv[i]), sl2, neg_m);
+              l2 += e0;
+              l3 += e1;
             }
-            float e = ex2_approx(tv);
-            if (partial && col >= valid) e = 0.0f;
-            pv[i] = e;
-            l_sum += e;
-          } else {
-            pv[i] = 0.0f;
+            pk[i >> 1] = pack_bf16(e0, e1);
           }
         }
-        // 32 columns = 64 bytes = four 16-byte groups of K-block (c >> 1)
-        uint8_t* blk = p_row + (c >> 1) * 16384;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g * 8 < width) {
-            uint4 pk;
-            pk.x = pack_bf16(pv[g * 8 + 0], pv[g * 8 + 1]);
-            pk.y = pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]);
-            pk.z = pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]);
-            pk.w = pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]);
-            const int grp = (c & 1) * 4 + g;
-            *reinterpret_cast<uint4*>(blk + ((grp ^ (r & 7)) << 4)) = pk;
-          }
-        }
+        if (width == 32) tmem_st_32x32b_x16(t_s + (c0 >> 1), pk);
+        else tmem_st_32x32b_x8(t_s + (c0 >> 1), pk);
       }
-      fence_proxy_async_smem();
+      l_sum += (l0 + l1) + (l2 + l3);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar_p[x]);
     }
@@ -406,7 +430,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
     for (int hseg = 0; hseg < 2; ++hseg) {
       uint32_t ov[32];
-      tmem_ld_32x32b_x32(t_o + hseg * 32, ov);
+      tmem_ld_x32(t_o + hseg * 32, ov);
       tmem_ld_wait();
       if (out_row >= 0) {
         __nv_bfloat16* dst = p.out + out_row * p.ld_out + head * ATT_D + hseg * 32;
@@ -434,7 +458,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 template <int KV_TILE, int BIAS>
 static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, const void* kv, long long ld_kv,
                             const AttParams& p) {
-  using S = AttSmem<KV_TILE>;
+  using S = AttSmem<KV_TILE, BIAS>;
   CUtensorMap tm_q, tm_kv;
   int rc = make_tensor_map_2d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_q, (uint64_t)p.rows_total,
                               (uint64_t)ld_q * 2, 64, 128, Swizzle::B128);

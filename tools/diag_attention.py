@@ -41,7 +41,7 @@ def rev_table_bias(q_heads, rel, pad_to):
     outs = []
     for h in range(q_heads.shape[0]):
         outs.append(ops.gemm(q_heads[h], w, None, out_dtype=torch.float32))
-    return torch.stack(outs).contiguous()
+    return torch.stack(outs).permute(1, 0, 2).contiguous()  # [rows, heads, pad]
 
 
 def ref_attention(qkv, n_seq, L, heads, scale, rel_h=None, rel_w=None, g=0):
@@ -63,7 +63,7 @@ def test_plain(n_seq=2, L=901, heads=12):
     g = torch.Generator(device="cuda").manual_seed(1)
     qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda", generator=g).to(torch.bfloat16)
     out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
-    ops.attention(qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64)
+    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64)
     torch.cuda.synchronize()
     return report(f"attention plain L={L}", out, ref_attention(qkv, n_seq, L, heads, 0.125), 2e-2)
 
@@ -78,7 +78,7 @@ def test_global(n_seq=1, heads=12):
     bh = rev_table_bias(qh, rel_h, 128)
     bw = rev_table_bias(qh, rel_w, 128)
     out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
-    ops.attention(qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=64)
+    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=64)
     torch.cuda.synchronize()
     ref = ref_attention(qkv, n_seq, L, heads, 0.125, rel_h, rel_w, gsz)
     return report("attention global64", out, ref, 2e-2)
@@ -96,12 +96,12 @@ def test_window(n_img=2, heads=12):
     bw = rev_table_bias(qh, rel_w, 64)
     ok = True
     out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
-    ops.attention(qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=14)
+    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=14)
     torch.cuda.synchronize()
     ref = ref_attention(qkv, n_seq, L, heads, 0.125, rel_h, rel_w, gsz)
     ok &= report("attention window14 (identity rows)", out, ref, 2e-2)
     out2 = torch.zeros(n_img * hw * hw, heads * 64, device="cuda", dtype=torch.bfloat16)
-    ops.attention(qkv, n_seq, L, heads, 0.125, out2, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=14, out_mode=1,
+    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out2, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=14, out_mode=1,
                   nwin=nwin, img_hw=hw)
     torch.cuda.synchronize()
     r = ref.view(n_img, nwin, nwin, 14, 14, -1).permute(0, 1, 3, 2, 4, 5).reshape(n_img, 70, 70, -1)[:, :hw, :hw]
@@ -177,9 +177,9 @@ def bench_attention():
         bh = bw = None
         if gsz:
             pad = 128 if gsz == 64 else 64
-            bh = torch.randn(heads, n_seq * L, pad, device="cuda") * 0.1
-            bw = torch.randn(heads, n_seq * L, pad, device="cuda") * 0.1
-        f = lambda: ops.attention(qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+            bh = torch.randn(n_seq * L, heads, pad, device="cuda") * 0.1
+            bw = torch.randn(n_seq * L, heads, pad, device="cuda") * 0.1
+        f = lambda: ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
         for _ in range(3):
             f()
         torch.cuda.synchronize()
