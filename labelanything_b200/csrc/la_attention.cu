@@ -50,16 +50,16 @@ struct AttParams {
 
 template <int KV_TILE, int BIAS>
 struct AttSmem {
-  static constexpr int STAGES = BIAS == 1 ? 3 : 4;          // K / V ring depth (the 64x64 bias variant needs room for rel_w)
+  static constexpr int STAGES = KV_TILE <= 64 ? 6 : 4;      // K / V ring depth
   static constexpr int Q_BYTES = 2 * 128 * 128;             // two Q tiles, 128 rows x 128 B
   static constexpr int KV_BYTES = KV_TILE * 128;            // one K or V tile
   static constexpr int KV_SLOT = ((KV_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_K = Q_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * KV_SLOT;
-  static constexpr int OFF_RW = OFF_V + STAGES * KV_SLOT;   // [256 rows][68] fp32 rel_w terms (64x64 bias variant)
+  static constexpr int OFF_RW = OFF_V + STAGES * KV_SLOT;   // [256 rows][68] fp32 rel_w staging (64x64 bias variant)
   static constexpr int RW_BYTES = BIAS == 1 ? 256 * ATT_RW_STRIDE : 0;
   static constexpr int OFF_BAR = OFF_RW + RW_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int TOTAL = OFF_BAR + 512 + 1024;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -78,6 +78,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   constexpr int GW = BIAS == ATT_BIAS_GLOBAL64 ? 64 : (BIAS == ATT_BIAS_WINDOW14 ? 14 : KV_TILE);
   constexpr int NG = KV_TILE / GW;
   static_assert(NG * GW == KV_TILE && KV_TILE % 16 == 0 && KV_TILE <= 128, "tile must hold whole key-grid rows");
+  // Tiles of <= 64 keys double-buffer the score tile in TMEM: S(j+1) is issued BEFORE the MMA warp waits for P(j), so
+  // the softmax warps never wait for the tensor pipe once the pipeline is full.
+  constexpr bool DB = KV_TILE <= 64;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,10 +90,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* empty_k = full_k + ATT_KV_STAGES;
   uint64_t* full_v = empty_k + ATT_KV_STAGES;
   uint64_t* empty_v = full_v + ATT_KV_STAGES;
-  uint64_t* bar_s = empty_v + ATT_KV_STAGES;       // 2
-  uint64_t* bar_p = bar_s + 2;                     // 2
-  uint64_t* bar_o = bar_p + 2;                     // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 2);
+  uint64_t* bar_s = empty_v + ATT_KV_STAGES;       // [Q tile][score buffer]: S ready
+  uint64_t* bar_p = bar_s + 4;                     // [Q tile][score buffer]: P written (128 arrivals).  Per buffer,
+                                                   // because with double buffering a fast warp may finish tile j+1
+                                                   // before a slow one has delivered its rows of tile j.
+  uint64_t* bar_pv = bar_p + 4;                    // [Q tile]: O += P V of the tile completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_pv + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,9 +118,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_init(&empty_v[s], 1);
     }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&bar_s[x], 1);
-      mbar_init(&bar_p[x], 128);
-      mbar_init(&bar_o[x], 1);
+      mbar_init(&bar_s[2 * x], 1);
+      mbar_init(&bar_s[2 * x + 1], 1);
+      mbar_init(&bar_p[2 * x], 128);
+      mbar_init(&bar_p[2 * x + 1], 128);
+      mbar_init(&bar_pv[x], 1);
     }
     fence_barrier_init();
   }
@@ -127,8 +134,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384); P (bf16) overlays the first KV_TILE/2
-  // columns of its S tile once the scores have been read.
+  // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384); with double buffering each S region holds
+  // two KV_TILE-wide score buffers.  P (bf16) overlays the first KV_TILE/2 columns of the score buffer it came from.
   const uint32_t TM_S = 0, TM_O = 256;
 
   if (warp < 4) {
@@ -164,19 +171,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (P in TMEM, V MN-major)
         const uint32_t q_base = smem_u32(smem);
 
-        auto issue_s = [&](int x, int kstage) {
+        auto issue_s = [&](int x, int kstage, int buf) {
           const uint32_t k_base = smem_u32(smem + S::OFF_K + kstage * S::KV_SLOT);
 #pragma unroll
           for (int ks = 0; ks < ATT_D / 16; ++ks) {
-            umma_bf16_ss(tmem_base + TM_S + x * 128, umma_smem_desc_sw128(q_base + x * 16384 + ks * 32),
+            umma_bf16_ss(tmem_base + TM_S + x * 128 + buf * KV_TILE, umma_smem_desc_sw128(q_base + x * 16384 + ks * 32),
                          umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
           }
         };
-        auto issue_pv = [&](int x, int vstage, bool acc) {
+        auto issue_pv = [&](int x, int vstage, int buf, bool acc) {
           const uint32_t v_base = smem_u32(smem + S::OFF_V + vstage * S::KV_SLOT);
 #pragma unroll
           for (int ks = 0; ks < KV_TILE / 16; ++ks) {
-            umma_bf16_ts(tmem_base + TM_O + x * 64, tmem_base + TM_S + x * 128 + ks * 8,
+            umma_bf16_ts(tmem_base + TM_O + x * 64, tmem_base + TM_S + x * 128 + buf * KV_TILE + ks * 8,
                          umma_smem_desc_sw128(v_base + ks * 2048), idesc_o, (acc || ks > 0) ? 1u : 0u);
           }
         };
@@ -184,10 +191,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         mbar_wait(bar_q, 0);
         mbar_wait(&full_k[0], 0);
         tc_fence_after();
-        issue_s(0, 0);
+        issue_s(0, 0, 0);
         umma_commit(&bar_s[0]);
-        issue_s(1, 0);
-        umma_commit(&bar_s[1]);
+        issue_s(1, 0, 0);
+        umma_commit(&bar_s[2]);
         umma_commit(&empty_k[0]);
 
         int kstage = 0, vstage = 0;
@@ -199,23 +206,33 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             kstage_next = 0;
             kphase_next ^= 1;
           }
+          const int buf = DB ? (j & 1) : 0, buf_next = DB ? ((j + 1) & 1) : 0;
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
-            mbar_wait(&bar_p[x], j & 1);
-            if (x == 0) mbar_wait(&full_v[vstage], vphase);
-            tc_fence_after();
-            issue_pv(x, vstage, j > 0);
-            if (x == 1) umma_commit(&empty_v[vstage]);
-            if (j + 1 < NT) {
+            if (DB && j + 1 < NT) {
+              // next score tile first: its buffer held P(j-1), whose PV MMA is already ahead of it in the pipe
               if (x == 0) {
                 mbar_wait(&full_k[kstage_next], kphase_next);
                 tc_fence_after();
               }
-              issue_s(x, kstage_next);   // overwrites P(j) of this Q tile: ordered behind PV(j) in the MMA pipe
-              umma_commit(&bar_s[x]);
+              issue_s(x, kstage_next, buf_next);
+              umma_commit(&bar_s[2 * x + buf_next]);
               if (x == 1) umma_commit(&empty_k[kstage_next]);
-            } else {
-              umma_commit(&bar_o[x]);
+            }
+            mbar_wait(&bar_p[2 * x + buf], DB ? ((j >> 1) & 1) : (j & 1));
+            if (x == 0) mbar_wait(&full_v[vstage], vphase);
+            tc_fence_after();
+            issue_pv(x, vstage, buf, j > 0);
+            umma_commit(&bar_pv[x]);
+            if (x == 1) umma_commit(&empty_v[vstage]);
+            if (!DB && j + 1 < NT) {
+              if (x == 0) {
+                mbar_wait(&full_k[kstage_next], kphase_next);
+                tc_fence_after();
+              }
+              issue_s(x, kstage_next, 0);   // overwrites P(j) of this Q tile: ordered behind PV(j) in the MMA pipe
+              umma_commit(&bar_s[2 * x]);
+              if (x == 1) umma_commit(&empty_k[kstage_next]);
             }
           }
           kstage = kstage_next;
@@ -236,38 +253,46 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int t = qpair * 256 + x * 128 + r;  // token index inside the sequence
     const bool row_valid = t < p.seq_len;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_addr + TM_S + x * 128;
+    const uint32_t t_s0 = tmem_base + lane_addr + TM_S + x * 128;
     const uint32_t t_o = tmem_base + lane_addr + TM_O + x * 64;
     const float sl2 = p.scale_log2;
     constexpr float LOG2E = 1.4426950408889634f;
 
-    // ---- rel-pos bias prologue (log2 units): rel_w terms of this query row.  14x14 windows: 14 registers;
-    //      64x64 grid: 64 floats staged in shared memory (own row, read back with LDS.128 in pass 1) ----
-    float rw2[BIAS == ATT_BIAS_WINDOW14 ? GW : 1];
+    // ---- rel-pos bias prologue (log2 units): the rel_w terms of this query row live in registers.  For the 64x64
+    //      grid the 32 rows of a warp are fetched cooperatively (coalesced 128-byte requests) through a shared-memory
+    //      staging area, each thread then reads its own row back with LDS.128 ----
+    float rw2[BIAS == ATT_BIAS_NONE ? 1 : GW];
     const float* bh_row = nullptr;
-    [[maybe_unused]] const float4* rw_s =
-        reinterpret_cast<const float4*>(smem + S::OFF_RW + (x * 128 + r) * ATT_RW_STRIDE);
     if constexpr (BIAS != ATT_BIAS_NONE) {
       const int tt = row_valid ? t : 0;
       const int qh = tt / GW, qw = tt % GW;
       const long long brow = ((seq_row0 + tt) * p.n_heads + head) * p.ldb;
-      const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
       bh_row = p.bias_h + brow + (GW - 1 - qh);
       if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+        const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
 #pragma unroll
         for (int i = 0; i < GW; ++i) rw2[i] = __ldg(bw_row + i) * LOG2E;
       } else {
-        float4* dst = reinterpret_cast<float4*>(smem + S::OFF_RW + (x * 128 + r) * ATT_RW_STRIDE);
+        static_assert(BIAS != ATT_BIAS_GLOBAL64 || GW == 64, "staging assumes 64 rel_w terms per row");
+        float* stage = reinterpret_cast<float*>(smem + S::OFF_RW + (x * 128 + quarter * 32) * ATT_RW_STRIDE);
+        const int t0 = qpair * 256 + x * 128 + quarter * 32;   // token of this warp's first row
+        for (int rr = 0; rr < 32; ++rr) {
+          const int t2 = (t0 + rr < p.seq_len) ? t0 + rr : 0;
+          const float* src = p.bias_w + ((seq_row0 + t2) * p.n_heads + head) * p.ldb + (GW - 1 - t2 % GW);
+          float* dst = stage + rr * (ATT_RW_STRIDE / 4);
+          dst[lane] = __ldg(src + lane);
+          dst[lane + 32] = __ldg(src + lane + 32);
+        }
+        __syncwarp();
+        const float4* own = reinterpret_cast<const float4*>(smem + S::OFF_RW + (x * 128 + r) * ATT_RW_STRIDE);
 #pragma unroll
         for (int i = 0; i < GW / 4; ++i) {
-          float4 w;
-          w.x = __ldg(bw_row + 4 * i) * LOG2E;
-          w.y = __ldg(bw_row + 4 * i + 1) * LOG2E;
-          w.z = __ldg(bw_row + 4 * i + 2) * LOG2E;
-          w.w = __ldg(bw_row + 4 * i + 3) * LOG2E;
-          dst[i] = w;   // only this thread reads it back: no barrier needed
+          const float4 w = own[i];
+          rw2[4 * i] = w.x * LOG2E;
+          rw2[4 * i + 1] = w.y * LOG2E;
+          rw2[4 * i + 2] = w.z * LOG2E;
+          rw2[4 * i + 3] = w.w * LOG2E;
         }
-        rw2[0] = 0.0f;
       }
     } else {
       rw2[0] = 0.0f;
@@ -281,8 +306,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // rel_h terms of the NG key-grid rows of this tile
       float rh2[NG];
       if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
-        rh2[0] = __ldg(bh_row + 2 * j) * LOG2E;
-        rh2[1] = __ldg(bh_row + 2 * j + 1) * LOG2E;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) rh2[i] = __ldg(bh_row + NG * j + i) * LOG2E;
       } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
 #pragma unroll
         for (int i = 0; i < NG; ++i) rh2[i] = (j * NG + i < GW) ? __ldg(bh_row + j * NG + i) * LOG2E : 0.0f;
@@ -290,7 +315,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         rh2[0] = 0.0f;
       }
 
-      mbar_wait(&bar_s[x], j & 1);
+      const int buf = DB ? (j & 1) : 0;
+      const uint32_t t_s = t_s0 + buf * KV_TILE;
+      mbar_wait(&bar_s[2 * x + buf], DB ? ((j >> 1) & 1) : (j & 1));
       tc_fence_after();
 
       // ---- the whole score row into registers: ONE pass over TMEM ----
@@ -307,48 +334,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
       // ---- pass 1: t = s * scale + rel_w (kept in place), tile max incl. rel_h ----
       float mx = -INFINITY;
-      if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
-        float ma0 = -INFINITY, ma1 = -INFINITY, mb0 = -INFINITY, mb1 = -INFINITY;
 #pragma unroll
-        for (int i4 = 0; i4 < GW / 4; ++i4) {
-          const float4 w = rw_s[i4];
-          const float wv[4] = {w.x, w.y, w.z, w.w};
+      for (int g = 0; g < NG; ++g) {
+        float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int i = 4 * i4 + k;
-            const float ta = fmaf(__uint_as_float(sv[i]), sl2, wv[k]);
-            const float tb = fmaf(__uint_as_float(sv[GW + i]), sl2, wv[k]);
-            sv[i] = __float_as_uint(ta);
-            sv[GW + i] = __float_as_uint(tb);
-            if (k & 1) {
-              ma1 = fmaxf(ma1, ta);
-              mb1 = fmaxf(mb1, tb);
-            } else {
-              ma0 = fmaxf(ma0, ta);
-              mb0 = fmaxf(mb0, tb);
-            }
+        for (int i = 0; i < GW; ++i) {
+          const int col = g * GW + i;
+          float tv;
+          if constexpr (BIAS == ATT_BIAS_NONE) {
+            tv = __uint_as_float(sv[col]) * sl2;
+          } else {
+            tv = fmaf(__uint_as_float(sv[col]), sl2, rw2[i]);
           }
+          sv[col] = __float_as_uint(tv);
+          if (i & 1) m1 = fmaxf(m1, tv);
+          else m0 = fmaxf(m0, tv);
         }
-        mx = fmaxf(fmaxf(ma0, ma1) + rh2[0], fmaxf(mb0, mb1) + rh2[1]);
-      } else {
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < GW; ++i) {
-            const int col = g * GW + i;
-            float tv;
-            if constexpr (BIAS == ATT_BIAS_NONE) {
-              tv = __uint_as_float(sv[col]) * sl2;
-            } else {
-              tv = fmaf(__uint_as_float(sv[col]), sl2, rw2[i]);
-            }
-            sv[col] = __float_as_uint(tv);
-            if (i & 1) m1 = fmaxf(m1, tv);
-            else m0 = fmaxf(m0, tv);
-          }
-          mx = fmaxf(mx, fmaxf(m0, m1) + rh2[g]);
-        }
+        mx = fmaxf(mx, fmaxf(m0, m1) + rh2[g]);
       }
 
       // ---- running max with lazy rescale (threshold 8 in log2 units => P <= 256) ----
@@ -362,7 +364,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         need = true;
       }
       if (__any_sync(0xffffffffu, need)) {
-        // O of this Q tile is complete up to tile j-1 (bar_s[x] of tile j was committed after PV(j-1)).
+        // O must hold everything up to tile j-1 before it is rescaled
+        mbar_wait(&bar_pv[x], (j - 1) & 1);
+        tc_fence_after();
 #pragma unroll
         for (int hseg = 0; hseg < 2; ++hseg) {
           uint32_t ov[32];
@@ -407,11 +411,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       l_sum += (l0 + l1) + (l2 + l3);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bar_p[x]);
+      mbar_arrive(&bar_p[2 * x + buf]);
     }
 
     // ---- epilogue: O / l -> bf16 -> global (with the window-unpartition row mapping) ----
-    mbar_wait(&bar_o[x], 0);
+    mbar_wait(&bar_pv[x], (NT - 1) & 1);
     tc_fence_after();
     long long out_row = -1;
     if (row_valid) {
@@ -512,12 +516,12 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!has_bias) {
     LA_CHECK_ARG(out_mode == 0, "la_attention_bf16: window output mapping needs the window bias mode");
-    return launch_attention<128, ATT_BIAS_NONE>(st, q, ld_q, kv, ld_kv, p);
+    return launch_attention<64, ATT_BIAS_NONE>(st, q, ld_q, kv, ld_kv, p);
   }
   if (grid_hw == 64) {
     LA_CHECK_ARG(seq_len == 4096 && ldb >= 127 && out_mode == 0,
                  "la_attention_bf16: 64x64 rel-pos mode expects seq_len 4096, ldb >= 127");
-    return launch_attention<128, ATT_BIAS_GLOBAL64>(st, q, ld_q, kv, ld_kv, p);
+    return launch_attention<64, ATT_BIAS_GLOBAL64>(st, q, ld_q, kv, ld_kv, p);
   }
   if (grid_hw == 14) {
     LA_CHECK_ARG(seq_len == 196 && ldb >= 27, "la_attention_bf16: 14x14 rel-pos mode expects seq_len 196, ldb >= 27");

@@ -1,0 +1,24 @@
+"""Run the fused attention kernel a few times (for ncu captures): python tools/run_attention.py [global|window|plain]"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch
+
+from labelanything_b200 import ops
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "global"
+heads = 12
+n_seq, L, gsz = {"global": (8, 4096, 64), "window": (200, 196, 14), "plain": (32, 901, 0)}[mode]
+qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda").to(torch.bfloat16)
+out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
+bh = bw = None
+if gsz:
+    pad = 128 if gsz == 64 else 64
+    bh = torch.randn(n_seq * L, heads, pad, device="cuda") * 0.1
+    bw = torch.randn(n_seq * L, heads, pad, device="cuda") * 0.1
+for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
+    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+torch.cuda.synchronize()
+print("done", mode)
