@@ -68,6 +68,10 @@ int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, co
                       const float* bias_h, const float* bias_w, int ldb, int grid_hw, void* out, long long ld_out,
                       int out_mode, int nwin, int img_hw);
 
+/* Diagnostics: when device_buffer != NULL, CTA (0,0,0) of every following la_attention_bf16 launch records clock64()
+ * stamps into it: int64 [3 roles (MMA issuer, softmax A, softmax B)][64 tiles][4 events]; NULL switches it off. */
+int la_attention_set_trace(void* device_buffer);
+
 /* ---- streaming row kernels ----------------------------------------------------------------------- */
 /* x = x_in[(row % x_mod) if x_mod > 0 else row] + delta[row]  (fp32 + bf16); optionally stored to x_out (may
  * alias x_in), plus the optional addends delta2[row] (bf16) and seq_add[row / seq_rows] (fp32, one vector per

@@ -46,7 +46,14 @@ struct AttParams {
   long long ld_out;
   int out_mode;  // 0: row = seq*seq_len + t ; 1: window unpartition
   int win, nwin, img_hw;  // out_mode 1: window size, windows per side, un-padded grid side
+  long long* trace;       // diagnostics (la_attention_set_trace): clock64 stamps of CTA (0,0,0), else nullptr
 };
+
+// trace layout: [role][tile][event] int64; roles: 0 = MMA thread, 1 = softmax A (warp 4 lane 0), 2 = softmax B
+constexpr int ATT_TRACE_TILES = 64, ATT_TRACE_EVENTS = 4;
+__device__ __forceinline__ void att_trace(const AttParams& p, bool on, int role, int tile, int ev) {
+  if (on && tile < ATT_TRACE_TILES) p.trace[(role * ATT_TRACE_TILES + tile) * ATT_TRACE_EVENTS + ev] = clock64();
+}
 
 template <int KV_TILE, int BIAS>
 struct AttSmem {
@@ -91,7 +98,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* full_v = empty_k + ATT_KV_STAGES;
   uint64_t* empty_v = full_v + ATT_KV_STAGES;
   uint64_t* bar_s = empty_v + ATT_KV_STAGES;       // [Q tile][score buffer]: S ready
-  uint64_t* bar_p = bar_s + 4;                     // [Q tile][score buffer]: P written (128 arrivals).  Per buffer,
+  uint64_t* bar_p = bar_s + 4;                     // [Q tile][score buffer]: P written (4 arrivals: one per warp).  Per buffer,
                                                    // because with double buffering a fast warp may finish tile j+1
                                                    // before a slow one has delivered its rows of tile j.
   uint64_t* bar_pv = bar_p + 4;                    // [Q tile]: O += P V of the tile completed
@@ -104,6 +111,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int seq = blockIdx.z;
   const int NT = (p.seq_len + KV_TILE - 1) / KV_TILE;
   const long long seq_row0 = static_cast<long long>(seq) * p.seq_len;
+  const bool tr = p.trace != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -120,8 +128,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     for (int x = 0; x < 2; ++x) {
       mbar_init(&bar_s[2 * x], 1);
       mbar_init(&bar_s[2 * x + 1], 1);
-      mbar_init(&bar_p[2 * x], 128);
-      mbar_init(&bar_p[2 * x + 1], 128);
+      mbar_init(&bar_p[2 * x], 4);        // one arrival per softmax warp
+      mbar_init(&bar_p[2 * x + 1], 4);
       mbar_init(&bar_pv[x], 1);
     }
     fence_barrier_init();
@@ -166,36 +174,47 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
     } else if (warp == 1) {
       // ------------------------------------ MMA issuer --------------------------------------
-      if (lane == 0) {
+      // The whole warp runs this loop converged (descriptors and addresses stay warp-uniform, so they live in
+      // uniform registers); one elected lane issues each group of tcgen05 instructions.
+      {
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, KV_TILE, 0, 0);  // S = Q K^T   (both K-major, smem)
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (P in TMEM, V MN-major)
         const uint32_t q_base = smem_u32(smem);
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-        auto issue_s = [&](int x, int kstage, int buf) {
+        // S_x(tile in K stage `kstage`) -> score buffer `buf`; then signal `bar_done` (and optionally free the K stage)
+        auto issue_s = [&](int x, int kstage, int buf, uint64_t* bar_done, uint64_t* bar_free) {
           const uint32_t k_base = smem_u32(smem + S::OFF_K + kstage * S::KV_SLOT);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < ATT_D / 16; ++ks) {
-            umma_bf16_ss(tmem_base + TM_S + x * 128 + buf * KV_TILE, umma_smem_desc_sw128(q_base + x * 16384 + ks * 32),
-                         umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
+            for (int ks = 0; ks < ATT_D / 16; ++ks) {
+              umma_bf16_ss(tm + TM_S + x * 128 + buf * KV_TILE, umma_smem_desc_sw128(q_base + x * 16384 + ks * 32),
+                           umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(bar_done);
+            if (bar_free != nullptr) umma_commit(bar_free);
           }
+          __syncwarp();
         };
-        auto issue_pv = [&](int x, int vstage, int buf, bool acc) {
+        auto issue_pv = [&](int x, int vstage, int buf, bool acc, uint64_t* bar_done, uint64_t* bar_free) {
           const uint32_t v_base = smem_u32(smem + S::OFF_V + vstage * S::KV_SLOT);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KV_TILE / 16; ++ks) {
-            umma_bf16_ts(tmem_base + TM_O + x * 64, tmem_base + TM_S + x * 128 + buf * KV_TILE + ks * 8,
-                         umma_smem_desc_sw128(v_base + ks * 2048), idesc_o, (acc || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < KV_TILE / 16; ++ks) {
+              umma_bf16_ts(tm + TM_O + x * 64, tm + TM_S + x * 128 + buf * KV_TILE + ks * 8,
+                           umma_smem_desc_sw128(v_base + ks * 2048), idesc_o, (acc || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(bar_done);
+            if (bar_free != nullptr) umma_commit(bar_free);
           }
+          __syncwarp();
         };
 
         mbar_wait(bar_q, 0);
         mbar_wait(&full_k[0], 0);
         tc_fence_after();
-        issue_s(0, 0, 0);
-        umma_commit(&bar_s[0]);
-        issue_s(1, 0, 0);
-        umma_commit(&bar_s[2]);
-        umma_commit(&empty_k[0]);
+        issue_s(0, 0, 0, &bar_s[0], nullptr);
+        issue_s(1, 0, 0, &bar_s[2], &empty_k[0]);
 
         int kstage = 0, vstage = 0;
         uint32_t kphase = 0, vphase = 0;
@@ -215,24 +234,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 mbar_wait(&full_k[kstage_next], kphase_next);
                 tc_fence_after();
               }
-              issue_s(x, kstage_next, buf_next);
-              umma_commit(&bar_s[2 * x + buf_next]);
-              if (x == 1) umma_commit(&empty_k[kstage_next]);
+              issue_s(x, kstage_next, buf_next, &bar_s[2 * x + buf_next], x == 1 ? &empty_k[kstage_next] : nullptr);
             }
             mbar_wait(&bar_p[2 * x + buf], DB ? ((j >> 1) & 1) : (j & 1));
+            att_trace(p, tr, 0, j, 2 * x);
             if (x == 0) mbar_wait(&full_v[vstage], vphase);
             tc_fence_after();
-            issue_pv(x, vstage, buf, j > 0);
-            umma_commit(&bar_pv[x]);
-            if (x == 1) umma_commit(&empty_v[vstage]);
+            issue_pv(x, vstage, buf, j > 0, &bar_pv[x], x == 1 ? &empty_v[vstage] : nullptr);
+            att_trace(p, tr, 0, j, 2 * x + 1);
             if (!DB && j + 1 < NT) {
               if (x == 0) {
                 mbar_wait(&full_k[kstage_next], kphase_next);
                 tc_fence_after();
               }
-              issue_s(x, kstage_next, 0);   // overwrites P(j) of this Q tile: ordered behind PV(j) in the MMA pipe
-              umma_commit(&bar_s[2 * x]);
-              if (x == 1) umma_commit(&empty_k[kstage_next]);
+              // overwrites P(j) of this Q tile: ordered behind PV(j) in the MMA pipe
+              issue_s(x, kstage_next, 0, &bar_s[2 * x], x == 1 ? &empty_k[kstage_next] : nullptr);
             }
           }
           kstage = kstage_next;
@@ -317,8 +333,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
       const int buf = DB ? (j & 1) : 0;
       const uint32_t t_s = t_s0 + buf * KV_TILE;
+      att_trace(p, tr && quarter == 0, 1 + x, j, 0);
       mbar_wait(&bar_s[2 * x + buf], DB ? ((j >> 1) & 1) : (j & 1));
       tc_fence_after();
+      att_trace(p, tr && quarter == 0, 1 + x, j, 1);
 
       // ---- the whole score row into registers: ONE pass over TMEM ----
       uint32_t sv[KV_TILE];
@@ -353,6 +371,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         mx = fmaxf(mx, fmaxf(m0, m1) + rh2[g]);
       }
 
+      att_trace(p, tr && quarter == 0, 1 + x, j, 2);
       // ---- running max with lazy rescale (threshold 8 in log2 units => P <= 256) ----
       float alpha = 1.0f;
       bool need = false;
@@ -411,7 +430,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       l_sum += (l0 + l1) + (l2 + l3);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bar_p[2 * x + buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[2 * x + buf]);
+      att_trace(p, tr && quarter == 0, 1 + x, j, 3);
     }
 
     // ---- epilogue: O / l -> bf16 -> global (with the window-unpartition row mapping) ----
@@ -480,6 +501,13 @@ static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, 
 
 }  // namespace la
 
+static long long* g_att_trace = nullptr;
+
+extern "C" int la_attention_set_trace(void* device_buffer) {
+  g_att_trace = static_cast<long long*>(device_buffer);
+  return LA_OK;
+}
+
 extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv,
                                  long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq,
                                  int seq_len, int n_heads, float scale, const float* bias_h, const float* bias_w,
@@ -513,6 +541,7 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
   p.win = grid_hw;
   p.nwin = nwin;
   p.img_hw = img_hw;
+  p.trace = g_att_trace;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!has_bias) {
     LA_CHECK_ARG(out_mode == 0, "la_attention_bf16: window output mapping needs the window bias mode");

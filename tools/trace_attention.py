@@ -1,0 +1,41 @@
+"""Timeline of one CTA of the fused attention kernel (clock64 stamps): python tools/trace_attention.py [global|plain]"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch
+
+from labelanything_b200 import _native, ops
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "global"
+heads = 12
+n_seq, L, gsz = {"global": (8, 4096, 64), "plain": (8, 4096, 0)}[mode]
+qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda").to(torch.bfloat16)
+out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
+bh = bw = None
+if gsz:
+    bh = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
+    bw = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
+tr = torch.zeros(3, 64, 4, dtype=torch.int64, device="cuda")
+for _ in range(2):
+    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+_native.lib().la_attention_set_trace(tr.data_ptr())
+ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+torch.cuda.synchronize()
+_native.lib().la_attention_set_trace(None)
+t = tr.cpu()
+t0 = int(t[t > 0].min())
+t = (t - t0).clamp(min=-1)
+print("tile | MMA: P_A seen, PV_A issued, P_B seen, PV_B issued | softA: waitS, gotS, max done, P arrived | softB: same")
+for j in list(range(0, 12)) + list(range(40, 46)):
+    print(j, t[0, j].tolist(), t[1, j].tolist(), t[2, j].tolist())
+d = t[1, 8:60]
+print("softmax A steady state: mean wait-for-S", float((d[:, 1] - d[:, 0]).float().mean()), "pass1", float((d[:, 2] - d[:, 1]).float().mean()),
+      "pass2+store", float((d[:, 3] - d[:, 2]).float().mean()), "period", float((d[1:, 3] - d[:-1, 3]).float().mean()))
+d = t[2, 8:60]
+print("softmax B steady state: mean wait-for-S", float((d[:, 1] - d[:, 0]).float().mean()), "pass1", float((d[:, 2] - d[:, 1]).float().mean()),
+      "pass2+store", float((d[:, 3] - d[:, 2]).float().mean()), "period", float((d[1:, 3] - d[:-1, 3]).float().mean()))
+m = t[0, 8:60]
+print("MMA: P_A seen -> PV_A issued", float((m[:, 1] - m[:, 0]).float().mean()), "PV_A issued -> P_B seen", float((m[:, 2] - m[:, 1]).float().mean()),
+      "P_B seen -> PV_B issued", float((m[:, 3] - m[:, 2]).float().mean()))
