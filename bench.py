@@ -252,8 +252,13 @@ def run_native(args) -> None:
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
-    fam = prof.summary()
+    detail = prof.summary()
     launches = prof.launches
+    fam: dict = {}   # kernel families (gemm.n2304.k768 -> gemm)
+    for k, v in detail.items():
+        f = fam.setdefault(k.split(".")[0], {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for kk in f:
+            f[kk] += v[kk]
     clocks = sampler.stop() if sampler else None
 
     # ---- timed region 2: end to end from pinned host memory ---------------------------------------------------
@@ -299,6 +304,11 @@ def run_native(args) -> None:
         if sd_cpu is not None:
             cpu = cpu_reference_sample(sd_cpu)
             cpu.pop("seconds_per_episode", None)
+        if args.detail:
+            for k, v in sorted(detail.items(), key=lambda kv: -kv[1]["ms"])[:24]:
+                print(f"# {k:34s} {v['launches'] // args.steps:5d} launches/step {v['ms'] / args.steps:8.2f} ms/step "
+                      f"{(v['flops'] / v['ms'] / 1e9) if v['flops'] else 0:8.1f} TFLOP/s {v['bytes'] / v['ms'] / 1e6:8.0f} GB/s",
+                      file=sys.stderr)
         line = {"metric": METRIC, "value": value, "unit": "episodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -323,6 +333,7 @@ def main() -> None:
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="episodes per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--detail", action="store_true", help="print the per-kernel-shape breakdown to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

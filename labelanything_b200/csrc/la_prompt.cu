@@ -175,7 +175,6 @@ __global__ void __launch_bounds__(256) build_src_kernel(const BuildSrcParams p) 
   const int rows_per_pass = blockDim.x / tpr;
   const int lr = threadIdx.x / tpr;         // row slot inside the pass
   const int c0 = (threadIdx.x % tpr) * 4;
-  if (lr >= rows_per_pass) return;
   const long long s = blockIdx.y;           // sequence index
   const int chunk = blockIdx.x;             // row chunk inside the sequence (grid.x)
   const int chunks = gridDim.x;
@@ -207,27 +206,57 @@ __global__ void __launch_bounds__(256) build_src_kernel(const BuildSrcParams p) 
         w[a][4 * q] = v.x; w[a][4 * q + 1] = v.y; w[a][4 * q + 2] = v.z; w[a][4 * q + 3] = v.w;
       }
   }
-  for (int t = t_begin + lr; t < t_end; t += rows_per_pass) {
-    const float4 f = __ldg(reinterpret_cast<const float4*>(p.feat + (bm * p.T + t) * p.D + c0));
-    float o[4] = {f.x + base[0], f.y + base[1], f.z + base[2], f.w + base[3]};
+  // Rows are processed in blocks of SRC_BLK: the block's 16-channel mask rows are staged in shared memory by a
+  // coalesced cooperative load (every thread of a row needs all 16 values), and each thread keeps 4 independent
+  // feature loads in flight -- the kernel is latency bound otherwise (one 16-byte load per thread per row).
+  constexpr int SRC_BLK = 32;
+  __shared__ float4 s_m16[SRC_BLK][4];
+  const float* feat_seq = p.feat + bm * p.T * static_cast<long long>(p.D) + c0;
+  __nv_bfloat16* out_seq = p.out + s * p.T * static_cast<long long>(p.D) + c0;
+  for (int blk = t_begin; blk < t_end; blk += SRC_BLK) {
     if (has_map) {
-      const float4* mp = reinterpret_cast<const float4*>(p.m16 + (s * p.T + t) * 16);
+      __syncthreads();
+      if (threadIdx.x < SRC_BLK * 4) {
+        const int rr = threadIdx.x >> 2, q = threadIdx.x & 3;
+        if (blk + rr < t_end)
+          s_m16[rr][q] = __ldg(reinterpret_cast<const float4*>(p.m16 + (s * p.T + blk + rr) * 16) + q);
+      }
+      __syncthreads();
+    }
+    for (int r0 = lr; r0 < SRC_BLK; r0 += 4 * rows_per_pass) {
+      float4 f[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 m = __ldg(mp + q);
+      for (int u = 0; u < 4; ++u) {
+        const int t = blk + r0 + u * rows_per_pass;
+        if (r0 + u * rows_per_pass < SRC_BLK && t < t_end)
+          f[u] = __ldg(reinterpret_cast<const float4*>(feat_seq + static_cast<long long>(t) * p.D));
+      }
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          o[a] = fmaf(w[a][4 * q], m.x, o[a]);
-          o[a] = fmaf(w[a][4 * q + 1], m.y, o[a]);
-          o[a] = fmaf(w[a][4 * q + 2], m.z, o[a]);
-          o[a] = fmaf(w[a][4 * q + 3], m.w, o[a]);
+      for (int u = 0; u < 4; ++u) {
+        const int rl = r0 + u * rows_per_pass;
+        const int t = blk + rl;
+        if (rl < SRC_BLK && t < t_end) {
+          float o[4] = {f[u].x + base[0], f[u].y + base[1], f[u].z + base[2], f[u].w + base[3]};
+          if (has_map) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 m = s_m16[rl][q];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                o[a] = fmaf(w[a][4 * q], m.x, o[a]);
+                o[a] = fmaf(w[a][4 * q + 1], m.y, o[a]);
+                o[a] = fmaf(w[a][4 * q + 2], m.z, o[a]);
+                o[a] = fmaf(w[a][4 * q + 3], m.w, o[a]);
+              }
+            }
+          }
+          uint2 pk;
+          pk.x = pack_bf16(o[0], o[1]);
+          pk.y = pack_bf16(o[2], o[3]);
+          *reinterpret_cast<uint2*>(out_seq + static_cast<long long>(t) * p.D) = pk;
         }
       }
     }
-    uint2 pk;
-    pk.x = pack_bf16(o[0], o[1]);
-    pk.y = pack_bf16(o[2], o[3]);
-    *reinterpret_cast<uint2*>(p.out + (s * p.T + t) * p.D + c0) = pk;
   }
 }
 

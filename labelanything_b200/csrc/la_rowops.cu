@@ -48,7 +48,11 @@ struct AddLnParams {
   int win, nwin, hw;            // map 1
 };
 
-__global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p) {
+// NVT: float4 slots per lane (compile time, >= ceil(d / 128)); POOL: the mean-pooling variant (keeps per-lane column sums).
+// Small NVT keeps the register count low enough for 4+ resident CTAs per SM, which is what hides the HBM latency.
+template <int NVT, bool POOL>
+__global__ void __launch_bounds__(256, (NVT <= 4 && !POOL) ? 4 : ((NVT <= 8 && !POOL) ? 3 : 2))
+add_layernorm_kernel(const AddLnParams p) {
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
   const int nv = p.d >> 7;            // full float4 groups per lane
@@ -71,9 +75,9 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
     row_step = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   }
   const bool any_y = p.y_out || p.y2_out || p.ype_out || p.pool_out;
-  float4 acc[ROW_MAXV + 1];
+  float4 acc[POOL ? NVT : 1];
 #pragma unroll
-  for (int i = 0; i <= ROW_MAXV; ++i) acc[i] = make_float4(0, 0, 0, 0);
+  for (int i = 0; i < (POOL ? NVT : 1); ++i) acc[i] = make_float4(0, 0, 0, 0);
 
   for (long long row = row_begin; row < row_end; row += row_step) {
     long long src = row, dst = row;
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
       }
       continue;
     }
-    float4 v[ROW_MAXV + 1];
+    float4 v[NVT];
     const long long xrow = p.x_mod > 0 ? src % p.x_mod : src;
     const float4* xin = p.x_in ? reinterpret_cast<const float4*>(p.x_in + xrow * p.d) : nullptr;
     const uint2* din = p.delta ? reinterpret_cast<const uint2*>(p.delta + src * p.d) : nullptr;
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
     const float4* sadd = p.seq_add ? reinterpret_cast<const float4*>(p.seq_add + (src / p.seq_rows) * p.d) : nullptr;
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i <= ROW_MAXV; ++i) {
+    for (int i = 0; i < NVT; ++i) {
       const bool on = (i < nv) || (i == nv && lane < tail);
       float4 a = make_float4(0, 0, 0, 0);
       if (on) {
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
       mean = sum / p.d;
       float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i <= ROW_MAXV; ++i) {
+      for (int i = 0; i < NVT; ++i) {
         const bool on = (i < nv) || (i == nv && lane < tail);
         if (on) {
           const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
       rstd = rsqrtf(sq / p.d + p.eps);
     }
 #pragma unroll
-    for (int i = 0; i <= ROW_MAXV; ++i) {
+    for (int i = 0; i < NVT; ++i) {
       const bool on = (i < nv) || (i == nv && lane < tail);
       if (on) {
         const int idx = i * 32 + lane;
@@ -223,20 +227,22 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const AddLnParams p)
           pk.y = pack_bf16(o.z + e.z, o.w + e.w);
           reinterpret_cast<uint2*>(p.ype_out + dst * p.d)[idx] = pk;
         }
-        acc[i].x += o.x;
-        acc[i].y += o.y;
-        acc[i].z += o.z;
-        acc[i].w += o.w;
+        if constexpr (POOL) {
+          acc[i].x += o.x;
+          acc[i].y += o.y;
+          acc[i].z += o.z;
+          acc[i].w += o.w;
+        }
       }
     }
   }
-  if (p.pool_out) {
+  if constexpr (POOL) {
     // deterministic reduction: lanes own disjoint channels; the CTA's warps are summed in a fixed order
     // through shared memory; one partial row per (sequence, slice).
     extern __shared__ float4 red[];  // [warps][d/4]
     const int dv = p.d >> 2;
 #pragma unroll
-    for (int i = 0; i <= ROW_MAXV; ++i) {
+    for (int i = 0; i < NVT; ++i) {
       const bool on = (i < nv) || (i == nv && lane < tail);
       if (on) red[warp_in_cta * dv + i * 32 + lane] = acc[i];
     }
@@ -411,7 +417,14 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   p.nwin = nwin;
   p.hw = hw;
   const int grid = grid_for(rows * 32, 256, 8);
-  add_layernorm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int need = (d + 127) / 128;
+  if (need <= 1) add_layernorm_kernel<1, false><<<grid, 256, 0, st>>>(p);
+  else if (need <= 2) add_layernorm_kernel<2, false><<<grid, 256, 0, st>>>(p);
+  else if (need <= 4) add_layernorm_kernel<4, false><<<grid, 256, 0, st>>>(p);
+  else if (need <= 6) add_layernorm_kernel<6, false><<<grid, 256, 0, st>>>(p);
+  else if (need <= 8) add_layernorm_kernel<8, false><<<grid, 256, 0, st>>>(p);
+  else add_layernorm_kernel<ROW_MAXV + 1, false><<<grid, 256, 0, st>>>(p);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
@@ -440,9 +453,12 @@ int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta
   p.d = d;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = 8 * static_cast<size_t>(d) * sizeof(float);
-  if (smem > 48 * 1024)
-    LA_CHECK_CUDA(cudaFuncSetAttribute(add_layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  add_layernorm_kernel<<<static_cast<int>(n_seq * slices), 256, smem, st>>>(p);
+  const int need = (d + 127) / 128;
+  const int grid = static_cast<int>(n_seq * slices);
+  if (need <= 2) add_layernorm_kernel<2, true><<<grid, 256, smem, st>>>(p);
+  else if (need <= 4) add_layernorm_kernel<4, true><<<grid, 256, smem, st>>>(p);
+  else if (need <= 8) add_layernorm_kernel<8, true><<<grid, 256, smem, st>>>(p);
+  else add_layernorm_kernel<ROW_MAXV + 1, true><<<grid, 256, smem, st>>>(p);
   LA_CHECK_CUDA(cudaGetLastError());
   pool_finish_kernel<<<grid_for(n_seq * d, 256, 8), 256, 0, st>>>(partial_ws, out, n_seq, slices, d,
                                                                  1.0f / rows_per_seq);

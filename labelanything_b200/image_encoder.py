@@ -103,7 +103,7 @@ class ImageEncoderViT(NativeModule):
             rel, pad = None, 0
             if a.use_rel_pos:
                 size = blk.window_size if blk.window_size > 0 else grid
-                pad = 128 if size > 32 else 64
+                pad = 128 if size > 32 else (64 if size > 16 else 32)   # table rows (2*size-1) rounded up
                 assert 2 * size - 1 <= pad and a.rel_pos_h.shape[1] == 64
                 rel = self.packed(
                     f"b{i}.rel:{size}",

@@ -102,7 +102,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     _cost(2.0 * M * N * K, 2.0 * (M * K + N * K) + M * N * out.element_size())
-    _call("gemm", "la_gemm_bf16", _stream(a), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
+    _call(f"gemm.n{N}.k{K}" if _PROF is not None else "gemm", "la_gemm_bf16", _stream(a), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
         bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0),
         DT_BF16 if out.dtype == torch.bfloat16 else DT_F32, M, N, K, act)
     return out
@@ -130,7 +130,7 @@ def attention(q: torch.Tensor, kv: torch.Tensor, n_seq: int, seq_len: int, n_hea
         ldb = bias_h.stride(1)
         assert bias_h.stride(0) == ldb * n_heads
     _cost(4.0 * n_seq * n_heads * seq_len * seq_len * 64, 2.0 * 4 * n_seq * seq_len * n_heads * 64)
-    _call("attention", "la_attention_bf16", _stream(q), q.data_ptr(), q.stride(0), q_off, kv.data_ptr(), kv.stride(0), k_off, v_off, q.shape[0], n_seq,
+    _call(f"attention.L{seq_len}" if _PROF is not None else "attention", "la_attention_bf16", _stream(q), q.data_ptr(), q.stride(0), q_off, kv.data_ptr(), kv.stride(0), k_off, v_off, q.shape[0], n_seq,
         seq_len, n_heads, float(scale), _ptr(bias_h), _ptr(bias_w), ldb, grid_hw, out.data_ptr(), out.stride(0),
         out_mode, nwin, img_hw)
     return out
@@ -159,7 +159,7 @@ def add_layernorm(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: 
     _cost(0.0, float(rows) * d * sum(sz for t, sz in ((x_in, 4 if x_mod == 0 else 0), (delta, 2), (delta2, 2), (x_out, 4),
                                                         (y_out, y_out.element_size() if y_out is not None else 0),
                                                         (y2_out, 4), (ype_out, 2)) if t is not None))
-    _call("add_layernorm", "la_add_layernorm", _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(delta2), _ptr(seq_add), seq_rows, _ptr(x_out),
+    _call(f"add_layernorm.d{d}.map{map_mode}" if _PROF is not None else "add_layernorm", "la_add_layernorm", _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(delta2), _ptr(seq_add), seq_rows, _ptr(x_out),
         _ptr(gamma), _ptr(beta), float(eps), act, _ptr(y_out),
         DT_F32 if (y_out is not None and y_out.dtype == torch.float32) else DT_BF16, _ptr(y2_out), _ptr(pe), pe_mod,
         _ptr(ype_out), rows, d, map_mode, seq_len, win, nwin, hw)
