@@ -12,7 +12,9 @@
 //   warp 0   : TMA producer   — A and W tiles (128B-swizzled boxes) into a STAGES-deep smem ring
 //   warp 1   : MMA issuer     — one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into TMEM
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue       — tcgen05.ld -> bias/activation -> swizzled smem staging -> TMA store
+//   warps 4-11: epilogue      — tcgen05.ld -> bias/activation -> swizzled smem staging -> TMA store; two warps per
+//                               TMEM lane quarter take alternate 128-byte column chunks, so the exact-GELU
+//                               epilogue of the MLP GEMM (K = 768: 6144 MMA cycles per tile) stays off the critical path
 // The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
 // the mainloop of tile i+1.
 #include "la_common.cuh"
@@ -23,7 +25,7 @@ namespace la {
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
 
 template <int BLOCK_N>
 struct GemmSmem {
@@ -31,8 +33,8 @@ struct GemmSmem {
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-  static constexpr int EPI_WARP_BYTES = 2 * 4096;  // two 32-row x 128-byte staging buffers per epilogue warp
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int EPI_WARP_BYTES = 4096;  // one 32-row x 128-byte staging buffer per epilogue warp
+  static constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
@@ -76,7 +78,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], 8);
     }
     fence_barrier_init();
   }
@@ -113,8 +115,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    // The whole warp walks the loop converged so that descriptors / addresses stay in uniform registers; one
+    // elected lane issues the tcgen05 instructions of each k-block.
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -123,33 +128,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tm + acc * BLOCK_N;
         for (int kb = 0; kb < k_blks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint32_t b_base = a_base + S::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-            const uint64_t a_desc = umma_smem_desc_sw128(a_base + k * GEMM_UMMA_K * 2);
-            const uint64_t b_desc = umma_smem_desc_sw128(b_base + k * GEMM_UMMA_K * 2);
-            umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+              const uint64_t a_desc = umma_smem_desc_sw128(a_base + k * GEMM_UMMA_K * 2);
+              const uint64_t b_desc = umma_smem_desc_sw128(b_base + k * GEMM_UMMA_K * 2);
+              umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (kb == k_blks - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == S::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
       }
     }
   } else if (warp >= 4) {
     // ------------------------------- epilogue -----------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint8_t* my_stage = epi_smem + q * S::EPI_WARP_BYTES;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which of the quarter's two warps: takes chunks half, half + 2, ...
+    uint8_t* buf = epi_smem + (half * 4 + q) * S::EPI_WARP_BYTES;
+    constexpr int LAST0 = ((NCHUNK - 1) / 2) * 2;                 // last chunk of the even warp
+    constexpr int LAST1 = NCHUNK >= 2 ? ((NCHUNK - 2) / 2) * 2 + 1 : -1;  // last chunk of the odd warp (none if 1 chunk)
+    const int last_c = half == 0 ? LAST0 : LAST1;
     int it = 0;
-    uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / n_blks) * GEMM_BLOCK_M;
       const int n0 = (tile % n_blks) * BLOCK_N;
@@ -158,20 +169,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+      if (last_c < 0) {   // nothing to read for this warp: release its share of the accumulator at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
+      for (int c = half; c < NCHUNK; c += 2) {
         const int col0 = c * CHUNK;
         float v[CHUNK];
+        {
+          uint32_t r[CHUNK];
 #pragma unroll
-        for (int j = 0; j < CHUNK / 32; ++j) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + col0 + j * 32, r);
+          for (int j = 0; j < CHUNK / 32; ++j) tmem_ld_x32(t_row + col0 + j * 32, r + j * 32);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[j * 32 + i] = __uint_as_float(r[i]);
+          for (int i = 0; i < CHUNK; ++i) v[i] = __uint_as_float(r[i]);
         }
-        if (c == NCHUNK - 1) {
-          // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+        if (c == last_c) {
+          // all TMEM reads of this warp for this accumulator are done -> hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -196,9 +212,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll
           for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
-        // staging buffer (double-buffered): make sure the TMA store issued two chunks ago has read it
-        uint8_t* buf = my_stage + (chunk_ctr & 1) * 4096;
-        if (lane == 0) tma_store_wait_read<1>();
+        // staging buffer: make sure the TMA store of this warp's previous chunk has read it
+        if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         uint8_t* row_ptr = buf + lane * 128;
         if constexpr (sizeof(OutT) == 2) {
