@@ -6,9 +6,13 @@
 //   258-304 (window partition / unpartition — folded into the output row mapping), and the HF ViT
 //   self-attention used by the MAE encoders (transformers/models/vit/modeling_vit.py:199-250).
 //
-// One CTA owns 256 consecutive query rows of one (sequence, head): two 128-row Q tiles ("A", "B") that
-// ping-pong on the tensor core while their softmax warpgroups run on the CUDA cores (FlashAttention-style
-// online softmax, accumulator O kept in TMEM and rescaled only when the running max grows by > 2^8).
+// Persistent kernel: one CTA per SM walks a static round-robin list of work items; an item is 256 consecutive
+// query rows of one (sequence, head): two 128-row Q tiles ("A", "B") that ping-pong on the tensor core while
+// their softmax warpgroups run on the CUDA cores (FlashAttention-style online softmax, accumulator O kept in
+// TMEM and rescaled only when the running max grows by > 2^8).  All pipelines (Q double buffer, K / V rings,
+// score buffers) keep running across item boundaries, so the loads and the first QK^T of item i+1 overlap the
+// last softmax tiles and the epilogue of item i -- this is what keeps the 14x14-window blocks (2 key tiles per
+// item) from being dominated by per-CTA set-up and load latency.
 //   warp 0      : TMA producer (Q once; K and V tiles through two independent smem rings)
 //   warp 1      : MMA issuer   (S = Q K^T into TMEM;  O += P V with P read from TMEM -- it overlays the scores it
 //                 was computed from -- and V as MN-major smem operand)
@@ -57,16 +61,17 @@ __device__ __forceinline__ void att_trace(const AttParams& p, bool on, int role,
 
 template <int KV_TILE, int BIAS>
 struct AttSmem {
-  static constexpr int STAGES = KV_TILE <= 64 ? 6 : 4;      // K / V ring depth
+  static constexpr int STAGES = KV_TILE <= 64 ? (BIAS == 1 ? 5 : 6) : 4;   // K / V ring depth
   static constexpr int Q_BYTES = 2 * 128 * 128;             // two Q tiles, 128 rows x 128 B
   static constexpr int KV_BYTES = KV_TILE * 128;            // one K or V tile
   static constexpr int KV_SLOT = ((KV_BYTES + 1023) / 1024) * 1024;
-  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_K = 2 * Q_BYTES;                 // Q is double-buffered across work items
   static constexpr int OFF_V = OFF_K + STAGES * KV_SLOT;
   static constexpr int OFF_RW = OFF_V + STAGES * KV_SLOT;   // [256 rows][68] fp32 rel_w staging (64x64 bias variant)
   static constexpr int RW_BYTES = BIAS == 1 ? 256 * ATT_RW_STRIDE : 0;
   static constexpr int OFF_BAR = OFF_RW + RW_BYTES;
   static constexpr int TOTAL = OFF_BAR + 512 + 1024;
+  static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const AttParams p) {
   using S = AttSmem<KV_TILE, BIAS>;
-  constexpr int ATT_KV_STAGES = S::STAGES;
+  constexpr int ST = S::STAGES;
   // bias(q, k) = rel_w[q][k % GW] + rel_h[q][k / GW]: a KV tile holds NG key-grid rows of GW keys
   constexpr int GW = BIAS == ATT_BIAS_GLOBAL64 ? 64 : (BIAS == ATT_BIAS_WINDOW14 ? 14 : KV_TILE);
   constexpr int NG = KV_TILE / GW;
@@ -92,34 +97,37 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
-  uint64_t* bar_q = bars;                          // 1
-  uint64_t* full_k = bars + 1;                     // ATT_KV_STAGES
-  uint64_t* empty_k = full_k + ATT_KV_STAGES;
-  uint64_t* full_v = empty_k + ATT_KV_STAGES;
-  uint64_t* empty_v = full_v + ATT_KV_STAGES;
-  uint64_t* bar_s = empty_v + ATT_KV_STAGES;       // [Q tile][score buffer]: S ready
-  uint64_t* bar_p = bar_s + 4;                     // [Q tile][score buffer]: P written (4 arrivals: one per warp).  Per buffer,
-                                                   // because with double buffering a fast warp may finish tile j+1
-                                                   // before a slow one has delivered its rows of tile j.
-  uint64_t* bar_pv = bar_p + 4;                    // [Q tile]: O += P V of the tile completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_pv + 2);
+  uint64_t* q_full = bars;                         // [Q buffer]
+  uint64_t* q_empty = q_full + 2;                  // [Q buffer]: every QK^T of the item has read it
+  uint64_t* full_k = q_empty + 2;                  // [stage]
+  uint64_t* empty_k = full_k + ST;
+  uint64_t* full_v = empty_k + ST;
+  uint64_t* empty_v = full_v + ST;
+  uint64_t* bar_s = empty_v + ST;                  // [Q tile][score buffer]: S ready
+  uint64_t* bar_p = bar_s + 4;                     // [Q tile][score buffer]: P written (one arrival per warp).  Per
+                                                   // buffer, because with double buffering a fast warp may finish
+                                                   // tile j+1 before a slow one has delivered its rows of tile j.
+  uint64_t* bar_pv = bar_p + 4;                    // [Q tile]: O += P V of a tile completed
+  uint64_t* o_empty = bar_pv + 2;                  // [Q tile]: the epilogue has read O (one arrival per warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qpair = blockIdx.x;
-  const int head = blockIdx.y;
-  const int seq = blockIdx.z;
-  const int NT = (p.seq_len + KV_TILE - 1) / KV_TILE;
-  const long long seq_row0 = static_cast<long long>(seq) * p.seq_len;
-  const bool tr = p.trace != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0;
+  const int NT = (p.seq_len + KV_TILE - 1) / KV_TILE;   // key tiles per item
+  const int n_qp = (p.seq_len + 255) >> 8;              // 256-row query pairs per sequence
+  const int n_items = p.n_seq * p.n_heads * n_qp;       // item = (seq, head, qpair), qpair fastest
+  const bool tr0 = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < ATT_KV_STAGES; ++s) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], 1);
+    }
+    for (int s = 0; s < ST; ++s) {
       mbar_init(&full_k[s], 1);
       mbar_init(&empty_k[s], 1);
       mbar_init(&full_v[s], 1);
@@ -128,9 +136,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     for (int x = 0; x < 2; ++x) {
       mbar_init(&bar_s[2 * x], 1);
       mbar_init(&bar_s[2 * x + 1], 1);
-      mbar_init(&bar_p[2 * x], 4);        // one arrival per softmax warp
+      mbar_init(&bar_p[2 * x], 4);
       mbar_init(&bar_p[2 * x + 1], 4);
       mbar_init(&bar_pv[x], 1);
+      mbar_init(&o_empty[x], 4);
     }
     fence_barrier_init();
   }
@@ -152,23 +161,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if (warp == 0) {
       // ------------------------------------ TMA producer ------------------------------------
       if (lane == 0) {
-        const int q_row = static_cast<int>(seq_row0) + qpair * 256;
-        mbar_arrive_expect_tx(bar_q, S::Q_BYTES);
-        tma_load_2d(smem, &tm_q, bar_q, p.q_off + head * ATT_D, q_row);
-        tma_load_2d(smem + 16384, &tm_q, bar_q, p.q_off + head * ATT_D, q_row + 128);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int j = 0; j < NT; ++j) {
-          const int kv_row = static_cast<int>(seq_row0) + j * KV_TILE;
-          mbar_wait(&empty_k[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_k[stage], S::KV_BYTES);
-          tma_load_2d(smem + S::OFF_K + stage * S::KV_SLOT, &tm_kv, &full_k[stage], p.k_off + head * ATT_D, kv_row);
-          mbar_wait(&empty_v[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_v[stage], S::KV_BYTES);
-          tma_load_2d(smem + S::OFF_V + stage * S::KV_SLOT, &tm_kv, &full_v[stage], p.v_off + head * ATT_D, kv_row);
-          if (++stage == ATT_KV_STAGES) {
-            stage = 0;
-            phase ^= 1;
+        int it = 0;
+        uint32_t g = 0;   // running key-tile counter: ring slot g % ST, phase (g / ST) & 1
+        for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+          const int qpair = w % n_qp;
+          const int head = (w / n_qp) % p.n_heads;
+          const int seq = w / (n_qp * p.n_heads);
+          const int row0 = seq * p.seq_len;
+          const int qb = it & 1;
+          mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[qb], S::Q_BYTES);
+          tma_load_2d(smem + qb * S::Q_BYTES, &tm_q, &q_full[qb], p.q_off + head * ATT_D, row0 + qpair * 256);
+          tma_load_2d(smem + qb * S::Q_BYTES + 16384, &tm_q, &q_full[qb], p.q_off + head * ATT_D,
+                      row0 + qpair * 256 + 128);
+          for (int j = 0; j < NT; ++j, ++g) {
+            const int stage = g % ST;
+            const uint32_t phase = (g / ST) & 1;
+            const int kv_row = row0 + j * KV_TILE;
+            mbar_wait(&empty_k[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_k[stage], S::KV_BYTES);
+            tma_load_2d(smem + S::OFF_K + stage * S::KV_SLOT, &tm_kv, &full_k[stage], p.k_off + head * ATT_D, kv_row);
+            mbar_wait(&empty_v[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_v[stage], S::KV_BYTES);
+            tma_load_2d(smem + S::OFF_V + stage * S::KV_SLOT, &tm_kv, &full_v[stage], p.v_off + head * ATT_D, kv_row);
           }
         }
       }
@@ -176,88 +191,93 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // ------------------------------------ MMA issuer --------------------------------------
       // The whole warp runs this loop converged (descriptors and addresses stay warp-uniform, so they live in
       // uniform registers); one elected lane issues each group of tcgen05 instructions.
-      {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, KV_TILE, 0, 0);  // S = Q K^T   (both K-major, smem)
-        constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (P in TMEM, V MN-major)
-        const uint32_t q_base = smem_u32(smem);
-        const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, KV_TILE, 0, 0);  // S = Q K^T   (both K-major, smem)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (P in TMEM, V MN-major)
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-        // S_x(tile in K stage `kstage`) -> score buffer `buf`; then signal `bar_done` (and optionally free the K stage)
-        auto issue_s = [&](int x, int kstage, int buf, uint64_t* bar_done, uint64_t* bar_free) {
-          const uint32_t k_base = smem_u32(smem + S::OFF_K + kstage * S::KV_SLOT);
-          if (elect_one()) {
+      // S_x(K tile in ring slot `kslot`) -> score buffer `buf`; then signal `bar_done` (and optionally free the slot)
+      auto issue_s = [&](int x, int qb, int kslot, int buf, uint64_t* bar_done, uint64_t* bar_free) {
+        const uint32_t q_base = smem_base + qb * S::Q_BYTES + x * 16384;
+        const uint32_t k_base = smem_base + S::OFF_K + kslot * S::KV_SLOT;
+        if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < ATT_D / 16; ++ks) {
-              umma_bf16_ss(tm + TM_S + x * 128 + buf * KV_TILE, umma_smem_desc_sw128(q_base + x * 16384 + ks * 32),
-                           umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
-            }
-            umma_commit(bar_done);
-            if (bar_free != nullptr) umma_commit(bar_free);
+          for (int ks = 0; ks < ATT_D / 16; ++ks) {
+            umma_bf16_ss(tm + TM_S + x * 128 + buf * KV_TILE, umma_smem_desc_sw128(q_base + ks * 32),
+                         umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
           }
-          __syncwarp();
-        };
-        auto issue_pv = [&](int x, int vstage, int buf, bool acc, uint64_t* bar_done, uint64_t* bar_free) {
-          const uint32_t v_base = smem_u32(smem + S::OFF_V + vstage * S::KV_SLOT);
-          if (elect_one()) {
+          umma_commit(bar_done);
+          if (bar_free != nullptr) umma_commit(bar_free);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int x, int vslot, int buf, bool acc, uint64_t* bar_done, uint64_t* bar_free) {
+        const uint32_t v_base = smem_base + S::OFF_V + vslot * S::KV_SLOT;
+        if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < KV_TILE / 16; ++ks) {
-              umma_bf16_ts(tm + TM_O + x * 64, tm + TM_S + x * 128 + buf * KV_TILE + ks * 8,
-                           umma_smem_desc_sw128(v_base + ks * 2048), idesc_o, (acc || ks > 0) ? 1u : 0u);
-            }
-            umma_commit(bar_done);
-            if (bar_free != nullptr) umma_commit(bar_free);
+          for (int ks = 0; ks < KV_TILE / 16; ++ks) {
+            umma_bf16_ts(tm + TM_O + x * 64, tm + TM_S + x * 128 + buf * KV_TILE + ks * 8,
+                         umma_smem_desc_sw128(v_base + ks * 2048), idesc_o, (acc || ks > 0) ? 1u : 0u);
           }
-          __syncwarp();
-        };
+          umma_commit(bar_done);
+          if (bar_free != nullptr) umma_commit(bar_free);
+        }
+        __syncwarp();
+      };
 
-        mbar_wait(bar_q, 0);
-        mbar_wait(&full_k[0], 0);
-        tc_fence_after();
-        issue_s(0, 0, 0, &bar_s[0], nullptr);
-        issue_s(1, 0, 0, &bar_s[2], &empty_k[0]);
-
-        int kstage = 0, vstage = 0;
-        uint32_t kphase = 0, vphase = 0;
+      int it = 0;
+      uint32_t g0 = 0;   // running key-tile counter at the start of the item
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it, g0 += NT) {
+        const int qb = it & 1;
+        const bool trace_on = tr0 && it == 0;
+        mbar_wait(&q_full[qb], (it >> 1) & 1);
+        {
+          const int slot = g0 % ST;
+          const int buf = DB ? (g0 & 1) : 0;
+          mbar_wait(&full_k[slot], (g0 / ST) & 1);
+          tc_fence_after();
+          // (non-DB: this overwrites P of the previous item's last tile, whose PV MMA is ahead of it in the pipe)
+          issue_s(0, qb, slot, buf, &bar_s[buf], nullptr);
+          issue_s(1, qb, slot, buf, &bar_s[2 + buf], &empty_k[slot]);
+        }
         for (int j = 0; j < NT; ++j) {
-          int kstage_next = kstage + 1;
-          uint32_t kphase_next = kphase;
-          if (kstage_next == ATT_KV_STAGES) {
-            kstage_next = 0;
-            kphase_next ^= 1;
-          }
-          const int buf = DB ? (j & 1) : 0, buf_next = DB ? ((j + 1) & 1) : 0;
+          const uint32_t g = g0 + j;
+          const int buf = DB ? (g & 1) : 0;
+          const uint32_t par = DB ? ((g >> 1) & 1) : (g & 1);
+          const int vslot = g % ST;
+          const int kslot_n = (g + 1) % ST;
+          const uint32_t kphase_n = ((g + 1) / ST) & 1;
+          const bool more = j + 1 < NT;
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
-            if (DB && j + 1 < NT) {
-              // next score tile first: its buffer held P(j-1), whose PV MMA is already ahead of it in the pipe
+            if (DB && more) {
+              // next score tile first: its buffer held P(g-1), whose PV MMA is already ahead of it in the pipe
               if (x == 0) {
-                mbar_wait(&full_k[kstage_next], kphase_next);
+                mbar_wait(&full_k[kslot_n], kphase_n);
                 tc_fence_after();
               }
-              issue_s(x, kstage_next, buf_next, &bar_s[2 * x + buf_next], x == 1 ? &empty_k[kstage_next] : nullptr);
+              issue_s(x, qb, kslot_n, buf ^ 1, &bar_s[2 * x + (buf ^ 1)], x == 1 ? &empty_k[kslot_n] : nullptr);
             }
-            mbar_wait(&bar_p[2 * x + buf], DB ? ((j >> 1) & 1) : (j & 1));
-            att_trace(p, tr, 0, j, 2 * x);
-            if (x == 0) mbar_wait(&full_v[vstage], vphase);
+            mbar_wait(&bar_p[2 * x + buf], par);
+            att_trace(p, trace_on, 0, j, 2 * x);
+            if (j == 0 && it > 0) mbar_wait(&o_empty[x], (it - 1) & 1);   // previous item's epilogue has read O
+            if (x == 0) mbar_wait(&full_v[vslot], (g / ST) & 1);
             tc_fence_after();
-            issue_pv(x, vstage, buf, j > 0, &bar_pv[x], x == 1 ? &empty_v[vstage] : nullptr);
-            att_trace(p, tr, 0, j, 2 * x + 1);
-            if (!DB && j + 1 < NT) {
+            issue_pv(x, vslot, buf, j > 0, &bar_pv[x], x == 1 ? &empty_v[vslot] : nullptr);
+            att_trace(p, trace_on, 0, j, 2 * x + 1);
+            if (!DB && more) {
               if (x == 0) {
-                mbar_wait(&full_k[kstage_next], kphase_next);
+                mbar_wait(&full_k[kslot_n], kphase_n);
                 tc_fence_after();
               }
-              // overwrites P(j) of this Q tile: ordered behind PV(j) in the MMA pipe
-              issue_s(x, kstage_next, 0, &bar_s[2 * x], x == 1 ? &empty_k[kstage_next] : nullptr);
+              // overwrites P(g) of this Q tile: ordered behind PV(g) in the MMA pipe
+              issue_s(x, qb, kslot_n, 0, &bar_s[2 * x], x == 1 ? &empty_k[kslot_n] : nullptr);
             }
-          }
-          kstage = kstage_next;
-          kphase = kphase_next;
-          if (++vstage == ATT_KV_STAGES) {
-            vstage = 0;
-            vphase ^= 1;
           }
         }
+        // every QK^T of this item has been issued: the Q buffer is free once they (all earlier MMAs) complete
+        if (elect_one()) umma_commit(&q_empty[qb]);
+        __syncwarp();
       }
     }
   } else {
@@ -266,207 +286,221 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int x = (warp - 4) >> 2;     // Q tile: 0 = A, 1 = B
     const int quarter = warp & 3;      // TMEM lane quarter
     const int r = quarter * 32 + lane;  // row inside the Q tile
-    const int t = qpair * 256 + x * 128 + r;  // token index inside the sequence
-    const bool row_valid = t < p.seq_len;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t t_s0 = tmem_base + lane_addr + TM_S + x * 128;
     const uint32_t t_o = tmem_base + lane_addr + TM_O + x * 64;
     const float sl2 = p.scale_log2;
     constexpr float LOG2E = 1.4426950408889634f;
 
-    // ---- rel-pos bias prologue (log2 units): the rel_w terms of this query row live in registers.  For the 64x64
-    //      grid the 32 rows of a warp are fetched cooperatively (coalesced 128-byte requests) through a shared-memory
-    //      staging area, each thread then reads its own row back with LDS.128 ----
-    float rw2[BIAS == ATT_BIAS_NONE ? 1 : GW];
-    const float* bh_row = nullptr;
-    if constexpr (BIAS != ATT_BIAS_NONE) {
-      const int tt = row_valid ? t : 0;
-      const int qh = tt / GW, qw = tt % GW;
-      const long long brow = ((seq_row0 + tt) * p.n_heads + head) * p.ldb;
-      bh_row = p.bias_h + brow + (GW - 1 - qh);
-      if constexpr (BIAS == ATT_BIAS_WINDOW14) {
-        const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
-#pragma unroll
-        for (int i = 0; i < GW; ++i) rw2[i] = __ldg(bw_row + i) * LOG2E;
-      } else {
-        static_assert(BIAS != ATT_BIAS_GLOBAL64 || GW == 64, "staging assumes 64 rel_w terms per row");
-        float* stage = reinterpret_cast<float*>(smem + S::OFF_RW + (x * 128 + quarter * 32) * ATT_RW_STRIDE);
-        const int t0 = qpair * 256 + x * 128 + quarter * 32;   // token of this warp's first row
-        for (int rr = 0; rr < 32; ++rr) {
-          const int t2 = (t0 + rr < p.seq_len) ? t0 + rr : 0;
-          const float* src = p.bias_w + ((seq_row0 + t2) * p.n_heads + head) * p.ldb + (GW - 1 - t2 % GW);
-          float* dst = stage + rr * (ATT_RW_STRIDE / 4);
-          dst[lane] = __ldg(src + lane);
-          dst[lane + 32] = __ldg(src + lane + 32);
-        }
-        __syncwarp();
-        const float4* own = reinterpret_cast<const float4*>(smem + S::OFF_RW + (x * 128 + r) * ATT_RW_STRIDE);
-#pragma unroll
-        for (int i = 0; i < GW / 4; ++i) {
-          const float4 w = own[i];
-          rw2[4 * i] = w.x * LOG2E;
-          rw2[4 * i + 1] = w.y * LOG2E;
-          rw2[4 * i + 2] = w.z * LOG2E;
-          rw2[4 * i + 3] = w.w * LOG2E;
-        }
-      }
-    } else {
-      rw2[0] = 0.0f;
-    }
+    int it = 0;
+    uint32_t g0 = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it, g0 += NT) {
+      const int qpair = w % n_qp;
+      const int head = (w / n_qp) % p.n_heads;
+      const int seq = w / (n_qp * p.n_heads);
+      const long long seq_row0 = static_cast<long long>(seq) * p.seq_len;
+      const int t = qpair * 256 + x * 128 + r;  // token index inside the sequence
+      const bool row_valid = t < p.seq_len;
+      const bool tr = tr0 && it == 0 && quarter == 0;
 
-    float m_used = -INFINITY;
-    float l_sum = 0.0f;
-
-    for (int j = 0; j < NT; ++j) {
-      const int valid = p.seq_len - j * KV_TILE;  // keys of this tile that exist (may exceed KV_TILE)
-      // rel_h terms of the NG key-grid rows of this tile
-      float rh2[NG];
-      if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
+      // ---- rel-pos bias prologue (log2 units): the rel_w terms of this query row live in registers.  For the 64x64
+      //      grid the 32 rows of a warp are fetched cooperatively (coalesced 128-byte requests) through a shared-memory
+      //      staging area, each thread then reads its own row back with LDS.128 ----
+      float rw2[BIAS == ATT_BIAS_NONE ? 1 : GW];
+      const float* bh_row = nullptr;
+      if constexpr (BIAS != ATT_BIAS_NONE) {
+        const int tt = row_valid ? t : 0;
+        const int qh = tt / GW, qw = tt % GW;
+        const long long brow = ((seq_row0 + tt) * p.n_heads + head) * p.ldb;
+        bh_row = p.bias_h + brow + (GW - 1 - qh);
+        if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+          const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
 #pragma unroll
-        for (int i = 0; i < NG; ++i) rh2[i] = __ldg(bh_row + NG * j + i) * LOG2E;
-      } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
-#pragma unroll
-        for (int i = 0; i < NG; ++i) rh2[i] = (j * NG + i < GW) ? __ldg(bh_row + j * NG + i) * LOG2E : 0.0f;
-      } else {
-        rh2[0] = 0.0f;
-      }
-
-      const int buf = DB ? (j & 1) : 0;
-      const uint32_t t_s = t_s0 + buf * KV_TILE;
-      att_trace(p, tr && quarter == 0, 1 + x, j, 0);
-      mbar_wait(&bar_s[2 * x + buf], DB ? ((j >> 1) & 1) : (j & 1));
-      tc_fence_after();
-      att_trace(p, tr && quarter == 0, 1 + x, j, 1);
-
-      // ---- the whole score row into registers: ONE pass over TMEM ----
-      uint32_t sv[KV_TILE];
-#pragma unroll
-      for (int c = 0; c + 32 <= KV_TILE; c += 32) tmem_ld_x32(t_s + c, sv + c);
-      if constexpr (KV_TILE % 32 != 0) tmem_ld_x16(t_s + (KV_TILE / 32) * 32, sv + (KV_TILE / 32) * 32);
-      tmem_ld_wait();
-      if (valid < KV_TILE) {   // ragged last tile: keys beyond the sequence get -inf
-#pragma unroll
-        for (int i = 0; i < KV_TILE; ++i)
-          if (i >= valid) sv[i] = 0xff800000u;
-      }
-
-      // ---- pass 1: t = s * scale + rel_w (kept in place), tile max incl. rel_h ----
-      float mx = -INFINITY;
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < GW; ++i) {
-          const int col = g * GW + i;
-          float tv;
-          if constexpr (BIAS == ATT_BIAS_NONE) {
-            tv = __uint_as_float(sv[col]) * sl2;
-          } else {
-            tv = fmaf(__uint_as_float(sv[col]), sl2, rw2[i]);
+          for (int i = 0; i < GW; ++i) rw2[i] = __ldg(bw_row + i) * LOG2E;
+        } else {
+          static_assert(BIAS != ATT_BIAS_GLOBAL64 || GW == 64, "staging assumes 64 rel_w terms per row");
+          float* stage = reinterpret_cast<float*>(smem + S::OFF_RW + (x * 128 + quarter * 32) * ATT_RW_STRIDE);
+          const int t0 = qpair * 256 + x * 128 + quarter * 32;   // token of this warp's first row
+          __syncwarp();   // the previous item's read-back of the staging rows is complete
+          for (int rr = 0; rr < 32; ++rr) {
+            const int t2 = (t0 + rr < p.seq_len) ? t0 + rr : 0;
+            const float* src = p.bias_w + ((seq_row0 + t2) * p.n_heads + head) * p.ldb + (GW - 1 - t2 % GW);
+            float* dst = stage + rr * (ATT_RW_STRIDE / 4);
+            dst[lane] = __ldg(src + lane);
+            dst[lane + 32] = __ldg(src + lane + 32);
           }
-          sv[col] = __float_as_uint(tv);
-          if (i & 1) m1 = fmaxf(m1, tv);
-          else m0 = fmaxf(m0, tv);
+          __syncwarp();
+          const float4* own = reinterpret_cast<const float4*>(smem + S::OFF_RW + (x * 128 + r) * ATT_RW_STRIDE);
+#pragma unroll
+          for (int i = 0; i < GW / 4; ++i) {
+            const float4 wv = own[i];
+            rw2[4 * i] = wv.x * LOG2E;
+            rw2[4 * i + 1] = wv.y * LOG2E;
+            rw2[4 * i + 2] = wv.z * LOG2E;
+            rw2[4 * i + 3] = wv.w * LOG2E;
+          }
         }
-        mx = fmaxf(mx, fmaxf(m0, m1) + rh2[g]);
+      } else {
+        rw2[0] = 0.0f;
       }
 
-      att_trace(p, tr && quarter == 0, 1 + x, j, 2);
-      // ---- running max with lazy rescale (threshold 8 in log2 units => P <= 256) ----
-      float alpha = 1.0f;
-      bool need = false;
-      if (j == 0) {
-        m_used = mx;
-      } else if (mx > m_used + 8.0f) {
-        alpha = ex2_approx(m_used - mx);
-        m_used = mx;
-        need = true;
-      }
-      if (__any_sync(0xffffffffu, need)) {
-        // O must hold everything up to tile j-1 before it is rescaled
-        mbar_wait(&bar_pv[x], (j - 1) & 1);
+      float m_used = -INFINITY;
+      float l_sum = 0.0f;
+
+      for (int j = 0; j < NT; ++j) {
+        const uint32_t g = g0 + j;
+        const int valid = p.seq_len - j * KV_TILE;  // keys of this tile that exist (may exceed KV_TILE)
+        // rel_h terms of the NG key-grid rows of this tile
+        float rh2[NG];
+        if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
+#pragma unroll
+          for (int i = 0; i < NG; ++i) rh2[i] = __ldg(bh_row + NG * j + i) * LOG2E;
+        } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+#pragma unroll
+          for (int i = 0; i < NG; ++i) rh2[i] = (j * NG + i < GW) ? __ldg(bh_row + j * NG + i) * LOG2E : 0.0f;
+        } else {
+          rh2[0] = 0.0f;
+        }
+
+        const int buf = DB ? (g & 1) : 0;
+        const uint32_t t_s = t_s0 + buf * KV_TILE;
+        att_trace(p, tr, 1 + x, j, 0);
+        mbar_wait(&bar_s[2 * x + buf], DB ? ((g >> 1) & 1) : (g & 1));
         tc_fence_after();
+        att_trace(p, tr, 1 + x, j, 1);
+
+        // ---- the whole score row into registers: ONE pass over TMEM ----
+        uint32_t sv[KV_TILE];
 #pragma unroll
-        for (int hseg = 0; hseg < 2; ++hseg) {
-          uint32_t ov[32];
-          tmem_ld_x32(t_o + hseg * 32, ov);
-          tmem_ld_wait();
+        for (int c = 0; c + 32 <= KV_TILE; c += 32) tmem_ld_x32(t_s + c, sv + c);
+        if constexpr (KV_TILE % 32 != 0) tmem_ld_x16(t_s + (KV_TILE / 32) * 32, sv + (KV_TILE / 32) * 32);
+        tmem_ld_wait();
+        if (valid < KV_TILE) {   // ragged last tile: keys beyond the sequence get -inf
 #pragma unroll
-          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-          tmem_st_x32(t_o + hseg * 32, ov);
+          for (int i = 0; i < KV_TILE; ++i)
+            if (i >= valid) sv[i] = 0xff800000u;
         }
-        l_sum *= alpha;
+
+        // ---- pass 1: t = s * scale + rel_w (kept in place), tile max incl. rel_h ----
+        float mx = -INFINITY;
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < GW; ++i) {
+            const int col = gi * GW + i;
+            float tv;
+            if constexpr (BIAS == ATT_BIAS_NONE) {
+              tv = __uint_as_float(sv[col]) * sl2;
+            } else {
+              tv = fmaf(__uint_as_float(sv[col]), sl2, rw2[i]);
+            }
+            sv[col] = __float_as_uint(tv);
+            if (i & 1) m1 = fmaxf(m1, tv);
+            else m0 = fmaxf(m0, tv);
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1) + rh2[gi]);
+        }
+
+        att_trace(p, tr, 1 + x, j, 2);
+        // ---- running max with lazy rescale (threshold 8 in log2 units => P <= 256) ----
+        float alpha = 1.0f;
+        bool need = false;
+        if (j == 0) {
+          m_used = mx;
+        } else if (mx > m_used + 8.0f) {
+          alpha = ex2_approx(m_used - mx);
+          m_used = mx;
+          need = true;
+        }
+        if (__any_sync(0xffffffffu, need)) {
+          // O must hold everything up to the previous tile before it is rescaled
+          mbar_wait(&bar_pv[x], (g - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int hseg = 0; hseg < 2; ++hseg) {
+            uint32_t ov[32];
+            tmem_ld_x32(t_o + hseg * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_x32(t_o + hseg * 32, ov);
+          }
+          l_sum *= alpha;
+        }
+
+        // ---- pass 2: P = exp2(t + rel_h - m) -> bf16 pairs -> TMEM (A operand of the PV MMA) over the score columns
+        //      just consumed, 32 columns (16 words) at a time so that the stores overlap the remaining exponentials ----
+        float offg[NG];
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) offg[gi] = rh2[gi] - m_used;
+        float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
+#pragma unroll
+        for (int c0 = 0; c0 < KV_TILE; c0 += 32) {
+          const int width = (KV_TILE - c0 >= 32) ? 32 : 16;
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            if (i < width) {
+              const int col = c0 + i;
+              const float e0 = ex2_approx(__uint_as_float(sv[col]) + offg[col / GW]);
+              const float e1 = ex2_approx(__uint_as_float(sv[col + 1]) + offg[(col + 1) / GW]);
+              if ((i & 2) == 0) {
+                l0 += e0;
+                l1 += e1;
+              } else {
+                l2 += e0;
+                l3 += e1;
+              }
+              pk[i >> 1] = pack_bf16(e0, e1);
+            }
+          }
+          if (width == 32) tmem_st_32x32b_x16(t_s + (c0 >> 1), pk);
+          else tmem_st_32x32b_x8(t_s + (c0 >> 1), pk);
+        }
+        l_sum += (l0 + l1) + (l2 + l3);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[2 * x + buf]);
+        att_trace(p, tr, 1 + x, j, 3);
       }
 
-      // ---- pass 2: P = exp2(t + rel_h - m) -> bf16 pairs -> TMEM (A operand of the PV MMA) over the score columns
-      //      just consumed, 32 columns (16 words) at a time so that the stores overlap the remaining exponentials ----
-      float offg[NG];
-#pragma unroll
-      for (int g = 0; g < NG; ++g) offg[g] = rh2[g] - m_used;
-      float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
-#pragma unroll
-      for (int c0 = 0; c0 < KV_TILE; c0 += 32) {
-        const int width = (KV_TILE - c0 >= 32) ? 32 : 16;
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          if (i < width) {
-            const int col = c0 + i;
-            const float e0 = ex2_approx(__uint_as_float(sv[col]) + offg[col / GW]);
-            const float e1 = ex2_approx(__uint_as_float(sv[col + 1]) + offg[(col + 1) / GW]);
-            if ((i & 2) == 0) {
-              l0 += e0;
-              l1 += e1;
-            } else {
-              l2 += e0;
-              l3 += e1;
-            }
-            pk[i >> 1] = pack_bf16(e0, e1);
-          }
+      // ---- epilogue: O / l -> bf16 -> global (with the window-unpartition row mapping) ----
+      mbar_wait(&bar_pv[x], (g0 + NT - 1) & 1);
+      tc_fence_after();
+      long long out_row = -1;
+      if (row_valid) {
+        if (p.out_mode == 0) {
+          out_row = seq_row0 + t;
+        } else {
+          const int per_img = p.nwin * p.nwin;
+          const int img = seq / per_img, wi = seq % per_img;
+          const int y = (wi / p.nwin) * p.win + t / p.win;
+          const int xx = (wi % p.nwin) * p.win + t % p.win;
+          if (y < p.img_hw && xx < p.img_hw)
+            out_row = (static_cast<long long>(img) * p.img_hw + y) * p.img_hw + xx;
         }
-        if (width == 32) tmem_st_32x32b_x16(t_s + (c0 >> 1), pk);
-        else tmem_st_32x32b_x8(t_s + (c0 >> 1), pk);
       }
-      l_sum += (l0 + l1) + (l2 + l3);
-      tmem_st_wait();
+      const float inv_l = 1.0f / l_sum;
+      uint32_t ov[64];
+      tmem_ld_x32(t_o, ov);
+      tmem_ld_x32(t_o + 32, ov + 32);
+      tmem_ld_wait();
+      // O is in registers: hand the accumulator back to the MMA warp before the global stores
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[2 * x + buf]);
-      att_trace(p, tr && quarter == 0, 1 + x, j, 3);
-    }
-
-    // ---- epilogue: O / l -> bf16 -> global (with the window-unpartition row mapping) ----
-    mbar_wait(&bar_pv[x], (NT - 1) & 1);
-    tc_fence_after();
-    long long out_row = -1;
-    if (row_valid) {
-      if (p.out_mode == 0) {
-        out_row = seq_row0 + t;
-      } else {
-        const int per_img = p.nwin * p.nwin;
-        const int img = seq / per_img, wi = seq % per_img;
-        const int y = (wi / p.nwin) * p.win + t / p.win;
-        const int xx = (wi % p.nwin) * p.win + t % p.win;
-        if (y < p.img_hw && xx < p.img_hw)
-          out_row = (static_cast<long long>(img) * p.img_hw + y) * p.img_hw + xx;
-      }
-    }
-    const float inv_l = 1.0f / l_sum;
-#pragma unroll
-    for (int hseg = 0; hseg < 2; ++hseg) {
-      uint32_t ov[32];
-      tmem_ld_x32(t_o + hseg * 32, ov);
-      tmem_ld_wait();
+      if (lane == 0) mbar_arrive(&o_empty[x]);
       if (out_row >= 0) {
-        __nv_bfloat16* dst = p.out + out_row * p.ld_out + head * ATT_D + hseg * 32;
+        __nv_bfloat16* dst = p.out + out_row * p.ld_out + head * ATT_D;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int gq = 0; gq < 8; ++gq) {
           uint4 pk;
-          pk.x = pack_bf16(__uint_as_float(ov[g * 8 + 0]) * inv_l, __uint_as_float(ov[g * 8 + 1]) * inv_l);
-          pk.y = pack_bf16(__uint_as_float(ov[g * 8 + 2]) * inv_l, __uint_as_float(ov[g * 8 + 3]) * inv_l);
-          pk.z = pack_bf16(__uint_as_float(ov[g * 8 + 4]) * inv_l, __uint_as_float(ov[g * 8 + 5]) * inv_l);
-          pk.w = pack_bf16(__uint_as_float(ov[g * 8 + 6]) * inv_l, __uint_as_float(ov[g * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+          pk.x = pack_bf16(__uint_as_float(ov[gq * 8 + 0]) * inv_l, __uint_as_float(ov[gq * 8 + 1]) * inv_l);
+          pk.y = pack_bf16(__uint_as_float(ov[gq * 8 + 2]) * inv_l, __uint_as_float(ov[gq * 8 + 3]) * inv_l);
+          pk.z = pack_bf16(__uint_as_float(ov[gq * 8 + 4]) * inv_l, __uint_as_float(ov[gq * 8 + 5]) * inv_l);
+          pk.w = pack_bf16(__uint_as_float(ov[gq * 8 + 6]) * inv_l, __uint_as_float(ov[gq * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + gq * 8) = pk;
         }
       }
     }
@@ -493,7 +527,8 @@ static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, 
   if (rc) return rc;
   auto kern = attention_fwd_kernel<KV_TILE, BIAS>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-  dim3 grid((p.seq_len + 255) / 256, p.n_heads, p.n_seq);
+  const long long items = static_cast<long long>((p.seq_len + 255) / 256) * p.n_heads * p.n_seq;
+  const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
   kern<<<grid, ATT_THREADS, S::TOTAL, stream>>>(tm_q, tm_kv, p);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
@@ -516,7 +551,8 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
   using namespace la;
   LA_CHECK_ARG(q && kv && out, "la_attention_bf16: null pointer");
   LA_CHECK_ARG(n_seq > 0 && seq_len > 0 && n_heads > 0, "la_attention_bf16: empty problem");
-  LA_CHECK_ARG(n_seq <= 65535 && n_heads <= 65535, "la_attention_bf16: n_seq/n_heads exceed the grid limits");
+  LA_CHECK_ARG(static_cast<long long>(n_seq) * n_heads * ((seq_len + 255) / 256) < (1ll << 31),
+               "la_attention_bf16: too many work items");
   LA_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
                "la_attention_bf16: strides/offsets must be multiples of 8 elements");
   LA_CHECK_ARG(rows_total >= static_cast<long long>(n_seq) * seq_len, "la_attention_bf16: rows_total too small");

@@ -51,7 +51,7 @@ struct AddLnParams {
 // NVT: float4 slots per lane (compile time, >= ceil(d / 128)); POOL: the mean-pooling variant (keeps per-lane column sums).
 // Small NVT keeps the register count low enough for 4+ resident CTAs per SM, which is what hides the HBM latency.
 template <int NVT, bool POOL>
-__global__ void __launch_bounds__(256, (NVT <= 4 && !POOL) ? 4 : ((NVT <= 8 && !POOL) ? 3 : 2))
+__global__ void __launch_bounds__(256, NVT <= 4 ? (POOL ? 3 : 4) : ((NVT <= 8 && !POOL) ? 3 : 2))
 add_layernorm_kernel(const AddLnParams p) {
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;

@@ -270,7 +270,10 @@ def run_two_way(tw: TwoWayTransformer, keys16: torch.Tensor, keys32: Optional[to
             keys16 = keys32 = None
         else:
             new16 = _empty(RT, D, torch.bfloat16, dev)
-            need32 = (not last) or want_keys_f32
+            # fp32 copy of the image tokens: residual of the next layer's norm4.  When the transformer output is only
+            # mean-pooled (prompt encoder) the bf16 copy doubles as the residual: its rounding error (2^-9 relative)
+            # averages out over the T pooled tokens, and it saves an 8-byte/element HBM round trip.
+            need32 = ((not last) and not pool) or want_keys_f32
             new32 = _empty(RT, D, torch.float32, dev) if need32 else None
             ops.add_layernorm(x_in, d1, g4, b4, e4, rows=RT, d=D, y_out=new16, y2_out=new32, delta2=d2,
                               seq_add=seq_add, seq_rows=T)
