@@ -23,6 +23,7 @@
 // by la_gemm_bf16 (q_head @ reversed_table^T), already shifted so that entry (gh-1 - qh + kh) is the bias
 // of key row kh for a query in grid row qh.
 #include "la_common.cuh"
+#include <cstdlib>
 
 namespace la {
 
@@ -51,6 +52,7 @@ struct AttParams {
   int out_mode;  // 0: row = seq*seq_len + t ; 1: window unpartition
   int win, nwin, img_hw;  // out_mode 1: window size, windows per side, un-padded grid side
   long long* trace;       // diagnostics (la_attention_set_trace): clock64 stamps of CTA (0,0,0), else nullptr
+  int debug;              // diagnostics (LA_ATT_DEBUG env): bit0 always rescale, bit1 never skip the O wait
 };
 
 // trace layout: [role][tile][event] int64; roles: 0 = MMA thread, 1 = softmax A (warp 4 lane 0), 2 = softmax B
@@ -107,8 +109,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* bar_p = bar_s + 4;                     // [Q tile][score buffer]: P written (one arrival per warp).  Per
                                                    // buffer, because with double buffering a fast warp may finish
                                                    // tile j+1 before a slow one has delivered its rows of tile j.
-  uint64_t* bar_pv = bar_p + 4;                    // [Q tile]: O += P V of a tile completed
-  uint64_t* o_empty = bar_pv + 2;                  // [Q tile]: the epilogue has read O (one arrival per warp)
+  uint64_t* bar_pv = bar_p + 4;                    // [Q tile][score buffer]: O += P V of a tile completed.  Per buffer
+                                                   // as well: with double buffering a softmax warp may run one tile
+                                                   // ahead of its siblings (S(g+1) is issued before P(g) is awaited), so
+                                                   // with ONE barrier flipping every tile a wait for PV(g) could be
+                                                   // satisfied by the parity of PV(g-2) while PV(g-1) is still pending.
+  uint64_t* o_empty = bar_pv + 4;                  // [Q tile]: the epilogue has read O (one arrival per warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -138,7 +144,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_init(&bar_s[2 * x + 1], 1);
       mbar_init(&bar_p[2 * x], 4);
       mbar_init(&bar_p[2 * x + 1], 4);
-      mbar_init(&bar_pv[x], 1);
+      mbar_init(&bar_pv[2 * x], 1);
+      mbar_init(&bar_pv[2 * x + 1], 1);
       mbar_init(&o_empty[x], 4);
     }
     fence_barrier_init();
@@ -263,7 +270,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             if (j == 0 && it > 0) mbar_wait(&o_empty[x], (it - 1) & 1);   // previous item's epilogue has read O
             if (x == 0) mbar_wait(&full_v[vslot], (g / ST) & 1);
             tc_fence_after();
-            issue_pv(x, vslot, buf, j > 0, &bar_pv[x], x == 1 ? &empty_v[vslot] : nullptr);
+            issue_pv(x, vslot, buf, j > 0, &bar_pv[2 * x + buf], x == 1 ? &empty_v[vslot] : nullptr);
             att_trace(p, trace_on, 0, j, 2 * x + 1);
             if (!DB && more) {
               if (x == 0) {
@@ -408,14 +415,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         bool need = false;
         if (j == 0) {
           m_used = mx;
-        } else if (mx > m_used + 8.0f) {
+        } else if (mx > m_used + 8.0f || (p.debug & 1)) {
           alpha = ex2_approx(m_used - mx);
           m_used = mx;
           need = true;
         }
         if (__any_sync(0xffffffffu, need)) {
           // O must hold everything up to the previous tile before it is rescaled
-          mbar_wait(&bar_pv[x], (g - 1) & 1);
+          mbar_wait(&bar_pv[2 * x + (DB ? ((g - 1) & 1) : 0)], DB ? (((g - 1) >> 1) & 1) : ((g - 1) & 1));
           tc_fence_after();
 #pragma unroll
           for (int hseg = 0; hseg < 2; ++hseg) {
@@ -467,7 +474,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
 
       // ---- epilogue: O / l -> bf16 -> global (with the window-unpartition row mapping) ----
-      mbar_wait(&bar_pv[x], (g0 + NT - 1) & 1);
+      {
+        const uint32_t gl = g0 + NT - 1;   // last tile of the item
+        mbar_wait(&bar_pv[2 * x + (DB ? (gl & 1) : 0)], DB ? ((gl >> 1) & 1) : (gl & 1));
+      }
       tc_fence_after();
       long long out_row = -1;
       if (row_valid) {
@@ -578,6 +588,7 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
   p.nwin = nwin;
   p.img_hw = img_hw;
   p.trace = g_att_trace;
+  { const char* e = getenv("LA_ATT_DEBUG"); p.debug = e ? atoi(e) : 0; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!has_bias) {
     LA_CHECK_ARG(out_mode == 0, "la_attention_bf16: window output mapping needs the window bias mode");
