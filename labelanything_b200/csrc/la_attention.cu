@@ -16,20 +16,27 @@
 //   warp 0      : TMA producer (Q once; K and V tiles through two independent smem rings)
 //   warp 1      : MMA issuer   (S = Q K^T into TMEM;  O += P V with P read from TMEM -- it overlays the scores it
 //                 was computed from -- and V as MN-major smem operand)
-//   warp 2      : TMEM allocator
+//   warp 2      : TMEM allocator; 64x64 rel-pos mode: rel_w operand builder for Q tile A
+//   warp 3      : 64x64 rel-pos mode: identity operand + rel_w operand builder for Q tile B
 //   warps 4-7   : softmax + epilogue for Q tile A     warps 8-11: same for Q tile B   (one thread per query row,
-//                 the whole 128-column score row held in registers: setmaxnreg gives these warps 224 registers)
+//                 the whole score row of a key tile held in registers: setmaxnreg gives these warps 216 registers)
 // The decomposed relative-position bias  rel_h[q, kh] + rel_w[q, kw]  is read from fp32 tables produced
 // by la_gemm_bf16 (q_head @ reversed_table^T), already shifted so that entry (gh-1 - qh + kh) is the bias
 // of key row kh for a query in grid row qh.
+//   * 14x14 windows: both terms are added by the softmax threads (14 + 8 registers per row).
+//   * 64x64 global blocks: a key tile is one key-grid row, so rel_h is ONE scalar per (query, tile) folded into the
+//     softmax offset, and rel_w[q, 0..63] is the same for every tile: warps 2/3 write it once per item as an fp16
+//     A operand and the MMA warp accumulates  A_w x (I / scale)  on top of  Q K^T  in TMEM (kind::f16, fp16 inputs),
+//     so the softmax threads see scores that already contain it -- no per-element bias arithmetic, no 64-register
+//     rel_w row (the MUFU/issue-bound softmax loop is the limiter of this kernel, the tensor pipe has slack).
 #include "la_common.cuh"
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 namespace la {
 
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_D = 64;
-constexpr int ATT_RW_STRIDE = 272;      // bytes per row of the rel_w staging area (68 floats: conflict-free LDS.128)
 constexpr int ATT_REGS_SOFTMAX = 216;  // setmaxnreg budget: 256 x 216 + 128 x 72 = 64512 = 384 threads x 168 (launch allocation)
 constexpr int ATT_REGS_CONTROL = 72;
 static_assert(256 * ATT_REGS_SOFTMAX + 128 * ATT_REGS_CONTROL <= ATT_THREADS * 168,
@@ -42,6 +49,7 @@ struct AttParams {
   int q_off, k_off, v_off;  // column (element) offsets of head 0 inside a qkv row
   long long rows_total;     // rows in the qkv matrix
   float scale_log2;         // softmax scale * log2(e)
+  float inv_scale;          // 1 / softmax scale
   // rel-pos bias tables: [rows_total][n_heads][ldb] fp32 (nullptr for ATT_BIAS_NONE)
   const float* bias_h;
   const float* bias_w;
@@ -69,9 +77,12 @@ struct AttSmem {
   static constexpr int KV_SLOT = ((KV_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_K = 2 * Q_BYTES;                 // Q is double-buffered across work items
   static constexpr int OFF_V = OFF_K + STAGES * KV_SLOT;
-  static constexpr int OFF_RW = OFF_V + STAGES * KV_SLOT;   // [256 rows][68] fp32 rel_w staging (64x64 bias variant)
-  static constexpr int RW_BYTES = BIAS == 1 ? 256 * ATT_RW_STRIDE : 0;
-  static constexpr int OFF_BAR = OFF_RW + RW_BYTES;
+  // 64x64 rel-pos mode: rel_w A operands [item parity][Q tile] (128 rows x 128 B, 128B-swizzled) + 64x64 identity
+  static constexpr int OFF_AW = OFF_V + STAGES * KV_SLOT;
+  static constexpr int AW_BYTES = BIAS == 1 ? 4 * 16384 : 0;
+  static constexpr int OFF_ID = OFF_AW + AW_BYTES;
+  static constexpr int ID_BYTES = BIAS == 1 ? 8192 : 0;
+  static constexpr int OFF_BAR = OFF_ID + ID_BYTES;
   static constexpr int TOTAL = OFF_BAR + 512 + 1024;
   static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 };
@@ -80,6 +91,42 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// sm_100 packed-pair / three-input forms: half the issue slots of the scalar instructions (FMNMX3, FFMA2, FADD2)
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// (d0, d1) = (a0, a1) * (b, b) + (c, c)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %4};\n\t"
+      "mov.b64 rc, {%5, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+// (d0, d1) += (a0, a1)
+__device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float a1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rd, {%0, %1};\n\t"
+      "add.rn.f32x2 rd, rd, ra;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1));
 }
 
 template <int KV_TILE, int BIAS>
@@ -95,6 +142,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   // Tiles of <= 64 keys double-buffer the score tile in TMEM: S(j+1) is issued BEFORE the MMA warp waits for P(j), so
   // the softmax warps never wait for the tensor pipe once the pipeline is full.
   constexpr bool DB = KV_TILE <= 64;
+  // 64x64 rel-pos mode: rel_w enters the scores through an extra MMA (see the header comment)
+  constexpr bool FOLD_W = BIAS == ATT_BIAS_GLOBAL64;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -115,7 +164,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                                                    // with ONE barrier flipping every tile a wait for PV(g) could be
                                                    // satisfied by the parity of PV(g-2) while PV(g-1) is still pending.
   uint64_t* o_empty = bar_pv + 4;                  // [Q tile]: the epilogue has read O (one arrival per warp)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* aw_full = o_empty + 2;                 // [item parity][Q tile]: rel_w A operand written (64x64 rel-pos mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aw_full + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -147,12 +197,27 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_init(&bar_pv[2 * x], 1);
       mbar_init(&bar_pv[2 * x + 1], 1);
       mbar_init(&o_empty[x], 4);
+      mbar_init(&aw_full[x], 1);
+      mbar_init(&aw_full[2 + x], 1);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
+  }
+  if constexpr (FOLD_W) {
+    if (warp == 3) {
+      // B operand of the bias MMA: I[n][k] / scale (64 x 64 fp16, K-major, 128B swizzle: 16-byte chunk c of row n
+      // sits at chunk position c ^ (n & 7))
+      uint8_t* idm = smem + S::OFF_ID;
+      for (int i = lane; i < S::ID_BYTES / 16; i += 32) reinterpret_cast<uint4*>(idm)[i] = make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();
+      for (int n = lane; n < 64; n += 32)
+        *reinterpret_cast<__half*>(idm + n * 128 + ((((n >> 3) ^ (n & 7))) << 4) + (n & 7) * 2) =
+            __float2half_rn(p.inv_scale);
+      fence_proxy_async_smem();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -200,6 +265,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // uniform registers); one elected lane issues each group of tcgen05 instructions.
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, KV_TILE, 0, 0);  // S = Q K^T   (both K-major, smem)
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (P in TMEM, V MN-major)
+      // S += A_w I/scale: fp16 operands (A/B format fields 0) -- 11 significant bits for the bias instead of 8
+      constexpr uint32_t idesc_w = umma_idesc_bf16(128, KV_TILE, 0, 0) & ~((7u << 7) | (7u << 10));
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
 
@@ -212,6 +279,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           for (int ks = 0; ks < ATT_D / 16; ++ks) {
             umma_bf16_ss(tm + TM_S + x * 128 + buf * KV_TILE, umma_smem_desc_sw128(q_base + ks * 32),
                          umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
+          }
+          if constexpr (FOLD_W) {
+            // S += A_w x I : adds rel_w[q, kw] / scale to column kw of every key tile (KV_TILE == 64 == grid width)
+            const uint32_t aw_base = smem_base + S::OFF_AW + (qb * 2 + x) * 16384;
+            const uint32_t id_base = smem_base + S::OFF_ID;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_bf16_ss(tm + TM_S + x * 128 + buf * KV_TILE, umma_smem_desc_sw128(aw_base + ks * 32),
+                           umma_smem_desc_sw128(id_base + ks * 32), idesc_w, 1u);
+            }
           }
           umma_commit(bar_done);
           if (bar_free != nullptr) umma_commit(bar_free);
@@ -238,6 +315,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int qb = it & 1;
         const bool trace_on = tr0 && it == 0;
         mbar_wait(&q_full[qb], (it >> 1) & 1);
+        if constexpr (FOLD_W) {
+          mbar_wait(&aw_full[qb * 2], (it >> 1) & 1);
+          mbar_wait(&aw_full[qb * 2 + 1], (it >> 1) & 1);
+        }
         {
           const int slot = g0 % ST;
           const int buf = DB ? (g0 & 1) : 0;
@@ -286,6 +367,43 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         if (elect_one()) umma_commit(&q_empty[qb]);
         __syncwarp();
       }
+    } else if constexpr (FOLD_W) {
+      // ------------------------- rel_w operand builders (warp 2: Q tile A, warp 3: Q tile B) -------------------------
+      // A_w[r][kw] = fp16(rel_w[q_r, kw]), r = row of the Q tile, read from the fp32 table (entry 63 - qw + kw of
+      // the query's row) with coalesced 256-byte requests and written in the 128B-swizzled K-major operand layout.
+      const int x = warp - 2;
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int qpair = w % n_qp;
+        const int head = (w / n_qp) % p.n_heads;
+        const int seq = w / (n_qp * p.n_heads);
+        const long long seq_row0 = static_cast<long long>(seq) * p.seq_len;
+        const int qb = it & 1;
+        // the buffer was last read by the score MMAs of item it-2 (same completion that frees the Q buffer)
+        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+        uint8_t* dst = smem + S::OFF_AW + (qb * 2 + x) * 16384;
+        const int t0 = qpair * 256 + x * 128;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 128; r0 += 8) {
+          float v0[8], v1[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int t = (t0 + r0 + u < p.seq_len) ? t0 + r0 + u : 0;
+            const float* src = p.bias_w + ((seq_row0 + t) * p.n_heads + head) * p.ldb + (63 - (t & 63)) + 2 * lane;
+            v0[u] = __ldg(src);
+            v1[u] = __ldg(src + 1);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = r0 + u;
+            *reinterpret_cast<uint32_t*>(dst + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4) =
+                pack_f16(v0[u], v1[u]);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aw_full[qb * 2 + x]);
+      }
     }
   } else {
     // ===================================== softmax warpgroups =====================================
@@ -298,6 +416,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t t_o = tmem_base + lane_addr + TM_O + x * 64;
     const float sl2 = p.scale_log2;
     constexpr float LOG2E = 1.4426950408889634f;
+    // bias arithmetic in the softmax threads only for the 14x14 windows (see the header comment)
+    constexpr bool WIN = BIAS == ATT_BIAS_WINDOW14;
 
     int it = 0;
     uint32_t g0 = 0;
@@ -308,61 +428,38 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const long long seq_row0 = static_cast<long long>(seq) * p.seq_len;
       const int t = qpair * 256 + x * 128 + r;  // token index inside the sequence
       const bool row_valid = t < p.seq_len;
-      const bool tr = tr0 && it == 0 && quarter == 0;
 
-      // ---- rel-pos bias prologue (log2 units): the rel_w terms of this query row live in registers.  For the 64x64
-      //      grid the 32 rows of a warp are fetched cooperatively (coalesced 128-byte requests) through a shared-memory
-      //      staging area, each thread then reads its own row back with LDS.128 ----
-      float rw2[BIAS == ATT_BIAS_NONE ? 1 : GW];
+      // ---- rel-pos bias prologue (log2 units) ----
+      float rw2[WIN ? GW : 1];
       const float* bh_row = nullptr;
       if constexpr (BIAS != ATT_BIAS_NONE) {
         const int tt = row_valid ? t : 0;
         const int qh = tt / GW, qw = tt % GW;
         const long long brow = ((seq_row0 + tt) * p.n_heads + head) * p.ldb;
         bh_row = p.bias_h + brow + (GW - 1 - qh);
-        if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+        if constexpr (WIN) {
           const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
 #pragma unroll
           for (int i = 0; i < GW; ++i) rw2[i] = __ldg(bw_row + i) * LOG2E;
-        } else {
-          static_assert(BIAS != ATT_BIAS_GLOBAL64 || GW == 64, "staging assumes 64 rel_w terms per row");
-          float* stage = reinterpret_cast<float*>(smem + S::OFF_RW + (x * 128 + quarter * 32) * ATT_RW_STRIDE);
-          const int t0 = qpair * 256 + x * 128 + quarter * 32;   // token of this warp's first row
-          __syncwarp();   // the previous item's read-back of the staging rows is complete
-          for (int rr = 0; rr < 32; ++rr) {
-            const int t2 = (t0 + rr < p.seq_len) ? t0 + rr : 0;
-            const float* src = p.bias_w + ((seq_row0 + t2) * p.n_heads + head) * p.ldb + (GW - 1 - t2 % GW);
-            float* dst = stage + rr * (ATT_RW_STRIDE / 4);
-            dst[lane] = __ldg(src + lane);
-            dst[lane + 32] = __ldg(src + lane + 32);
-          }
-          __syncwarp();
-          const float4* own = reinterpret_cast<const float4*>(smem + S::OFF_RW + (x * 128 + r) * ATT_RW_STRIDE);
-#pragma unroll
-          for (int i = 0; i < GW / 4; ++i) {
-            const float4 wv = own[i];
-            rw2[4 * i] = wv.x * LOG2E;
-            rw2[4 * i + 1] = wv.y * LOG2E;
-            rw2[4 * i + 2] = wv.z * LOG2E;
-            rw2[4 * i + 3] = wv.w * LOG2E;
-          }
         }
-      } else {
-        rw2[0] = 0.0f;
       }
+      if constexpr (!WIN) rw2[0] = 0.0f;
 
       float m_used = -INFINITY;
       float l_sum = 0.0f;
+      float rh_next = 0.0f;   // 64x64 mode: rel_h term of the next key tile (= key-grid row), fetched one tile ahead
+      if constexpr (FOLD_W) rh_next = __ldg(bh_row);
 
       for (int j = 0; j < NT; ++j) {
         const uint32_t g = g0 + j;
         const int valid = p.seq_len - j * KV_TILE;  // keys of this tile that exist (may exceed KV_TILE)
         // rel_h terms of the NG key-grid rows of this tile
         float rh2[NG];
-        if constexpr (BIAS == ATT_BIAS_GLOBAL64) {
-#pragma unroll
-          for (int i = 0; i < NG; ++i) rh2[i] = __ldg(bh_row + NG * j + i) * LOG2E;
-        } else if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+        if constexpr (FOLD_W) {
+          static_assert(!FOLD_W || NG == 1, "one key-grid row per tile");
+          rh2[0] = rh_next * LOG2E;
+          if (j + 1 < NT) rh_next = __ldg(bh_row + j + 1);
+        } else if constexpr (WIN) {
 #pragma unroll
           for (int i = 0; i < NG; ++i) rh2[i] = (j * NG + i < GW) ? __ldg(bh_row + j * NG + i) * LOG2E : 0.0f;
         } else {
@@ -371,10 +468,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
         const int buf = DB ? (g & 1) : 0;
         const uint32_t t_s = t_s0 + buf * KV_TILE;
-        att_trace(p, tr, 1 + x, j, 0);
         mbar_wait(&bar_s[2 * x + buf], DB ? ((g >> 1) & 1) : (g & 1));
         tc_fence_after();
-        att_trace(p, tr, 1 + x, j, 1);
 
         // ---- the whole score row into registers: ONE pass over TMEM ----
         uint32_t sv[KV_TILE];
@@ -388,28 +483,38 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             if (i >= valid) sv[i] = 0xff800000u;
         }
 
-        // ---- pass 1: t = s * scale + rel_w (kept in place), tile max incl. rel_h ----
-        float mx = -INFINITY;
+        // ---- pass 1: tile max in log2 units ----
+        float mx;
+        if constexpr (WIN) {
+          // t = s * scale + rel_w (kept in place), max incl. rel_h
+          mx = -INFINITY;
 #pragma unroll
-        for (int gi = 0; gi < NG; ++gi) {
-          float m0 = -INFINITY, m1 = -INFINITY;
+          for (int gi = 0; gi < NG; ++gi) {
+            float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < GW; ++i) {
-            const int col = gi * GW + i;
-            float tv;
-            if constexpr (BIAS == ATT_BIAS_NONE) {
-              tv = __uint_as_float(sv[col]) * sl2;
-            } else {
-              tv = fmaf(__uint_as_float(sv[col]), sl2, rw2[i]);
+            for (int i = 0; i < GW; ++i) {
+              const int col = gi * GW + i;
+              const float tv = fmaf(__uint_as_float(sv[col]), sl2, rw2[i]);
+              sv[col] = __float_as_uint(tv);
+              if (i & 1) m1 = fmaxf(m1, tv);
+              else m0 = fmaxf(m0, tv);
             }
-            sv[col] = __float_as_uint(tv);
-            if (i & 1) m1 = fmaxf(m1, tv);
-            else m0 = fmaxf(m0, tv);
+            mx = fmaxf(mx, fmaxf(m0, m1) + rh2[gi]);
           }
-          mx = fmaxf(mx, fmaxf(m0, m1) + rh2[gi]);
+        } else {
+          // raw scores (rel_w already inside them in the 64x64 mode): max first, scale once (scale > 0)
+          static_assert(WIN || KV_TILE % 8 == 0, "max tree works on groups of 8");
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < KV_TILE; i += 8) {
+            m0 = max3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+            m1 = max3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+            m2 = max3(m2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+            m3 = max3(m3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+          }
+          mx = fmaf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), sl2, rh2[0]);
         }
 
-        att_trace(p, tr, 1 + x, j, 2);
         // ---- running max with lazy rescale (threshold 8 in log2 units => P <= 256) ----
         float alpha = 1.0f;
         bool need = false;
@@ -436,8 +541,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           l_sum *= alpha;
         }
 
-        // ---- pass 2: P = exp2(t + rel_h - m) -> bf16 pairs -> TMEM (A operand of the PV MMA) over the score columns
-        //      just consumed, 32 columns (16 words) at a time so that the stores overlap the remaining exponentials ----
+        // ---- pass 2: P = exp2(t - m) -> bf16 pairs -> TMEM (A operand of the PV MMA) over the score columns just
+        //      consumed, 32 columns (16 words) at a time so that the stores overlap the remaining exponentials ----
         float offg[NG];
 #pragma unroll
         for (int gi = 0; gi < NG; ++gi) offg[gi] = rh2[gi] - m_used;
@@ -450,15 +555,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           for (int i = 0; i < 32; i += 2) {
             if (i < width) {
               const int col = c0 + i;
-              const float e0 = ex2_approx(__uint_as_float(sv[col]) + offg[col / GW]);
-              const float e1 = ex2_approx(__uint_as_float(sv[col + 1]) + offg[(col + 1) / GW]);
-              if ((i & 2) == 0) {
-                l0 += e0;
-                l1 += e1;
+              float a0, a1;
+              if constexpr (WIN) {
+                a0 = __uint_as_float(sv[col]) + offg[col / GW];
+                a1 = __uint_as_float(sv[col + 1]) + offg[(col + 1) / GW];
               } else {
-                l2 += e0;
-                l3 += e1;
+                ffma2(a0, a1, __uint_as_float(sv[col]), __uint_as_float(sv[col + 1]), sl2, offg[0]);
               }
+              const float e0 = ex2_approx(a0);
+              const float e1 = ex2_approx(a1);
+              if ((i & 2) == 0) fadd2_acc(l0, l1, e0, e1);
+              else fadd2_acc(l2, l3, e0, e1);
               pk[i >> 1] = pack_bf16(e0, e1);
             }
           }
@@ -470,7 +577,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[2 * x + buf]);
-        att_trace(p, tr, 1 + x, j, 3);
       }
 
       // ---- epilogue: O / l -> bf16 -> global (with the window-unpartition row mapping) ----
@@ -578,6 +684,7 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
   p.v_off = v_off;
   p.rows_total = rows_total;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.inv_scale = 1.0f / scale;
   p.bias_h = bias_h;
   p.bias_w = bias_w;
   p.ldb = ldb;
