@@ -69,7 +69,8 @@ int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, co
                       int out_mode, int nwin, int img_hw);
 
 /* Diagnostics: when device_buffer != NULL, CTA (0,0,0) of every following la_attention_bf16 launch records clock64()
- * stamps into it: int64 [3 roles (MMA issuer, softmax A, softmax B)][64 tiles][4 events]; NULL switches it off. */
+ * stamps into it: int64 [5 roles (MMA issuers, softmax A / B first warp, softmax A / B last warp)][192 tiles]
+ * [4 events]; NULL switches it off. */
 int la_attention_set_trace(void* device_buffer);
 
 /* ---- streaming row kernels ----------------------------------------------------------------------- */

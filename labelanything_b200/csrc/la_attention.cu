@@ -14,10 +14,9 @@
 // last softmax tiles and the epilogue of item i -- this is what keeps the 14x14-window blocks (2 key tiles per
 // item) from being dominated by per-CTA set-up and load latency.
 //   warp 0      : TMA producer (Q once; K and V tiles through two independent smem rings)
-//   warp 1      : MMA issuer   (S = Q K^T into TMEM;  O += P V with P read from TMEM -- it overlays the scores it
-//                 was computed from -- and V as MN-major smem operand)
-//   warp 2      : TMEM allocator; 64x64 rel-pos mode: rel_w operand builder for Q tile A
-//   warp 3      : 64x64 rel-pos mode: identity operand + rel_w operand builder for Q tile B
+//   warps 1, 3  : MMA issuers for Q tile A / B (S = Q K^T into TMEM;  O += P V with P read from TMEM -- it overlays
+//                 the scores it was computed from -- and V as MN-major smem operand)
+//   warp 2      : TMEM allocator; 64x64 rel-pos mode: identity operand + rel_w operand builder
 //   warps 4-7   : softmax + epilogue for Q tile A     warps 8-11: same for Q tile B   (one thread per query row,
 //                 the whole score row of a key tile held in registers: setmaxnreg gives these warps 216 registers)
 // The decomposed relative-position bias  rel_h[q, kh] + rel_w[q, kw]  is read from fp32 tables produced
@@ -37,10 +36,16 @@ namespace la {
 
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_D = 64;
-constexpr int ATT_REGS_SOFTMAX = 216;  // setmaxnreg budget: 256 x 216 + 128 x 72 = 64512 = 384 threads x 168 (launch allocation)
-constexpr int ATT_REGS_CONTROL = 72;
-static_assert(256 * ATT_REGS_SOFTMAX + 128 * ATT_REGS_CONTROL <= ATT_THREADS * 168,
-              "setmaxnreg.inc can only hand out what the CTA was launched with (168 registers x 384 threads)");
+// setmaxnreg budget: 256 softmax threads + 128 control threads share 384 x 168 = 64512 registers (launch allocation).
+// 64-key tiles keep 64 score registers per thread and leave the control warps 104; the 112-key window tiles need
+// everything the softmax threads can get.
+template <int KV_TILE>
+struct AttRegs {
+  static constexpr int SOFTMAX = KV_TILE <= 64 ? 200 : 216;
+  static constexpr int CONTROL = KV_TILE <= 64 ? 104 : 72;
+  static_assert(256 * SOFTMAX + 128 * CONTROL <= ATT_THREADS * 168,
+                "setmaxnreg.inc can only hand out what the CTA was launched with (168 registers x 384 threads)");
+};
 
 enum AttBias : int { ATT_BIAS_NONE = 0, ATT_BIAS_GLOBAL64 = 1, ATT_BIAS_WINDOW14 = 2 };
 
@@ -63,8 +68,9 @@ struct AttParams {
   int debug;              // diagnostics (LA_ATT_DEBUG env): bit0 always rescale, bit1 never skip the O wait
 };
 
-// trace layout: [role][tile][event] int64; roles: 0 = MMA thread, 1 = softmax A (warp 4 lane 0), 2 = softmax B
-constexpr int ATT_TRACE_TILES = 64, ATT_TRACE_EVENTS = 4;
+// trace layout: [role][tile][event] int64; roles: 0 = MMA issuers, 1 / 2 = softmax A / B first warp (lane 0), 3 / 4 =
+// softmax A / B last warp
+constexpr int ATT_TRACE_TILES = 192, ATT_TRACE_EVENTS = 4;   // the first three items of a 64-tile-per-item run
 __device__ __forceinline__ void att_trace(const AttParams& p, bool on, int role, int tile, int ev) {
   if (on && tile < ATT_TRACE_TILES) p.trace[(role * ATT_TRACE_TILES + tile) * ATT_TRACE_EVENTS + ev] = clock64();
 }
@@ -181,13 +187,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&q_full[b], 1);
-      mbar_init(&q_empty[b], 1);
+      mbar_init(&q_empty[b], 2);   // one commit per Q tile
     }
     for (int s = 0; s < ST; ++s) {
       mbar_init(&full_k[s], 1);
-      mbar_init(&empty_k[s], 1);
+      mbar_init(&empty_k[s], 2);   // the score MMAs of both Q tiles
       mbar_init(&full_v[s], 1);
-      mbar_init(&empty_v[s], 1);
+      mbar_init(&empty_v[s], 2);   // the PV MMAs of both Q tiles
     }
     for (int x = 0; x < 2; ++x) {
       mbar_init(&bar_s[2 * x], 1);
@@ -207,7 +213,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     tmem_relinquish();
   }
   if constexpr (FOLD_W) {
-    if (warp == 3) {
+    if (warp == 2) {
       // B operand of the bias MMA: I[n][k] / scale (64 x 64 fp16, K-major, 128B swizzle: 16-byte chunk c of row n
       // sits at chunk position c ^ (n & 7))
       uint8_t* idm = smem + S::OFF_ID;
@@ -229,7 +235,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
   if (warp < 4) {
     // ===================================== control warpgroup =====================================
-    setmaxnreg_dec<ATT_REGS_CONTROL>();
+    setmaxnreg_dec<AttRegs<KV_TILE>::CONTROL>();
     if (warp == 0) {
       // ------------------------------------ TMA producer ------------------------------------
       if (lane == 0) {
@@ -259,119 +265,107 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           }
         }
       }
-    } else if (warp == 1) {
-      // ------------------------------------ MMA issuer --------------------------------------
-      // The whole warp runs this loop converged (descriptors and addresses stay warp-uniform, so they live in
-      // uniform registers); one elected lane issues each group of tcgen05 instructions.
+    } else if (warp == 1 || warp == 3) {
+      // ------------------------------------ MMA issuers -------------------------------------
+      // One issuer warp per Q tile (warp 1: tile A, warp 3: tile B), each running its own chain: whenever the softmax
+      // warps of its tile deliver P(g), it issues  O += P(g) V(g)  and right behind it  S(g + LA)  into the score
+      // buffer that PV has just been queued to read (in-order tensor pipe), LA = 2 with double-buffered scores.  So a
+      // score tile is always issued a full tile ahead of its consumer, and a slow Q tile never delays the other one.
+      // The two chains only meet in the K / V rings, whose slots are released by the commits of both (mbarrier count
+      // 2).  Tiles are numbered g = 0, 1, ... across the items of this CTA.
+      // The issue path is kept short on purpose: one thread feeds the tensor pipe with 32..48-cycle instructions
+      // (M128 x N64 x K16), so descriptor arithmetic between them is what starves it.  All descriptors are
+      // base + small offset on pre-shifted 32-bit low words (the high word is a constant), one elect per tile.
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, KV_TILE, 0, 0);  // S = Q K^T   (both K-major, smem)
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (P in TMEM, V MN-major)
       // S += A_w I/scale: fp16 operands (A/B format fields 0) -- 11 significant bits for the bias instead of 8
       constexpr uint32_t idesc_w = umma_idesc_bf16(128, KV_TILE, 0, 0) & ~((7u << 7) | (7u << 10));
+      constexpr uint32_t LA = DB ? 2 : 1;
+      const int x = warp == 1 ? 0 : 1;
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t lo_q = desc_lo(smem_base + x * 16384);                  // + qb * (Q_BYTES >> 4) + 2 * ks
+      const uint32_t lo_k = desc_lo(smem_base + S::OFF_K);                   // + slot * (KV_SLOT >> 4) + 2 * ks
+      const uint32_t lo_v = desc_lo(smem_base + S::OFF_V);                   // + slot * (KV_SLOT >> 4) + 128 * ks
+      const uint32_t lo_aw = desc_lo(smem_base + S::OFF_AW + x * 16384);     // + qb * (32768 >> 4) + 2 * ks
+      const uint32_t lo_id = desc_lo(smem_base + S::OFF_ID);                 // + 2 * ks
+      const uint32_t tm_s = tm + TM_S + x * 128;                             // + buf * KV_TILE
+      const uint32_t tm_o = tm + TM_O + x * 64;
+      const uint32_t n_my = (static_cast<uint32_t>(n_items) > blockIdx.x)
+                                ? (static_cast<uint32_t>(n_items) - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const uint32_t total = n_my * static_cast<uint32_t>(NT);
 
-      // S_x(K tile in ring slot `kslot`) -> score buffer `buf`; then signal `bar_done` (and optionally free the slot)
-      auto issue_s = [&](int x, int qb, int kslot, int buf, uint64_t* bar_done, uint64_t* bar_free) {
-        const uint32_t q_base = smem_base + qb * S::Q_BYTES + x * 16384;
-        const uint32_t k_base = smem_base + S::OFF_K + kslot * S::KV_SLOT;
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < ATT_D / 16; ++ks) {
-            umma_bf16_ss(tm + TM_S + x * 128 + buf * KV_TILE, umma_smem_desc_sw128(q_base + ks * 32),
-                         umma_smem_desc_sw128(k_base + ks * 32), idesc_s, ks > 0 ? 1u : 0u);
-          }
-          if constexpr (FOLD_W) {
-            // S += A_w x I : adds rel_w[q, kw] / scale to column kw of every key tile (KV_TILE == 64 == grid width)
-            const uint32_t aw_base = smem_base + S::OFF_AW + (qb * 2 + x) * 16384;
-            const uint32_t id_base = smem_base + S::OFF_ID;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_bf16_ss(tm + TM_S + x * 128 + buf * KV_TILE, umma_smem_desc_sw128(aw_base + ks * 32),
-                           umma_smem_desc_sw128(id_base + ks * 32), idesc_w, 1u);
-            }
-          }
-          umma_commit(bar_done);
-          if (bar_free != nullptr) umma_commit(bar_free);
-        }
-        __syncwarp();
+      struct Cursor { uint32_t g, it, j; };   // tile counter, item, tile inside the item
+      auto advance = [&](Cursor& c) {
+        ++c.g;
+        if (++c.j == static_cast<uint32_t>(NT)) { c.j = 0; ++c.it; }
       };
-      auto issue_pv = [&](int x, int vslot, int buf, bool acc, uint64_t* bar_done, uint64_t* bar_free) {
-        const uint32_t v_base = smem_base + S::OFF_V + vslot * S::KV_SLOT;
-        if (elect_one()) {
+      // (elected thread) S(c) into its score buffer; signals bar_s, releases the K slot (and Q / A_w after the last tile)
+      auto mma_s = [&](const Cursor& c) {
+        const uint32_t qb = c.it & 1;
+        const uint32_t slot = c.g % ST;
+        const uint32_t buf = DB ? (c.g & 1) : 0;
+        const uint32_t d = tm_s + buf * KV_TILE;
+        const uint32_t aq = lo_q + qb * (S::Q_BYTES >> 4);
+        const uint32_t bk = lo_k + slot * (S::KV_SLOT >> 4);
 #pragma unroll
-          for (int ks = 0; ks < KV_TILE / 16; ++ks) {
-            umma_bf16_ts(tm + TM_O + x * 64, tm + TM_S + x * 128 + buf * KV_TILE + ks * 8,
-                         umma_smem_desc_sw128(v_base + ks * 2048), idesc_o, (acc || ks > 0) ? 1u : 0u);
-          }
-          umma_commit(bar_done);
-          if (bar_free != nullptr) umma_commit(bar_free);
-        }
-        __syncwarp();
-      };
-
-      int it = 0;
-      uint32_t g0 = 0;   // running key-tile counter at the start of the item
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it, g0 += NT) {
-        const int qb = it & 1;
-        const bool trace_on = tr0 && it == 0;
-        mbar_wait(&q_full[qb], (it >> 1) & 1);
+        for (int ks = 0; ks < ATT_D / 16; ++ks) umma_ss_lo(d, aq + 2 * ks, bk + 2 * ks, idesc_s, ks > 0);
         if constexpr (FOLD_W) {
-          mbar_wait(&aw_full[qb * 2], (it >> 1) & 1);
-          mbar_wait(&aw_full[qb * 2 + 1], (it >> 1) & 1);
-        }
-        {
-          const int slot = g0 % ST;
-          const int buf = DB ? (g0 & 1) : 0;
-          mbar_wait(&full_k[slot], (g0 / ST) & 1);
-          tc_fence_after();
-          // (non-DB: this overwrites P of the previous item's last tile, whose PV MMA is ahead of it in the pipe)
-          issue_s(0, qb, slot, buf, &bar_s[buf], nullptr);
-          issue_s(1, qb, slot, buf, &bar_s[2 + buf], &empty_k[slot]);
-        }
-        for (int j = 0; j < NT; ++j) {
-          const uint32_t g = g0 + j;
-          const int buf = DB ? (g & 1) : 0;
-          const uint32_t par = DB ? ((g >> 1) & 1) : (g & 1);
-          const int vslot = g % ST;
-          const int kslot_n = (g + 1) % ST;
-          const uint32_t kphase_n = ((g + 1) / ST) & 1;
-          const bool more = j + 1 < NT;
+          // S += A_w x I / scale : adds rel_w[q, kw] to column kw of every key tile (KV_TILE == 64 == grid width)
+          const uint32_t aw = lo_aw + qb * (32768 >> 4);
 #pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            if (DB && more) {
-              // next score tile first: its buffer held P(g-1), whose PV MMA is already ahead of it in the pipe
-              if (x == 0) {
-                mbar_wait(&full_k[kslot_n], kphase_n);
-                tc_fence_after();
-              }
-              issue_s(x, qb, kslot_n, buf ^ 1, &bar_s[2 * x + (buf ^ 1)], x == 1 ? &empty_k[kslot_n] : nullptr);
-            }
-            mbar_wait(&bar_p[2 * x + buf], par);
-            att_trace(p, trace_on, 0, j, 2 * x);
-            if (j == 0 && it > 0) mbar_wait(&o_empty[x], (it - 1) & 1);   // previous item's epilogue has read O
-            if (x == 0) mbar_wait(&full_v[vslot], (g / ST) & 1);
-            tc_fence_after();
-            issue_pv(x, vslot, buf, j > 0, &bar_pv[2 * x + buf], x == 1 ? &empty_v[vslot] : nullptr);
-            att_trace(p, trace_on, 0, j, 2 * x + 1);
-            if (!DB && more) {
-              if (x == 0) {
-                mbar_wait(&full_k[kslot_n], kphase_n);
-                tc_fence_after();
-              }
-              // overwrites P(g) of this Q tile: ordered behind PV(g) in the MMA pipe
-              issue_s(x, qb, kslot_n, 0, &bar_s[2 * x], x == 1 ? &empty_k[kslot_n] : nullptr);
-            }
-          }
+          for (int ks = 0; ks < 4; ++ks) umma_ss_lo(d, aw + 2 * ks, lo_id + 2 * ks, idesc_w, true);
         }
-        // every QK^T of this item has been issued: the Q buffer is free once they (all earlier MMAs) complete
-        if (elect_one()) umma_commit(&q_empty[qb]);
+        umma_commit(&bar_s[2 * x + buf]);
+        umma_commit(&empty_k[slot]);
+        if (c.j + 1 == static_cast<uint32_t>(NT)) umma_commit(&q_empty[qb]);
+      };
+      auto wait_s_inputs = [&](const Cursor& c) {
+        const int qb = c.it & 1;
+        if (c.j == 0) {
+          mbar_wait(&q_full[qb], (c.it >> 1) & 1);
+          if constexpr (FOLD_W) mbar_wait(&aw_full[qb * 2 + x], (c.it >> 1) & 1);
+        }
+        mbar_wait(&full_k[c.g % ST], (c.g / ST) & 1);
+      };
+
+      Cursor sc{0, 0, 0}, pc{0, 0, 0};   // next score tile to issue / next P tile to consume
+      for (uint32_t i = 0; i < LA && sc.g < total; ++i) {
+        wait_s_inputs(sc);
+        tc_fence_after();
+        if (elect_one()) mma_s(sc);
         __syncwarp();
+        advance(sc);
+      }
+      while (pc.g < total) {
+        const uint32_t buf = DB ? (pc.g & 1) : 0;
+        const uint32_t vslot = pc.g % ST;
+        const bool more = sc.g < total;
+        if (more) wait_s_inputs(sc);   // long since there: K is loaded ST tiles ahead
+        mbar_wait(&full_v[vslot], (pc.g / ST) & 1);
+        if (pc.j == 0 && pc.it > 0) mbar_wait(&o_empty[x], (pc.it - 1) & 1);   // previous item's epilogue has read O
+        mbar_wait(&bar_p[2 * x + buf], DB ? ((pc.g >> 1) & 1) : (pc.g & 1));
+        tc_fence_after();
+        att_trace(p, tr0, 0, pc.g, 2 * x);
+        if (elect_one()) {
+          const uint32_t a_p = tm_s + buf * KV_TILE;
+          const uint32_t bv = lo_v + vslot * (S::KV_SLOT >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KV_TILE / 16; ++ks)
+            umma_ts_lo(tm_o, a_p + ks * 8, bv + ks * (2048 >> 4), idesc_o, pc.j > 0 || ks > 0);
+          umma_commit(&bar_pv[2 * x + buf]);
+          umma_commit(&empty_v[vslot]);
+          if (more) mma_s(sc);
+        }
+        __syncwarp();
+        att_trace(p, tr0, 0, pc.g, 2 * x + 1);
+        advance(pc);
+        if (more) advance(sc);
       }
     } else if constexpr (FOLD_W) {
-      // ------------------------- rel_w operand builders (warp 2: Q tile A, warp 3: Q tile B) -------------------------
+      // ------------------------------- rel_w operand builder (warp 2, both Q tiles) -------------------------------
       // A_w[r][kw] = fp16(rel_w[q_r, kw]), r = row of the Q tile, read from the fp32 table (entry 63 - qw + kw of
       // the query's row) with coalesced 256-byte requests and written in the 128B-swizzled K-major operand layout.
-      const int x = warp - 2;
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const int qpair = w % n_qp;
@@ -381,20 +375,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int qb = it & 1;
         // the buffer was last read by the score MMAs of item it-2 (same completion that frees the Q buffer)
         mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+#pragma unroll 1
+        for (int x = 0; x < 2; ++x) {
         uint8_t* dst = smem + S::OFF_AW + (qb * 2 + x) * 16384;
         const int t0 = qpair * 256 + x * 128;
 #pragma unroll 1
-        for (int r0 = 0; r0 < 128; r0 += 8) {
-          float v0[8], v1[8];
+        for (int r0 = 0; r0 < 128; r0 += 16) {
+          float v0[16], v1[16];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 16; ++u) {
             const int t = (t0 + r0 + u < p.seq_len) ? t0 + r0 + u : 0;
             const float* src = p.bias_w + ((seq_row0 + t) * p.n_heads + head) * p.ldb + (63 - (t & 63)) + 2 * lane;
             v0[u] = __ldg(src);
             v1[u] = __ldg(src + 1);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 16; ++u) {
             const int r = r0 + u;
             *reinterpret_cast<uint32_t*>(dst + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4) =
                 pack_f16(v0[u], v1[u]);
@@ -403,11 +399,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&aw_full[qb * 2 + x]);
+        }
       }
     }
   } else {
     // ===================================== softmax warpgroups =====================================
-    setmaxnreg_inc<ATT_REGS_SOFTMAX>();
+    setmaxnreg_inc<AttRegs<KV_TILE>::SOFTMAX>();
     const int x = (warp - 4) >> 2;     // Q tile: 0 = A, 1 = B
     const int quarter = warp & 3;      // TMEM lane quarter
     const int r = quarter * 32 + lane;  // row inside the Q tile
@@ -419,6 +416,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     // bias arithmetic in the softmax threads only for the 14x14 windows (see the header comment)
     constexpr bool WIN = BIAS == ATT_BIAS_WINDOW14;
 
+    // rel_h table row of this thread's query in work item w2 (pointer to the entry of key-grid row 0)
+    auto bh_row_of = [&](int w2) -> const float* {
+      const int qpair2 = w2 % n_qp;
+      const int head2 = (w2 / n_qp) % p.n_heads;
+      const long long row0 = static_cast<long long>(w2 / (n_qp * p.n_heads)) * p.seq_len;
+      const int t2 = qpair2 * 256 + x * 128 + r;
+      const int tt = t2 < p.seq_len ? t2 : 0;
+      return p.bias_h + ((row0 + tt) * p.n_heads + head2) * p.ldb + (GW - 1 - tt / GW);
+    };
+    // the next item's row pointer and (64x64 mode) its first rel_h term are fetched before the epilogue of the current
+    // item, so the global-load latency is off the item-to-item critical path
+    const float* bh_row_pre = nullptr;
+    float rh_pre = 0.0f;
+    if constexpr (BIAS != ATT_BIAS_NONE) {
+      if (static_cast<int>(blockIdx.x) < n_items) {
+        bh_row_pre = bh_row_of(blockIdx.x);
+        if constexpr (FOLD_W) rh_pre = __ldg(bh_row_pre);
+      }
+    }
+
     int it = 0;
     uint32_t g0 = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it, g0 += NT) {
@@ -428,16 +445,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const long long seq_row0 = static_cast<long long>(seq) * p.seq_len;
       const int t = qpair * 256 + x * 128 + r;  // token index inside the sequence
       const bool row_valid = t < p.seq_len;
+      const bool tr = tr0 && (quarter == 0 || quarter == 3);
+      const int tr_role = 1 + x + (quarter == 3 ? 2 : 0);
 
       // ---- rel-pos bias prologue (log2 units) ----
       float rw2[WIN ? GW : 1];
-      const float* bh_row = nullptr;
+      const float* bh_row = bh_row_pre;
       if constexpr (BIAS != ATT_BIAS_NONE) {
-        const int tt = row_valid ? t : 0;
-        const int qh = tt / GW, qw = tt % GW;
-        const long long brow = ((seq_row0 + tt) * p.n_heads + head) * p.ldb;
-        bh_row = p.bias_h + brow + (GW - 1 - qh);
         if constexpr (WIN) {
+          const int tt = row_valid ? t : 0;
+          const int qw = tt % GW;
+          const long long brow = ((seq_row0 + tt) * p.n_heads + head) * p.ldb;
           const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
 #pragma unroll
           for (int i = 0; i < GW; ++i) rw2[i] = __ldg(bw_row + i) * LOG2E;
@@ -448,7 +466,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       float m_used = -INFINITY;
       float l_sum = 0.0f;
       float rh_next = 0.0f;   // 64x64 mode: rel_h term of the next key tile (= key-grid row), fetched one tile ahead
-      if constexpr (FOLD_W) rh_next = __ldg(bh_row);
+      if constexpr (FOLD_W) rh_next = rh_pre;
 
       for (int j = 0; j < NT; ++j) {
         const uint32_t g = g0 + j;
@@ -468,8 +486,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
         const int buf = DB ? (g & 1) : 0;
         const uint32_t t_s = t_s0 + buf * KV_TILE;
+        att_trace(p, tr, tr_role, g, 0);
         mbar_wait(&bar_s[2 * x + buf], DB ? ((g >> 1) & 1) : (g & 1));
         tc_fence_after();
+        att_trace(p, tr, tr_role, g, 1);
 
         // ---- the whole score row into registers: ONE pass over TMEM ----
         uint32_t sv[KV_TILE];
@@ -515,6 +535,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           mx = fmaf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), sl2, rh2[0]);
         }
 
+        att_trace(p, tr, tr_role, g, 2);
         // ---- running max with lazy rescale (threshold 8 in log2 units => P <= 256) ----
         float alpha = 1.0f;
         bool need = false;
@@ -577,6 +598,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[2 * x + buf]);
+        att_trace(p, tr, tr_role, g, 3);
+      }
+
+      if constexpr (BIAS != ATT_BIAS_NONE) {
+        if (w + static_cast<int>(gridDim.x) < n_items) {
+          bh_row_pre = bh_row_of(w + gridDim.x);
+          if constexpr (FOLD_W) rh_pre = __ldg(bh_row_pre);
+        }
       }
 
       // ---- epilogue: O / l -> bf16 -> global (with the window-unpartition row mapping) ----

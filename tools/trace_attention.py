@@ -17,7 +17,7 @@ bh = bw = None
 if gsz:
     bh = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
     bw = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
-tr = torch.zeros(3, 64, 4, dtype=torch.int64, device="cuda")
+tr = torch.zeros(5, 192, 4, dtype=torch.int64, device="cuda")
 for _ in range(2):
     ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
 _native.lib().la_attention_set_trace(tr.data_ptr())
@@ -28,8 +28,8 @@ t = tr.cpu()
 t0 = int(t[t > 0].min())
 t = (t - t0).clamp(min=-1)
 print("tile | MMA: P_A seen, PV_A issued, P_B seen, PV_B issued | softA: waitS, gotS, max done, P arrived | softB: same")
-for j in list(range(0, 12)) + list(range(40, 46)):
-    print(j, t[0, j].tolist(), t[1, j].tolist(), t[2, j].tolist())
+for j in list(range(0, 4)) + list(range(58, 72)) + list(range(124, 134)):
+    print(j, t[0, j].tolist(), t[1, j].tolist(), t[2, j].tolist(), t[3, j].tolist(), t[4, j].tolist())
 d = t[1, 8:60]
 print("softmax A steady state: mean wait-for-S", float((d[:, 1] - d[:, 0]).float().mean()), "pass1", float((d[:, 2] - d[:, 1]).float().mean()),
       "pass2+store", float((d[:, 3] - d[:, 2]).float().mean()), "period", float((d[1:, 3] - d[:-1, 3]).float().mean()))
