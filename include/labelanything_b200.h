@@ -58,7 +58,7 @@ int la_gemm_bf16(void* stream, const void* a, long long lda, const void* w, long
  * Optional decomposed relative-position bias (bias_h/bias_w != NULL): fp32 tables [rows_total][n_heads][ldb]
  * with table[row][h][grid_hw-1 - q_pos + k_pos] = q_row(h) . rel_pos[q_pos - k_pos + grid_hw-1], i.e. the
  * product of the head's q rows with the REVERSED rel_pos table (computed with la_gemm_bf16); grid_hw = 64
- * (global blocks, seq_len 4096) or 14 (windowed blocks, seq_len 196).
+ * (global blocks, seq_len 4096).  The 14x14 windowed blocks use la_attention_window_bf16 below.
  * out_mode 0: out row = sequence*seq_len + token.  out_mode 1: window un-partition: sequence = image*nwin^2
  * + window, token (ty,tx) of window (wy,wx) goes to image row (wy*14+ty)*img_hw + wx*14+tx, padded
  * positions are dropped.
@@ -67,6 +67,18 @@ int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, co
                       int k_off, int v_off, long long rows_total, int n_seq, int seq_len, int n_heads, float scale,
                       const float* bias_h, const float* bias_w, int ldb, int grid_hw, void* out, long long ld_out,
                       int out_mode, int nwin, int img_hw);
+
+/* 14x14-window attention of the SAM ViT blocks (seq_len 196, head_dim 64) with the decomposed relative-position
+ * bias computed INSIDE the kernel: rel_table is the bf16 operand [2 * rel_pad][64], rel_pad = 32, rows [0, 27) = the
+ * REVERSED rel_pos_h table (row i = rel_pos_h[26 - i]), rows [rel_pad, rel_pad + 27) = the reversed rel_pos_w table,
+ * all other rows zero.  Per work item one extra tcgen05.mma forms T = Q_tile x rel_table^T in tensor memory and the
+ * bias of key (kh, kw) for a query at (qh, qw) is T[13 - qh + kh] + T[rel_pad + 13 - qw + kw] -- same arithmetic as
+ * the fp32 tables of la_attention_bf16 without their HBM round trip.  out_mode / nwin / img_hw as above.
+ *   label_anything/models/image_encoder.py:239-255,258-304,319-376 */
+int la_attention_window_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
+                             int k_off, int v_off, long long rows_total, int n_seq, int n_heads, float scale,
+                             const void* rel_table, int rel_pad, void* out, long long ld_out, int out_mode, int nwin,
+                             int img_hw);
 
 /* Diagnostics: when device_buffer != NULL, CTA (0,0,0) of every following la_attention_bf16 launch records clock64()
  * stamps into it: int64 [5 roles (MMA issuers, softmax A / B first warp, softmax A / B last warp)][192 tiles]

@@ -36,6 +36,7 @@ namespace la {
 
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_D = 64;
+constexpr int ATT_STG_STRIDE = 272;     // bytes per row of the table staging area (68 floats: conflict-free STS.128)
 // setmaxnreg budget: 256 softmax threads + 128 control threads share 384 x 168 = 64512 registers (launch allocation).
 // 64-key tiles keep 64 score registers per thread and leave the control warps 104; the 112-key window tiles need
 // everything the softmax threads can get.
@@ -59,6 +60,7 @@ struct AttParams {
   const float* bias_h;
   const float* bias_w;
   int ldb;
+  int rel_pad;              // window mode: rows of each (h / w) half of the reversed rel-pos operand (32)
   // output
   __nv_bfloat16* out;
   long long ld_out;
@@ -68,8 +70,9 @@ struct AttParams {
   int debug;              // diagnostics (LA_ATT_DEBUG env): bit0 always rescale, bit1 never skip the O wait
 };
 
-// trace layout: [role][tile][event] int64; roles: 0 = MMA issuers, 1 / 2 = softmax A / B first warp (lane 0), 3 / 4 =
-// softmax A / B last warp
+// trace layout: [role][tile][event] int64; roles: 0 = MMA issuers (P seen / next S issued, per Q tile), 1 / 2 = softmax
+// A / B first warp (wait S, got S, max done, P delivered), 3 / 4 = the same warps' item boundaries, indexed by item
+// (O ready, epilogue stores issued, window tables ready, prologue done)
 constexpr int ATT_TRACE_TILES = 192, ATT_TRACE_EVENTS = 4;   // the first three items of a 64-tile-per-item run
 __device__ __forceinline__ void att_trace(const AttParams& p, bool on, int role, int tile, int ev) {
   if (on && tile < ATT_TRACE_TILES) p.trace[(role * ATT_TRACE_TILES + tile) * ATT_TRACE_EVENTS + ev] = clock64();
@@ -77,7 +80,7 @@ __device__ __forceinline__ void att_trace(const AttParams& p, bool on, int role,
 
 template <int KV_TILE, int BIAS>
 struct AttSmem {
-  static constexpr int STAGES = KV_TILE <= 64 ? (BIAS == 1 ? 5 : 6) : 4;   // K / V ring depth
+  static constexpr int STAGES = KV_TILE <= 64 ? (BIAS == 1 ? 5 : 6) : 3;   // K / V ring depth
   static constexpr int Q_BYTES = 2 * 128 * 128;             // two Q tiles, 128 rows x 128 B
   static constexpr int KV_BYTES = KV_TILE * 128;            // one K or V tile
   static constexpr int KV_SLOT = ((KV_BYTES + 1023) / 1024) * 1024;
@@ -88,7 +91,13 @@ struct AttSmem {
   static constexpr int AW_BYTES = BIAS == 1 ? 4 * 16384 : 0;
   static constexpr int OFF_ID = OFF_AW + AW_BYTES;
   static constexpr int ID_BYTES = BIAS == 1 ? 8192 : 0;
-  static constexpr int OFF_BAR = OFF_ID + ID_BYTES;
+  // 14x14 window mode: the reversed rel_pos tables as a B operand ([64 entries][64 channels] bf16, 128B-swizzled) and a
+  // per-row staging area for the table products T = Q x rel^T ([256 rows][68] fp32)
+  static constexpr int OFF_REL = OFF_ID + ID_BYTES;
+  static constexpr int REL_BYTES = BIAS == 2 ? 8192 : 0;
+  static constexpr int OFF_STG = OFF_REL + REL_BYTES;
+  static constexpr int STG_BYTES = BIAS == 2 ? 256 * ATT_STG_STRIDE : 0;
+  static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
   static constexpr int TOTAL = OFF_BAR + 512 + 1024;
   static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 };
@@ -138,7 +147,7 @@ __device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float 
 template <int KV_TILE, int BIAS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                     const AttParams p) {
+                     const __grid_constant__ CUtensorMap tm_rel, const AttParams p) {
   using S = AttSmem<KV_TILE, BIAS>;
   constexpr int ST = S::STAGES;
   // bias(q, k) = rel_w[q][k % GW] + rel_h[q][k / GW]: a KV tile holds NG key-grid rows of GW keys
@@ -171,7 +180,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                                                    // satisfied by the parity of PV(g-2) while PV(g-1) is still pending.
   uint64_t* o_empty = bar_pv + 4;                  // [Q tile]: the epilogue has read O (one arrival per warp)
   uint64_t* aw_full = o_empty + 2;                 // [item parity][Q tile]: rel_w A operand written (64x64 rel-pos mode)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aw_full + 4);
+  uint64_t* rel_full = aw_full + 4;                // window mode: rel-pos operand loaded (once)
+  uint64_t* bar_t = rel_full + 1;                  // [Q tile] window mode: table product T of the item ready in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_t + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -183,6 +194,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
+    if constexpr (BIAS == ATT_BIAS_WINDOW14) tma_prefetch_desc(&tm_rel);
   }
   if (warp == 1 && lane == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -205,7 +217,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_init(&o_empty[x], 4);
       mbar_init(&aw_full[x], 1);
       mbar_init(&aw_full[2 + x], 1);
+      mbar_init(&bar_t[x], 1);
     }
+    mbar_init(rel_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -231,7 +245,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384); with double buffering each S region holds
   // two KV_TILE-wide score buffers.  P (bf16) overlays the first KV_TILE/2 columns of the score buffer it came from.
-  const uint32_t TM_S = 0, TM_O = 256;
+  // Window mode: table products T_A [384,448) T_B [448,512).
+  const uint32_t TM_S = 0, TM_O = 256, TM_T = 384;
 
   if (warp < 4) {
     // ===================================== control warpgroup =====================================
@@ -239,6 +254,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if (warp == 0) {
       // ------------------------------------ TMA producer ------------------------------------
       if (lane == 0) {
+        if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+          mbar_arrive_expect_tx(rel_full, S::REL_BYTES);
+          tma_load_2d(smem + S::OFF_REL, &tm_rel, rel_full, 0, 0);
+        }
         int it = 0;
         uint32_t g = 0;   // running key-tile counter: ring slot g % ST, phase (g / ST) & 1
         for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
@@ -289,6 +308,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const uint32_t lo_v = desc_lo(smem_base + S::OFF_V);                   // + slot * (KV_SLOT >> 4) + 128 * ks
       const uint32_t lo_aw = desc_lo(smem_base + S::OFF_AW + x * 16384);     // + qb * (32768 >> 4) + 2 * ks
       const uint32_t lo_id = desc_lo(smem_base + S::OFF_ID);                 // + 2 * ks
+      const uint32_t lo_rel = desc_lo(smem_base + S::OFF_REL);               // + 2 * ks
       const uint32_t tm_s = tm + TM_S + x * 128;                             // + buf * KV_TILE
       const uint32_t tm_o = tm + TM_O + x * 64;
       const uint32_t n_my = (static_cast<uint32_t>(n_items) > blockIdx.x)
@@ -308,6 +328,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t d = tm_s + buf * KV_TILE;
         const uint32_t aq = lo_q + qb * (S::Q_BYTES >> 4);
         const uint32_t bk = lo_k + slot * (S::KV_SLOT >> 4);
+        if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+          // first tile of an item: T = Q x rel^T (the decomposed rel-pos products of the tile's 128 queries with the
+          // 2 x 27 table rows) for the softmax warps' prologue; overwrites the previous item's T, which they have
+          // consumed before delivering the P tile that triggered this issue
+          if (c.j == 0) {
+            constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 0, 0);
+#pragma unroll
+            for (int ks = 0; ks < ATT_D / 16; ++ks)
+              umma_ss_lo(tm + TM_T + x * 64, aq + 2 * ks, lo_rel + 2 * ks, idesc_t, ks > 0);
+            umma_commit(&bar_t[x]);
+          }
+        }
 #pragma unroll
         for (int ks = 0; ks < ATT_D / 16; ++ks) umma_ss_lo(d, aq + 2 * ks, bk + 2 * ks, idesc_s, ks > 0);
         if constexpr (FOLD_W) {
@@ -325,6 +357,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         if (c.j == 0) {
           mbar_wait(&q_full[qb], (c.it >> 1) & 1);
           if constexpr (FOLD_W) mbar_wait(&aw_full[qb * 2 + x], (c.it >> 1) & 1);
+          if constexpr (BIAS == ATT_BIAS_WINDOW14) {
+            if (c.it == 0) mbar_wait(rel_full, 0);
+          }
         }
         mbar_wait(&full_k[c.g % ST], (c.g / ST) & 1);
       };
@@ -429,7 +464,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     // item, so the global-load latency is off the item-to-item critical path
     const float* bh_row_pre = nullptr;
     float rh_pre = 0.0f;
-    if constexpr (BIAS != ATT_BIAS_NONE) {
+    if constexpr (FOLD_W) {
       if (static_cast<int>(blockIdx.x) < n_items) {
         bh_row_pre = bh_row_of(blockIdx.x);
         if constexpr (FOLD_W) rh_pre = __ldg(bh_row_pre);
@@ -445,24 +480,47 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const long long seq_row0 = static_cast<long long>(seq) * p.seq_len;
       const int t = qpair * 256 + x * 128 + r;  // token index inside the sequence
       const bool row_valid = t < p.seq_len;
-      const bool tr = tr0 && (quarter == 0 || quarter == 3);
-      const int tr_role = 1 + x + (quarter == 3 ? 2 : 0);
+      const bool tr = tr0 && quarter == 0;
+      const int tr_role = 1 + x;
 
       // ---- rel-pos bias prologue (log2 units) ----
       float rw2[WIN ? GW : 1];
+      float rh_all[WIN ? 2 * NG : 1];   // window mode: rel_h terms of all 14 key-grid rows (+ 2 zeros), log2 units
       const float* bh_row = bh_row_pre;
-      if constexpr (BIAS != ATT_BIAS_NONE) {
-        if constexpr (WIN) {
-          const int tt = row_valid ? t : 0;
-          const int qw = tt % GW;
-          const long long brow = ((seq_row0 + tt) * p.n_heads + head) * p.ldb;
-          const float* bw_row = p.bias_w + brow + (GW - 1 - qw);
+      if constexpr (WIN) {
+        // T[row][e] = q_row . rel_rev[e] sits in TMEM (issued with the item's first score tile): entries [0, 27) are
+        // the rel_h products, [rel_pad, rel_pad + 27) the rel_w products, and the bias of key (kh, kw) for a query at
+        // (qh, qw) is T[13 - qh + kh] + T[rel_pad + 13 - qw + kw].  The shift differs per row, so each thread parks
+        // its row in shared memory and reads the 2 x 14 entries it needs back.
+        static_assert(!WIN || 2 * NG >= GW, "two key tiles cover the 14 key-grid rows");
+        float* srow = reinterpret_cast<float*>(smem + S::OFF_STG + (x * 128 + r) * ATT_STG_STRIDE);
+        mbar_wait(&bar_t[x], it & 1);
+        tc_fence_after();
+        att_trace(p, tr, 3 + x, it, 2);
+        {
+          uint32_t tb[64];
+          tmem_ld_x32(tmem_base + lane_addr + TM_T + x * 64, tb);
+          tmem_ld_x32(tmem_base + lane_addr + TM_T + x * 64 + 32, tb + 32);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < GW; ++i) rw2[i] = __ldg(bw_row + i) * LOG2E;
+          for (int i = 0; i < 16; ++i)
+            reinterpret_cast<uint4*>(srow)[i] = make_uint4(tb[4 * i], tb[4 * i + 1], tb[4 * i + 2], tb[4 * i + 3]);
         }
+        __syncwarp();
+        const int tt = row_valid ? t : 0;
+        const int qh = tt / GW, qw = tt % GW;
+        const float* th = srow + (GW - 1 - qh);
+        const float* tw = srow + p.rel_pad + (GW - 1 - qw);
+#pragma unroll
+        for (int i = 0; i < GW; ++i) rw2[i] = tw[i] * LOG2E;
+#pragma unroll
+        for (int i = 0; i < 2 * NG; ++i) rh_all[i] = i < GW ? th[i] * LOG2E : 0.0f;
+      } else {
+        rw2[0] = 0.0f;
+        rh_all[0] = 0.0f;
       }
-      if constexpr (!WIN) rw2[0] = 0.0f;
 
+      att_trace(p, tr, 3 + x, it, 3);
       float m_used = -INFINITY;
       float l_sum = 0.0f;
       float rh_next = 0.0f;   // 64x64 mode: rel_h term of the next key tile (= key-grid row), fetched one tile ahead
@@ -479,7 +537,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           if (j + 1 < NT) rh_next = __ldg(bh_row + j + 1);
         } else if constexpr (WIN) {
 #pragma unroll
-          for (int i = 0; i < NG; ++i) rh2[i] = (j * NG + i < GW) ? __ldg(bh_row + j * NG + i) * LOG2E : 0.0f;
+          for (int i = 0; i < NG; ++i) rh2[i] = j == 0 ? rh_all[i] : rh_all[NG + i];
         } else {
           rh2[0] = 0.0f;
         }
@@ -601,7 +659,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         att_trace(p, tr, tr_role, g, 3);
       }
 
-      if constexpr (BIAS != ATT_BIAS_NONE) {
+      if constexpr (FOLD_W) {
         if (w + static_cast<int>(gridDim.x) < n_items) {
           bh_row_pre = bh_row_of(w + gridDim.x);
           if constexpr (FOLD_W) rh_pre = __ldg(bh_row_pre);
@@ -614,6 +672,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         mbar_wait(&bar_pv[2 * x + (DB ? (gl & 1) : 0)], DB ? ((gl >> 1) & 1) : (gl & 1));
       }
       tc_fence_after();
+      att_trace(p, tr, 3 + x, it, 0);
       long long out_row = -1;
       if (row_valid) {
         if (p.out_mode == 0) {
@@ -648,6 +707,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           *reinterpret_cast<uint4*>(dst + gq * 8) = pk;
         }
       }
+      att_trace(p, tr, 3 + x, it, 1);
     }
   }
 
@@ -661,9 +721,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 template <int KV_TILE, int BIAS>
 static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, const void* kv, long long ld_kv,
-                            const AttParams& p) {
+                            const AttParams& p, const void* rel = nullptr) {
   using S = AttSmem<KV_TILE, BIAS>;
-  CUtensorMap tm_q, tm_kv;
+  CUtensorMap tm_q, tm_kv, tm_rel;
   int rc = make_tensor_map_2d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_q, (uint64_t)p.rows_total,
                               (uint64_t)ld_q * 2, 64, 128, Swizzle::B128);
   if (rc) return rc;
@@ -674,7 +734,12 @@ static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, 
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   const long long items = static_cast<long long>((p.seq_len + 255) / 256) * p.n_heads * p.n_seq;
   const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
-  kern<<<grid, ATT_THREADS, S::TOTAL, stream>>>(tm_q, tm_kv, p);
+  tm_rel = tm_q;
+  if (rel != nullptr) {   // [2 * rel_pad = 64 rows][64 channels] bf16
+    rc = make_tensor_map_2d(&tm_rel, rel, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64, 64, 128, 64, 64, Swizzle::B128);
+    if (rc) return rc;
+  }
+  kern<<<grid, ATT_THREADS, S::TOTAL, stream>>>(tm_q, tm_kv, tm_rel, p);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
@@ -688,22 +753,23 @@ extern "C" int la_attention_set_trace(void* device_buffer) {
   return LA_OK;
 }
 
-extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv,
-                                 long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq,
-                                 int seq_len, int n_heads, float scale, const float* bias_h, const float* bias_w,
-                                 int ldb, int grid_hw, void* out, long long ld_out, int out_mode, int nwin,
-                                 int img_hw) {
+static int attention_dispatch(const char* fn, void* stream, const void* q, long long ld_q, int q_off, const void* kv,
+                              long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq, int seq_len,
+                              int n_heads, float scale, const float* bias_h, const float* bias_w, int ldb,
+                              const void* rel_table, int rel_pad, int grid_hw, void* out, long long ld_out,
+                              int out_mode, int nwin, int img_hw) {
   using namespace la;
-  LA_CHECK_ARG(q && kv && out, "la_attention_bf16: null pointer");
-  LA_CHECK_ARG(n_seq > 0 && seq_len > 0 && n_heads > 0, "la_attention_bf16: empty problem");
+  LA_CHECK_ARG(q && kv && out, "%s: null pointer", fn);
+  LA_CHECK_ARG(n_seq > 0 && seq_len > 0 && n_heads > 0, "%s: empty problem", fn);
+  LA_CHECK_ARG(scale > 0.0f, "%s: the softmax scale must be positive", fn);
   LA_CHECK_ARG(static_cast<long long>(n_seq) * n_heads * ((seq_len + 255) / 256) < (1ll << 31),
-               "la_attention_bf16: too many work items");
+               "%s: too many work items", fn);
   LA_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
-               "la_attention_bf16: strides/offsets must be multiples of 8 elements");
-  LA_CHECK_ARG(rows_total >= static_cast<long long>(n_seq) * seq_len, "la_attention_bf16: rows_total too small");
-  LA_CHECK_ARG(rows_total < (1ll << 31), "la_attention_bf16: rows_total exceeds TMA coordinate range");
+               "%s: strides/offsets must be multiples of 8 elements", fn);
+  LA_CHECK_ARG(rows_total >= static_cast<long long>(n_seq) * seq_len, "%s: rows_total too small", fn);
+  LA_CHECK_ARG(rows_total < (1ll << 31), "%s: rows_total exceeds TMA coordinate range", fn);
   const bool has_bias = bias_h != nullptr || bias_w != nullptr;
-  LA_CHECK_ARG(!has_bias || (bias_h && bias_w), "la_attention_bf16: bias_h and bias_w must come together");
+  LA_CHECK_ARG(!has_bias || (bias_h && bias_w), "%s: bias_h and bias_w must come together", fn);
   AttParams p;
   p.n_seq = n_seq;
   p.seq_len = seq_len;
@@ -717,6 +783,7 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
   p.bias_h = bias_h;
   p.bias_w = bias_w;
   p.ldb = ldb;
+  p.rel_pad = rel_pad;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ld_out = ld_out;
   p.out_mode = out_mode;
@@ -726,21 +793,45 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
   p.trace = g_att_trace;
   { const char* e = getenv("LA_ATT_DEBUG"); p.debug = e ? atoi(e) : 0; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rel_table != nullptr) {
+    LA_CHECK_ARG(grid_hw == 14 && seq_len == 196 && rel_pad == 32,
+                 "%s: in-kernel rel-pos tables are built for 14x14 windows (seq_len 196, rel_pad 32)", fn);
+    LA_CHECK_ARG((reinterpret_cast<uintptr_t>(rel_table) & 15) == 0, "%s: rel_table must be 16-byte aligned", fn);
+    LA_CHECK_ARG(out_mode == 0 || (nwin > 0 && img_hw > 0 && n_seq % (nwin * nwin) == 0),
+                 "%s: bad window-unpartition parameters", fn);
+    return launch_attention<112, ATT_BIAS_WINDOW14>(st, q, ld_q, kv, ld_kv, p, rel_table);
+  }
   if (!has_bias) {
-    LA_CHECK_ARG(out_mode == 0, "la_attention_bf16: window output mapping needs the window bias mode");
+    LA_CHECK_ARG(out_mode == 0, "%s: window output mapping needs the window mode", fn);
     return launch_attention<64, ATT_BIAS_NONE>(st, q, ld_q, kv, ld_kv, p);
   }
   if (grid_hw == 64) {
-    LA_CHECK_ARG(seq_len == 4096 && ldb >= 127 && out_mode == 0,
-                 "la_attention_bf16: 64x64 rel-pos mode expects seq_len 4096, ldb >= 127");
+    LA_CHECK_ARG(seq_len == 4096 && ldb >= 127 && out_mode == 0, "%s: 64x64 rel-pos mode expects seq_len 4096, ldb >= 127",
+                 fn);
     return launch_attention<64, ATT_BIAS_GLOBAL64>(st, q, ld_q, kv, ld_kv, p);
   }
-  if (grid_hw == 14) {
-    LA_CHECK_ARG(seq_len == 196 && ldb >= 27, "la_attention_bf16: 14x14 rel-pos mode expects seq_len 196, ldb >= 27");
-    LA_CHECK_ARG(out_mode == 0 || (nwin > 0 && img_hw > 0 && n_seq % (nwin * nwin) == 0),
-                 "la_attention_bf16: bad window-unpartition parameters");
-    return launch_attention<112, ATT_BIAS_WINDOW14>(st, q, ld_q, kv, ld_kv, p);
-  }
-  set_last_error("la_attention_bf16: unsupported rel-pos grid %d (built for 64 and 14)", grid_hw);
+  set_last_error("%s: unsupported rel-pos grid %d (fp32 tables: 64; 14x14 windows go through la_attention_window_bf16)",
+                 fn, grid_hw);
   return LA_ERR_UNSUPPORTED;
+}
+
+extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv,
+                                 long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq,
+                                 int seq_len, int n_heads, float scale, const float* bias_h, const float* bias_w,
+                                 int ldb, int grid_hw, void* out, long long ld_out, int out_mode, int nwin,
+                                 int img_hw) {
+  return attention_dispatch("la_attention_bf16", stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total, n_seq,
+                            seq_len, n_heads, scale, bias_h, bias_w, ldb, nullptr, 0, grid_hw, out, ld_out, out_mode,
+                            nwin, img_hw);
+}
+
+extern "C" int la_attention_window_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv,
+                                        long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq,
+                                        int n_heads, float scale, const void* rel_table, int rel_pad, void* out,
+                                        long long ld_out, int out_mode, int nwin, int img_hw) {
+  using namespace la;
+  LA_CHECK_ARG(rel_table != nullptr, "la_attention_window_bf16: rel_table is required");
+  return attention_dispatch("la_attention_window_bf16", stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total,
+                            n_seq, 196, n_heads, scale, nullptr, nullptr, 0, rel_table, rel_pad, 14, out, ld_out,
+                            out_mode, nwin, img_hw);
 }

@@ -112,6 +112,25 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def attention_window(q: torch.Tensor, kv: torch.Tensor, n_seq: int, n_heads: int, scale: float, out: torch.Tensor,
+                     q_off: int, k_off: int, v_off: int, rel_table: torch.Tensor, rel_pad: int, out_mode: int = 0,
+                     nwin: int = 0, img_hw: int = 0) -> torch.Tensor:
+    """Fused MHSA over 14x14 windows (196 tokens, head_dim 64) with the decomposed rel-pos bias formed in-kernel from
+    rel_table = bf16 [2 * rel_pad, 64] (reversed rel_pos_h rows, then reversed rel_pos_w rows; see the C header)."""
+    _require_cuda(q, kv, out, rel_table)
+    for t in (q, kv, out):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    assert q.shape[0] == kv.shape[0]
+    assert rel_table.dtype == torch.bfloat16 and rel_table.is_contiguous() and rel_table.shape == (2 * rel_pad, 64)
+    L = 196
+    _cost(4.0 * n_seq * n_heads * L * L * 64 + 2.0 * n_seq * n_heads * L * 64 * 2 * rel_pad,
+          2.0 * 4 * n_seq * L * n_heads * 64)
+    _call(f"attention.L{L}" if _PROF is not None else "attention", "la_attention_window_bf16", _stream(q), q.data_ptr(),
+          q.stride(0), q_off, kv.data_ptr(), kv.stride(0), k_off, v_off, q.shape[0], n_seq, n_heads, float(scale),
+          rel_table.data_ptr(), rel_pad, out.data_ptr(), out.stride(0), out_mode, nwin, img_hw)
+    return out
+
+
 def attention(q: torch.Tensor, kv: torch.Tensor, n_seq: int, seq_len: int, n_heads: int, scale: float,
               out: torch.Tensor, q_off: int, k_off: int, v_off: int, bias_h: torch.Tensor | None = None,
               bias_w: torch.Tensor | None = None, grid_hw: int = 0, out_mode: int = 0, nwin: int = 0,

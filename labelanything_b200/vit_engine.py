@@ -4,7 +4,7 @@ The engine is weight-layout agnostic: `image_encoder.ImageEncoderViT` and `build
 their parameters into `BlockWeights` and call `run_vit`.  Per transformer block (image_encoder.py:181-197 /
 modeling_vit.py:315-346) the launches are
 
-    add+LN1 (window partition folded in) -> Q GEMM, KV GEMM -> [rel-pos table GEMM] -> fused attention
+    add+LN1 (window partition folded in) -> Q GEMM, KV GEMM -> [rel-pos table GEMM, global blocks] -> fused attention
     (window un-partition folded in) -> proj GEMM -> add+LN2 -> lin1 GEMM (+GELU) -> lin2 GEMM
 
 with the fp32 residual stream updated inside the add+LN kernels, so every GEMM writes bf16 with a plain
@@ -93,18 +93,25 @@ def run_vit(spec: VitSpec, x: torch.Tensor, n_img: int, out_dtype: torch.dtype) 
         q = ops.gemm(y, bw.wq, bw.bq)
         kv = ops.gemm(y, bw.wkv, bw.bkv)
         del y
-        bias_h = bias_w = None
-        grid_hw = 0
-        if bw.rel_table is not None:
-            P = bw.rel_pad
-            tab = ops.gemm(q.view(r_att * heads, 64), bw.rel_table, None, out_dtype=torch.float32)
-            tab = tab.view(r_att, heads, 2 * P)
-            bias_h, bias_w = tab[:, :, :P], tab[:, :, P:]
-            grid_hw = win if win > 0 else g
         att = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
-        ops.attention(q, kv, n_seq, seq_len, heads, scale, att, 0, 0, d, bias_h, bias_w, grid_hw=grid_hw,
-                      out_mode=1 if win > 0 else 0, nwin=nwin, img_hw=g)
-        del q, kv, bias_h, bias_w
+        if bw.rel_table is not None and win > 0:
+            # windowed block: the rel-pos table products are formed inside the attention kernel
+            assert win == 14, "native windowed attention is built for 14x14 windows"
+            ops.attention_window(q, kv, n_seq, heads, scale, att, 0, 0, d, bw.rel_table, bw.rel_pad, out_mode=1,
+                                 nwin=nwin, img_hw=g)
+        else:
+            bias_h = bias_w = None
+            grid_hw = 0
+            if bw.rel_table is not None:
+                P = bw.rel_pad
+                tab = ops.gemm(q.view(r_att * heads, 64), bw.rel_table, None, out_dtype=torch.float32)
+                tab = tab.view(r_att, heads, 2 * P)
+                bias_h, bias_w = tab[:, :, :P], tab[:, :, P:]
+                grid_hw = g
+            ops.attention(q, kv, n_seq, seq_len, heads, scale, att, 0, 0, d, bias_h, bias_w, grid_hw=grid_hw,
+                          out_mode=1 if win > 0 else 0, nwin=nwin, img_hw=g)
+            del bias_h, bias_w
+        del q, kv
         delta = ops.gemm(att, bw.wproj, bw.bproj)
         del att
         y2 = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)

@@ -87,6 +87,14 @@ def _rev_bias(ops, q_heads, rel, pad_to):
                        ).permute(1, 0, 2).contiguous()
 
 
+def _rel_operand(rel_h, rel_w, pad):
+    """bf16 [2 * pad, 64]: reversed rel_pos_h rows (zero padded to `pad`) then reversed rel_pos_w rows."""
+    w = torch.zeros(2 * pad, 64, device=rel_h.device, dtype=torch.bfloat16)
+    w[: rel_h.shape[0]] = torch.flip(rel_h, dims=[0]).to(torch.bfloat16)
+    w[pad: pad + rel_w.shape[0]] = torch.flip(rel_w, dims=[0]).to(torch.bfloat16)
+    return w
+
+
 def _ref_attention(qkv, n_seq, L, heads, scale, rel_h=None, rel_w=None, g=0):
     q, k, v = qkv.float().view(n_seq, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
     att = (q * scale) @ k.transpose(-1, -2)
@@ -119,11 +127,16 @@ def test_fused_attention_matches_torch(mode, n_seq, L, gsz, qscale):
     if gsz:
         rel_h = torch.randn(2 * gsz - 1, 64, device="cuda", generator=g) * 0.1
         rel_w = torch.randn(2 * gsz - 1, 64, device="cuda", generator=g) * 0.1
-        qh = qkv[:, : heads * 64].reshape(n_seq * L, heads, 64).permute(1, 0, 2).contiguous()
-        pad = 128 if gsz == 64 else 32
-        bh, bw = _rev_bias(ops, qh, rel_h, pad), _rev_bias(ops, qh, rel_w, pad)
     out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
-    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+    if gsz == 14:
+        # windows: the table products are formed inside the kernel from the reversed rel-pos operand
+        ops.attention_window(qkv, qkv, n_seq, heads, 0.125, out, 0, heads * 64, 2 * heads * 64,
+                             _rel_operand(rel_h, rel_w, 32), 32)
+    else:
+        if gsz:
+            qh = qkv[:, : heads * 64].reshape(n_seq * L, heads, 64).permute(1, 0, 2).contiguous()
+            bh, bw = _rev_bias(ops, qh, rel_h, 128), _rev_bias(ops, qh, rel_w, 128)
+        ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
     ref = _ref_attention(qkv, n_seq, L, heads, 0.125, rel_h, rel_w, gsz)
     # P and the output are rounded to bf16 (2^-9 each, P errors average over the keys): 1e-2 relative + 1e-2 absolute
     # of outputs that are O(0.1-1) — the bound the torch sdpa bf16 kernels meet on the same inputs
@@ -137,13 +150,12 @@ def test_window_attention_unpartition_drops_padding():
     g = _gen(3)
     qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda", generator=g).to(torch.bfloat16)
     rel = torch.randn(27, 64, device="cuda", generator=g) * 0.1
-    qh = qkv[:, : heads * 64].reshape(n_seq * L, heads, 64).permute(1, 0, 2).contiguous()
-    b = _rev_bias(ops, qh, rel, 32)
+    op = _rel_operand(rel, rel, 32)
     flat = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
-    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, flat, 0, heads * 64, 2 * heads * 64, b, b, grid_hw=14)
+    ops.attention_window(qkv, qkv, n_seq, heads, 0.125, flat, 0, heads * 64, 2 * heads * 64, op, 32)
     out = torch.zeros(n_img * hw * hw, heads * 64, device="cuda", dtype=torch.bfloat16)
-    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, b, b, grid_hw=14, out_mode=1,
-                  nwin=nwin, img_hw=hw)
+    ops.attention_window(qkv, qkv, n_seq, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, op, 32, out_mode=1,
+                         nwin=nwin, img_hw=hw)
     r = flat.view(n_img, nwin, nwin, 14, 14, -1).permute(0, 1, 3, 2, 4, 5).reshape(n_img, 70, 70, -1)[:, :hw, :hw]
     assert torch.equal(out, r.reshape(n_img * hw * hw, -1))      # same arithmetic, only the row mapping differs
 

@@ -44,6 +44,13 @@ def rev_table_bias(q_heads, rel, pad_to):
     return torch.stack(outs).permute(1, 0, 2).contiguous()  # [rows, heads, pad]
 
 
+def rel_operand(rel_h, rel_w, pad):
+    w = torch.zeros(2 * pad, 64, device=rel_h.device, dtype=torch.bfloat16)
+    w[: rel_h.shape[0]] = torch.flip(rel_h, dims=[0]).to(torch.bfloat16)
+    w[pad: pad + rel_w.shape[0]] = torch.flip(rel_w, dims=[0]).to(torch.bfloat16)
+    return w
+
+
 def ref_attention(qkv, n_seq, L, heads, scale, rel_h=None, rel_w=None, g=0):
     q, k, v = qkv.float().view(n_seq, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
     att = (q * scale) @ k.transpose(-1, -2)
@@ -91,18 +98,16 @@ def test_window(n_img=2, heads=12):
     qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda", generator=g).to(torch.bfloat16)
     rel_h = torch.randn(27, 64, device="cuda", generator=g) * 0.1
     rel_w = torch.randn(27, 64, device="cuda", generator=g) * 0.1
-    qh = qkv[:, : heads * 64].reshape(n_seq * L, heads, 64).permute(1, 0, 2).contiguous()
-    bh = rev_table_bias(qh, rel_h, 64)
-    bw = rev_table_bias(qh, rel_w, 64)
+    op = rel_operand(rel_h, rel_w, 32)
     ok = True
     out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
-    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=14)
+    ops.attention_window(qkv, qkv, n_seq, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, op, 32)
     torch.cuda.synchronize()
     ref = ref_attention(qkv, n_seq, L, heads, 0.125, rel_h, rel_w, gsz)
     ok &= report("attention window14 (identity rows)", out, ref, 2e-2)
     out2 = torch.zeros(n_img * hw * hw, heads * 64, device="cuda", dtype=torch.bfloat16)
-    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out2, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=14, out_mode=1,
-                  nwin=nwin, img_hw=hw)
+    ops.attention_window(qkv, qkv, n_seq, heads, 0.125, out2, 0, heads * 64, 2 * heads * 64, op, 32, out_mode=1,
+                         nwin=nwin, img_hw=hw)
     torch.cuda.synchronize()
     r = ref.view(n_img, nwin, nwin, 14, 14, -1).permute(0, 1, 3, 2, 4, 5).reshape(n_img, 70, 70, -1)[:, :hw, :hw]
     ok &= report("attention window14 (unpartition)", out2, r.reshape(n_img * hw * hw, -1), 2e-2)
@@ -175,11 +180,14 @@ def bench_attention():
         qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda").to(torch.bfloat16)
         out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
         bh = bw = None
-        if gsz:
-            pad = 128 if gsz == 64 else 64
-            bh = torch.randn(n_seq * L, heads, pad, device="cuda") * 0.1
-            bw = torch.randn(n_seq * L, heads, pad, device="cuda") * 0.1
-        f = lambda: ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+        if gsz == 64:
+            bh = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
+            bw = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
+        if gsz == 14:
+            op = rel_operand(torch.randn(27, 64, device="cuda") * 0.1, torch.randn(27, 64, device="cuda") * 0.1, 32)
+            f = lambda: ops.attention_window(qkv, qkv, n_seq, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, op, 32)
+        else:
+            f = lambda: ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
         for _ in range(3):
             f()
         torch.cuda.synchronize()

@@ -13,12 +13,18 @@ heads = 12
 n_seq, L, gsz = {"global": (8, 4096, 64), "window": (200, 196, 14), "plain": (32, 901, 0)}[mode]
 qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda").to(torch.bfloat16)
 out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
-bh = bw = None
-if gsz:
-    pad = 128 if gsz == 64 else 64
-    bh = torch.randn(n_seq * L, heads, pad, device="cuda") * 0.1
-    bw = torch.randn(n_seq * L, heads, pad, device="cuda") * 0.1
+bh = bw = op = None
+if gsz == 64:
+    bh = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
+    bw = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
+if gsz == 14:
+    op = torch.zeros(64, 64, device="cuda", dtype=torch.bfloat16)
+    op[:27] = (torch.randn(27, 64, device="cuda") * 0.1).to(torch.bfloat16)
+    op[32:59] = (torch.randn(27, 64, device="cuda") * 0.1).to(torch.bfloat16)
 for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
-    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+    if gsz == 14:
+        ops.attention_window(qkv, qkv, n_seq, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, op, 32)
+    else:
+        ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
 torch.cuda.synchronize()
 print("done", mode)

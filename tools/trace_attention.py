@@ -10,27 +10,42 @@ from labelanything_b200 import _native, ops
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "global"
 heads = 12
-n_seq, L, gsz = {"global": (8, 4096, 64), "plain": (8, 4096, 0)}[mode]
+n_seq, L, gsz = {"global": (8, 4096, 64), "plain": (8, 4096, 0), "window": (200, 196, 14)}[mode]
 qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda").to(torch.bfloat16)
 out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
 bh = bw = None
-if gsz:
+if gsz == 64:
     bh = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
     bw = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
 tr = torch.zeros(5, 192, 4, dtype=torch.int64, device="cuda")
+op = torch.zeros(64, 64, device="cuda", dtype=torch.bfloat16)
+op[:27] = (torch.randn(27, 64, device="cuda") * 0.1).to(torch.bfloat16)
+op[32:59] = (torch.randn(27, 64, device="cuda") * 0.1).to(torch.bfloat16)
+
+
+def run():
+    if gsz == 14:
+        ops.attention_window(qkv, qkv, n_seq, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, op, 32)
+    else:
+        ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+
+
 for _ in range(2):
-    ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+    run()
 _native.lib().la_attention_set_trace(tr.data_ptr())
-ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
+run()
 torch.cuda.synchronize()
 _native.lib().la_attention_set_trace(None)
 t = tr.cpu()
 t0 = int(t[t > 0].min())
 t = (t - t0).clamp(min=-1)
 print("tile | MMA: P_A seen, PV_A issued, P_B seen, PV_B issued | softA: waitS, gotS, max done, P arrived | softB: same")
-for j in list(range(0, 4)) + list(range(58, 72)) + list(range(124, 134)):
+for j in (list(range(0, 4)) + list(range(58, 72)) + list(range(124, 134))) if mode != "window" else list(range(0, 24)):
     print(j, t[0, j].tolist(), t[1, j].tolist(), t[2, j].tolist(), t[3, j].tolist(), t[4, j].tolist())
 d = t[1, 8:60]
+print("item boundaries (softmax A): O ready, epilogue done, T ready, prologue done")
+for i in range(0, 8):
+    print(i, t[3, i].tolist(), " B:", t[4, i].tolist())
 print("softmax A steady state: mean wait-for-S", float((d[:, 1] - d[:, 0]).float().mean()), "pass1", float((d[:, 2] - d[:, 1]).float().mean()),
       "pass2+store", float((d[:, 3] - d[:, 2]).float().mean()), "period", float((d[1:, 3] - d[:-1, 3]).float().mean()))
 d = t[2, 8:60]
