@@ -14,6 +14,7 @@
 // All are pure streaming kernels: 16-byte vectorised, coalesced along the channel dimension, grid sized in
 // multiples of the SM count; the roofline that bounds them is HBM bandwidth.
 #include "la_common.cuh"
+#include <cstdlib>
 
 namespace la {
 
@@ -263,6 +264,156 @@ add_layernorm_kernel(const AddLnParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Staged variant for the ViT block LayerNorms (the hot case: x += delta; y = LN(x) as bf16; identity or
+// window-partition row mapping).  Same arithmetic as add_layernorm_kernel, different data movement: every warp
+// owns a 3-deep ring of row buffers in shared memory that is filled by bulk async copies (cp.async.bulk, completion
+// on an mbarrier), so each warp keeps three rows of reads in flight while it reduces / normalises / stores the
+// current one -- with one-row-at-a-time register loads the kernel sat at ~4 TB/s because the reads of a warp stop
+// during its compute-and-store phase.  2 CTAs x 8 warps x 3 rows x 4.5 KB = 216 KB of reads in flight per SM.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LN_STAGES = 3;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NVT>
+__global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddLnParams p) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nv = p.d >> 7;
+  const int tail = (p.d & 127) >> 2;
+  const uint32_t xbytes = static_cast<uint32_t>(p.d) * 4;
+  const uint32_t dbytes = p.delta ? static_cast<uint32_t>(p.d) * 2 : 0;
+  const uint32_t slot_bytes = (xbytes + dbytes + 127) & ~127u;
+  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * LN_STAGES * slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(8) * LN_STAGES * slot_bytes) + warp * LN_STAGES;
+  if (lane == 0) {
+    for (int s = 0; s < LN_STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+
+  const long long n_warps = static_cast<long long>(gridDim.x) * 8;
+  const long long first = static_cast<long long>(blockIdx.x) * 8 + warp;
+
+  // row mapping (map_mode 0: identity; 1: window partition with zero padding, image_encoder.py:258-279)
+  auto map_row = [&](long long row, long long& src, bool& pad) {
+    src = row;
+    pad = false;
+    if (p.map_mode == 1) {
+      const int w2 = p.win * p.win;
+      const long long widx = row / w2;
+      const int tin = static_cast<int>(row - widx * w2);
+      const int per_img = p.nwin * p.nwin;
+      const long long img = widx / per_img;
+      const int wi = static_cast<int>(widx - img * per_img);
+      const int wy = wi / p.nwin, ty = tin / p.win;
+      const int y = wy * p.win + ty;
+      const int x = (wi - wy * p.nwin) * p.win + (tin - ty * p.win);
+      pad = (y >= p.hw) || (x >= p.hw);
+      src = (img * p.hw + y) * p.hw + x;
+    }
+  };
+  auto issue = [&](long long row, int slot) {   // lane 0
+    long long src;
+    bool pad;
+    map_row(row, src, pad);
+    if (pad) return;
+    uint8_t* dst = ring + static_cast<size_t>(slot) * slot_bytes;
+    mbar_arrive_expect_tx(&bars[slot], xbytes + dbytes);
+    bulk_load(dst, p.x_in + src * p.d, xbytes, &bars[slot]);
+    if (dbytes) bulk_load(dst + xbytes, p.delta + src * p.d, dbytes, &bars[slot]);
+  };
+
+  if (lane == 0) {
+    for (int s = 0; s < LN_STAGES; ++s) {
+      const long long row = first + s * n_warps;
+      if (row < p.rows) issue(row, s);
+    }
+  }
+  uint32_t phases = 0;   // bit s: parity of the next completion of slot s
+  const float inv_d = 1.0f / static_cast<float>(p.d);
+  int slot = 0;
+  for (long long row = first; row < p.rows; row += n_warps) {
+    long long src;
+    bool pad;
+    map_row(row, src, pad);
+    uint8_t* yrow = static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(row) * p.d * 2;
+    if (pad) {
+      for (int i = lane; i < p.d / 8; i += 32) reinterpret_cast<uint4*>(yrow)[i] = make_uint4(0, 0, 0, 0);
+    } else {
+      const uint8_t* buf = ring + static_cast<size_t>(slot) * slot_bytes;
+      mbar_wait(&bars[slot], (phases >> slot) & 1);
+      phases ^= 1u << slot;
+      const float4* xs = reinterpret_cast<const float4*>(buf);
+      const uint2* ds = reinterpret_cast<const uint2*>(buf + xbytes);
+      float4 v[NVT];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < NVT; ++i) {
+        const bool on = (i < nv) || (i == nv && lane < tail);
+        float4 a = make_float4(0, 0, 0, 0);
+        if (on) {
+          const int idx = i * 32 + lane;
+          a = xs[idx];
+          if (dbytes) {
+            const uint2 dv = ds[idx];
+            const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
+            const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
+            a.x += __low2float(d01);
+            a.y += __high2float(d01);
+            a.z += __low2float(d23);
+            a.w += __high2float(d23);
+          }
+          if (p.x_out) reinterpret_cast<float4*>(p.x_out + src * p.d)[idx] = a;
+        }
+        v[i] = a;
+        sum += a.x + a.y + a.z + a.w;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * inv_d;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NVT; ++i) {
+        const bool on = (i < nv) || (i == nv && lane < tail);
+        if (on) {
+          const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+          sq += dx * dx + dy * dy + dz * dz + dw * dw;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * inv_d + p.eps);
+#pragma unroll
+      for (int i = 0; i < NVT; ++i) {
+        const bool on = (i < nv) || (i == nv && lane < tail);
+        if (on) {
+          const int idx = i * 32 + lane;
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + idx);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta) + idx);
+          uint2 pk;
+          pk.x = pack_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+          pk.y = pack_bf16((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+          reinterpret_cast<uint2*>(yrow)[idx] = pk;
+        }
+      }
+    }
+    // every lane has read its part of the slot: refill it with the row LN_STAGES ahead.  Rows that are pure padding
+    // neither load nor wait, but they still advance the slot so that issue order == consume order.
+    __syncwarp();
+    const long long nxt = row + LN_STAGES * n_warps;
+    if (lane == 0 && nxt < p.rows) issue(nxt, slot);
+    slot = slot + 1 == LN_STAGES ? 0 : slot + 1;
+  }
+}
+
 // out[s, :] = scale * sum_p partial[s, p, :]
 __global__ void __launch_bounds__(256)
 pool_finish_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n_seq, int slices, int d,
@@ -416,9 +567,30 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   p.win = win;
   p.nwin = nwin;
   p.hw = hw;
-  const int grid = grid_for(rows * 32, 256, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int need = (d + 127) / 128;
+  // the ViT block case goes through the staged kernel (bulk async row copies, 3 rows in flight per warp)
+  const bool staged = x_in && x_mod == 0 && !delta2 && !seq_add && !y2_out && !ype_out && act == LA_ACT_NONE && gamma &&
+                      y_out && y_dtype != LA_DTYPE_F32 && (map_mode == 0 || map_mode == 1) && need <= 8 &&
+                      rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr;
+  if (staged) {
+    const uint32_t slot_bytes = (static_cast<uint32_t>(d) * (delta ? 6 : 4) + 127) & ~127u;
+    const int smem = 8 * LN_STAGES * static_cast<int>(slot_bytes) + 8 * LN_STAGES * 8;
+    if (smem <= 112 * 1024) {
+      const int sgrid = grid_for(rows * 32, 256, 2);
+      auto launch = [&](auto kern) -> int {
+        LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<sgrid, 256, smem, st>>>(p);
+        LA_CHECK_CUDA(cudaGetLastError());
+        return LA_OK;
+      };
+      if (need <= 2) return launch(add_layernorm_staged_kernel<2>);
+      if (need <= 4) return launch(add_layernorm_staged_kernel<4>);
+      if (need <= 6) return launch(add_layernorm_staged_kernel<6>);
+      return launch(add_layernorm_staged_kernel<8>);
+    }
+  }
+  const int grid = grid_for(rows * 32, 256, need <= 4 ? 4 : (need <= 8 ? 3 : 2));
   if (need <= 1) add_layernorm_kernel<1, false><<<grid, 256, 0, st>>>(p);
   else if (need <= 2) add_layernorm_kernel<2, false><<<grid, 256, 0, st>>>(p);
   else if (need <= 4) add_layernorm_kernel<4, false><<<grid, 256, 0, st>>>(p);

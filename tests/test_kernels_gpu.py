@@ -176,6 +176,14 @@ def test_add_layernorm_modes():
     assert torch.equal(x1, xr)                                    # fp32 add: exact
     _close(y2, ln, 1e-5, 1e-5, "LN fp32")
     _close(y, ln, 2 ** -8, 1e-3, "LN bf16")
+    # the ViT block case (in-place residual update + bf16 LN output) runs through the staged bulk-copy kernel
+    x2, ys = x.clone(), torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    ops.add_layernorm(x2, delta, gamma, beta, 1e-6, rows=rows, d=d, x_out=x2, y_out=ys)
+    assert torch.equal(x2, xr)
+    _close(ys, ln, 2 ** -8, 1e-3, "LN staged bf16")
+    x3 = x.clone()
+    ops.add_layernorm(x3, None, gamma, beta, 1e-6, rows=rows, d=d, y_out=ys)      # no branch output to add
+    _close(ys, F.layer_norm(x, (d,), gamma, beta, 1e-6), 2 ** -8, 1e-3, "LN staged, x only")
     # window partition with zero padding (F.pad after norm1)
     nwin, win = 5, 14
     orow = I * nwin * nwin * win * win
