@@ -378,6 +378,50 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(h, copysignf(e, x), h);
 }
 
+// Two exact-erf GELUs at once on the sm_100 packed fp32x2 forms (FFMA2 / FMUL2): the same A&S 7.1.28 evaluation as
+// gelu_erf with half the issue slots -- the GELU epilogue of the MLP GEMM is instruction-issue bound
+// (128 x 256 outputs per tile against 6144 tensor cycles at K = 768).
+//   gelu(x) = h + |h| * erf(|x| / sqrt 2),  h = x / 2
+__device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
+  const float z0 = fabsf(x0) * 0.70710678118654752f, z1 = fabsf(x1) * 0.70710678118654752f;
+  float r0, r1;
+  asm("{\n\t"
+      ".reg .b64 z, p, c, one;\n\t"
+      ".reg .f32 q0, q1;\n\t"
+      "mov.b64 z, {%2, %3};\n\t"
+      "mov.b64 c, {%4, %4};\n\t"
+      "mov.b64 p, {%5, %5};\n\t"
+      "fma.rn.f32x2 p, c, z, p;\n\t"      // a6 z + a5
+      "mov.b64 c, {%6, %6};\n\t"
+      "fma.rn.f32x2 p, p, z, c;\n\t"      // .. + a4
+      "mov.b64 c, {%7, %7};\n\t"
+      "fma.rn.f32x2 p, p, z, c;\n\t"      // .. + a3
+      "mov.b64 c, {%8, %8};\n\t"
+      "fma.rn.f32x2 p, p, z, c;\n\t"      // .. + a2
+      "mov.b64 c, {%9, %9};\n\t"
+      "fma.rn.f32x2 p, p, z, c;\n\t"      // .. + a1
+      "mov.b64 one, {%10, %10};\n\t"
+      "fma.rn.f32x2 p, p, z, one;\n\t"    // .. + 1
+      "mul.rn.f32x2 p, p, p;\n\t"
+      "mul.rn.f32x2 p, p, p;\n\t"
+      "mul.rn.f32x2 p, p, p;\n\t"
+      "mul.rn.f32x2 p, p, p;\n\t"         // (..)^16 ; +inf for huge |x| -> rcp 0 -> erf 1
+      "mov.b64 {q0, q1}, p;\n\t"
+      "rcp.approx.ftz.f32 q0, q0;\n\t"
+      "rcp.approx.ftz.f32 q1, q1;\n\t"
+      "mov.b64 p, {q0, q1};\n\t"
+      "mov.b64 c, {%11, %11};\n\t"
+      "fma.rn.f32x2 p, p, c, one;\n\t"    // erf = 1 - 1/(..)^16
+      "mov.b64 {%0, %1}, p;\n\t"
+      "}"
+      : "=f"(r0), "=f"(r1)
+      : "f"(z0), "f"(z1), "f"(0.0000430638f), "f"(0.0002765672f), "f"(0.0001520143f), "f"(0.0092705272f),
+        "f"(0.0422820123f), "f"(0.0705230784f), "f"(1.0f), "f"(-1.0f));
+  const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+  x0 = fmaf(fabsf(h0), r0, h0);
+  x1 = fmaf(fabsf(h1), r1, h1);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace la

@@ -207,7 +207,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         }
         if (act == LA_ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < CHUNK; ++i) v[i] = gelu_erf(v[i]);
+          for (int i = 0; i < CHUNK; i += 2) gelu_erf_x2(v[i], v[i + 1]);
         } else if (act == LA_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.0f);
