@@ -39,6 +39,12 @@ SAM512 = dict(image_embed_dim=768, embed_dim=EMBED_DIM, image_size=IMAGE_SIZE, u
 EPISODE_GFLOP = 26 * (965.64 + 22.55) + 150 * 10.855 + 28.7
 
 
+# DRAM traffic per launch (MB) of the kernels that can dominate the step, from the committed `ncu --set full` captures
+# (profiles/r01_ncu_{attention,gemm,layernorm}_v2.txt) taken at the bench's launch size (one 32-image encoder chunk)
+NCU_TRAFFIC_MB = {"attention.L4096": 2019.5, "attention.L196": 904.6, "gemm.n3072.k768": 207.9, "gemm.n768.k3072": 812.0,
+                  "add_layernorm.d768.map0": 1150.8}
+
+
 def _peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -306,15 +312,22 @@ def run_native(args) -> None:
     if rank == 0:
         peaks = _peaks()
         kernel_ms = sum(f["ms"] for f in fam.values())
-        top = max(fam, key=lambda k: fam[k]["ms"])
-        f = fam[top]
-        tensor_bound = f["flops"] > 0 and top in ("gemm", "attention")
+        # dominant kernel = the launch shape with the largest share of the step (e.g. attention.L4096: the 64x64
+        # global-attention instantiation of la_attention_bf16 on one 32-image chunk)
+        top = max(detail, key=lambda k: detail[k]["ms"])
+        f = detail[top]
+        tensor_bound = f["flops"] > 0 and top.split(".")[0] in ("gemm", "attention")
         if tensor_bound:
             achieved, peak, unit = f["flops"] / f["ms"] / 1e9, peaks["bf16_tflops_sustained"], "TFLOP/s"
         else:
             achieved, peak, unit = f["bytes"] / f["ms"] / 1e6, peaks["hbm_gbs"], "GB/s"
+        traffic = NCU_TRAFFIC_MB.get(top) if B == 8 else None
         roofline = {"kernel": top, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
-                    "unit": unit, "frac": achieved / peak, "traffic": None, "peak_source": peaks["_source"],
+                    "unit": unit, "frac": achieved / peak,
+                    "traffic": None if traffic is None else traffic * 1e6, "traffic_unit": "bytes per launch",
+                    "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_*_v2.txt",
+                    "algorithmic_per_launch": {"flops": f["flops"] / f["launches"], "bytes": f["bytes"] / f["launches"]},
+                    "peak_source": peaks["_source"],
                     "avg_launch_ms": f["ms"] / f["launches"], "share_of_kernel_time": f["ms"] / kernel_ms,
                     "whole_step": {"achieved": EPISODE_GFLOP * episodes / ms, "unit": "TFLOP/s",
                                    "frac": EPISODE_GFLOP * episodes / ms / peaks["bf16_tflops_sustained"]},
