@@ -36,6 +36,13 @@ namespace la {
 
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_D = 64;
+// every ATT_POLY_EXP-th pair of scores of the 64-key modes takes the polynomial exp2 (0 = never)
+#ifndef ATT_POLY_EXP
+#define ATT_POLY_EXP 4
+#endif
+#ifndef ATT_TS_OPERANDS
+#define ATT_TS_OPERANDS 1
+#endif
 constexpr int ATT_STG_STRIDE = 272;     // bytes per row of the table staging area (68 floats: conflict-free STS.128)
 // setmaxnreg budget: 256 softmax threads + 128 control threads share 384 x 168 = 64512 registers (launch allocation).
 // 64-key tiles keep 64 score registers per thread and leave the control warps 104; the 112-key window tiles need
@@ -131,6 +138,39 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
       : "=f"(d0), "=f"(d1)
       : "f"(a0), "f"(a1), "f"(b), "f"(c));
 }
+// 2^a for two arguments on the FMA pipe instead of the MUFU: a = n + f, n = round(a), |f| <= 1/2 (magic-number rounding),
+// 2^f by a degree-3 minimax polynomial (relative error 7.5e-5 -- far below the bf16 rounding of P), 2^n by adding
+// n to the exponent field.  MUFU.EX2 issues at a quarter of the FMA rate, and the exponentials are what bounds the
+// softmax warps at head_dim 64, so a fraction of every score row takes this path (the FlashAttention-4 trick).
+// Arguments are clamped at -126 (result ~1e-38 instead of 0 for masked keys); the caller guarantees a <= 8.
+__device__ __forceinline__ void exp2_poly_x2(float& a0, float& a1) {
+  const float x0 = fmaxf(a0, -126.0f), x1 = fmaxf(a1, -126.0f);
+  uint32_t t0, t1, p0, p1;
+  asm("{\n\t"
+      ".reg .b64 x, t, r, f, p, c;\n\t"
+      "mov.b64 x, {%4, %5};\n\t"
+      "mov.b64 c, {%6, %6};\n\t"
+      "add.rn.f32x2 t, x, c;\n\t"          // t = x + 1.5 * 2^23: round(x) in the low mantissa bits
+      "mov.b64 c, {%7, %7};\n\t"
+      "add.rn.f32x2 r, t, c;\n\t"          // r = round(x)
+      "mov.b64 c, {%8, %8};\n\t"
+      "fma.rn.f32x2 f, r, c, x;\n\t"       // f = x - r
+      "mov.b64 p, {%9, %9};\n\t"
+      "mov.b64 c, {%10, %10};\n\t"
+      "fma.rn.f32x2 p, p, f, c;\n\t"
+      "mov.b64 c, {%11, %11};\n\t"
+      "fma.rn.f32x2 p, p, f, c;\n\t"
+      "mov.b64 c, {%12, %12};\n\t"
+      "fma.rn.f32x2 p, p, f, c;\n\t"
+      "mov.b64 {%0, %1}, t;\n\t"
+      "mov.b64 {%2, %3}, p;\n\t"
+      "}"
+      : "=r"(t0), "=r"(t1), "=r"(p0), "=r"(p1)
+      : "f"(x0), "f"(x1), "f"(12582912.0f), "f"(-12582912.0f), "f"(-1.0f), "f"(0.0551716685f), "f"(0.2426111251f),
+        "f"(0.6932609677f), "f"(0.9999280572f));
+  a0 = __uint_as_float(p0 + (t0 << 23));
+  a1 = __uint_as_float(p1 + (t1 << 23));
+}
 // (d0, d1) += (a0, a1)
 __device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float a1) {
   asm("{\n\t"
@@ -157,6 +197,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   // Tiles of <= 64 keys double-buffer the score tile in TMEM: S(j+1) is issued BEFORE the MMA warp waits for P(j), so
   // the softmax warps never wait for the tensor pipe once the pipeline is full.
   constexpr bool DB = KV_TILE <= 64;
+  constexpr bool TSQ = KV_TILE == 64 && ATT_TS_OPERANDS;
+  // Score buffers per Q tile in TMEM.  With three (no TMEM-resident A operands) a score tile is issued THREE tiles
+  // ahead of its consumer, which takes the P -> PV -> next-S issue latency of the shared tensor pipe (~1200 cycles with
+  // both chains queued) off the softmax warps' critical path; two buffers leave room for Q / A_w in tensor memory.
+  constexpr uint32_t NBUF = DB ? (TSQ ? 2 : 3) : 1;
   // 64x64 rel-pos mode: rel_w enters the scores through an extra MMA (see the header comment)
   constexpr bool FOLD_W = BIAS == ATT_BIAS_GLOBAL64;
 
@@ -170,15 +215,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* full_v = empty_k + ST;
   uint64_t* empty_v = full_v + ST;
   uint64_t* bar_s = empty_v + ST;                  // [Q tile][score buffer]: S ready
-  uint64_t* bar_p = bar_s + 4;                     // [Q tile][score buffer]: P written (one arrival per warp).  Per
+  uint64_t* bar_p = bar_s + 6;                     // [Q tile][score buffer]: P written (one arrival per warp).  Per
                                                    // buffer, because with double buffering a fast warp may finish
                                                    // tile j+1 before a slow one has delivered its rows of tile j.
-  uint64_t* bar_pv = bar_p + 4;                    // [Q tile][score buffer]: O += P V of a tile completed.  Per buffer
+  uint64_t* bar_pv = bar_p + 6;                    // [Q tile][score buffer]: O += P V of a tile completed.  Per buffer
                                                    // as well: with double buffering a softmax warp may run one tile
                                                    // ahead of its siblings (S(g+1) is issued before P(g) is awaited), so
                                                    // with ONE barrier flipping every tile a wait for PV(g) could be
                                                    // satisfied by the parity of PV(g-2) while PV(g-1) is still pending.
-  uint64_t* o_empty = bar_pv + 4;                  // [Q tile]: the epilogue has read O (one arrival per warp)
+  uint64_t* o_empty = bar_pv + 6;                  // [Q tile]: the epilogue has read O (one arrival per warp)
   uint64_t* aw_full = o_empty + 2;                 // [item parity][Q tile]: rel_w A operand written (64x64 rel-pos mode)
   uint64_t* rel_full = aw_full + 4;                // window mode: rel-pos operand loaded (once)
   uint64_t* bar_t = rel_full + 1;                  // [Q tile] window mode: table product T of the item ready in TMEM
@@ -208,12 +253,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_init(&empty_v[s], 2);   // the PV MMAs of both Q tiles
     }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&bar_s[2 * x], 1);
-      mbar_init(&bar_s[2 * x + 1], 1);
-      mbar_init(&bar_p[2 * x], 4);
-      mbar_init(&bar_p[2 * x + 1], 4);
-      mbar_init(&bar_pv[2 * x], 1);
-      mbar_init(&bar_pv[2 * x + 1], 1);
+      for (int b = 0; b < 3; ++b) {
+        mbar_init(&bar_s[3 * x + b], 1);
+        mbar_init(&bar_p[3 * x + b], 4);
+        mbar_init(&bar_pv[3 * x + b], 1);
+      }
       mbar_init(&o_empty[x], 4);
       mbar_init(&aw_full[x], 1);
       mbar_init(&aw_full[2 + x], 1);
@@ -245,8 +289,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384); with double buffering each S region holds
   // two KV_TILE-wide score buffers.  P (bf16) overlays the first KV_TILE/2 columns of the score buffer it came from.
-  // Window mode: table products T_A [384,448) T_B [448,512).
-  const uint32_t TM_S = 0, TM_O = 256, TM_T = 384;
+  // Window mode: table products T_A [384,448) T_B [448,512).  64-key modes: the A operands of the score MMAs live in
+  // tensor memory too (copied from shared memory once per item with tcgen05.cp): Q_A [384,416) A_w_A [416,448)
+  // Q_B [448,480) A_w_B [480,512) -- an M128 x N64 x K16 MMA costs 32 cycles with A in TMEM against 48 with both
+  // operands in shared memory (profiles/r01_micro_tcgen05.txt), and the tensor pipe is what bounds the 64x64 mode.
+  // With three score buffers per Q tile (no TMEM-resident operands): S_A [0,192) S_B [192,384) O_A [384,448) O_B [448,512).
+  const uint32_t TM_S = 0, TM_O = NBUF == 3 ? 384 : 256, TM_T = 384;
+  constexpr uint32_t S_SPAN = NBUF == 3 ? 192 : 128;   // TMEM columns between the score regions of the two Q tiles
 
   if (warp < 4) {
     // ===================================== control warpgroup =====================================
@@ -299,7 +348,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (P in TMEM, V MN-major)
       // S += A_w I/scale: fp16 operands (A/B format fields 0) -- 11 significant bits for the bias instead of 8
       constexpr uint32_t idesc_w = umma_idesc_bf16(128, KV_TILE, 0, 0) & ~((7u << 7) | (7u << 10));
-      constexpr uint32_t LA = DB ? 2 : 1;
+      constexpr uint32_t LA = NBUF;
       const int x = warp == 1 ? 0 : 1;
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -309,7 +358,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const uint32_t lo_aw = desc_lo(smem_base + S::OFF_AW + x * 16384);     // + qb * (32768 >> 4) + 2 * ks
       const uint32_t lo_id = desc_lo(smem_base + S::OFF_ID);                 // + 2 * ks
       const uint32_t lo_rel = desc_lo(smem_base + S::OFF_REL);               // + 2 * ks
-      const uint32_t tm_s = tm + TM_S + x * 128;                             // + buf * KV_TILE
+      const uint32_t tm_s = tm + TM_S + x * S_SPAN;                          // + buf * KV_TILE
       const uint32_t tm_o = tm + TM_O + x * 64;
       const uint32_t n_my = (static_cast<uint32_t>(n_items) > blockIdx.x)
                                 ? (static_cast<uint32_t>(n_items) - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -324,7 +373,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       auto mma_s = [&](const Cursor& c) {
         const uint32_t qb = c.it & 1;
         const uint32_t slot = c.g % ST;
-        const uint32_t buf = DB ? (c.g & 1) : 0;
+        const uint32_t buf = c.g % NBUF;
         const uint32_t d = tm_s + buf * KV_TILE;
         const uint32_t aq = lo_q + qb * (S::Q_BYTES >> 4);
         const uint32_t bk = lo_k + slot * (S::KV_SLOT >> 4);
@@ -340,17 +389,42 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             umma_commit(&bar_t[x]);
           }
         }
-#pragma unroll
-        for (int ks = 0; ks < ATT_D / 16; ++ks) umma_ss_lo(d, aq + 2 * ks, bk + 2 * ks, idesc_s, ks > 0);
-        if constexpr (FOLD_W) {
-          // S += A_w x I / scale : adds rel_w[q, kw] to column kw of every key tile (KV_TILE == 64 == grid width)
+        if constexpr (TSQ) {
           const uint32_t aw = lo_aw + qb * (32768 >> 4);
+          const uint32_t tq = tm + TM_T + x * 64;
+          if (c.j == 0) {
+            // first tile of an item: Q (and A_w) tiles -> tensor memory, one 128-row x 32-byte K slice per copy.
+            // tcgen05.cp and tcgen05.mma execute in issue order, so the copies queue up behind the previous item's
+            // score MMAs that still read the old operands, and the shared-memory tiles are free once they are done.
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_ss_lo(d, aw + 2 * ks, lo_id + 2 * ks, idesc_w, true);
+            for (int ks = 0; ks < 4; ++ks) tmem_cp_128x256b(tq + ks * 8, aq + 2 * ks);
+            if constexpr (FOLD_W) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) tmem_cp_128x256b(tq + 32 + ks * 8, aw + 2 * ks);
+            }
+            umma_commit(&q_empty[qb]);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_ts_lo(d, tq + ks * 8, bk + 2 * ks, idesc_s, ks > 0);
+          if constexpr (FOLD_W) {
+            // S += A_w x I / scale : adds rel_w[q, kw] to column kw of every key tile (KV_TILE == 64 == grid width)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_ts_lo(d, tq + 32 + ks * 8, lo_id + 2 * ks, idesc_w, true);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < ATT_D / 16; ++ks) umma_ss_lo(d, aq + 2 * ks, bk + 2 * ks, idesc_s, ks > 0);
+          if constexpr (FOLD_W) {
+            const uint32_t aw = lo_aw + qb * (32768 >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_ss_lo(d, aw + 2 * ks, lo_id + 2 * ks, idesc_w, true);
+          }
         }
-        umma_commit(&bar_s[2 * x + buf]);
+        umma_commit(&bar_s[3 * x + buf]);
         umma_commit(&empty_k[slot]);
-        if (c.j + 1 == static_cast<uint32_t>(NT)) umma_commit(&q_empty[qb]);
+        if constexpr (!TSQ) {
+          if (c.j + 1 == static_cast<uint32_t>(NT)) umma_commit(&q_empty[qb]);
+        }
       };
       auto wait_s_inputs = [&](const Cursor& c) {
         const int qb = c.it & 1;
@@ -373,13 +447,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         advance(sc);
       }
       while (pc.g < total) {
-        const uint32_t buf = DB ? (pc.g & 1) : 0;
+        const uint32_t buf = pc.g % NBUF;
         const uint32_t vslot = pc.g % ST;
         const bool more = sc.g < total;
         if (more) wait_s_inputs(sc);   // long since there: K is loaded ST tiles ahead
         mbar_wait(&full_v[vslot], (pc.g / ST) & 1);
         if (pc.j == 0 && pc.it > 0) mbar_wait(&o_empty[x], (pc.it - 1) & 1);   // previous item's epilogue has read O
-        mbar_wait(&bar_p[2 * x + buf], DB ? ((pc.g >> 1) & 1) : (pc.g & 1));
+        mbar_wait(&bar_p[3 * x + buf], (pc.g / NBUF) & 1);
         tc_fence_after();
         att_trace(p, tr0, 0, pc.g, 2 * x);
         if (elect_one()) {
@@ -388,7 +462,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
           for (int ks = 0; ks < KV_TILE / 16; ++ks)
             umma_ts_lo(tm_o, a_p + ks * 8, bv + ks * (2048 >> 4), idesc_o, pc.j > 0 || ks > 0);
-          umma_commit(&bar_pv[2 * x + buf]);
+          umma_commit(&bar_pv[3 * x + buf]);
           umma_commit(&empty_v[vslot]);
           if (more) mma_s(sc);
         }
@@ -444,7 +518,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int quarter = warp & 3;      // TMEM lane quarter
     const int r = quarter * 32 + lane;  // row inside the Q tile
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s0 = tmem_base + lane_addr + TM_S + x * 128;
+    const uint32_t t_s0 = tmem_base + lane_addr + TM_S + x * S_SPAN;
     const uint32_t t_o = tmem_base + lane_addr + TM_O + x * 64;
     const float sl2 = p.scale_log2;
     constexpr float LOG2E = 1.4426950408889634f;
@@ -542,10 +616,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           rh2[0] = 0.0f;
         }
 
-        const int buf = DB ? (g & 1) : 0;
+        const uint32_t buf = g % NBUF;
         const uint32_t t_s = t_s0 + buf * KV_TILE;
         att_trace(p, tr, tr_role, g, 0);
-        mbar_wait(&bar_s[2 * x + buf], DB ? ((g >> 1) & 1) : (g & 1));
+        mbar_wait(&bar_s[3 * x + buf], (g / NBUF) & 1);
         tc_fence_after();
         att_trace(p, tr, tr_role, g, 1);
 
@@ -606,7 +680,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
         if (__any_sync(0xffffffffu, need)) {
           // O must hold everything up to the previous tile before it is rescaled
-          mbar_wait(&bar_pv[2 * x + (DB ? ((g - 1) & 1) : 0)], DB ? (((g - 1) >> 1) & 1) : ((g - 1) & 1));
+          mbar_wait(&bar_pv[3 * x + (g - 1) % NBUF], ((g - 1) / NBUF) & 1);
           tc_fence_after();
 #pragma unroll
           for (int hseg = 0; hseg < 2; ++hseg) {
@@ -641,8 +715,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
               } else {
                 ffma2(a0, a1, __uint_as_float(sv[col]), __uint_as_float(sv[col + 1]), sl2, offg[0]);
               }
-              const float e0 = ex2_approx(a0);
-              const float e1 = ex2_approx(a1);
+              float e0, e1;
+              if (!WIN && ATT_POLY_EXP > 0 && ((col >> 1) % ATT_POLY_EXP) == ATT_POLY_EXP - 1) {
+                e0 = a0;
+                e1 = a1;
+                exp2_poly_x2(e0, e1);
+              } else {
+                e0 = ex2_approx(a0);
+                e1 = ex2_approx(a1);
+              }
               if ((i & 2) == 0) fadd2_acc(l0, l1, e0, e1);
               else fadd2_acc(l2, l3, e0, e1);
               pk[i >> 1] = pack_bf16(e0, e1);
@@ -655,7 +736,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_p[2 * x + buf]);
+        if (lane == 0) mbar_arrive(&bar_p[3 * x + buf]);
         att_trace(p, tr, tr_role, g, 3);
       }
 
@@ -669,7 +750,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // ---- epilogue: O / l -> bf16 -> global (with the window-unpartition row mapping) ----
       {
         const uint32_t gl = g0 + NT - 1;   // last tile of the item
-        mbar_wait(&bar_pv[2 * x + (DB ? (gl & 1) : 0)], DB ? ((gl >> 1) & 1) : (gl & 1));
+        mbar_wait(&bar_pv[3 * x + gl % NBUF], (gl / NBUF) & 1);
       }
       tc_fence_after();
       att_trace(p, tr, 3 + x, it, 0);

@@ -224,6 +224,18 @@ __device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uin
       "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate ? 1u : 0u), "r"(0x40004040u)
       : "memory");
 }
+// shared memory -> tensor memory: 128 rows x 32 bytes of the tile described by the (pre-shifted) descriptor low word,
+// written to 8 columns starting at taddr (row r -> lane r); ordered with tcgen05.mma in issue order.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint32_t src_lo) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 ds;\n\t"
+      "mov.b64 ds, {%1, %2};\n\t"
+      "tcgen05.cp.cta_group::1.128x256b [%0], ds;\n\t"
+      "}\n" ::"r"(taddr),
+      "r"(src_lo), "r"(0x40004040u)
+      : "memory");
+}
 // all previously issued tcgen05.mma of this thread -> arrive(1) on the mbarrier when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
