@@ -18,6 +18,7 @@
 // The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
 // the mainloop of tile i+1.
 #include "la_common.cuh"
+#include <cstdlib>
 #include "../../include/labelanything_b200.h"
 
 namespace la {
@@ -27,12 +28,17 @@ constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;
 
-template <int BLOCK_N>
+// CTA2: the CTA-pair variant (cta_group::2): a 256 x BLOCK_N tile per cluster of two CTAs, each CTA holding its 128
+// rows of A and HALF of the W tile, so a stage is 32 KB instead of 48 KB (6 stages instead of 4) and each MMA reads
+// 8 KB instead of 12 KB of operands per CTA.  With one CTA per tile the kernel is shared-memory-bandwidth bound:
+// 96 B/clk of operand reads plus 96 B/clk of TMA fills against 128 B/clk.
+template <int BLOCK_N, bool CTA2 = false>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;
+  static constexpr int B_BYTES = B_ROWS * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int STAGES = CTA2 ? 6 : (BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8));
   static constexpr int EPI_WARP_BYTES = 4096;  // one 32-row x 128-byte staging buffer per epilogue warp
   static constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;
   static constexpr int BAR_BYTES = 256;
@@ -40,12 +46,17 @@ struct GemmSmem {
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
 };
 
-template <int BLOCK_N, typename OutT>
+template <int BLOCK_N, typename OutT, bool CTA2 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                          const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N,
                          int K, int act) {
-  using S = GemmSmem<BLOCK_N>;
+  using S = GemmSmem<BLOCK_N, CTA2>;
+  // CTA pair: rank 0 (leader) issues the MMAs of both; every CTA loads and stores its own 128 rows
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0;
+  constexpr int TILE_M = CTA2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M;
+  const int tile0 = CTA2 ? blockIdx.x >> 1 : blockIdx.x;
+  const int tile_step = CTA2 ? gridDim.x >> 1 : gridDim.x;
   constexpr int CHUNK = 128 / (int)sizeof(OutT);  // output columns per staging row (128 bytes)
   constexpr int NCHUNK = BLOCK_N / CHUNK;
 
@@ -62,9 +73,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const int lane = threadIdx.x & 31;
 
   const int n_blks = (N + BLOCK_N - 1) / BLOCK_N;
-  const int m_blks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int m_blks = (M + TILE_M - 1) / TILE_M;
   const int num_tiles = n_blks * m_blks;
   const int k_blks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int act_code = act;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -78,16 +90,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);
+      mbar_init(&tmem_empty[a], CTA2 ? 16 : 8);   // the epilogue warps of both CTAs release the leader's accumulator
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, S::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc_2cta(tmem_slot, S::TMEM_COLS);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, S::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -96,16 +114,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_blks) * GEMM_BLOCK_M;
-        const int n0 = (tile % n_blks) * BLOCK_N;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / n_blks) * TILE_M + rank * GEMM_BLOCK_M;
+        const int n0 = (tile % n_blks) * BLOCK_N + rank * S::B_ROWS * (CTA2 ? 1 : 0);
         for (int kb = 0; kb < k_blks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * S::STAGE_BYTES;
           uint8_t* b_dst = a_dst + S::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-          tma_load_2d(a_dst, &tm_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
-          tma_load_2d(b_dst, &tm_w, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          if constexpr (CTA2) {
+            // both CTAs' boxes are counted on the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+            tma_load_2d_2cta(a_dst, &tm_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+            tma_load_2d_2cta(b_dst, &tm_w, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            tma_load_2d(a_dst, &tm_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+            tma_load_2d(b_dst, &tm_w, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          }
           if (++stage == S::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -116,14 +141,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
     // The whole warp walks the loop converged so that descriptors / addresses stay in uniform registers; one
-    // elected lane issues the tcgen05 instructions of each k-block.
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+    // elected lane issues the tcgen05 instructions of each k-block.  CTA pair: only the leader issues.
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N);
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -139,10 +164,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
               const uint64_t a_desc = umma_smem_desc_sw128(a_base + k * GEMM_UMMA_K * 2);
               const uint64_t b_desc = umma_smem_desc_sw128(b_base + k * GEMM_UMMA_K * 2);
-              umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if constexpr (CTA2) umma_bf16_ss_2cta(d_tmem, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-            if (kb == k_blks - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            if constexpr (CTA2) {
+              umma_commit_2cta_mc(&empty_bar[stage], 3);                         // frees the slot in both CTAs
+              if (kb == k_blks - 1) umma_commit_2cta_mc(&tmem_full[acc], 3);     // both epilogues
+            } else {
+              umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+              if (kb == k_blks - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           if (++stage == S::STAGES) {
@@ -161,8 +192,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     constexpr int LAST1 = NCHUNK >= 2 ? ((NCHUNK - 2) / 2) * 2 + 1 : -1;  // last chunk of the odd warp (none if 1 chunk)
     const int last_c = half == 0 ? LAST0 : LAST1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / n_blks) * GEMM_BLOCK_M;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+      const int m0 = (tile / n_blks) * TILE_M + rank * GEMM_BLOCK_M;
       const int n0 = (tile % n_blks) * BLOCK_N;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -172,7 +203,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       if (last_c < 0) {   // nothing to read for this warp: release its share of the accumulator at once
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if constexpr (CTA2) mbar_arrive_leader(&tmem_empty[acc]);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
       }
 #pragma unroll 1
       for (int c = half; c < NCHUNK; c += 2) {
@@ -190,7 +224,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           // all TMEM reads of this warp for this accumulator are done -> hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+          if constexpr (CTA2) mbar_arrive_leader(&tmem_empty[acc]);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
         }
         if (bias != nullptr) {
 #pragma unroll
@@ -205,10 +242,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             }
           }
         }
-        if (act == LA_ACT_GELU) {
+        if (act_code == LA_ACT_GELU) {
 #pragma unroll
           for (int i = 0; i < CHUNK; i += 2) gelu_erf_x2(v[i], v[i + 1]);
-        } else if (act == LA_ACT_RELU) {
+        } else if (act_code == LA_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
@@ -246,10 +283,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // neither CTA leaves (or frees tensor memory) while its peer still works
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, S::TMEM_COLS);
+    if constexpr (CTA2) tmem_dealloc_2cta(tmem_base, S::TMEM_COLS);
+    else tmem_dealloc(tmem_base, S::TMEM_COLS);
   }
+}
+
+// CTA-pair launch: clusters of 2 CTAs, 256 x 256 tiles
+template <typename OutT>
+static int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
+                            const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int act) {
+  using S = GemmSmem<256, true>;
+  auto kern = gemm_bf16_tcgen05_kernel<256, OutT, true>;
+  LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  const int tiles = ((N + 255) / 256) * ((M + 255) / 256);
+  const int pairs = sm_count() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_w, tm_out, bias, M, N, K, act));
+  return LA_OK;
 }
 
 template <int BLOCK_N, typename OutT>
@@ -287,17 +351,20 @@ extern "C" int la_gemm_bf16(void* stream, const void* a, long long lda, const vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   const int block_n = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+  // big problems run on CTA pairs (W boxes of 128 rows: each CTA loads half of the 256-wide tile)
+  const bool pair = block_n == 256 && M >= 2048 && getenv("LA_GEMM_1CTA") == nullptr;
   CUtensorMap tm_a, tm_w, tm_out;
   int rc = make_tensor_map_2d(&tm_a, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)M,
                               (uint64_t)lda * 2, GEMM_BLOCK_K, GEMM_BLOCK_M, Swizzle::B128);
   if (rc) return rc;
   rc = make_tensor_map_2d(&tm_w, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2,
-                          GEMM_BLOCK_K, (uint32_t)block_n, Swizzle::B128);
+                          GEMM_BLOCK_K, (uint32_t)(pair ? 128 : block_n), Swizzle::B128);
   if (rc) return rc;
   if (out_dtype == LA_DTYPE_BF16) {
     rc = make_tensor_map_2d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)N, (uint64_t)M,
                             (uint64_t)ldo * 2, 64, 32, Swizzle::B128);
     if (rc) return rc;
+    if (pair) return launch_gemm_2cta<__nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
     if (block_n == 256) return launch_gemm<256, __nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
     if (block_n == 128) return launch_gemm<128, __nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
     return launch_gemm<64, __nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
@@ -305,6 +372,7 @@ extern "C" int la_gemm_bf16(void* stream, const void* a, long long lda, const vo
     rc = make_tensor_map_2d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)N, (uint64_t)M,
                             (uint64_t)ldo * 4, 32, 32, Swizzle::B128);
     if (rc) return rc;
+    if (pair) return launch_gemm_2cta<float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
     if (block_n == 256) return launch_gemm<256, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
     if (block_n == 128) return launch_gemm<128, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
     return launch_gemm<64, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);

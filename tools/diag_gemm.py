@@ -109,8 +109,8 @@ if __name__ == "__main__":
     ok &= run(300, 256, 136, out_dtype=torch.float32)
     P("ALL_OK" if ok else "SOME_FAILED")
     if ok:
-        bench(32768, 2304, 768)
-        bench(32768, 768, 768)
-        bench(32768, 3072, 768, act=1)
-        bench(32768, 768, 3072)
+        bench(131072, 768, 768)
+        bench(131072, 1536, 768)
+        bench(131072, 3072, 768, act=1)
+        bench(131072, 768, 3072)
         bench(8192, 8192, 8192)
