@@ -272,7 +272,7 @@ add_layernorm_kernel(const AddLnParams p) {
 // current one -- with one-row-at-a-time register loads the kernel sat at ~4 TB/s because the reads of a warp stop
 // during its compute-and-store phase.  2 CTAs x 8 warps x 3 rows x 4.5 KB = 216 KB of reads in flight per SM.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int LN_STAGES = 3;
+constexpr int LN_MAX_STAGES = 8;
 
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -281,26 +281,48 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
-template <int NVT>
-__global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddLnParams p) {
+// Every warp owns a ring of `stages` slots; a slot holds a CHUNK of `rpc` consecutive rows (fp32 part, then the bf16
+// part) fetched by ONE bulk copy per operand -- the bulk-copy engine has a per-operation cost of the order of 100
+// cycles, so 1 KB rows (the prompt encoder's bf16 image tokens) must be moved several at a time to reach HBM speed.
+// rpc = 1 when rows are remapped (window partition).  POOL: the mean-pool variant -- CTA = (sequence, slice), nothing
+// but per-CTA column sums of y is written (prompt_encoder.py:733-735).
+template <int NVT, bool POOL, bool HAS_X, bool HAS_D>
+__global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddLnParams p, const int stages, const int rpc) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nv = p.d >> 7;
   const int tail = (p.d & 127) >> 2;
-  const uint32_t xbytes = static_cast<uint32_t>(p.d) * 4;
-  const uint32_t dbytes = p.delta ? static_cast<uint32_t>(p.d) * 2 : 0;
-  const uint32_t slot_bytes = (xbytes + dbytes + 127) & ~127u;
-  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * LN_STAGES * slot_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(8) * LN_STAGES * slot_bytes) + warp * LN_STAGES;
+  const uint32_t xbytes = HAS_X ? static_cast<uint32_t>(p.d) * 4 : 0;
+  const uint32_t dbytes = HAS_D ? static_cast<uint32_t>(p.d) * 2 : 0;
+  const uint32_t slot_bytes = (static_cast<uint32_t>(rpc) * (xbytes + dbytes) + 127) & ~127u;
+  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * stages * slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(8) * stages * slot_bytes) + warp * LN_MAX_STAGES;
   if (lane == 0) {
-    for (int s = 0; s < LN_STAGES; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncwarp();
 
-  const long long n_warps = static_cast<long long>(gridDim.x) * 8;
-  const long long first = static_cast<long long>(blockIdx.x) * 8 + warp;
+  // this warp's chunks: rows [base + c * rpc, min(base + (c + 1) * rpc, row_end)) for c = c_first, c_first + c_step, ...
+  long long base, row_end, c_first, c_step;
+  if constexpr (POOL) {
+    const long long seq = blockIdx.x / p.pool_slices;
+    const int sl = blockIdx.x % p.pool_slices;
+    const int per = (p.pool_rows + p.pool_slices - 1) / p.pool_slices;
+    base = seq * p.pool_rows + static_cast<long long>(sl) * per;
+    const long long e = base + per;
+    const long long seq_end = (seq + 1) * p.pool_rows;
+    row_end = e < seq_end ? e : seq_end;
+    c_first = warp;
+    c_step = 8;
+  } else {
+    base = 0;
+    row_end = p.rows;
+    c_first = static_cast<long long>(blockIdx.x) * 8 + warp;
+    c_step = static_cast<long long>(gridDim.x) * 8;
+  }
+  const long long n_chunks = row_end > base ? (row_end - base + rpc - 1) / rpc : 0;
 
   // row mapping (map_mode 0: identity; 1: window partition with zero padding, image_encoder.py:258-279)
   auto map_row = [&](long long row, long long& src, bool& pad) {
@@ -320,98 +342,206 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
       src = (img * p.hw + y) * p.hw + x;
     }
   };
-  auto issue = [&](long long row, int slot) {   // lane 0
+  auto issue = [&](long long chunk, int slot) {   // lane 0
+    const long long row0 = base + chunk * rpc;
     long long src;
     bool pad;
-    map_row(row, src, pad);
+    map_row(row0, src, pad);   // rpc == 1 whenever rows are remapped
     if (pad) return;
+    const uint32_t n = static_cast<uint32_t>(row_end - row0 < rpc ? row_end - row0 : rpc);
     uint8_t* dst = ring + static_cast<size_t>(slot) * slot_bytes;
-    mbar_arrive_expect_tx(&bars[slot], xbytes + dbytes);
-    bulk_load(dst, p.x_in + src * p.d, xbytes, &bars[slot]);
-    if (dbytes) bulk_load(dst + xbytes, p.delta + src * p.d, dbytes, &bars[slot]);
+    mbar_arrive_expect_tx(&bars[slot], n * (xbytes + dbytes));
+    if constexpr (HAS_X) bulk_load(dst, p.x_in + src * p.d, n * xbytes, &bars[slot]);
+    if constexpr (HAS_D) bulk_load(dst + rpc * xbytes, p.delta + src * p.d, n * dbytes, &bars[slot]);
   };
 
   if (lane == 0) {
-    for (int s = 0; s < LN_STAGES; ++s) {
-      const long long row = first + s * n_warps;
-      if (row < p.rows) issue(row, s);
+    for (int s = 0; s < stages; ++s) {
+      const long long c = c_first + s * c_step;
+      if (c < n_chunks) issue(c, s);
     }
   }
   uint32_t phases = 0;   // bit s: parity of the next completion of slot s
   const float inv_d = 1.0f / static_cast<float>(p.d);
+  const size_t ebytes = p.y_f32 ? 4 : 2;
+  // gamma / beta (and the current sequence's seq_add vector) live in registers: re-reading them per row through L1
+  // costs more load bandwidth than the row itself when rows are 1 KB of bf16
+  float4 gmv[NVT], btv[NVT], sav[NVT];
+#pragma unroll
+  for (int i = 0; i < NVT; ++i) {
+    const bool on = (i < nv) || (i == nv && lane < tail);
+    gmv[i] = on ? __ldg(reinterpret_cast<const float4*>(p.gamma) + i * 32 + lane) : make_float4(0, 0, 0, 0);
+    btv[i] = on ? __ldg(reinterpret_cast<const float4*>(p.beta) + i * 32 + lane) : make_float4(0, 0, 0, 0);
+    sav[i] = make_float4(0, 0, 0, 0);
+  }
+  long long sa_seq = -1;
+  float4 acc[POOL ? NVT : 1];
+#pragma unroll
+  for (int i = 0; i < (POOL ? NVT : 1); ++i) acc[i] = make_float4(0, 0, 0, 0);
   int slot = 0;
-  for (long long row = first; row < p.rows; row += n_warps) {
-    long long src;
+  for (long long chunk = c_first; chunk < n_chunks; chunk += c_step) {
+    const long long row0 = base + chunk * rpc;
+    const int n = static_cast<int>(row_end - row0 < rpc ? row_end - row0 : rpc);
+    long long src0;
     bool pad;
-    map_row(row, src, pad);
-    uint8_t* yrow = static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(row) * p.d * 2;
+    map_row(row0, src0, pad);
     if (pad) {
-      for (int i = lane; i < p.d / 8; i += 32) reinterpret_cast<uint4*>(yrow)[i] = make_uint4(0, 0, 0, 0);
+      uint8_t* yrow = static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(row0) * p.d * ebytes;
+      if (p.y_f32) {
+        for (int i = lane; i < p.d / 4; i += 32) reinterpret_cast<float4*>(yrow)[i] = make_float4(0, 0, 0, 0);
+      } else {
+        for (int i = lane; i < p.d / 8; i += 32) reinterpret_cast<uint4*>(yrow)[i] = make_uint4(0, 0, 0, 0);
+      }
     } else {
       const uint8_t* buf = ring + static_cast<size_t>(slot) * slot_bytes;
       mbar_wait(&bars[slot], (phases >> slot) & 1);
       phases ^= 1u << slot;
-      const float4* xs = reinterpret_cast<const float4*>(buf);
-      const uint2* ds = reinterpret_cast<const uint2*>(buf + xbytes);
-      float4 v[NVT];
-      float sum = 0.f;
+      for (int rr = 0; rr < n; ++rr) {
+        const long long row = row0 + rr, src = src0 + rr;
+        const float4* xs = reinterpret_cast<const float4*>(buf + static_cast<size_t>(rr) * xbytes);
+        const uint2* ds = reinterpret_cast<const uint2*>(buf + static_cast<size_t>(rpc) * xbytes + static_cast<size_t>(rr) * dbytes);
+        if (p.seq_add) {
+          const long long sq_ = src / p.seq_rows;
+          if (sq_ != sa_seq) {   // warp-uniform
+            sa_seq = sq_;
+            const float4* sadd = reinterpret_cast<const float4*>(p.seq_add + sq_ * p.d);
 #pragma unroll
-      for (int i = 0; i < NVT; ++i) {
-        const bool on = (i < nv) || (i == nv && lane < tail);
-        float4 a = make_float4(0, 0, 0, 0);
-        if (on) {
-          const int idx = i * 32 + lane;
-          a = xs[idx];
-          if (dbytes) {
-            const uint2 dv = ds[idx];
-            const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
-            const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
-            a.x += __low2float(d01);
-            a.y += __high2float(d01);
-            a.z += __low2float(d23);
-            a.w += __high2float(d23);
+            for (int i = 0; i < NVT; ++i)
+              if ((i < nv) || (i == nv && lane < tail)) sav[i] = __ldg(sadd + i * 32 + lane);
           }
-          if (p.x_out) reinterpret_cast<float4*>(p.x_out + src * p.d)[idx] = a;
         }
-        v[i] = a;
-        sum += a.x + a.y + a.z + a.w;
-      }
+        float4 v[NVT];
+        float sum = 0.f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float mean = sum * inv_d;
-      float sq = 0.f;
-#pragma unroll
-      for (int i = 0; i < NVT; ++i) {
-        const bool on = (i < nv) || (i == nv && lane < tail);
-        if (on) {
-          const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
-          sq += dx * dx + dy * dy + dz * dz + dw * dw;
+        for (int i = 0; i < NVT; ++i) {
+          const bool on = (i < nv) || (i == nv && lane < tail);
+          float4 a = make_float4(0, 0, 0, 0);
+          if (on) {
+            const int idx = i * 32 + lane;
+            if constexpr (HAS_X) a = xs[idx];
+            if constexpr (HAS_D) {
+              const uint2 dv = ds[idx];
+              const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
+              const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
+              a.x += __low2float(d01);
+              a.y += __high2float(d01);
+              a.z += __low2float(d23);
+              a.w += __high2float(d23);
+            }
+            a.x += sav[i].x;
+            a.y += sav[i].y;
+            a.z += sav[i].z;
+            a.w += sav[i].w;
+            if (p.x_out) reinterpret_cast<float4*>(p.x_out + src * p.d)[idx] = a;
+          }
+          v[i] = a;
+          sum += a.x + a.y + a.z + a.w;
         }
-      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-      const float rstd = rsqrtf(sq * inv_d + p.eps);
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * inv_d;
+        float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < NVT; ++i) {
-        const bool on = (i < nv) || (i == nv && lane < tail);
-        if (on) {
-          const int idx = i * 32 + lane;
-          const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + idx);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta) + idx);
-          uint2 pk;
-          pk.x = pack_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-          pk.y = pack_bf16((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-          reinterpret_cast<uint2*>(yrow)[idx] = pk;
+        for (int i = 0; i < NVT; ++i) {
+          const bool on = (i < nv) || (i == nv && lane < tail);
+          if (on) {
+            const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+            sq += dx * dx + dy * dy + dz * dz + dw * dw;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq * inv_d + p.eps);
+        uint8_t* yrow = POOL ? nullptr : static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(row) * p.d * ebytes;
+#pragma unroll
+        for (int i = 0; i < NVT; ++i) {
+          const bool on = (i < nv) || (i == nv && lane < tail);
+          if (on) {
+            const int idx = i * 32 + lane;
+            const float4 g = gmv[i], b = btv[i];
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * g.x + b.x;
+            o.y = (v[i].y - mean) * rstd * g.y + b.y;
+            o.z = (v[i].z - mean) * rstd * g.z + b.z;
+            o.w = (v[i].w - mean) * rstd * g.w + b.w;
+            if constexpr (POOL) {
+              acc[i].x += o.x;
+              acc[i].y += o.y;
+              acc[i].z += o.z;
+              acc[i].w += o.w;
+            } else if (p.y_f32) {
+              reinterpret_cast<float4*>(yrow)[idx] = o;
+            } else {
+              uint2 pk;
+              pk.x = pack_bf16(o.x, o.y);
+              pk.y = pack_bf16(o.z, o.w);
+              reinterpret_cast<uint2*>(yrow)[idx] = pk;
+            }
+          }
         }
       }
     }
-    // every lane has read its part of the slot: refill it with the row LN_STAGES ahead.  Rows that are pure padding
+    // every lane has read its part of the slot: refill it with the chunk `stages` ahead.  Chunks that are pure padding
     // neither load nor wait, but they still advance the slot so that issue order == consume order.
     __syncwarp();
-    const long long nxt = row + LN_STAGES * n_warps;
-    if (lane == 0 && nxt < p.rows) issue(nxt, slot);
-    slot = slot + 1 == LN_STAGES ? 0 : slot + 1;
+    const long long nxt = chunk + stages * c_step;
+    if (lane == 0 && nxt < n_chunks) issue(nxt, slot);
+    slot = slot + 1 == stages ? 0 : slot + 1;
   }
+  if constexpr (POOL) {
+    // deterministic reduction: lanes own disjoint channels; the CTA's warps are summed in a fixed order through
+    // shared memory (behind the ring and its barriers); one partial row per (sequence, slice)
+    float4* red = reinterpret_cast<float4*>(ln_smem + static_cast<size_t>(8) * stages * slot_bytes + 8 * LN_MAX_STAGES * 8);
+    const int dv = p.d >> 2;
+#pragma unroll
+    for (int i = 0; i < NVT; ++i) {
+      const bool on = (i < nv) || (i == nv && lane < tail);
+      if (on) red[warp * dv + i * 32 + lane] = acc[i];
+    }
+    __syncthreads();
+    float4* dstp = reinterpret_cast<float4*>(p.pool_out + static_cast<long long>(blockIdx.x) * p.d);
+    for (int c = threadIdx.x; c < dv; c += blockDim.x) {
+      float4 t = red[c];
+      for (int w = 1; w < 8; ++w) {
+        const float4 u = red[w * dv + c];
+        t.x += u.x;
+        t.y += u.y;
+        t.z += u.z;
+        t.w += u.w;
+      }
+      dstp[c] = t;
+    }
+  }
+}
+
+// ring geometry: chunks of up to 4.5 KB (1 row when rows are remapped), as many stages as fit in 112 KB per CTA
+// (2 CTAs per SM), at most 8
+struct LnRing {
+  int stages, rpc, smem;
+};
+static inline LnRing ln_ring_for(uint32_t row_bytes, bool remapped, size_t extra) {
+  LnRing r;
+  r.rpc = remapped ? 1 : static_cast<int>(4608 / row_bytes);
+  if (r.rpc < 1) r.rpc = 1;
+  if (r.rpc > 8) r.rpc = 8;
+  const uint32_t slot = (static_cast<uint32_t>(r.rpc) * row_bytes + 127) & ~127u;
+  r.stages = static_cast<int>((112 * 1024 - extra - 8 * LN_MAX_STAGES * 8) / (8 * static_cast<size_t>(slot)));
+  if (r.stages > LN_MAX_STAGES) r.stages = LN_MAX_STAGES;
+  r.smem = 8 * r.stages * static_cast<int>(slot) + 8 * LN_MAX_STAGES * 8 + static_cast<int>(extra);
+  return r;
+}
+
+template <int NVT, bool POOL>
+static int launch_staged(cudaStream_t st, const AddLnParams& p, int grid, const LnRing& ring) {
+  auto go = [&](auto kern) -> int {
+    LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ring.smem));
+    kern<<<grid, 256, ring.smem, st>>>(p, ring.stages, ring.rpc);
+    LA_CHECK_CUDA(cudaGetLastError());
+    return LA_OK;
+  };
+  if (p.x_in && p.delta) return go(add_layernorm_staged_kernel<NVT, POOL, true, true>);
+  if (p.x_in) return go(add_layernorm_staged_kernel<NVT, POOL, true, false>);
+  return go(add_layernorm_staged_kernel<NVT, POOL, false, true>);
 }
 
 // out[s, :] = scale * sum_p partial[s, p, :]
@@ -570,24 +700,17 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int need = (d + 127) / 128;
   // the ViT block case goes through the staged kernel (bulk async row copies, 3 rows in flight per warp)
-  const bool staged = x_in && x_mod == 0 && !delta2 && !seq_add && !y2_out && !ype_out && act == LA_ACT_NONE && gamma &&
-                      y_out && y_dtype != LA_DTYPE_F32 && (map_mode == 0 || map_mode == 1) && need <= 8 &&
-                      rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr;
+  const bool staged = x_mod == 0 && !delta2 && !y2_out && !ype_out && act == LA_ACT_NONE && gamma && y_out &&
+                      (map_mode == 0 || map_mode == 1) && need <= 8 && d % 32 == 0 && rows >= 4096 &&
+                      getenv("LA_LN_UNSTAGED") == nullptr;
   if (staged) {
-    const uint32_t slot_bytes = (static_cast<uint32_t>(d) * (delta ? 6 : 4) + 127) & ~127u;
-    const int smem = 8 * LN_STAGES * static_cast<int>(slot_bytes) + 8 * LN_STAGES * 8;
-    if (smem <= 112 * 1024) {
-      const int sgrid = grid_for(rows * 32, 256, 2);
-      auto launch = [&](auto kern) -> int {
-        LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<sgrid, 256, smem, st>>>(p);
-        LA_CHECK_CUDA(cudaGetLastError());
-        return LA_OK;
-      };
-      if (need <= 2) return launch(add_layernorm_staged_kernel<2>);
-      if (need <= 4) return launch(add_layernorm_staged_kernel<4>);
-      if (need <= 6) return launch(add_layernorm_staged_kernel<6>);
-      return launch(add_layernorm_staged_kernel<8>);
+    const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0)), map_mode != 0, 0);
+    if (ring.stages >= 2) {
+      const int sgrid = grid_for((rows + ring.rpc - 1) / ring.rpc * 32, 256, 2);
+      if (need <= 2) return launch_staged<2, false>(st, p, sgrid, ring);
+      if (need <= 4) return launch_staged<4, false>(st, p, sgrid, ring);
+      if (need <= 6) return launch_staged<6, false>(st, p, sgrid, ring);
+      return launch_staged<8, false>(st, p, sgrid, ring);
     }
   }
   const int grid = grid_for(rows * 32, 256, need <= 4 ? 4 : (need <= 8 ? 3 : 2));
@@ -627,6 +750,21 @@ int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta
   const size_t smem = 8 * static_cast<size_t>(d) * sizeof(float);
   const int need = (d + 127) / 128;
   const int grid = static_cast<int>(n_seq * slices);
+  // big problems: the staged (bulk-copy ring) variant
+  if (!delta2 && need <= 8 && d % 32 == 0 && p.rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr) {
+    const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0)), false, smem);
+    if (ring.stages >= 2) {
+      int rc;
+      if (need <= 2) rc = launch_staged<2, true>(st, p, grid, ring);
+      else if (need <= 4) rc = launch_staged<4, true>(st, p, grid, ring);
+      else rc = launch_staged<8, true>(st, p, grid, ring);
+      if (rc) return rc;
+      pool_finish_kernel<<<grid_for(n_seq * d, 256, 8), 256, 0, st>>>(partial_ws, out, n_seq, slices, d,
+                                                                     1.0f / rows_per_seq);
+      LA_CHECK_CUDA(cudaGetLastError());
+      return LA_OK;
+    }
+  }
   if (need <= 2) add_layernorm_kernel<2, true><<<grid, 256, smem, st>>>(p);
   else if (need <= 4) add_layernorm_kernel<4, true><<<grid, 256, smem, st>>>(p);
   else if (need <= 8) add_layernorm_kernel<8, true><<<grid, 256, smem, st>>>(p);

@@ -47,6 +47,7 @@ def _gen(seed):
     (1000, 128, 512, 2, torch.bfloat16, True),     # ReLU epilogue, N = one 128 tile
     (1000, 64, 576, 0, torch.bfloat16, True),      # spatial conv as GEMM (K = 9 * 64)
     (300, 256, 136, 0, torch.float32, True),       # ragged K (TMA zero fill), fp32 out
+    (3000, 384, 128, 0, torch.bfloat16, True),     # CTA-pair path with an M tail and a half-filled N tile
     (12, 512, 512, 0, torch.float32, False),       # a handful of token rows
     (2048, 64, 64, 0, torch.float32, False),       # rel-pos table GEMM
 ])
@@ -220,6 +221,21 @@ def test_add_layernorm_modes():
     _close(y5pe, r5 + pe.repeat(S, 1), 2 ** -8, 2e-3, "LN + pe")
     pooled = ops.add_layernorm_meanpool(None, k16, gm, bt, 1e-5, S, T, D, delta2=d2, seq_add=sa)
     _close(pooled, r5.view(S, T, D).mean(1), 1e-5, 1e-5, "LN meanpool")
+    # the prompt-encoder norm4 at a size that takes the staged kernels: bf16 rows only + per-sequence vector, fp32 /
+    # bf16 outputs, and the mean-pool variant
+    T, S, D = 1024, 6, 512
+    k16 = torch.randn(S * T, D, device="cuda", generator=g).to(torch.bfloat16)
+    sa = torch.randn(S, D, device="cuda", generator=g)
+    gm, bt = torch.randn(D, device="cuda", generator=g), torch.randn(D, device="cuda", generator=g)
+    r6 = F.layer_norm(k16.float() + sa.repeat_interleave(T, 0), (D,), gm, bt, 1e-5)
+    y6 = torch.empty(S * T, D, device="cuda")
+    ops.add_layernorm(None, k16, gm, bt, 1e-5, rows=S * T, d=D, y_out=y6, seq_add=sa, seq_rows=T)
+    _close(y6, r6, 1e-5, 1e-5, "LN staged seq_add fp32")
+    y6b = torch.empty(S * T, D, device="cuda", dtype=torch.bfloat16)
+    ops.add_layernorm(None, k16, gm, bt, 1e-5, rows=S * T, d=D, y_out=y6b, seq_add=sa, seq_rows=T)
+    _close(y6b, r6, 2 ** -8, 2e-3, "LN staged seq_add bf16")
+    pooled = ops.add_layernorm_meanpool(None, k16, gm, bt, 1e-5, S, T, D, seq_add=sa)
+    _close(pooled, r6.view(S, T, D).mean(1), 1e-5, 1e-5, "LN staged meanpool")
 
 
 def test_layout_and_index_kernels_are_exact():
