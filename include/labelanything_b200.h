@@ -50,6 +50,15 @@ int la_device_check(void); /* LA_OK iff the current device is sm_100 */
 int la_gemm_bf16(void* stream, const void* a, long long lda, const void* w, long long ldw, const float* bias,
                  void* out, long long ldo, int out_dtype, int M, int N, int K, int act);
 
+/* 3x3 convolution (stride 1, zero padding 1) as an implicit GEMM on the CTA-pair tcgen05 kernel: x is a token-major
+ * bf16 feature map [n_img, H, W, C] (W = 64, H % 4 == 0, C % 64 == 0), w the bf16 weight [N, 9*C] with column
+ * (ky*3 + kx)*C + ci (row stride ldw), out [n_img*H*W, N] bf16 / fp32 (row stride ldo); out = act(conv(x) + bias).
+ * The im2col matrix is never written: every k-block is one 4-D TMA box at the tap's shifted coordinates and the
+ * border is zero-filled by the TMA unit.  Replaces Conv2d(3x3) of the necks: label_anything/models/build_lam.py:162-168,
+ * image_encoder.py:92-108. */
+int la_conv3x3_bf16(void* stream, const void* x, int n_img, int H, int W, int C, const void* w, long long ldw,
+                    const float* bias, void* out, long long ldo, int out_dtype, int N, int act);
+
 /* ---- fused attention ----------------------------------------------------------------------------- */
 /* Multi-head self-attention, head_dim 64, over n_seq sequences of seq_len tokens stored as consecutive rows
  * of the projection matrices q [rows_total, ld_q] and kv [rows_total, ld_kv] (bf16; they may be the same

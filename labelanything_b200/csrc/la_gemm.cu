@@ -46,11 +46,16 @@ struct GemmSmem {
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
 };
 
-template <int BLOCK_N, typename OutT, bool CTA2 = false>
+// CONV (CTA-pair variant only): implicit-GEMM 3x3 convolution, stride 1, zero padding 1, over a token-major bf16
+// feature map [n_img, H, W = 64, C]: A is never materialised -- k-block (tap, channel chunk) of the 128 pixels of a
+// CTA (two image rows) is ONE 4-D TMA box [64 ch, 64 w, 2 h, 1 img] fetched at the tap's shifted coordinates, and the
+// out-of-bounds rows / columns of the border are zero-filled by the TMA unit.  conv_c = C, conv_h = H; K = 9 * C.
+template <int BLOCK_N, typename OutT, bool CTA2 = false, bool CONV = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                          const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N,
-                         int K, int act) {
+                         int K, int act, int conv_c = 0, int conv_h = 0) {
+  static_assert(!CONV || CTA2, "the implicit-GEMM convolution is built on the CTA-pair kernel");
   using S = GemmSmem<BLOCK_N, CTA2>;
   // CTA pair: rank 0 (leader) issues the MMAs of both; every CTA loads and stores its own 128 rows
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0;
@@ -124,7 +129,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           if constexpr (CTA2) {
             // both CTAs' boxes are counted on the leader's barrier
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
-            tma_load_2d_2cta(a_dst, &tm_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+            if constexpr (CONV) {
+              const int cpb = conv_c / GEMM_BLOCK_K;            // channel chunks per tap
+              const int tap = kb / cpb, c0 = (kb - tap * cpb) * GEMM_BLOCK_K;
+              const int img = m0 / (conv_h * 64), y0 = (m0 - img * conv_h * 64) / 64;
+              tma_load_4d_2cta(a_dst, &tm_a, &full_bar[stage], c0, tap % 3 - 1, y0 + tap / 3 - 1, img);
+            } else {
+              tma_load_2d_2cta(a_dst, &tm_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
+            }
             tma_load_2d_2cta(b_dst, &tm_w, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
@@ -292,11 +304,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 }
 
 // CTA-pair launch: clusters of 2 CTAs, 256 x 256 tiles
-template <typename OutT>
+template <typename OutT, bool CONV = false>
 static int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
-                            const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int act) {
+                            const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int act,
+                            int conv_c = 0, int conv_h = 0) {
   using S = GemmSmem<256, true>;
-  auto kern = gemm_bf16_tcgen05_kernel<256, OutT, true>;
+  auto kern = gemm_bf16_tcgen05_kernel<256, OutT, true, CONV>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   const int tiles = ((N + 255) / 256) * ((M + 255) / 256);
   const int pairs = sm_count() / 2;
@@ -312,7 +325,7 @@ static int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tm_a, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_w, tm_out, bias, M, N, K, act));
+  LA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_w, tm_out, bias, M, N, K, act, conv_c, conv_h));
   return LA_OK;
 }
 
@@ -326,7 +339,7 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tm_a, const CUten
   const int m_blks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int tiles = n_blks * m_blks;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tm_a, tm_w, tm_out, bias, M, N, K, act);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tm_a, tm_w, tm_out, bias, M, N, K, act, 0, 0);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
@@ -377,4 +390,43 @@ extern "C" int la_gemm_bf16(void* stream, const void* a, long long lda, const vo
     if (block_n == 128) return launch_gemm<128, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
     return launch_gemm<64, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
   }
+}
+
+extern "C" int la_conv3x3_bf16(void* stream, const void* x, int n_img, int H, int W, int C, const void* w,
+                               long long ldw, const float* bias, void* out, long long ldo, int out_dtype, int N,
+                               int act) {
+  using namespace la;
+  LA_CHECK_ARG(x && w && out, "la_conv3x3_bf16: null pointer");
+  LA_CHECK_ARG(n_img > 0 && H > 0 && N > 0, "la_conv3x3_bf16: empty problem");
+  LA_CHECK_ARG(W == 64 && H % 4 == 0, "la_conv3x3_bf16: built for 64-wide feature maps with H %% 4 == 0 (got %dx%d)", H, W);
+  LA_CHECK_ARG(C % 64 == 0 && N >= 256 && N % 8 == 0, "la_conv3x3_bf16: C must be a multiple of 64 and N >= 256");
+  LA_CHECK_ARG(ldw % 8 == 0 && ldw >= 9ll * C, "la_conv3x3_bf16: ldw must cover the 9*C taps");
+  LA_CHECK_ARG(out_dtype == LA_DTYPE_BF16 || out_dtype == LA_DTYPE_F32, "la_conv3x3_bf16: bad out_dtype %d", out_dtype);
+  LA_CHECK_ARG((ldo * (out_dtype == LA_DTYPE_BF16 ? 2 : 4)) % 16 == 0, "la_conv3x3_bf16: ldo must give 16B rows");
+  LA_CHECK_ARG((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+               "la_conv3x3_bf16: pointers must be 16-byte aligned");
+  LA_CHECK_ARG(act >= LA_ACT_NONE && act <= LA_ACT_RELU, "la_conv3x3_bf16: bad act %d", act);
+  const long long Mll = static_cast<long long>(n_img) * H * W;
+  LA_CHECK_ARG(Mll < (1ll << 31), "la_conv3x3_bf16: too many pixels");
+  const int M = static_cast<int>(Mll), K = 9 * C;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tm_a, tm_w, tm_out;
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+  const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  const uint32_t box[4] = {64, 64, 2, 1};
+  int rc = make_tensor_map_4d(&tm_a, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dims, strides, box, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_w, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2,
+                          GEMM_BLOCK_K, 128, Swizzle::B128);
+  if (rc) return rc;
+  if (out_dtype == LA_DTYPE_BF16) {
+    rc = make_tensor_map_2d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2,
+                            64, 32, Swizzle::B128);
+    if (rc) return rc;
+    return launch_gemm_2cta<__nv_bfloat16, true>(st, tm_a, tm_w, tm_out, bias, M, N, K, act, C, H);
+  }
+  rc = make_tensor_map_2d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 4, 32,
+                          32, Swizzle::B128);
+  if (rc) return rc;
+  return launch_gemm_2cta<float, true>(st, tm_a, tm_w, tm_out, bias, M, N, K, act, C, H);
 }

@@ -88,6 +88,26 @@ int make_tensor_map_3d(CUtensorMap* map, const void* base, CUtensorMapDataType d
   return LA_OK;
 }
 
+int make_tensor_map_4d(CUtensorMap* map, const void* base, CUtensorMapDataType dtype, const uint64_t dims[4],
+                       const uint64_t strides_bytes[3], const uint32_t box[4], Swizzle swizzle) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return LA_ERR_CUDA;
+  }
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, dtype, 4, const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  to_cu(swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
+    return LA_ERR_CUDA;
+  }
+  return LA_OK;
+}
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;

@@ -11,6 +11,7 @@ from . import _native
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 DT_BF16, DT_F32 = 0, 1
+_DTC = {torch.bfloat16: DT_BF16, torch.float32: DT_F32}
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -110,6 +111,29 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act
 
 def _ptr(t):
     return t.data_ptr() if t is not None else None
+
+
+def conv3x3_supported(h: int, w: int, c: int, n: int) -> bool:
+    """Shapes the implicit-GEMM 3x3 convolution is built for (anything else goes through im2col_3x3 + gemm)."""
+    return w == 64 and h % 4 == 0 and c % 64 == 0 and n >= 256 and n % 8 == 0
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, n_img: int, h: int, wd: int, c: int,
+            act: int = ACT_NONE, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """3x3 / stride 1 / zero-pad 1 convolution of a token-major bf16 map [n_img*h*wd, c] with w [N, 9c] (column =
+    (ky*3+kx)*c + ci) as an implicit GEMM (4-D TMA loads at shifted coordinates; no im2col matrix)."""
+    _require_cuda(x, w, bias)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == n_img * h * wd * c
+    assert w.dtype == torch.bfloat16 and w.dim() == 2 and w.shape[1] == 9 * c and w.stride(1) == 1
+    N = w.shape[0]
+    assert conv3x3_supported(h, wd, c, N), (h, wd, c, N)
+    assert bias is None or (bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous())
+    out = torch.empty((n_img * h * wd, N), dtype=out_dtype, device=x.device)
+    M = n_img * h * wd
+    _cost(2.0 * M * N * 9 * c, 2.0 * (M * c + N * 9 * c) + M * N * out.element_size())
+    _call(f"conv3x3.n{N}.c{c}" if _PROF is not None else "conv3x3", "la_conv3x3_bf16", _stream(x), x.data_ptr(), n_img, h,
+          wd, c, w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(), out.stride(0), _DTC[out.dtype], N, act)
+    return out
 
 
 def attention_window(q: torch.Tensor, kv: torch.Tensor, n_seq: int, n_heads: int, scale: float, out: torch.Tensor,

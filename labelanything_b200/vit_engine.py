@@ -163,9 +163,12 @@ def run_neck(nw: NeckWeights, tokens: torch.Tensor, n_img: int, g: int, out_dtyp
     y1 = torch.empty((rows, co), dtype=torch.bfloat16, device=tokens.device)
     ops.add_layernorm(t1, None, nw.ln1_w, nw.ln1_b, nw.eps, rows=rows, d=co, y_out=y1)
     del t1
-    col = ops.im2col_3x3(y1, n_img, g, g, co)
-    t2 = ops.gemm(col, nw.w3, None, out_dtype=torch.float32)
-    del col
+    if ops.conv3x3_supported(g, g, co, nw.w3.shape[0]):
+        t2 = ops.conv3x3(y1, nw.w3, None, n_img, g, g, co, out_dtype=torch.float32)   # implicit GEMM, no im2col
+    else:
+        col = ops.im2col_3x3(y1, n_img, g, g, co)
+        t2 = ops.gemm(col, nw.w3, None, out_dtype=torch.float32)
+        del col
     out = torch.empty((rows, co), dtype=out_dtype, device=tokens.device)
     ops.add_layernorm(t2, None, nw.ln2_w, nw.ln2_b, nw.eps, rows=rows, d=co, y_out=out)
     return out

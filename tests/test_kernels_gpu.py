@@ -79,6 +79,27 @@ def test_gemm_strided_operand_and_output_views():
     _close(y, a.float() @ w.float().t(), 1e-4, 1e-4, "gemm strided")
 
 
+def test_conv3x3_implicit_gemm_matches_torch():
+    """3x3 conv of the necks as an implicit GEMM (4-D TMA boxes at shifted coordinates, zero-filled borders)."""
+    ops = _ops()
+    g = _gen(11)
+    n_img, H, W, C, N = 3, 64, 64, 128, 256
+    x = torch.randn(n_img, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C)).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g)
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()          # column = (ky*3 + kx)*C + ci
+    y = ops.conv3x3(x.view(-1, C), wp, b, n_img, H, W, C, out_dtype=torch.float32)
+    r = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    _close(y, r, 1e-4, 1e-4, "conv3x3 fp32")
+    y16 = ops.conv3x3(x.view(-1, C), wp, None, n_img, H, W, C, act=ops.ACT_RELU)
+    r16 = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, padding=1)).permute(0, 2, 3, 1).reshape(-1, N)
+    _close(y16, r16, 2 ** -8, 2e-3, "conv3x3 bf16 relu")
+    # same result as the explicit im2col + GEMM path
+    col = ops.im2col_3x3(x.view(-1, C).contiguous(), n_img, H, W, C)
+    y2 = ops.gemm(col, wp, b, out_dtype=torch.float32)
+    _close(y, y2, 1e-5, 1e-5, "conv3x3 vs im2col + gemm")
+
+
 # ---------------------------------------------------------------------------------------------- fused attention
 def _rev_bias(ops, q_heads, rel, pad_to):
     trev = torch.flip(rel, dims=[0]).to(torch.bfloat16)
