@@ -40,6 +40,10 @@ constexpr int ATT_D = 64;
 #ifndef ATT_POLY_EXP
 #define ATT_POLY_EXP 4
 #endif
+// ... and of the 112-key window mode (0: measured no gain there -- that kernel is bound by its per-item latency chain)
+#ifndef ATT_POLY_EXP_WIN
+#define ATT_POLY_EXP_WIN 0
+#endif
 #ifndef ATT_TS_OPERANDS
 #define ATT_TS_OPERANDS 1
 #endif
@@ -170,6 +174,31 @@ __device__ __forceinline__ void exp2_poly_x2(float& a0, float& a1) {
         "f"(0.6932609677f), "f"(0.9999280572f));
   a0 = __uint_as_float(p0 + (t0 << 23));
   a1 = __uint_as_float(p1 + (t1 << 23));
+}
+// (d0, d1) = (a0, a1) * (b, b) + (c0, c1)
+__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %4};\n\t"
+      "mov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
+}
+// (d0, d1) = (a0, a1) + (b, b)
+__device__ __forceinline__ void fadd2s(float& d0, float& d1, float a0, float a1, float b) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %4};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b));
 }
 // (d0, d1) += (a0, a1)
 __device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float a1) {
@@ -642,14 +671,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           mx = -INFINITY;
 #pragma unroll
           for (int gi = 0; gi < NG; ++gi) {
+            static_assert(!WIN || GW % 2 == 0, "score pairs stay inside one key-grid row");
             float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < GW; ++i) {
+            for (int i = 0; i < GW; i += 2) {
               const int col = gi * GW + i;
-              const float tv = fmaf(__uint_as_float(sv[col]), sl2, rw2[i]);
-              sv[col] = __float_as_uint(tv);
-              if (i & 1) m1 = fmaxf(m1, tv);
-              else m0 = fmaxf(m0, tv);
+              float t0, t1;
+              ffma2v(t0, t1, __uint_as_float(sv[col]), __uint_as_float(sv[col + 1]), sl2, rw2[i], rw2[i + 1]);
+              sv[col] = __float_as_uint(t0);
+              sv[col + 1] = __float_as_uint(t1);
+              if (i & 2) m1 = max3(m1, t0, t1);
+              else m0 = max3(m0, t0, t1);
             }
             mx = fmaxf(mx, fmaxf(m0, m1) + rh2[gi]);
           }
@@ -710,13 +742,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
               const int col = c0 + i;
               float a0, a1;
               if constexpr (WIN) {
-                a0 = __uint_as_float(sv[col]) + offg[col / GW];
-                a1 = __uint_as_float(sv[col + 1]) + offg[(col + 1) / GW];
+                fadd2s(a0, a1, __uint_as_float(sv[col]), __uint_as_float(sv[col + 1]), offg[col / GW]);
               } else {
                 ffma2(a0, a1, __uint_as_float(sv[col]), __uint_as_float(sv[col + 1]), sl2, offg[0]);
               }
               float e0, e1;
-              if (!WIN && ATT_POLY_EXP > 0 && ((col >> 1) % ATT_POLY_EXP) == ATT_POLY_EXP - 1) {
+              constexpr int POLY = WIN ? ATT_POLY_EXP_WIN : ATT_POLY_EXP;
+              if (POLY > 0 && ((col >> 1) % POLY) == POLY - 1) {
                 e0 = a0;
                 e1 = a1;
                 exp2_poly_x2(e0, e1);
