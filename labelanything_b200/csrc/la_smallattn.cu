@@ -150,9 +150,12 @@ __global__ void __launch_bounds__(256) attn_query_parallel_kernel(const TokAttPa
 // ------------------------------------------------------------------------------------------------------
 // key-parallel: one warp per (sequence, split, head); QB queries per pass
 // ------------------------------------------------------------------------------------------------------
-constexpr int KP_QB = 4;
+// KP_QB: queries handled per pass over the keys (1 for the single-token sequences of mask-only prompts, which keeps
+// the register count low enough for KP_UNROLL key groups of loads in flight per warp -- the kernel is a pure HBM
+// stream and was latency bound with one group in flight).
+constexpr int KP_UNROLL = 4;
 
-template <int DH>
+template <int DH, int KP_QB>
 __global__ void __launch_bounds__(256) attn_key_parallel_kernel(const TokAttParams p) {
   constexpr int G = DH / 8;
   constexpr int KG = 32 / G;  // keys per warp iteration
@@ -185,30 +188,59 @@ __global__ void __launch_bounds__(256) attn_key_parallel_kernel(const TokAttPara
           acc[a][i] = 0.f;
         }
       }
-      for (int j0 = k_begin; j0 < k_end; j0 += KG) {
-        const int j = j0 + kg;
-        const bool on = j < k_end;
-        const int jj = on ? j : k_end - 1;
-        float kk[8], vv[8];
-        load8(kp + static_cast<long long>(jj) * p.ld_k, kk);
-        load8(vp + static_cast<long long>(jj) * p.ld_v, vv);
-        if (p.k_add) add8(p.k_add + static_cast<long long>(jj) * p.ld_kadd + col, kk);
+      for (int j0 = k_begin; j0 < k_end; j0 += KG * KP_UNROLL) {
+        // KP_UNROLL key groups: all loads first (raw 16-byte pieces), then the online-softmax updates
+        uint4 kraw[KP_UNROLL], vraw[KP_UNROLL];
+        float4 ka0[KP_UNROLL], ka1[KP_UNROLL];
+        bool on[KP_UNROLL];
 #pragma unroll
-        for (int a = 0; a < KP_QB; ++a) {
-          float s = 0.f;
+        for (int u = 0; u < KP_UNROLL; ++u) {
+          const int j = j0 + u * KG + kg;
+          on[u] = j < k_end;
+          const int jj = on[u] ? j : k_end - 1;
+          kraw[u] = *reinterpret_cast<const uint4*>(kp + static_cast<long long>(jj) * p.ld_k);
+          vraw[u] = *reinterpret_cast<const uint4*>(vp + static_cast<long long>(jj) * p.ld_v);
+          if (p.k_add) {
+            const float4* ap = reinterpret_cast<const float4*>(p.k_add + static_cast<long long>(jj) * p.ld_kadd + col);
+            ka0[u] = __ldg(ap);
+            ka1[u] = __ldg(ap + 1);
+          }
+        }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s = fmaf(q[a][i], kk[i], s);
+        for (int u = 0; u < KP_UNROLL; ++u) {
+          float kk[8], vv[8];
+          {
+            const __nv_bfloat162* hk = reinterpret_cast<const __nv_bfloat162*>(&kraw[u]);
+            const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&vraw[u]);
 #pragma unroll
-          for (int o = 1; o < G; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (!on) s = -INFINITY;
-          const float mn = fmaxf(m[a], s);
-          // mn == -inf only while this key group has seen no key at all: keep the state untouched
-          const float c = (mn == -INFINITY) ? 1.f : ex2f(m[a] - mn);
-          const float pw = (mn == -INFINITY) ? 0.f : ex2f(s - mn);
-          l[a] = fmaf(l[a], c, pw);
+            for (int i = 0; i < 4; ++i) {
+              kk[2 * i] = __low2float(hk[i]);
+              kk[2 * i + 1] = __high2float(hk[i]);
+              vv[2 * i] = __low2float(hv[i]);
+              vv[2 * i + 1] = __high2float(hv[i]);
+            }
+          }
+          if (p.k_add) {
+            kk[0] += ka0[u].x; kk[1] += ka0[u].y; kk[2] += ka0[u].z; kk[3] += ka0[u].w;
+            kk[4] += ka1[u].x; kk[5] += ka1[u].y; kk[6] += ka1[u].z; kk[7] += ka1[u].w;
+          }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[a][i] = fmaf(acc[a][i], c, pw * vv[i]);
-          m[a] = mn;
+          for (int a = 0; a < KP_QB; ++a) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = fmaf(q[a][i], kk[i], s);
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (!on[u]) s = -INFINITY;
+            const float mn = fmaxf(m[a], s);
+            // mn == -inf only while this key group has seen no key at all: keep the state untouched
+            const float c = (mn == -INFINITY) ? 1.f : ex2f(m[a] - mn);
+            const float pw = (mn == -INFINITY) ? 0.f : ex2f(s - mn);
+            l[a] = fmaf(l[a], c, pw);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[a][i] = fmaf(acc[a][i], c, pw * vv[i]);
+            m[a] = mn;
+          }
         }
       }
       // merge the KG key groups of the warp
@@ -284,7 +316,8 @@ static int launch_tokens(cudaStream_t st, const TokAttParams& p, bool key_parall
   if (key_parallel) {
     const long long grid = static_cast<long long>(p.n_seq) * p.splits;
     const int threads = 32 * (p.n_heads < 8 ? p.n_heads : 8);
-    attn_key_parallel_kernel<DH><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
+    if (p.nq == 1) attn_key_parallel_kernel<DH, 1><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
+    else attn_key_parallel_kernel<DH, 4><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
     LA_CHECK_CUDA(cudaGetLastError());
     if (p.splits > 1) {
       const long long total = static_cast<long long>(p.n_seq) * p.n_heads * p.nq * DH;
