@@ -170,6 +170,20 @@ struct BuildSrcParams {
 };
 
 // One thread owns 4 channels and keeps its 4x16 slice of W6 in registers; a CTA walks the rows of one sequence.
+// (d0, d1) += (a0, a1) * (b, b)   (sm_100 FFMA2)
+__device__ __forceinline__ void fma2_pair(float& d0, float& d1, float a0, float a1, float b) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %4};\n\t"
+      "mov.b64 rd, {%0, %1};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rd;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1), "f"(b));
+}
+
 __global__ void __launch_bounds__(256) build_src_kernel(const BuildSrcParams p) {
   const int tpr = p.D >> 2;                 // threads per row
   const int rows_per_pass = blockDim.x / tpr;
@@ -209,7 +223,8 @@ __global__ void __launch_bounds__(256) build_src_kernel(const BuildSrcParams p) 
   // Rows are processed in blocks of SRC_BLK: the block's 16-channel mask rows are staged in shared memory by a
   // coalesced cooperative load (every thread of a row needs all 16 values), and each thread keeps 4 independent
   // feature loads in flight -- the kernel is latency bound otherwise (one 16-byte load per thread per row).
-  constexpr int SRC_BLK = 32;
+  constexpr int SRC_BLK = 64;
+  constexpr int SRC_INFLIGHT = 8;   // independent 16-byte feature loads per thread
   __shared__ float4 s_m16[SRC_BLK][4];
   const float* feat_seq = p.feat + bm * p.T * static_cast<long long>(p.D) + c0;
   __nv_bfloat16* out_seq = p.out + s * p.T * static_cast<long long>(p.D) + c0;
@@ -223,16 +238,16 @@ __global__ void __launch_bounds__(256) build_src_kernel(const BuildSrcParams p) 
       }
       __syncthreads();
     }
-    for (int r0 = lr; r0 < SRC_BLK; r0 += 4 * rows_per_pass) {
-      float4 f[4];
+    for (int r0 = lr; r0 < SRC_BLK; r0 += SRC_INFLIGHT * rows_per_pass) {
+      float4 f[SRC_INFLIGHT];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < SRC_INFLIGHT; ++u) {
         const int t = blk + r0 + u * rows_per_pass;
         if (r0 + u * rows_per_pass < SRC_BLK && t < t_end)
           f[u] = __ldg(reinterpret_cast<const float4*>(feat_seq + static_cast<long long>(t) * p.D));
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < SRC_INFLIGHT; ++u) {
         const int rl = r0 + u * rows_per_pass;
         const int t = blk + rl;
         if (rl < SRC_BLK && t < t_end) {
@@ -242,11 +257,11 @@ __global__ void __launch_bounds__(256) build_src_kernel(const BuildSrcParams p) 
             for (int q = 0; q < 4; ++q) {
               const float4 m = s_m16[rl][q];
 #pragma unroll
-              for (int a = 0; a < 4; ++a) {
-                o[a] = fmaf(w[a][4 * q], m.x, o[a]);
-                o[a] = fmaf(w[a][4 * q + 1], m.y, o[a]);
-                o[a] = fmaf(w[a][4 * q + 2], m.z, o[a]);
-                o[a] = fmaf(w[a][4 * q + 3], m.w, o[a]);
+              for (int a = 0; a < 4; a += 2) {   // packed fp32x2: two output channels per instruction
+                fma2_pair(o[a], o[a + 1], w[a][4 * q], w[a + 1][4 * q], m.x);
+                fma2_pair(o[a], o[a + 1], w[a][4 * q + 1], w[a + 1][4 * q + 1], m.y);
+                fma2_pair(o[a], o[a + 1], w[a][4 * q + 2], w[a + 1][4 * q + 2], m.z);
+                fma2_pair(o[a], o[a + 1], w[a][4 * q + 3], w[a + 1][4 * q + 3], m.w);
               }
             }
           }
