@@ -40,9 +40,9 @@ EPISODE_GFLOP = 26 * (965.64 + 22.55) + 150 * 10.855 + 28.7
 
 
 # DRAM traffic per launch (MB) of the kernels that can dominate the step, from the committed `ncu --set full` captures
-# (profiles/r01_ncu_{attention,gemm,layernorm}_v2.txt) taken at the bench's launch size (one 32-image encoder chunk)
-NCU_TRAFFIC_MB = {"attention.L4096": 2019.5, "attention.L196": 904.6, "gemm.n3072.k768": 207.9, "gemm.n768.k3072": 812.0,
-                  "add_layernorm.d768.map0": 1150.8}
+# (profiles/r01_ncu_{attention,gemm,layernorm}_v3.txt) taken at the bench's launch size (one 32-image encoder chunk)
+NCU_TRAFFIC_MB = {"attention.L4096": 2014.3, "attention.L196": 905.1, "gemm.n3072.k768": 964.0, "gemm.n768.k3072": 1007.2,
+                  "gemm.n768.k768": 361.7, "gemm.n1536.k768": 554.9, "add_layernorm.d768.map0": 1151.0}
 
 
 def _peaks() -> dict:
@@ -334,7 +334,7 @@ def run_native(args) -> None:
         roofline = {"kernel": top, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
                     "unit": unit, "frac": achieved / peak,
                     "traffic": None if traffic is None else traffic * 1e6, "traffic_unit": "bytes per launch",
-                    "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_*_v2.txt",
+                    "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_*_v3.txt",
                     "algorithmic_per_launch": {"flops": f["flops"] / f["launches"], "bytes": f["bytes"] / f["launches"]},
                     "peak_source": peaks["_source"],
                     "avg_launch_ms": f["ms"] / f["launches"], "share_of_kernel_time": f["ms"] / kernel_ms,
