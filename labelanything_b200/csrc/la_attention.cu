@@ -576,12 +576,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
     int it = 0;
     uint32_t g0 = 0;
+    // window mode: one 256-row pair per sequence, so a thread's token and its position in the window never change
+    [[maybe_unused]] const int w_t = x * 128 + r;
+    [[maybe_unused]] const int w_ty = w_t / GW, w_tx = w_t - (w_t / GW) * GW;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it, g0 += NT) {
-      const int qpair = w % n_qp;
-      const int head = (w / n_qp) % p.n_heads;
-      const int seq = w / (n_qp * p.n_heads);
+      const int qpair = WIN ? 0 : w % n_qp;
+      const int head = WIN ? w % p.n_heads : (w / n_qp) % p.n_heads;
+      const int seq = WIN ? w / p.n_heads : w / (n_qp * p.n_heads);
       const long long seq_row0 = static_cast<long long>(seq) * p.seq_len;
-      const int t = qpair * 256 + x * 128 + r;  // token index inside the sequence
+      const int t = WIN ? w_t : qpair * 256 + x * 128 + r;  // token index inside the sequence
       const bool row_valid = t < p.seq_len;
       const bool tr = tr0 && quarter == 0;
       const int tr_role = 1 + x;
@@ -610,8 +613,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             reinterpret_cast<uint4*>(srow)[i] = make_uint4(tb[4 * i], tb[4 * i + 1], tb[4 * i + 2], tb[4 * i + 3]);
         }
         __syncwarp();
-        const int tt = row_valid ? t : 0;
-        const int qh = tt / GW, qw = tt % GW;
+        const int qh = row_valid ? w_ty : 0, qw = row_valid ? w_tx : 0;
         const float* th = srow + (GW - 1 - qh);
         const float* tw = srow + p.rel_pad + (GW - 1 - qw);
 #pragma unroll
@@ -658,7 +660,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         for (int c = 0; c + 32 <= KV_TILE; c += 32) tmem_ld_x32(t_s + c, sv + c);
         if constexpr (KV_TILE % 32 != 0) tmem_ld_x16(t_s + (KV_TILE / 32) * 32, sv + (KV_TILE / 32) * 32);
         tmem_ld_wait();
-        if (valid < KV_TILE) {   // ragged last tile: keys beyond the sequence get -inf
+        if constexpr (WIN) {
+          // 196 keys = 112 + 84: the second tile's last 28 columns are beyond the window (compile-time positions)
+          if (j == 1) {
+#pragma unroll
+            for (int i = 196 - KV_TILE; i < KV_TILE; ++i) sv[i] = 0xff800000u;
+          }
+        } else if (valid < KV_TILE) {   // ragged last tile: keys beyond the sequence get -inf
 #pragma unroll
           for (int i = 0; i < KV_TILE; ++i)
             if (i >= valid) sv[i] = 0xff800000u;
@@ -792,9 +800,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           out_row = seq_row0 + t;
         } else {
           const int per_img = p.nwin * p.nwin;
-          const int img = seq / per_img, wi = seq % per_img;
-          const int y = (wi / p.nwin) * p.win + t / p.win;
-          const int xx = (wi % p.nwin) * p.win + t % p.win;
+          const int img = seq / per_img, wi = seq - img * per_img;
+          const int wy = wi / p.nwin;
+          const int y = wy * p.win + (WIN ? w_ty : t / p.win);
+          const int xx = (wi - wy * p.nwin) * p.win + (WIN ? w_tx : t % p.win);
           if (y < p.img_hw && xx < p.img_hw)
             out_row = (static_cast<long long>(img) * p.img_hw + y) * p.img_hw + xx;
         }
