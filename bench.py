@@ -217,6 +217,8 @@ def run_native(args) -> None:
     sd_cpu = {k: v.clone() for k, v in lam.state_dict().items()} if (rank == 0 and world == 1 and not args.no_cpu) else None
     lam.prompt_encoder.class_encoder.fixed_rows = torch.arange(N_WAYS + 1)
     lam = lam.cuda()
+    if args.chunk > 0:
+        lam.image_encoder.max_images_per_chunk = args.chunk
 
     host = make_episode(B, N_WAYS, K_SHOTS, IMAGE_SIZE, seed=100 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
@@ -330,11 +332,18 @@ def run_native(args) -> None:
             achieved, peak, unit = f["flops"] / f["ms"] / 1e9, peaks["bf16_tflops_sustained"], "TFLOP/s"
         else:
             achieved, peak, unit = f["bytes"] / f["ms"] / 1e6, peaks["hbm_gbs"], "GB/s"
-        traffic = NCU_TRAFFIC_MB.get(top) if B == 8 else None
+        # the captures were taken on 32-image launches; encoder launches scale linearly with the images per chunk
+        n_img = B * (N_WAYS * K_SHOTS + 1)
+        cap = lam.image_encoder.max_images_per_chunk
+        per_chunk = -(-n_img // -(-n_img // cap))
+        traffic = NCU_TRAFFIC_MB.get(top)
+        if traffic is not None:
+            traffic *= per_chunk / 32.0
         roofline = {"kernel": top, "bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak,
                     "unit": unit, "frac": achieved / peak,
                     "traffic": None if traffic is None else traffic * 1e6, "traffic_unit": "bytes per launch",
-                    "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_*_v3.txt",
+                    "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum on a 32-image launch "
+                                      "(profiles/r01_ncu_*_v3.txt), scaled to this run's images per chunk",
                     "algorithmic_per_launch": {"flops": f["flops"] / f["launches"], "bytes": f["bytes"] / f["launches"]},
                     "peak_source": peaks["_source"],
                     "avg_launch_ms": f["ms"] / f["launches"], "share_of_kernel_time": f["ms"] / kernel_ms,
@@ -378,6 +387,7 @@ def main() -> None:
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="episodes per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--chunk", type=int, default=0, help="images per encoder chunk (0 = the model's default)")
     ap.add_argument("--detail", action="store_true", help="print the per-kernel-shape breakdown to stderr")
     args = ap.parse_args()
     if args.impl == "reference":

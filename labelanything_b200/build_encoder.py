@@ -133,8 +133,12 @@ class ViTModelWrapper(ViTModel):
         pos = self._pos_table(gh, gw)
         pixel_values = pixel_values.float().contiguous()
         outs = []
-        for s in range(0, I, self.max_images_per_chunk):
-            n = min(self.max_images_per_chunk, I - s)
+        # balanced chunks (208 images -> 4 x 52, not 3 x 64 + 16): every launch of a kernel then has the same size, and
+        # the persistent kernels' last-wave loss is paid on fewer, larger launches
+        n_chunks = -(-I // self.max_images_per_chunk)
+        per_chunk = -(-I // n_chunks)
+        for s in range(0, I, per_chunk):
+            n = min(per_chunk, I - s)
             cols = ops.im2col_patch16(pixel_values[s:s + n])
             patch = ops.gemm(cols, w_pe, b_pe)
             del cols

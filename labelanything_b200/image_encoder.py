@@ -90,7 +90,7 @@ class ImageEncoderViT(NativeModule):
             nn.Conv2d(embed_dim, out_chans, kernel_size=1, bias=False), LayerNorm2d(out_chans),
             nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False), LayerNorm2d(out_chans))
         #: images per launch group; bounds the workspace (~125 MB per 1024-px image)
-        self.max_images_per_chunk = 32
+        self.max_images_per_chunk = 64   # upper bound; chunks are balanced (see encode_tokens)
 
     # ------------------------------------------------------------------ weight packing
     def _spec(self, grid: int) -> VitSpec:
@@ -138,8 +138,12 @@ class ImageEncoderViT(NativeModule):
         pos = f32(self, "pos", self.pos_embed).view(g * g, -1) if self.pos_embed is not None else None
         nw = pack_neck(self, self.neck) if self.project_last_hidden else None
         outs, lasts = [], []
-        for s in range(0, I, self.max_images_per_chunk):
-            n = min(self.max_images_per_chunk, I - s)
+        # balanced chunks (208 images -> 4 x 52, not 3 x 64 + 16): every launch of a kernel then has the same size, and
+        # the persistent kernels' last-wave loss is paid on fewer, larger launches
+        n_chunks = -(-I // self.max_images_per_chunk)
+        per_chunk = -(-I // n_chunks)
+        for s in range(0, I, per_chunk):
+            n = min(per_chunk, I - s)
             cols = ops.im2col_patch16(images[s:s + n])
             patch = ops.gemm(cols, w_pe, b_pe)
             del cols
