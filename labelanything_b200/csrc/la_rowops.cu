@@ -701,7 +701,7 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   const int need = (d + 127) / 128;
   // the ViT block case goes through the staged kernel (bulk async row copies, 3 rows in flight per warp)
   const bool staged = x_mod == 0 && !delta2 && !y2_out && !ype_out && act == LA_ACT_NONE && gamma && y_out &&
-                      (map_mode == 0 || map_mode == 1) && need <= 8 && d % 32 == 0 && rows >= 4096 &&
+                      (map_mode == 0 || map_mode == 1) && need <= 6 && d % 32 == 0 && rows >= 4096 &&
                       getenv("LA_LN_UNSTAGED") == nullptr;
   if (staged) {
     const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0)), map_mode != 0, 0);
@@ -709,8 +709,7 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
       const int sgrid = grid_for((rows + ring.rpc - 1) / ring.rpc * 32, 256, 2);
       if (need <= 2) return launch_staged<2, false>(st, p, sgrid, ring);
       if (need <= 4) return launch_staged<4, false>(st, p, sgrid, ring);
-      if (need <= 6) return launch_staged<6, false>(st, p, sgrid, ring);
-      return launch_staged<8, false>(st, p, sgrid, ring);
+      return launch_staged<6, false>(st, p, sgrid, ring);   // wider rows (ViT-L) keep the register-load kernel
     }
   }
   const int grid = grid_for(rows * 32, 256, need <= 4 ? 4 : (need <= 8 ? 3 : 2));
@@ -751,13 +750,12 @@ int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta
   const int need = (d + 127) / 128;
   const int grid = static_cast<int>(n_seq * slices);
   // big problems: the staged (bulk-copy ring) variant
-  if (!delta2 && need <= 8 && d % 32 == 0 && p.rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr) {
+  if (!delta2 && need <= 4 && d % 32 == 0 && p.rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr) {
     const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0)), false, smem);
     if (ring.stages >= 2) {
       int rc;
       if (need <= 2) rc = launch_staged<2, true>(st, p, grid, ring);
-      else if (need <= 4) rc = launch_staged<4, true>(st, p, grid, ring);
-      else rc = launch_staged<8, true>(st, p, grid, ring);
+      else rc = launch_staged<4, true>(st, p, grid, ring);
       if (rc) return rc;
       pool_finish_kernel<<<grid_for(n_seq * d, 256, 8), 256, 0, st>>>(partial_ws, out, n_seq, slices, d,
                                                                      1.0f / rows_per_seq);
