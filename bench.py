@@ -327,7 +327,7 @@ def run_native(args) -> None:
         # global-attention instantiation of la_attention_bf16 on one 32-image chunk)
         top = max(detail, key=lambda k: detail[k]["ms"])
         f = detail[top]
-        tensor_bound = f["flops"] > 0 and top.split(".")[0] in ("gemm", "attention", "conv3x3")
+        tensor_bound = f["flops"] > 0 and top.split(".")[0] in ("gemm", "gemm_acc", "attention", "conv3x3")
         if tensor_bound:
             achieved, peak, unit = f["flops"] / f["ms"] / 1e9, peaks["bf16_tflops_sustained"], "TFLOP/s"
         else:

@@ -50,6 +50,13 @@ int la_device_check(void); /* LA_OK iff the current device is sm_100 */
 int la_gemm_bf16(void* stream, const void* a, long long lda, const void* w, long long ldw, const float* bias,
                  void* out, long long ldo, int out_dtype, int M, int N, int K, int act);
 
+/* x[M,N] (fp32, row stride ldx) += a @ w^T + bias: the residual add of the ViT blocks done in the epilogue of the
+ * GEMM that produces the branch, in fp32 on the fp32 accumulator (each epilogue warp TMA-loads its chunk of x into the
+ * staging buffer it stores from).  CTA-pair kernel only: M >= 2048, N >= 256.
+ *   label_anything/models/image_encoder.py:181-197 (x = x + mlp(norm2(x))) */
+int la_gemm_bf16_accumulate(void* stream, const void* a, long long lda, const void* w, long long ldw, const float* bias,
+                            float* x, long long ldx, int M, int N, int K);
+
 /* 3x3 convolution (stride 1, zero padding 1) as an implicit GEMM on the CTA-pair tcgen05 kernel: x is a token-major
  * bf16 feature map [n_img, H, W, C] (W = 64, H % 4 == 0, C % 64 == 0), w the bf16 weight [N, 9*C] with column
  * (ky*3 + kx)*C + ci (row stride ldw), out [n_img*H*W, N] bf16 / fp32 (row stride ldo); out = act(conv(x) + bias).

@@ -50,12 +50,16 @@ struct GemmSmem {
 // feature map [n_img, H, W = 64, C]: A is never materialised -- k-block (tap, channel chunk) of the 128 pixels of a
 // CTA (two image rows) is ONE 4-D TMA box [64 ch, 64 w, 2 h, 1 img] fetched at the tap's shifted coordinates, and the
 // out-of-bounds rows / columns of the border are zero-filled by the TMA unit.  conv_c = C, conv_h = H; K = 9 * C.
-template <int BLOCK_N, typename OutT, bool CTA2 = false, bool CONV = false>
+// RESID (fp32 output only): out += A W^T + bias, i.e. the output tensor is also the residual operand.  Each epilogue
+// warp TMA-loads its 32 x 32 chunk of `out` into the staging buffer it will store from, adds the accumulator in place
+// and stores it back -- the residual stream's read and write ride under the tensor-core mainloop of the next tile.
+template <int BLOCK_N, typename OutT, bool CTA2 = false, bool CONV = false, bool RESID = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                          const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N,
                          int K, int act, int conv_c = 0, int conv_h = 0) {
   static_assert(!CONV || CTA2, "the implicit-GEMM convolution is built on the CTA-pair kernel");
+  static_assert(!RESID || sizeof(OutT) == 4, "the residual epilogue accumulates into an fp32 tensor");
   using S = GemmSmem<BLOCK_N, CTA2>;
   // CTA pair: rank 0 (leader) issues the MMAs of both; every CTA loads and stores its own 128 rows
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0;
@@ -72,7 +76,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tmem_full = empty_bar + S::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* resid_bar = tmem_empty + 2;   // [epilogue warp] RESID: the warp's chunk of `out` has landed in its staging buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,6 +102,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], CTA2 ? 16 : 8);   // the epilogue warps of both CTAs release the leader's accumulator
     }
+    for (int w8 = 0; w8 < 8; ++w8) mbar_init(&resid_bar[w8], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -203,12 +209,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     constexpr int LAST0 = ((NCHUNK - 1) / 2) * 2;                 // last chunk of the even warp
     constexpr int LAST1 = NCHUNK >= 2 ? ((NCHUNK - 2) / 2) * 2 + 1 : -1;  // last chunk of the odd warp (none if 1 chunk)
     const int last_c = half == 0 ? LAST0 : LAST1;
+    [[maybe_unused]] uint32_t rphase = 0;
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int m0 = (tile / n_blks) * TILE_M + rank * GEMM_BLOCK_M;
       const int n0 = (tile % n_blks) * BLOCK_N;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      [[maybe_unused]] uint64_t* rbar = &resid_bar[half * 4 + q];
+      auto load_resid = [&](int c) {   // lane 0: this warp's 32 x CHUNK piece of `out` -> staging buffer
+        tma_store_wait_read<0>();      // the previous store from the buffer has read it
+        mbar_arrive_expect_tx(rbar, S::EPI_WARP_BYTES);
+        tma_load_2d(buf, &tm_out, rbar, n0 + c * CHUNK, m0 + q * 32);
+      };
+      if constexpr (RESID) {
+        if (lane == 0 && half < NCHUNK) load_resid(half);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
@@ -261,10 +277,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll
           for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
-        // staging buffer: make sure the TMA store of this warp's previous chunk has read it
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
         uint8_t* row_ptr = buf + lane * 128;
+        if constexpr (RESID) {
+          // out chunk (loaded by TMA, 128B-swizzled like the store layout) + accumulator, in place
+          mbar_wait(rbar, rphase);
+          rphase ^= 1;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 xr = *reinterpret_cast<const float4*>(row_ptr + ((g ^ (lane & 7)) << 4));
+            v[g * 4 + 0] += xr.x;
+            v[g * 4 + 1] += xr.y;
+            v[g * 4 + 2] += xr.z;
+            v[g * 4 + 3] += xr.w;
+          }
+        } else {
+          // staging buffer: make sure the TMA store of this warp's previous chunk has read it
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
         if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -287,6 +317,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         if (lane == 0) {
           tma_store_2d(&tm_out, buf, n0 + col0, m0 + q * 32);
           tma_store_commit();
+          if constexpr (RESID) {
+            if (c + 2 < NCHUNK) load_resid(c + 2);   // next chunk of this tile (after the store has read the buffer)
+          }
         }
       }
     }
@@ -304,12 +337,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 }
 
 // CTA-pair launch: clusters of 2 CTAs, 256 x 256 tiles
-template <typename OutT, bool CONV = false>
+template <typename OutT, bool CONV = false, bool RESID = false>
 static int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
                             const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int act,
                             int conv_c = 0, int conv_h = 0) {
   using S = GemmSmem<256, true>;
-  auto kern = gemm_bf16_tcgen05_kernel<256, OutT, true, CONV>;
+  auto kern = gemm_bf16_tcgen05_kernel<256, OutT, true, CONV, RESID>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   const int tiles = ((N + 255) / 256) * ((M + 255) / 256);
   const int pairs = sm_count() / 2;
@@ -429,4 +462,27 @@ extern "C" int la_conv3x3_bf16(void* stream, const void* x, int n_img, int H, in
                           32, Swizzle::B128);
   if (rc) return rc;
   return launch_gemm_2cta<float, true>(st, tm_a, tm_w, tm_out, bias, M, N, K, act, C, H);
+}
+
+extern "C" int la_gemm_bf16_accumulate(void* stream, const void* a, long long lda, const void* w, long long ldw,
+                                       const float* bias, float* x, long long ldx, int M, int N, int K) {
+  using namespace la;
+  LA_CHECK_ARG(a && w && x, "la_gemm_bf16_accumulate: null pointer");
+  LA_CHECK_ARG(M >= 2048 && N >= 256 && K > 0, "la_gemm_bf16_accumulate: built for the CTA-pair kernel (M >= 2048, N >= 256)");
+  LA_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && N % 8 == 0 && ldx % 4 == 0,
+               "la_gemm_bf16_accumulate: K/lda/ldw/N must be multiples of 8, ldx of 4");
+  LA_CHECK_ARG((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(x)) % 16 == 0,
+               "la_gemm_bf16_accumulate: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tm_a, tm_w, tm_out;
+  int rc = make_tensor_map_2d(&tm_a, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2,
+                              GEMM_BLOCK_K, GEMM_BLOCK_M, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_w, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2,
+                          GEMM_BLOCK_K, 128, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_out, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)N, (uint64_t)M, (uint64_t)ldx * 4, 32, 32,
+                          Swizzle::B128);
+  if (rc) return rc;
+  return launch_gemm_2cta<float, false, true>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE);
 }

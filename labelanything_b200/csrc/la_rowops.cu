@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
     const long long row0 = base + chunk * rpc;
     long long src;
     bool pad;
-    map_row(row0, src, pad);   // rpc == 1 whenever rows are remapped
+    map_row(row0, src, pad);   // remapped rows: the launcher only allows chunks that share src contiguity and padding
     if (pad) return;
     const uint32_t n = static_cast<uint32_t>(row_end - row0 < rpc ? row_end - row0 : rpc);
     uint8_t* dst = ring + static_cast<size_t>(slot) * slot_bytes;
@@ -386,11 +386,11 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
     bool pad;
     map_row(row0, src0, pad);
     if (pad) {
-      uint8_t* yrow = static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(row0) * p.d * ebytes;
+      uint8_t* yrow = static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(row0) * p.d * ebytes;   // n consecutive rows
       if (p.y_f32) {
-        for (int i = lane; i < p.d / 4; i += 32) reinterpret_cast<float4*>(yrow)[i] = make_float4(0, 0, 0, 0);
+        for (int i = lane; i < n * (p.d / 4); i += 32) reinterpret_cast<float4*>(yrow)[i] = make_float4(0, 0, 0, 0);
       } else {
-        for (int i = lane; i < p.d / 8; i += 32) reinterpret_cast<uint4*>(yrow)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = lane; i < n * (p.d / 8); i += 32) reinterpret_cast<uint4*>(yrow)[i] = make_uint4(0, 0, 0, 0);
       }
     } else {
       const uint8_t* buf = ring + static_cast<size_t>(slot) * slot_bytes;
@@ -514,18 +514,25 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
   }
 }
 
-// ring geometry: chunks of up to 4.5 KB (1 row when rows are remapped), as many stages as fit in 112 KB per CTA
-// (2 CTAs per SM), at most 8
+// ring geometry: chunks of up to 6 KB -- the bulk-copy engine sustains roughly one operation per 200 cycles per SM, so
+// 3 KB rows moved one at a time cap the kernel near 3.7 TB/s -- and as many stages as fit in 112 KB per CTA (2 CTAs
+// per SM), at most 8.  max_rpc: 1 or 2 when rows are remapped (window partition: a chunk must stay inside one
+// window row and be all-valid or all-padding).
 struct LnRing {
   int stages, rpc, smem;
 };
-static inline LnRing ln_ring_for(uint32_t row_bytes, bool remapped, size_t extra) {
+static inline LnRing ln_ring_for(uint32_t row_bytes, int max_rpc, size_t extra) {
   LnRing r;
-  r.rpc = remapped ? 1 : static_cast<int>(4608 / row_bytes);
+  r.rpc = static_cast<int>(6144 / row_bytes);
+  if (r.rpc > max_rpc) r.rpc = max_rpc;
   if (r.rpc < 1) r.rpc = 1;
   if (r.rpc > 8) r.rpc = 8;
-  const uint32_t slot = (static_cast<uint32_t>(r.rpc) * row_bytes + 127) & ~127u;
-  r.stages = static_cast<int>((112 * 1024 - extra - 8 * LN_MAX_STAGES * 8) / (8 * static_cast<size_t>(slot)));
+  uint32_t slot;
+  for (;; --r.rpc) {   // at least 3 chunks in flight per warp (2 if even a single row is that large)
+    slot = (static_cast<uint32_t>(r.rpc) * row_bytes + 127) & ~127u;
+    r.stages = static_cast<int>((112 * 1024 - extra - 8 * LN_MAX_STAGES * 8) / (8 * static_cast<size_t>(slot)));
+    if (r.stages >= 3 || r.rpc == 1) break;
+  }
   if (r.stages > LN_MAX_STAGES) r.stages = LN_MAX_STAGES;
   r.smem = 8 * r.stages * static_cast<int>(slot) + 8 * LN_MAX_STAGES * 8 + static_cast<int>(extra);
   return r;
@@ -704,7 +711,10 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
                       (map_mode == 0 || map_mode == 1) && need <= 6 && d % 32 == 0 && rows >= 4096 &&
                       getenv("LA_LN_UNSTAGED") == nullptr;
   if (staged) {
-    const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0)), map_mode != 0, 0);
+    // window partition: pairs of rows (tx, tx + 1) with tx even share a window row and their padding status when the
+    // window side and the grid side are even
+    const int max_rpc = map_mode == 0 ? 8 : ((win % 2 == 0 && hw % 2 == 0) ? 2 : 1);
+    const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0)), max_rpc, 0);
     if (ring.stages >= 2) {
       const int sgrid = grid_for((rows + ring.rpc - 1) / ring.rpc * 32, 256, 2);
       if (need <= 2) return launch_staged<2, false>(st, p, sgrid, ring);
@@ -751,7 +761,7 @@ int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta
   const int grid = static_cast<int>(n_seq * slices);
   // big problems: the staged (bulk-copy ring) variant
   if (!delta2 && need <= 4 && d % 32 == 0 && p.rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr) {
-    const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0)), false, smem);
+    const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0)), 8, smem);
     if (ring.stages >= 2) {
       int rc;
       if (need <= 2) rc = launch_staged<2, true>(st, p, grid, ring);

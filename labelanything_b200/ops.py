@@ -113,6 +113,26 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def gemm_accumulate_supported(m: int, n: int) -> bool:
+    import os
+    return m >= 2048 and n >= 256 and n % 8 == 0 and not os.environ.get("LA_NO_GEMM_ACCUMULATE")
+
+
+def gemm_accumulate(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, x: torch.Tensor) -> torch.Tensor:
+    """x (fp32, in place) += a @ w.T + bias, the add done in fp32 in the GEMM epilogue."""
+    _require_cuda(a, w, bias, x)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.shape[1] == w.shape[1] and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert x.dtype == torch.float32 and x.shape == (M, N) and x.stride(1) == 1 and gemm_accumulate_supported(M, N)
+    assert bias is None or (bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous())
+    _cost(2.0 * M * N * K, 2.0 * (M * K + N * K) + 8.0 * M * N)
+    _call(f"gemm_acc.n{N}.k{K}" if _PROF is not None else "gemm", "la_gemm_bf16_accumulate", _stream(a), a.data_ptr(),
+          a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), x.data_ptr(), x.stride(0), M, N, K)
+    return x
+
+
 def conv3x3_supported(h: int, w: int, c: int, n: int) -> bool:
     """Shapes the implicit-GEMM 3x3 convolution is built for (anything else goes through im2col_3x3 + gemm)."""
     return w == 64 and h % 4 == 0 and c % 64 == 0 and n >= 256 and n % 8 == 0

@@ -5,10 +5,10 @@ their parameters into `BlockWeights` and call `run_vit`.  Per transformer block 
 modeling_vit.py:315-346) the launches are
 
     add+LN1 (window partition folded in) -> Q GEMM, KV GEMM -> [rel-pos table GEMM, global blocks] -> fused attention
-    (window un-partition folded in) -> proj GEMM -> add+LN2 -> lin1 GEMM (+GELU) -> lin2 GEMM
+    (window un-partition folded in) -> proj GEMM -> add+LN2 -> lin1 GEMM (+GELU) -> lin2 GEMM (+ residual)
 
-with the fp32 residual stream updated inside the add+LN kernels, so every GEMM writes bf16 with a plain
-bias/activation epilogue.  Images are processed in chunks to bound the workspace (HBM-resident, ~125 MB per
+The fp32 residual stream is updated inside add+LN2 (attention branch) and in the epilogue of the lin2 GEMM (MLP
+branch, `ops.gemm_accumulate`); every other GEMM writes bf16 with a plain bias/activation epilogue.  Images are processed in chunks to bound the workspace (HBM-resident, ~125 MB per
 1024-px image).
 """
 from __future__ import annotations
@@ -118,7 +118,13 @@ def run_vit(spec: VitSpec, x: torch.Tensor, n_img: int, out_dtype: torch.dtype) 
         ops.add_layernorm(x, delta, bw.ln2_w, bw.ln2_b, spec.eps, rows=rows, d=d, x_out=x, y_out=y2)
         h = ops.gemm(y2, bw.w1, bw.b1, act=ops.ACT_GELU)
         del y2
-        delta = ops.gemm(h, bw.w2, bw.b2)
+        if ops.gemm_accumulate_supported(rows, d):
+            # x += h @ W2^T + b in the GEMM epilogue (fp32, on the accumulator): lin2's mainloop is long enough to hide
+            # the residual stream's read and write, and the next LayerNorm only reads x
+            ops.gemm_accumulate(h, bw.w2, bw.b2, x)
+            delta = None
+        else:
+            delta = ops.gemm(h, bw.w2, bw.b2)
         del h
     out = torch.empty((n_img * g * g, d), dtype=out_dtype, device=dev)
     if spec.n_cls:

@@ -69,6 +69,21 @@ def test_gemm_matches_torch(M, N, K, act, out_dtype, bias):
         _close(y, r, 1e-4, 1e-4, "gemm fp32")         # fp32 accumulation order only
 
 
+def test_gemm_accumulate_in_place():
+    """x += a @ w^T + b with the add done in fp32 on the accumulator (lin2 of the ViT blocks)."""
+    ops = _ops()
+    g = _gen(21)
+    for M, N, K in ((4900, 768, 3072), (4096, 768, 768), (2500, 384, 128)):
+        a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+        w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+        b = torch.randn(N, device="cuda", generator=g)
+        x = torch.randn(M, N, device="cuda", generator=g)
+        r = x + a.float() @ w.float().t() + b
+        y = ops.gemm_accumulate(a, w, b, x)
+        assert y.data_ptr() == x.data_ptr()
+        _close(x, r, 1e-4, 1e-4, f"gemm accumulate {M}x{N}x{K}")
+
+
 def test_gemm_strided_operand_and_output_views():
     ops = _ops()
     g = _gen(5)

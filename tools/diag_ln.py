@@ -34,6 +34,15 @@ def main():
     y = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
     ms = timeit(lambda: ops.add_layernorm(x, delta, gm, bt, 1e-6, rows=rows, d=d, x_out=x, y_out=y))
     print(f"[{tag}] vit block d768 rows {rows}: {ms:.3f} ms = {rows * d * 12 / ms / 1e6:.0f} GB/s")
+    ms = timeit(lambda: ops.add_layernorm(x, None, gm, bt, 1e-6, rows=rows, d=d, y_out=y))
+    print(f"[{tag}] vit LN1 (x only) d768 rows {rows}: {ms:.3f} ms = {rows * d * 6 / ms / 1e6:.0f} GB/s")
+    n_img, nwin, win, hw = 32, 5, 14, 64
+    orow = n_img * nwin * nwin * win * win
+    yw = torch.empty(orow, d, device="cuda", dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.add_layernorm(x, None, gm, bt, 1e-6, rows=orow, d=d, y_out=yw, map_mode=1, win=win, nwin=nwin, hw=hw))
+    print(f"[{tag}] vit LN1 window partition (x only) rows {orow}: {ms:.3f} ms = {(rows * d * 4 + orow * d * 2) / ms / 1e6:.0f} GB/s")
+    ms = timeit(lambda: ops.add_layernorm(x, delta, gm, bt, 1e-6, rows=orow, d=d, x_out=x, y_out=yw, map_mode=1, win=win, nwin=nwin, hw=hw))
+    print(f"[{tag}] vit LN1 window partition (x += delta) rows {orow}: {ms:.3f} ms = {(rows * d * 10 + orow * d * 2) / ms / 1e6:.0f} GB/s")
     # (b) prompt-encoder norm4: bf16 rows + per-sequence vector -> bf16
     S, T, d = 300, 4096, 512
     k16 = torch.randn(S * T, d, device="cuda", generator=g).to(torch.bfloat16)
