@@ -39,6 +39,17 @@ def test_bad_arguments_are_rejected_with_a_message():
     assert b"head_dim" in lib.la_last_error()
     assert lib.la_attention_tokens_splits(4, 1, 4096) >= 1 and lib.la_attention_tokens_splits(4, 4096, 9) == 0
     assert lib.la_attention_tokens_workspace_bytes(1200, 1, 4096, 8, 32) >= 0
+    # the entry points added for the encoder hot path state what they are built for
+    assert lib.la_conv3x3_bf16(None, p, 1, 30, 30, 256, p, 2304, None, p, 256, 0, 256, 0) == -1
+    assert b"64-wide feature maps" in lib.la_last_error()
+    assert lib.la_gemm_bf16_accumulate(None, p, 64, p, 64, None, p, 256, 128, 256, 64) == -1
+    assert b"CTA-pair kernel" in lib.la_last_error()
+    assert lib.la_attention_window_bf16(None, p, 2304, 0, p, 2304, 768, 1536, 196, 1, 12, 0.125, p, 16, p, 768, 0, 0,
+                                        0) == -1
+    assert b"rel_pad 32" in lib.la_last_error()
+    assert lib.la_attention_window_bf16(None, p, 2304, 0, p, 2304, 768, 1536, 196, 1, 12, 0.125, None, 32, p, 768, 0,
+                                        0, 0) == -1
+    assert b"rel_table is required" in lib.la_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
