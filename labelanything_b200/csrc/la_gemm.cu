@@ -32,15 +32,16 @@ constexpr int GEMM_THREADS = 384;
 // rows of A and HALF of the W tile, so a stage is 32 KB instead of 48 KB (6 stages instead of 4) and each MMA reads
 // 8 KB instead of 12 KB of operands per CTA.  With one CTA per tile the kernel is shared-memory-bandwidth bound:
 // 96 B/clk of operand reads plus 96 B/clk of TMA fills against 128 B/clk.
-template <int BLOCK_N, bool CTA2 = false>
+template <int BLOCK_N, bool CTA2 = false, bool RES2 = false>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;
   static constexpr int B_BYTES = B_ROWS * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CTA2 ? 6 : (BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8));
+  static constexpr int STAGES = CTA2 ? (RES2 ? 5 : 6) : (BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8));
   static constexpr int EPI_WARP_BYTES = 4096;  // one 32-row x 128-byte staging buffer per epilogue warp
-  static constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;
+  // RES2: a second buffer per epilogue warp receives the residual chunk one chunk ahead of its use
+  static constexpr int EPI_BYTES = (RES2 ? 16 : 8) * EPI_WARP_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
@@ -53,14 +54,17 @@ struct GemmSmem {
 // RESID (fp32 output only): out += A W^T + bias, i.e. the output tensor is also the residual operand.  Each epilogue
 // warp TMA-loads its 32 x 32 chunk of `out` into the staging buffer it will store from, adds the accumulator in place
 // and stores it back -- the residual stream's read and write ride under the tensor-core mainloop of the next tile.
-template <int BLOCK_N, typename OutT, bool CTA2 = false, bool CONV = false, bool RESID = false>
+// RESID == 2: the residual chunk is fetched into a buffer of its own, ONE CHUNK AHEAD (also across tiles), so the
+// epilogue never waits for a load -- what the short-K proj GEMM needs (its tile lasts 3 us, four exposed L2/HBM
+// round trips per tile would make it epilogue bound).
+template <int BLOCK_N, typename OutT, bool CTA2 = false, bool CONV = false, int RESID = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                          const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N,
                          int K, int act, int conv_c = 0, int conv_h = 0) {
   static_assert(!CONV || CTA2, "the implicit-GEMM convolution is built on the CTA-pair kernel");
-  static_assert(!RESID || sizeof(OutT) == 4, "the residual epilogue accumulates into an fp32 tensor");
-  using S = GemmSmem<BLOCK_N, CTA2>;
+  static_assert(RESID == 0 || sizeof(OutT) == 4, "the residual epilogue accumulates into an fp32 tensor");
+  using S = GemmSmem<BLOCK_N, CTA2, RESID == 2>;
   // CTA pair: rank 0 (leader) issues the MMAs of both; every CTA loads and stores its own 128 rows
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0;
   constexpr int TILE_M = CTA2 ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M;
@@ -210,6 +214,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     constexpr int LAST1 = NCHUNK >= 2 ? ((NCHUNK - 2) / 2) * 2 + 1 : -1;  // last chunk of the odd warp (none if 1 chunk)
     const int last_c = half == 0 ? LAST0 : LAST1;
     [[maybe_unused]] uint32_t rphase = 0;
+    [[maybe_unused]] uint8_t* rbuf = epi_smem + (8 + half * 4 + q) * S::EPI_WARP_BYTES;   // RESID == 2 only
+    [[maybe_unused]] uint64_t* rbar2 = &resid_bar[half * 4 + q];
+    // RESID == 2: fetch the 32 x CHUNK piece of `out` at (tile t, chunk c) into rbuf (lane 0)
+    auto prefetch_resid = [&](int t, int c) {
+      const int pm0 = (t / n_blks) * TILE_M + rank * GEMM_BLOCK_M;
+      const int pn0 = (t % n_blks) * BLOCK_N;
+      mbar_arrive_expect_tx(rbar2, S::EPI_WARP_BYTES);
+      tma_load_2d(rbuf, &tm_out, rbar2, pn0 + c * CHUNK, pm0 + q * 32);
+    };
+    if constexpr (RESID == 2) {
+      if (lane == 0 && half < NCHUNK && tile0 < num_tiles) prefetch_resid(tile0, half);
+    }
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int m0 = (tile / n_blks) * TILE_M + rank * GEMM_BLOCK_M;
@@ -222,7 +238,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         mbar_arrive_expect_tx(rbar, S::EPI_WARP_BYTES);
         tma_load_2d(buf, &tm_out, rbar, n0 + c * CHUNK, m0 + q * 32);
       };
-      if constexpr (RESID) {
+      if constexpr (RESID == 1) {
         if (lane == 0 && half < NCHUNK) load_resid(half);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -278,7 +294,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
         uint8_t* row_ptr = buf + lane * 128;
-        if constexpr (RESID) {
+        if constexpr (RESID == 2) {
+          // the chunk arrived in rbuf (requested one chunk ago): add it, hand rbuf to the next request, then wait for
+          // the store buffer as in the plain path
+          mbar_wait(rbar2, rphase);
+          rphase ^= 1;
+          const uint8_t* rrow = rbuf + lane * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 xr = *reinterpret_cast<const float4*>(rrow + ((g ^ (lane & 7)) << 4));
+            v[g * 4 + 0] += xr.x;
+            v[g * 4 + 1] += xr.y;
+            v[g * 4 + 2] += xr.z;
+            v[g * 4 + 3] += xr.w;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            if (c + 2 < NCHUNK) prefetch_resid(tile, c + 2);
+            else if (tile + tile_step < num_tiles) prefetch_resid(tile + tile_step, half);
+            tma_store_wait_read<0>();
+          }
+          __syncwarp();
+        } else if constexpr (RESID == 1) {
           // out chunk (loaded by TMA, 128B-swizzled like the store layout) + accumulator, in place
           mbar_wait(rbar, rphase);
           rphase ^= 1;
@@ -317,7 +354,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         if (lane == 0) {
           tma_store_2d(&tm_out, buf, n0 + col0, m0 + q * 32);
           tma_store_commit();
-          if constexpr (RESID) {
+          if constexpr (RESID == 1) {
             if (c + 2 < NCHUNK) load_resid(c + 2);   // next chunk of this tile (after the store has read the buffer)
           }
         }
@@ -337,11 +374,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 }
 
 // CTA-pair launch: clusters of 2 CTAs, 256 x 256 tiles
-template <typename OutT, bool CONV = false, bool RESID = false>
+template <typename OutT, bool CONV = false, int RESID = 0>
 static int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
                             const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int act,
                             int conv_c = 0, int conv_h = 0) {
-  using S = GemmSmem<256, true>;
+  using S = GemmSmem<256, true, RESID == 2>;
   auto kern = gemm_bf16_tcgen05_kernel<256, OutT, true, CONV, RESID>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   const int tiles = ((N + 255) / 256) * ((M + 255) / 256);
@@ -484,5 +521,10 @@ extern "C" int la_gemm_bf16_accumulate(void* stream, const void* a, long long ld
   rc = make_tensor_map_2d(&tm_out, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)N, (uint64_t)M, (uint64_t)ldx * 4, 32, 32,
                           Swizzle::B128);
   if (rc) return rc;
-  return launch_gemm_2cta<float, false, true>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE);
+  // long-K GEMMs hide the residual chunk's load behind their own tile; short-K ones get the prefetching epilogue
+  // (one pipeline stage less, a second staging buffer per epilogue warp)
+  const char* e = getenv("LA_GEMM_ACC_MODE");
+  const int mode = e ? atoi(e) : (K >= 2048 ? 1 : 2);
+  if (mode == 2) return launch_gemm_2cta<float, false, 2>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE);
+  return launch_gemm_2cta<float, false, 1>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE);
 }

@@ -54,6 +54,10 @@ class VitSpec:
     final_ln_b: Optional[torch.Tensor] = None
 
 
+# experiment switch: also take the attention branch's residual add in the proj GEMM epilogue (prefetching variant)
+_FUSE_PROJ = bool(__import__("os").environ.get("LA_FUSE_PROJ"))
+
+
 def reversed_rel_table(rel_pos: torch.Tensor, size: int, pad_to: int) -> torch.Tensor:
     """rel_pos [L, 64] -> [pad_to, 64] with row i = rel_pos'[2*size-2 - i], rel_pos' = table resized (linear) to
     2*size-1 rows when L differs (get_rel_pos, image_encoder.py:319-330)."""
@@ -84,12 +88,14 @@ def run_vit(spec: VitSpec, x: torch.Tensor, n_img: int, out_dtype: torch.dtype) 
             seq_len, n_seq = win * win, n_img * nwin * nwin
             r_att = n_seq * seq_len
             y = torch.empty((r_att, d), dtype=torch.bfloat16, device=dev)
-            ops.add_layernorm(x, delta, bw.ln1_w, bw.ln1_b, spec.eps, rows=r_att, d=d, x_out=x, y_out=y,
+            ops.add_layernorm(x, delta, bw.ln1_w, bw.ln1_b, spec.eps, rows=r_att, d=d,
+                              x_out=x if delta is not None else None, y_out=y,
                               map_mode=1, win=win, nwin=nwin, hw=g)
         else:
             win, nwin, seq_len, n_seq, r_att = 0, 0, T, n_img, rows
             y = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
-            ops.add_layernorm(x, delta, bw.ln1_w, bw.ln1_b, spec.eps, rows=rows, d=d, x_out=x, y_out=y)
+            ops.add_layernorm(x, delta, bw.ln1_w, bw.ln1_b, spec.eps, rows=rows, d=d,
+                              x_out=x if delta is not None else None, y_out=y)
         q = ops.gemm(y, bw.wq, bw.bq)
         kv = ops.gemm(y, bw.wkv, bw.bkv)
         del y
@@ -112,10 +118,15 @@ def run_vit(spec: VitSpec, x: torch.Tensor, n_img: int, out_dtype: torch.dtype) 
                           out_mode=1 if win > 0 else 0, nwin=nwin, img_hw=g)
             del bias_h, bias_w
         del q, kv
-        delta = ops.gemm(att, bw.wproj, bw.bproj)
+        if _FUSE_PROJ and ops.gemm_accumulate_supported(rows, d):
+            ops.gemm_accumulate(att, bw.wproj, bw.bproj, x)
+            delta = None
+        else:
+            delta = ops.gemm(att, bw.wproj, bw.bproj)
         del att
         y2 = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
-        ops.add_layernorm(x, delta, bw.ln2_w, bw.ln2_b, spec.eps, rows=rows, d=d, x_out=x, y_out=y2)
+        ops.add_layernorm(x, delta, bw.ln2_w, bw.ln2_b, spec.eps, rows=rows, d=d, x_out=x if delta is not None else None,
+                          y_out=y2)
         h = ops.gemm(y2, bw.w1, bw.b1, act=ops.ACT_GELU)
         del y2
         if ops.gemm_accumulate_supported(rows, d):
