@@ -329,17 +329,19 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
     src = row;
     pad = false;
     if (p.map_mode == 1) {
-      const int w2 = p.win * p.win;
-      const long long widx = row / w2;
-      const int tin = static_cast<int>(row - widx * w2);
-      const int per_img = p.nwin * p.nwin;
-      const long long img = widx / per_img;
-      const int wi = static_cast<int>(widx - img * per_img);
-      const int wy = wi / p.nwin, ty = tin / p.win;
-      const int y = wy * p.win + ty;
-      const int x = (wi - wy * p.nwin) * p.win + (tin - ty * p.win);
-      pad = (y >= p.hw) || (x >= p.hw);
-      src = (img * p.hw + y) * p.hw + x;
+      // 32-bit index arithmetic (the launcher guarantees rows < 2^31): these divisions sit on the refill path
+      const uint32_t r32 = static_cast<uint32_t>(row);
+      const uint32_t w2 = p.win * p.win;
+      const uint32_t widx = r32 / w2;
+      const uint32_t tin = r32 - widx * w2;
+      const uint32_t per_img = p.nwin * p.nwin;
+      const uint32_t img = widx / per_img;
+      const uint32_t wi = widx - img * per_img;
+      const uint32_t wy = wi / p.nwin, ty = tin / p.win;
+      const uint32_t y = wy * p.win + ty;
+      const uint32_t x = (wi - wy * p.nwin) * p.win + (tin - ty * p.win);
+      pad = (y >= static_cast<uint32_t>(p.hw)) || (x >= static_cast<uint32_t>(p.hw));
+      src = (static_cast<long long>(img) * p.hw + y) * p.hw + x;
     }
   };
   auto issue = [&](long long chunk, int slot) {   // lane 0
@@ -708,6 +710,7 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   const int need = (d + 127) / 128;
   // the ViT block case goes through the staged kernel (bulk async row copies, 3 rows in flight per warp)
   const bool staged = x_mod == 0 && !delta2 && !y2_out && !ype_out && act == LA_ACT_NONE && gamma && y_out &&
+                      rows < (1ll << 31) &&
                       (map_mode == 0 || map_mode == 1) && need <= 6 && d % 32 == 0 && rows >= 4096 &&
                       getenv("LA_LN_UNSTAGED") == nullptr;
   if (staged) {
