@@ -288,7 +288,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         }
         if (act_code == LA_ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < CHUNK; i += 2) gelu_erf_x2(v[i], v[i + 1]);
+          for (int i = 0; i < CHUNK; i += 2) {
+            if constexpr (sizeof(OutT) == 2) gelu_tanh_erf_x2(v[i], v[i + 1]);   // error far below the bf16 rounding
+            else gelu_erf_x2(v[i], v[i + 1]);
+          }
         } else if (act_code == LA_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < CHUNK; ++i) v[i] = fmaxf(v[i], 0.0f);
