@@ -35,6 +35,7 @@ extern "C" {
 /* element types of outputs */
 #define LA_DTYPE_BF16 0
 #define LA_DTYPE_F32 1
+#define LA_DTYPE_F16 2
 
 /* ---- library management ------------------------------------------------------------------------- */
 const char* la_last_error(void); /* thread-local message of the last failing call */
@@ -43,7 +44,7 @@ int la_device_check(void); /* LA_OK iff the current device is sm_100 */
 
 /* ---- dense contraction -------------------------------------------------------------------------- */
 /* out[M,N] = act(a[M,K] @ w[N,K]^T + bias[N]);  a, w bf16 with K contiguous (nn.Linear weight layout),
- * fp32 accumulation on tcgen05 tensor cores, out bf16 or fp32.  lda/ldw/ldo are row strides in elements.
+ * fp32 accumulation on tcgen05 tensor cores, out bf16, fp32 or fp16 (out_dtype = LA_DTYPE_*).  lda/ldw/ldo are row strides in elements.
  * Replaces every nn.Linear / 1x1 Conv2d / im2col'd Conv2d / stride==kernel ConvTranspose2d on the path:
  *   label_anything/models/image_encoder.py:227-228,242,253,402-410; common.py:28-37,82-85,108-110,146;
  *   build_lam.py:150-171; mask_decoder.py:206-255,776-804. */
@@ -71,7 +72,8 @@ int la_conv3x3_bf16(void* stream, const void* x, int n_img, int H, int W, int C,
  * of the projection matrices q [rows_total, ld_q] and kv [rows_total, ld_kv] (bf16; they may be the same
  * packed qkv buffer).  Head h reads q at column q_off + 64*h and k / v at columns {k,v}_off + 64*h of kv.
  * softmax(scale * q k^T + bias) v -> out [.., ld_out] bf16 at columns 64*h.
- * Optional decomposed relative-position bias (bias_h/bias_w != NULL): fp32 tables [rows_total][n_heads][ldb]
+ * Optional decomposed relative-position bias (bias_h/bias_w != NULL): tables [rows_total][n_heads][ldb], fp32 or
+ * fp16 (bias_dtype = LA_DTYPE_F32 / LA_DTYPE_F16; the rel_w part is rounded to fp16 inside the kernel anyway)
  * with table[row][h][grid_hw-1 - q_pos + k_pos] = q_row(h) . rel_pos[q_pos - k_pos + grid_hw-1], i.e. the
  * product of the head's q rows with the REVERSED rel_pos table (computed with la_gemm_bf16); grid_hw = 64
  * (global blocks, seq_len 4096).  The 14x14 windowed blocks use la_attention_window_bf16 below.
@@ -81,8 +83,8 @@ int la_conv3x3_bf16(void* stream, const void* x, int n_img, int H, int W, int C,
  *   label_anything/models/image_encoder.py:239-255,282-304,340-376; transformers modeling_vit.py:199-250 */
 int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
                       int k_off, int v_off, long long rows_total, int n_seq, int seq_len, int n_heads, float scale,
-                      const float* bias_h, const float* bias_w, int ldb, int grid_hw, void* out, long long ld_out,
-                      int out_mode, int nwin, int img_hw);
+                      const void* bias_h, const void* bias_w, int bias_dtype, int ldb, int grid_hw, void* out,
+                      long long ld_out, int out_mode, int nwin, int img_hw);
 
 /* 14x14-window attention of the SAM ViT blocks (seq_len 196, head_dim 64) with the decomposed relative-position
  * bias computed INSIDE the kernel: rel_table is the bf16 operand [2 * rel_pad][64], rel_pad = 32, rows [0, 27) = the

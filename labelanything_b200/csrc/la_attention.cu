@@ -29,8 +29,9 @@
 //     so the softmax threads see scores that already contain it -- no per-element bias arithmetic, no 64-register
 //     rel_w row (the MUFU/issue-bound softmax loop is the limiter of this kernel, the tensor pipe has slack).
 #include "la_common.cuh"
-#include <cstdlib>
+#include <type_traits>
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace la {
 
@@ -68,8 +69,8 @@ struct AttParams {
   float scale_log2;         // softmax scale * log2(e)
   float inv_scale;          // 1 / softmax scale
   // rel-pos bias tables: [rows_total][n_heads][ldb] fp32 (nullptr for ATT_BIAS_NONE)
-  const float* bias_h;
-  const float* bias_w;
+  const void* bias_h;   // fp32 or fp16 tables (template parameter TF16)
+  const void* bias_w;
   int ldb;
   int rel_pad;              // window mode: rows of each (h / w) half of the reversed rel-pos operand (32)
   // output
@@ -213,7 +214,7 @@ __device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float 
       : "f"(a0), "f"(a1));
 }
 
-template <int KV_TILE, int BIAS>
+template <int KV_TILE, int BIAS, bool TF16 = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_rel, const AttParams p) {
@@ -519,11 +520,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int t0 = qpair * 256 + x * 128;
 #pragma unroll 1
         for (int r0 = 0; r0 < 128; r0 += 16) {
+          if constexpr (TF16) {
+            // fp16 table: the 64 entries of a row start at a 2-byte aligned offset; fetch the aligned 32-bit words
+            // around this lane's pair and funnel them (the shift is the same for the whole row)
+            uint32_t w0[16], w1[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int t = (t0 + r0 + u < p.seq_len) ? t0 + r0 + u : 0;
+              const long long e = ((seq_row0 + t) * p.n_heads + head) * p.ldb + (63 - (t & 63));
+              const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<const __half*>(p.bias_w) + (e & ~1ll)) + lane;
+              w0[u] = __ldg(src);
+              w1[u] = __ldg(src + 1);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int r = r0 + u;
+              const int t = (t0 + r < p.seq_len) ? t0 + r : 0;
+              const bool odd = ((63 - (t & 63)) & 1) != 0;   // ldb and the view offset are even
+              const uint32_t pr = odd ? __byte_perm(w0[u], w1[u], 0x5432) : w0[u];
+              *reinterpret_cast<uint32_t*>(dst + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4) = pr;
+            }
+          } else {
           float v0[16], v1[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const int t = (t0 + r0 + u < p.seq_len) ? t0 + r0 + u : 0;
-            const float* src = p.bias_w + ((seq_row0 + t) * p.n_heads + head) * p.ldb + (63 - (t & 63)) + 2 * lane;
+            const float* src = static_cast<const float*>(p.bias_w) + ((seq_row0 + t) * p.n_heads + head) * p.ldb + (63 - (t & 63)) + 2 * lane;
             v0[u] = __ldg(src);
             v1[u] = __ldg(src + 1);
           }
@@ -532,6 +554,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const int r = r0 + u;
             *reinterpret_cast<uint32_t*>(dst + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4) =
                 pack_f16(v0[u], v1[u]);
+          }
           }
         }
         fence_proxy_async_smem();
@@ -555,18 +578,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     constexpr bool WIN = BIAS == ATT_BIAS_WINDOW14;
 
     // rel_h table row of this thread's query in work item w2 (pointer to the entry of key-grid row 0)
-    auto bh_row_of = [&](int w2) -> const float* {
+    using BT = typename std::conditional<TF16, __half, float>::type;   // rel-pos table element
+    // table entries travel in their storage type and are converted where they are consumed: a conversion placed
+    // right behind the load would stall the thread for the full load latency once per key tile
+    auto tab_f32 = [](BT v) -> float {
+      if constexpr (TF16) return __half2float(v); else return v;
+    };
+    auto bh_row_of = [&](int w2) -> const BT* {
       const int qpair2 = w2 % n_qp;
       const int head2 = (w2 / n_qp) % p.n_heads;
       const long long row0 = static_cast<long long>(w2 / (n_qp * p.n_heads)) * p.seq_len;
       const int t2 = qpair2 * 256 + x * 128 + r;
       const int tt = t2 < p.seq_len ? t2 : 0;
-      return p.bias_h + ((row0 + tt) * p.n_heads + head2) * p.ldb + (GW - 1 - tt / GW);
+      return static_cast<const BT*>(p.bias_h) + ((row0 + tt) * p.n_heads + head2) * p.ldb + (GW - 1 - tt / GW);
     };
     // the next item's row pointer and (64x64 mode) its first rel_h term are fetched before the epilogue of the current
     // item, so the global-load latency is off the item-to-item critical path
-    const float* bh_row_pre = nullptr;
-    float rh_pre = 0.0f;
+    const BT* bh_row_pre = nullptr;
+    BT rh_pre = BT(0.0f);
     if constexpr (FOLD_W) {
       if (static_cast<int>(blockIdx.x) < n_items) {
         bh_row_pre = bh_row_of(blockIdx.x);
@@ -592,7 +621,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // ---- rel-pos bias prologue (log2 units) ----
       float rw2[WIN ? GW : 1];
       float rh_all[WIN ? 2 * NG : 1];   // window mode: rel_h terms of all 14 key-grid rows (+ 2 zeros), log2 units
-      const float* bh_row = bh_row_pre;
+      const BT* bh_row = bh_row_pre;
       if constexpr (WIN) {
         // T[row][e] = q_row . rel_rev[e] sits in TMEM (issued with the item's first score tile): entries [0, 27) are
         // the rel_h products, [rel_pad, rel_pad + 27) the rel_w products, and the bias of key (kh, kw) for a query at
@@ -628,7 +657,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       att_trace(p, tr, 3 + x, it, 3);
       float m_used = -INFINITY;
       float l_sum = 0.0f;
-      float rh_next = 0.0f;   // 64x64 mode: rel_h term of the next key tile (= key-grid row), fetched one tile ahead
+      BT rh_next = BT(0.0f);   // 64x64 mode: rel_h term of the next key tile (= key-grid row), fetched one tile ahead
       if constexpr (FOLD_W) rh_next = rh_pre;
 
       for (int j = 0; j < NT; ++j) {
@@ -638,7 +667,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         float rh2[NG];
         if constexpr (FOLD_W) {
           static_assert(!FOLD_W || NG == 1, "one key-grid row per tile");
-          rh2[0] = rh_next * LOG2E;
+          rh2[0] = tab_f32(rh_next) * LOG2E;
           if (j + 1 < NT) rh_next = __ldg(bh_row + j + 1);
         } else if constexpr (WIN) {
 #pragma unroll
@@ -841,7 +870,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
 }
 
-template <int KV_TILE, int BIAS>
+template <int KV_TILE, int BIAS, bool TF16 = false>
 static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, const void* kv, long long ld_kv,
                             const AttParams& p, const void* rel = nullptr) {
   using S = AttSmem<KV_TILE, BIAS>;
@@ -852,7 +881,7 @@ static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, 
   rc = make_tensor_map_2d(&tm_kv, kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_kv, (uint64_t)p.rows_total,
                           (uint64_t)ld_kv * 2, 64, KV_TILE, Swizzle::B128);
   if (rc) return rc;
-  auto kern = attention_fwd_kernel<KV_TILE, BIAS>;
+  auto kern = attention_fwd_kernel<KV_TILE, BIAS, TF16>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   const long long items = static_cast<long long>((p.seq_len + 255) / 256) * p.n_heads * p.n_seq;
   const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
@@ -877,8 +906,8 @@ extern "C" int la_attention_set_trace(void* device_buffer) {
 
 static int attention_dispatch(const char* fn, void* stream, const void* q, long long ld_q, int q_off, const void* kv,
                               long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq, int seq_len,
-                              int n_heads, float scale, const float* bias_h, const float* bias_w, int ldb,
-                              const void* rel_table, int rel_pad, int grid_hw, void* out, long long ld_out,
+                              int n_heads, float scale, const void* bias_h, const void* bias_w, int bias_dtype,
+                              int ldb, const void* rel_table, int rel_pad, int grid_hw, void* out, long long ld_out,
                               int out_mode, int nwin, int img_hw) {
   using namespace la;
   LA_CHECK_ARG(q && kv && out, "%s: null pointer", fn);
@@ -930,6 +959,12 @@ static int attention_dispatch(const char* fn, void* stream, const void* q, long 
   if (grid_hw == 64) {
     LA_CHECK_ARG(seq_len == 4096 && ldb >= 127 && out_mode == 0, "%s: 64x64 rel-pos mode expects seq_len 4096, ldb >= 127",
                  fn);
+    LA_CHECK_ARG(bias_dtype == LA_DTYPE_F32 || bias_dtype == LA_DTYPE_F16, "%s: tables are fp32 or fp16", fn);
+    if (bias_dtype == LA_DTYPE_F16) {
+      LA_CHECK_ARG(ldb % 2 == 0 && (reinterpret_cast<uintptr_t>(bias_w) & 3) == 0 && ldb >= 128,
+                   "%s: fp16 tables need an even ldb >= 128 and 4-byte aligned rows", fn);
+      return launch_attention<64, ATT_BIAS_GLOBAL64, true>(st, q, ld_q, kv, ld_kv, p);
+    }
     return launch_attention<64, ATT_BIAS_GLOBAL64>(st, q, ld_q, kv, ld_kv, p);
   }
   set_last_error("%s: unsupported rel-pos grid %d (fp32 tables: 64; 14x14 windows go through la_attention_window_bf16)",
@@ -939,11 +974,11 @@ static int attention_dispatch(const char* fn, void* stream, const void* q, long 
 
 extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv,
                                  long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq,
-                                 int seq_len, int n_heads, float scale, const float* bias_h, const float* bias_w,
-                                 int ldb, int grid_hw, void* out, long long ld_out, int out_mode, int nwin,
+                                 int seq_len, int n_heads, float scale, const void* bias_h, const void* bias_w,
+                                 int bias_dtype, int ldb, int grid_hw, void* out, long long ld_out, int out_mode, int nwin,
                                  int img_hw) {
   return attention_dispatch("la_attention_bf16", stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total, n_seq,
-                            seq_len, n_heads, scale, bias_h, bias_w, ldb, nullptr, 0, grid_hw, out, ld_out, out_mode,
+                            seq_len, n_heads, scale, bias_h, bias_w, bias_dtype, ldb, nullptr, 0, grid_hw, out, ld_out, out_mode,
                             nwin, img_hw);
 }
 
@@ -954,6 +989,6 @@ extern "C" int la_attention_window_bf16(void* stream, const void* q, long long l
   using namespace la;
   LA_CHECK_ARG(rel_table != nullptr, "la_attention_window_bf16: rel_table is required");
   return attention_dispatch("la_attention_window_bf16", stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total,
-                            n_seq, 196, n_heads, scale, nullptr, nullptr, 0, rel_table, rel_pad, 14, out, ld_out,
+                            n_seq, 196, n_heads, scale, nullptr, nullptr, LA_DTYPE_F32, 0, rel_table, rel_pad, 14, out, ld_out,
                             out_mode, nwin, img_hw);
 }

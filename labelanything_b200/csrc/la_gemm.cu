@@ -19,6 +19,8 @@
 // the mainloop of tile i+1.
 #include "la_common.cuh"
 #include <cstdlib>
+#include <type_traits>
+#include <cuda_fp16.h>
 #include "../../include/labelanything_b200.h"
 
 namespace la {
@@ -51,6 +53,17 @@ struct GemmSmem {
 // feature map [n_img, H, W = 64, C]: A is never materialised -- k-block (tap, channel chunk) of the 128 pixels of a
 // CTA (two image rows) is ONE 4-D TMA box [64 ch, 64 w, 2 h, 1 img] fetched at the tap's shifted coordinates, and the
 // out-of-bounds rows / columns of the border are zero-filled by the TMA unit.  conv_c = C, conv_h = H; K = 9 * C.
+// two fp32 -> one packed 16-bit pair of the output type
+template <typename OutT>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if constexpr (std::is_same<OutT, __half>::value) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    return pack_bf16(lo, hi);
+  }
+}
+
 // RESID (fp32 output only): out += A W^T + bias, i.e. the output tensor is also the residual operand.  Each epilogue
 // warp TMA-loads its 32 x 32 chunk of `out` into the staging buffer it will store from, adds the accumulator in place
 // and stores it back -- the residual stream's read and write ride under the tensor-core mainloop of the next tile.
@@ -339,10 +352,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             uint4 pk;
-            pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-            pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-            pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-            pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+            pk.x = pack2<OutT>(v[g * 8 + 0], v[g * 8 + 1]);
+            pk.y = pack2<OutT>(v[g * 8 + 2], v[g * 8 + 3]);
+            pk.z = pack2<OutT>(v[g * 8 + 4], v[g * 8 + 5]);
+            pk.w = pack2<OutT>(v[g * 8 + 6], v[g * 8 + 7]);
             *reinterpret_cast<uint4*>(row_ptr + ((g ^ (lane & 7)) << 4)) = pk;
           }
         } else {
@@ -427,8 +440,9 @@ extern "C" int la_gemm_bf16(void* stream, const void* a, long long lda, const vo
   LA_CHECK_ARG(M > 0 && N > 0 && K > 0, "la_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   LA_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "la_gemm_bf16: K/lda/ldw must be multiples of 8");
   LA_CHECK_ARG(N % 8 == 0, "la_gemm_bf16: N must be a multiple of 8 (got %d)", N);
-  LA_CHECK_ARG(out_dtype == LA_DTYPE_BF16 || out_dtype == LA_DTYPE_F32, "la_gemm_bf16: bad out_dtype %d", out_dtype);
-  LA_CHECK_ARG((ldo * (out_dtype == LA_DTYPE_BF16 ? 2 : 4)) % 16 == 0, "la_gemm_bf16: ldo must give 16B rows");
+  LA_CHECK_ARG(out_dtype == LA_DTYPE_BF16 || out_dtype == LA_DTYPE_F32 || out_dtype == LA_DTYPE_F16,
+               "la_gemm_bf16: bad out_dtype %d", out_dtype);
+  LA_CHECK_ARG((ldo * (out_dtype == LA_DTYPE_F32 ? 4 : 2)) % 16 == 0, "la_gemm_bf16: ldo must give 16B rows");
   LA_CHECK_ARG((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) %
                        16 ==
                    0,
@@ -446,7 +460,16 @@ extern "C" int la_gemm_bf16(void* stream, const void* a, long long lda, const vo
   rc = make_tensor_map_2d(&tm_w, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2,
                           GEMM_BLOCK_K, (uint32_t)(pair ? 128 : block_n), Swizzle::B128);
   if (rc) return rc;
-  if (out_dtype == LA_DTYPE_BF16) {
+  if (out_dtype == LA_DTYPE_F16) {   // rel-pos tables (no activation: the GELU forms are tuned for bf16 / fp32)
+    LA_CHECK_ARG(act == LA_ACT_NONE, "la_gemm_bf16: fp16 output has no activation epilogue");
+    rc = make_tensor_map_2d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2,
+                            64, 32, Swizzle::B128);
+    if (rc) return rc;
+    if (pair) return launch_gemm_2cta<__half>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+    if (block_n == 256) return launch_gemm<256, __half>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+    if (block_n == 128) return launch_gemm<128, __half>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+    return launch_gemm<64, __half>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
+  } else if (out_dtype == LA_DTYPE_BF16) {
     rc = make_tensor_map_2d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)N, (uint64_t)M,
                             (uint64_t)ldo * 2, 64, 32, Swizzle::B128);
     if (rc) return rc;

@@ -10,8 +10,8 @@ import torch
 from . import _native
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
-DT_BF16, DT_F32 = 0, 1
-_DTC = {torch.bfloat16: DT_BF16, torch.float32: DT_F32}
+DT_BF16, DT_F32, DT_F16 = 0, 1, 2
+_DTC = {torch.bfloat16: DT_BF16, torch.float32: DT_F32, torch.float16: DT_F16}
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -99,13 +99,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act
     N = w.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=a.device)
-    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in _DTC
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     _cost(2.0 * M * N * K, 2.0 * (M * K + N * K) + M * N * out.element_size())
     _call(f"gemm.n{N}.k{K}" if _PROF is not None else "gemm", "la_gemm_bf16", _stream(a), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
         bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0),
-        DT_BF16 if out.dtype == torch.bfloat16 else DT_F32, M, N, K, act)
+        _DTC[out.dtype], M, N, K, act)
     return out
 
 
@@ -180,21 +180,22 @@ def attention(q: torch.Tensor, kv: torch.Tensor, n_seq: int, seq_len: int, n_hea
               bias_w: torch.Tensor | None = None, grid_hw: int = 0, out_mode: int = 0, nwin: int = 0,
               img_hw: int = 0) -> torch.Tensor:
     """Fused MHSA (head_dim 64); q [rows, ld_q], kv [rows, ld_kv] bf16 (may be one packed buffer).
-    bias_h / bias_w: fp32 views [rows, heads, >=2g-1] sharing one row stride (see the C header)."""
+    bias_h / bias_w: fp32 or fp16 views [rows, heads, >=2g-1] sharing one row stride (see the C header)."""
     _require_cuda(q, kv, out, bias_h, bias_w)
     for t in (q, kv, out):
         assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
     assert q.shape[0] == kv.shape[0]
     ldb = 0
     if bias_h is not None:
-        assert bias_h.dtype == torch.float32 and bias_w.dtype == torch.float32
+        assert bias_h.dtype in (torch.float32, torch.float16) and bias_w.dtype == bias_h.dtype
         assert bias_h.dim() == 3 and bias_h.shape[:2] == (q.shape[0], n_heads) and bias_w.shape[:2] == bias_h.shape[:2]
         assert bias_h.stride(2) == 1 and bias_w.stride(2) == 1 and bias_h.stride() == bias_w.stride()
         ldb = bias_h.stride(1)
         assert bias_h.stride(0) == ldb * n_heads
     _cost(4.0 * n_seq * n_heads * seq_len * seq_len * 64, 2.0 * 4 * n_seq * seq_len * n_heads * 64)
     _call(f"attention.L{seq_len}" if _PROF is not None else "attention", "la_attention_bf16", _stream(q), q.data_ptr(), q.stride(0), q_off, kv.data_ptr(), kv.stride(0), k_off, v_off, q.shape[0], n_seq,
-        seq_len, n_heads, float(scale), _ptr(bias_h), _ptr(bias_w), ldb, grid_hw, out.data_ptr(), out.stride(0),
+        seq_len, n_heads, float(scale), _ptr(bias_h), _ptr(bias_w),
+        _DTC[bias_h.dtype] if bias_h is not None else DT_F32, ldb, grid_hw, out.data_ptr(), out.stride(0),
         out_mode, nwin, img_hw)
     return out
 

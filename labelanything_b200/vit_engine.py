@@ -56,6 +56,9 @@ class VitSpec:
 
 # experiment switch: also take the attention branch's residual add in the proj GEMM epilogue (prefetching variant)
 _FUSE_PROJ = bool(__import__("os").environ.get("LA_FUSE_PROJ"))
+# element type of the global blocks' rel-pos tables q . rel_pos (the rel_w half is rounded to fp16 inside the attention
+# kernel either way; fp16 halves the table traffic).  LA_REL_TABLE_F32=1 keeps the fp32 tables.
+_TABLE_DTYPE = torch.float32 if __import__("os").environ.get("LA_REL_TABLE_F32") else torch.float16
 
 
 def reversed_rel_table(rel_pos: torch.Tensor, size: int, pad_to: int) -> torch.Tensor:
@@ -110,7 +113,7 @@ def run_vit(spec: VitSpec, x: torch.Tensor, n_img: int, out_dtype: torch.dtype) 
             grid_hw = 0
             if bw.rel_table is not None:
                 P = bw.rel_pad
-                tab = ops.gemm(q.view(r_att * heads, 64), bw.rel_table, None, out_dtype=torch.float32)
+                tab = ops.gemm(q.view(r_att * heads, 64), bw.rel_table, None, out_dtype=_TABLE_DTYPE)
                 tab = tab.view(r_att, heads, 2 * P)
                 bias_h, bias_w = tab[:, :, :P], tab[:, :, P:]
                 grid_hw = g

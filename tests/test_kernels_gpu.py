@@ -50,6 +50,8 @@ def _gen(seed):
     (3000, 384, 128, 0, torch.bfloat16, True),     # CTA-pair path with an M tail and a half-filled N tile
     (12, 512, 512, 0, torch.float32, False),       # a handful of token rows
     (2048, 64, 64, 0, torch.float32, False),       # rel-pos table GEMM
+    (4096, 256, 64, 0, torch.float16, False),      # rel-pos table GEMM of the global blocks, fp16 out (CTA pair)
+    (1000, 128, 64, 0, torch.float16, False),      # fp16 out, single-CTA tiles
 ])
 def test_gemm_matches_torch(M, N, K, act, out_dtype, bias):
     ops = _ops()
@@ -65,6 +67,8 @@ def test_gemm_matches_torch(M, N, K, act, out_dtype, bias):
     assert y.dtype == out_dtype and y.shape == (M, N)
     if out_dtype == torch.bfloat16:
         _close(y, r, 2 ** -8, 2e-3, "gemm bf16")      # one bf16 rounding of the result
+    elif out_dtype == torch.float16:
+        _close(y, r, 2 ** -11, 1e-4, "gemm fp16")     # one fp16 rounding of the result
     else:
         _close(y, r, 1e-4, 1e-4, "gemm fp32")         # fp32 accumulation order only
 
@@ -116,11 +120,11 @@ def test_conv3x3_implicit_gemm_matches_torch():
 
 
 # ---------------------------------------------------------------------------------------------- fused attention
-def _rev_bias(ops, q_heads, rel, pad_to):
+def _rev_bias(ops, q_heads, rel, pad_to, dtype=torch.float32):
     trev = torch.flip(rel, dims=[0]).to(torch.bfloat16)
     w = torch.zeros(pad_to, 64, device=rel.device, dtype=torch.bfloat16)
     w[: trev.shape[0]] = trev
-    return torch.stack([ops.gemm(q_heads[h], w, None, out_dtype=torch.float32) for h in range(q_heads.shape[0])]
+    return torch.stack([ops.gemm(q_heads[h], w, None, out_dtype=dtype) for h in range(q_heads.shape[0])]
                        ).permute(1, 0, 2).contiguous()
 
 
@@ -151,11 +155,13 @@ def _ref_attention(qkv, n_seq, L, heads, scale, rel_h=None, rel_w=None, g=0):
     ("plain", 1, 4096, 0, 4.0),        # large logits: forces the lazy O rescale path
     ("global", 1, 4096, 64, 1.0),      # SAM global block with decomposed rel-pos bias
     ("global", 2, 4096, 64, 4.0),      # + rescales, two sequences (persistent loop over items)
+    ("global16", 1, 4096, 64, 1.0),    # fp16 rel-pos tables (what the encoder engine feeds the global blocks)
+    ("global16", 2, 4096, 64, 4.0),
     ("window", 50, 196, 14, 1.0),      # SAM 14x14 windows (2 images x 25 windows)
 ])
 def test_fused_attention_matches_torch(mode, n_seq, L, gsz, qscale):
     ops = _ops()
-    heads = 12 if mode != "global" else 4
+    heads = 12 if not mode.startswith("global") else 4
     g = _gen(L + n_seq)
     qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda", generator=g)
     qkv[:, : heads * 64] *= qscale
@@ -172,7 +178,8 @@ def test_fused_attention_matches_torch(mode, n_seq, L, gsz, qscale):
     else:
         if gsz:
             qh = qkv[:, : heads * 64].reshape(n_seq * L, heads, 64).permute(1, 0, 2).contiguous()
-            bh, bw = _rev_bias(ops, qh, rel_h, 128), _rev_bias(ops, qh, rel_w, 128)
+            td = torch.float16 if mode == "global16" else torch.float32
+            bh, bw = _rev_bias(ops, qh, rel_h, 128, td), _rev_bias(ops, qh, rel_w, 128, td)
         ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
     ref = _ref_attention(qkv, n_seq, L, heads, 0.125, rel_h, rel_w, gsz)
     # P and the output are rounded to bf16 (2^-9 each, P errors average over the keys): 1e-2 relative + 1e-2 absolute

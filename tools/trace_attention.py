@@ -1,4 +1,4 @@
-"""Timeline of one CTA of the fused attention kernel (clock64 stamps): python tools/trace_attention.py [global|plain]"""
+"""Timeline of one CTA of the fused attention kernel (clock64 stamps): python tools/trace_attention.py [global|plain|window] [f16]"""
 import sys
 from pathlib import Path
 
@@ -9,14 +9,15 @@ import torch
 from labelanything_b200 import _native, ops
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "global"
+tab_dtype = torch.float16 if len(sys.argv) > 2 and sys.argv[2] == "f16" else torch.float32
 heads = 12
 n_seq, L, gsz = {"global": (8, 4096, 64), "plain": (8, 4096, 0), "window": (200, 196, 14)}[mode]
 qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda").to(torch.bfloat16)
 out = torch.zeros(n_seq * L, heads * 64, device="cuda", dtype=torch.bfloat16)
 bh = bw = None
 if gsz == 64:
-    bh = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
-    bw = torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1
+    bh = (torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1).to(tab_dtype)
+    bw = (torch.randn(n_seq * L, heads, 128, device="cuda") * 0.1).to(tab_dtype)
 tr = torch.zeros(5, 192, 4, dtype=torch.int64, device="cuda")
 op = torch.zeros(64, 64, device="cuda", dtype=torch.bfloat16)
 op[:27] = (torch.randn(27, 64, device="cuda") * 0.1).to(torch.bfloat16)
@@ -30,8 +31,15 @@ def run():
         ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
 
 
-for _ in range(2):
+for _ in range(3):
     run()
+e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+e0.record()
+for _ in range(10):
+    run()
+e1.record()
+torch.cuda.synchronize()
+print(f"{mode} tables={tab_dtype}: {e0.elapsed_time(e1) / 10:.3f} ms per launch")
 _native.lib().la_attention_set_trace(tr.data_ptr())
 run()
 torch.cuda.synchronize()
