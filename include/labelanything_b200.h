@@ -229,6 +229,24 @@ int la_postprocess_masks(void* stream, const float* logits, float* out, const in
                          const unsigned char* flag_gts, int batch, int classes, int low_h, int low_w, int image_size,
                          int out_h, int out_w);
 
+/* ---- after the logits: prediction, global labels, confusion matrix ----------------------- */
+/* One pass over [batch, classes, pixels] fp32 logits (or over int64 local predictions preds_in [batch, pixels]):
+ *   pred = argmax over classes (first maximum, NaN wins: torch.argmax);
+ *   pred, target = label_map[b][.] applied to values in [0, map_len) (others, e.g. -100, pass through) -- the
+ *     composition of to_global_multiclass's sequential substitutions, built by the host;
+ *   preds_out / gt_out (int64 [batch, pixels], optional) receive the mapped labels;
+ *   confmat[target * num_classes + pred] += 1 for every pixel whose target != ignore_index (int64 [G, G],
+ *     ACCUMULATED, optional); pixels with target or pred outside [0, num_classes) are skipped and counted in
+ *     invalid[0] (torchmetrics raises for them under validate_args).
+ * Any of logits / preds_in / gt / label_map / outputs may be NULL (label remapping only, argmax only, ...).
+ * Replaces  label_anything/experiment/run.py:520-541,696-704 (`outputs.argmax(dim=1)`, to_global_multiclass,
+ * metric update), label_anything/data/utils.py:567-590, label_anything/utils/metrics.py:28-42 and the confusion
+ * matrix update of torchmetrics 1.7.1 MulticlassJaccardIndex (third party, uv.lock:2672-2673). */
+int la_label_confusion(void* stream, const float* logits, const long long* preds_in, const long long* gt,
+                       const long long* label_map, long long* preds_out, long long* gt_out, long long* confmat,
+                       long long* invalid, int batch, int classes, long long pixels, int map_len, int num_classes,
+                       long long ignore_index);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ _CTYPE = {
     "const int*": ctypes.c_void_p,
     "int*": ctypes.c_void_p,
     "const long long*": ctypes.c_void_p,
+    "long long*": ctypes.c_void_p,
     "const unsigned char*": ctypes.c_void_p,
     "int": ctypes.c_int,
     "long long": ctypes.c_longlong,

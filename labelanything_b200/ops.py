@@ -471,3 +471,40 @@ def permute_rows(x: torch.Tensor, outer: int, na: int, nb: int) -> torch.Tensor:
     out = torch.empty_like(x)
     _call("permute_rows", "la_permute_rows", _stream(x), x.data_ptr(), out.data_ptr(), outer, na, nb, x.shape[1])
     return out
+
+
+def label_confusion(logits: torch.Tensor | None, preds: torch.Tensor | None, gt: torch.Tensor | None,
+                    label_map: torch.Tensor | None, confmat: torch.Tensor | None = None,
+                    invalid: torch.Tensor | None = None, ignore_index: int = -100, want_preds: bool = True,
+                    want_gt: bool = True):
+    """argmax over classes (or int64 `preds`), label_map[b][.] on predictions and gt, confmat[target, pred] += 1
+    (int64 [G, G], accumulated in place).  logits [B, C, *spatial] fp32, preds / gt [B, *spatial] int64,
+    label_map [B, map_len] int64.  Returns (mapped preds or None, mapped gt or None)."""
+    _require_cuda(logits, preds, gt, label_map, confmat, invalid)
+    ref = logits if logits is not None else (preds if preds is not None else gt)
+    B = ref.shape[0]
+    spatial = tuple(ref.shape[2:]) if logits is not None else tuple(ref.shape[1:])
+    P = 1
+    for s in spatial:
+        P *= s
+    C = logits.shape[1] if logits is not None else 0
+    if logits is not None:
+        assert logits.dtype == torch.float32 and logits.is_contiguous()
+    for t in (preds, gt):
+        assert t is None or (t.dtype == torch.int64 and t.is_contiguous() and tuple(t.shape) == (B,) + spatial), \
+            "labels must be contiguous int64 [B, *spatial]"
+    assert label_map is None or (label_map.dtype == torch.int64 and label_map.is_contiguous() and label_map.shape[0] == B)
+    G = 0
+    if confmat is not None:
+        assert confmat.dtype == torch.int64 and confmat.is_contiguous() and confmat.dim() == 2 and confmat.shape[0] == confmat.shape[1]
+        assert invalid is not None and invalid.dtype == torch.int64 and invalid.numel() == 1
+        G = confmat.shape[0]
+    have_pred = logits is not None or preds is not None
+    preds_out = torch.empty((B,) + spatial, dtype=torch.int64, device=ref.device) if (want_preds and have_pred) else None
+    gt_out = torch.empty((B,) + spatial, dtype=torch.int64, device=ref.device) if (want_gt and gt is not None) else None
+    _cost(0.0, float(B) * P * (4 * C + (8 if preds is not None else 0) + (8 if gt is not None else 0)
+                               + (8 if preds_out is not None else 0) + (8 if gt_out is not None else 0)))
+    _call("label_confusion", "la_label_confusion", _stream(ref), _ptr(logits), _ptr(preds), _ptr(gt), _ptr(label_map),
+          _ptr(preds_out), _ptr(gt_out), _ptr(confmat), _ptr(invalid), B, C, P,
+          label_map.shape[1] if label_map is not None else 0, G, int(ignore_index))
+    return preds_out, gt_out

@@ -1,7 +1,7 @@
 """Generate the committed golden fixtures under tests/golden/ from the UNMODIFIED reference.
 
 TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference); the fixtures it writes are
-what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512]
+what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512] [metrics]
 
 Every fixture stores: the oracle `cfg`, the inputs, the reference outputs and either the full state dict
 (tiny models) or the synthetic-weight seed (real-size models; weights are a pure function of
@@ -246,8 +246,40 @@ def sam512(models):
     print("sam512_5w5s.pt", out["logits"].shape)
 
 
+def metrics_f4(models):
+    """Post-logits step: torch.argmax + the reference's own to_global_multiclass on seeded
+    inputs with ties, -inf planes, NaNs and ignore_index targets; the confusion matrix is torch.bincount of the
+    reference's global labels (torchmetrics itself is not installed: its reduce stays unpinned)."""
+    from label_anything.data.utils import to_global_multiclass
+
+    g = torch.Generator().manual_seed(4)
+    cases = []
+    categories = {k: {"name": str(k)} for k in (1, 2, 3, 5, 7, 8, 11, 13, 17, 20)}       # 10 categories -> G = 11
+    for B, C, H, W, classes in [
+        (3, 5, 24, 20, [[[7, 3], [3, 13]], [[1, 2, 3, 5]], [[20, 17], [17], [8]]]),       # chained substitutions
+        (2, 3, 7, 9, [[[2]], [[11, 5]]]),                                                  # odd sizes (scalar path)
+        (1, 6, 32, 32, [[[1, 2, 3, 5, 7]]]),
+    ]:
+        logits = torch.randn(B, C, H, W, generator=g)
+        logits[:, :, : H // 3] = torch.round(logits[:, :, : H // 3])                      # ties
+        logits[0, C - 1] = float("-inf")                                                   # absent class
+        logits[0, :, -1, -1] = float("-inf")                                               # all -inf -> 0
+        logits[-1, 1, 0, :3] = float("nan")
+        gt = torch.randint(0, C, (B, H, W), generator=g)
+        gt[:, -2:, :] = -100
+        preds = logits.argmax(dim=1)
+        glob_preds, glob_gt = to_global_multiclass(classes, categories, preds, gt)
+        G = len(categories) + 1
+        keep = glob_gt != -100
+        conf = torch.bincount(glob_gt[keep] * G + glob_preds[keep], minlength=G * G).reshape(G, G)
+        cases.append({"logits": logits, "gt": gt, "classes": classes, "preds": preds, "glob_preds": glob_preds,
+                      "glob_gt": glob_gt, "confmat": conf, "num_classes": G})
+    torch.save({"meta": _meta(), "categories": categories, "cases": cases}, GOLD / "metrics_f4.pt")
+    print("metrics_f4.pt", [tuple(c["logits"].shape) for c in cases])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tiny", "mae256", "samvit"]
+    which = sys.argv[1:] or ["tiny", "mae256", "samvit", "metrics"]
     models = ref_import.import_reference()
     torch.set_num_threads(8)
     if "tiny" in which:
@@ -259,3 +291,5 @@ if __name__ == "__main__":
         samvit(models)
     if "sam512" in which:
         sam512(models)
+    if "metrics" in which:
+        metrics_f4(models)

@@ -1,0 +1,115 @@
+"""Post-logits step on CPU: the numpy oracle against the fixture generated from the UNMODIFIED
+reference (`to_global_multiclass` + torch.argmax), the host-side label table, the IoU reductions, the C-ABI argument
+checks and the 2-rank state reduction."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+import metrics_oracle as mo  # noqa: E402
+
+from labelanything_b200 import _native  # noqa: E402
+from labelanything_b200.metrics import MeanIoU, StrictMeanIoU, chain_label_map  # noqa: E402
+
+GOLD = torch.load(ROOT / "tests" / "golden" / "metrics_f4.pt", weights_only=False)
+
+
+@pytest.mark.parametrize("case", range(len(GOLD["cases"])))
+def test_oracle_matches_the_reference_fixture(case):
+    c = GOLD["cases"][case]
+    preds = mo.argmax_dim1(c["logits"].numpy())
+    assert np.array_equal(preds, c["preds"].numpy())                      # ties, -inf planes, NaN
+    gp, gg = mo.to_global_multiclass(c["classes"], GOLD["categories"], preds, c["gt"].numpy())
+    assert np.array_equal(gp, c["glob_preds"].numpy()) and np.array_equal(gg, c["glob_gt"].numpy())
+    conf = mo.confusion_matrix(gp, gg, c["num_classes"], ignore_index=-100)
+    assert np.array_equal(conf, c["confmat"].numpy())
+    assert conf.sum() == int((c["gt"] != -100).sum())
+
+
+@pytest.mark.parametrize("case", range(len(GOLD["cases"])))
+def test_chained_label_table_reproduces_the_sequential_substitutions(case):
+    c = GOLD["cases"][case]
+    table = chain_label_map(c["classes"], GOLD["categories"], map_len=c["logits"].shape[1] + 2)
+    for name in ("preds", "gt"):
+        local, glob = c[name], c["glob_" + name]
+        inside = (local >= 0) & (local < table.shape[1])
+        idx = local.clamp(0, table.shape[1] - 1)
+        b = torch.arange(local.shape[0]).view(-1, 1, 1).expand_as(local)
+        mapped = torch.where(inside, table[b, idx], local)
+        assert torch.equal(mapped, glob), name
+
+
+def test_chain_differs_from_a_one_shot_lookup():
+    # classes {3, 7} of categories (1, 3, 5, 7): local 1 -> 2 -> 4 because the second substitution sees the first
+    t = chain_label_map([[[7, 3], [3]]], {1: {}, 3: {}, 5: {}, 7: {}})
+    assert t.tolist() == [[0, 4, 4]]
+    assert chain_label_map([[[7, 3]]], {1: {}, 3: {}, 5: {}, 7: {}}, compact=False).tolist() == [[0, 3, 7]]
+
+
+def test_iou_reductions_match_the_oracle_and_a_hand_example():
+    conf = torch.tensor([[50, 2, 0, 0], [3, 20, 0, 0], [0, 0, 0, 0], [4, 0, 0, 10]])
+    j = [50 / 59, 20 / 25, 0.0, 10 / 14]                                  # class 2 is absent: weight 0
+    want = (j[0] + j[1] + j[3]) / 3
+    assert abs(float(MeanIoU._macro_jaccard(conf, -100)) - want) < 1e-6
+    assert abs(float(mo.macro_jaccard(conf.numpy(), -100)) - want) < 1e-6
+    m = StrictMeanIoU(num_classes=4, ignore_index=-100, device="cpu")
+    m.confmat.copy_(conf)
+    strict = (want * 4 - 50 / 59) / 3                                     # utils/metrics.py:31-35
+    assert abs(float(m.compute()) - strict) < 1e-6
+    assert abs(float(mo.strict_mean_iou(conf.numpy(), -100)) - strict) < 1e-6
+    m._invalid += 1
+    with pytest.raises(RuntimeError, match="outside"):
+        m.compute()
+
+
+def test_label_confusion_argument_checks():
+    lib = _native.lib()
+    assert lib.la_label_confusion(None, None, None, None, None, None, None, None, None, 1, 2, 16, 0, 0, -100) == -1
+    assert b"nothing to read" in lib.la_last_error()
+    assert lib.la_label_confusion(None, None, None, None, None, None, None, None, None, 0, 2, 16, 0, 0, -100) == -1
+    assert b"empty problem" in lib.la_last_error()
+
+
+def test_updates_refuse_cpu_tensors():
+    m = MeanIoU(num_classes=3, ignore_index=-100, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.update(torch.zeros(1, 4, 4, dtype=torch.int64), torch.zeros(1, 4, 4, dtype=torch.int64))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = StrictMeanIoU(num_classes=3, ignore_index=-100, device="cpu")
+        m.confmat += torch.tensor([[5, 1, 0], [0, 4, 2], [1, 0, 3]]) * (rank + 1)
+        m.sync()
+        if rank == 0:
+            q.put((m.confmat.tolist(), float(m.compute())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_state_reduction():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    conf, value = q.get()
+    assert conf == [[15, 3, 0], [0, 12, 6], [3, 0, 9]]
+    want = mo.strict_mean_iou(np.array(conf), -100)
+    assert abs(value - float(want)) < 1e-6
