@@ -247,6 +247,27 @@ int la_label_confusion(void* stream, const float* logits, const long long* preds
                        long long* invalid, int batch, int classes, long long pixels, int map_len, int num_classes,
                        long long ignore_index);
 
+/* ---- loss of the training / validation step (first piece) ---------------------------------- */
+/* Label-frequency class weights of get_weight_matrix_from_labels (label_anything/loss/utils.py:17-42):
+ * hist (int64 [classes + 2], overwritten) = counts of labels 0..classes-1, of ignore_index, of anything else;
+ * class_w[c] = 1 / log(1.1 + n_c / n) for the classes that occur, 1 otherwise (the weight of ignored pixels is 0). */
+int la_label_class_weights(void* stream, const long long* labels, long long n, int classes, long long ignore_index,
+                           long long* hist, float* class_w);
+
+/* Focal loss with optional class weighting over logits [batch, classes, pixels] fp32, target int64 [batch, pixels]:
+ *   ce = cross_entropy(x, target) (0 where target == ignore_index), pt = exp(-ce),
+ *   loss = mean|sum((1 - pt)^gamma * class_w[target] * ce)          -> loss_out[0] (deterministic summation)
+ *   grad_out (optional, [batch, classes, pixels]) = grad_scale[0] * d loss / d logits (grad_scale NULL = 1)
+ *   wtarget_out (optional, [batch, pixels]) = class_w[target] (0 where ignored): the reference's weight matrix.
+ *     (logits may be NULL when only wtarget_out is requested.)
+ * workspace: la_focal_loss_workspace_bytes() bytes, zero-initialised once by the caller, reusable across calls on
+ * one stream.  Replaces label_anything/loss/focal.py:8-25 and the focal branch of LabelAnythingLoss.logits_loss
+ * (label_anything/loss/__init__.py:67-92). */
+long long la_focal_loss_workspace_bytes(void);
+int la_focal_loss(void* stream, const float* logits, const long long* target, const float* class_w,
+                  const float* grad_scale, float* loss_out, float* grad_out, float* wtarget_out, void* workspace,
+                  int batch, int classes, long long pixels, float gamma, long long ignore_index, int mean);
+
 #ifdef __cplusplus
 }
 #endif

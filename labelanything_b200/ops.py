@@ -508,3 +508,54 @@ def label_confusion(logits: torch.Tensor | None, preds: torch.Tensor | None, gt:
           _ptr(preds_out), _ptr(gt_out), _ptr(confmat), _ptr(invalid), B, C, P,
           label_map.shape[1] if label_map is not None else 0, G, int(ignore_index))
     return preds_out, gt_out
+
+
+_LOSS_WS: dict = {}
+
+
+def _loss_workspace(device: torch.device) -> torch.Tensor:
+    """Zero-initialised scratch of la_focal_loss (per device and stream; the kernel leaves it reusable)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _LOSS_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(_native.lib().la_focal_loss_workspace_bytes() // 8 + 1, dtype=torch.float64, device=device)
+        _LOSS_WS[key] = ws
+    return ws
+
+
+def label_class_weights(labels: torch.Tensor, classes: int, ignore_index: int = -100):
+    """-> (class_w fp32 [classes], hist int64 [classes + 2]) of loss/utils.py:17-42 (see the C header)."""
+    _require_cuda(labels)
+    assert labels.dtype == torch.int64 and labels.is_contiguous()
+    hist = torch.empty(classes + 2, dtype=torch.int64, device=labels.device)
+    w = torch.empty(classes, dtype=torch.float32, device=labels.device)
+    _cost(0.0, 8.0 * labels.numel())
+    _call("label_class_weights", "la_label_class_weights", _stream(labels), labels.data_ptr(), labels.numel(), classes,
+          int(ignore_index), hist.data_ptr(), w.data_ptr())
+    return w, hist
+
+
+def focal_loss(logits: torch.Tensor, target: torch.Tensor, class_w: torch.Tensor | None, gamma: float,
+               ignore_index: int = -100, mean: bool = True, want_loss: bool = True, want_grad: bool = False,
+               grad_scale: torch.Tensor | None = None, want_wtarget: bool = False):
+    """-> (loss fp32 [] or None, grad like logits or None, wtarget [B, *spatial] or None)."""
+    _require_cuda(logits, target, class_w, grad_scale)
+    if logits is None:      # weight map only
+        assert class_w is not None and not want_loss and not want_grad
+        B, C, P = target.shape[0], class_w.numel(), target.numel() // target.shape[0]
+    else:
+        assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() >= 2
+        B, C = logits.shape[:2]
+        P = logits.numel() // (B * C)
+    assert target.dtype == torch.int64 and target.is_contiguous() and target.numel() == B * P
+    assert class_w is None or (class_w.dtype == torch.float32 and class_w.is_contiguous() and class_w.numel() == C)
+    assert grad_scale is None or (grad_scale.dtype == torch.float32 and grad_scale.numel() == 1)
+    loss = torch.empty((), dtype=torch.float32, device=target.device) if want_loss else None
+    grad = torch.empty_like(logits) if want_grad else None
+    wt = torch.empty(target.shape, dtype=torch.float32, device=target.device) if want_wtarget else None
+    ws = _loss_workspace(target.device) if want_loss else None
+    _cost(0.0, float(B) * P * (4 * C + 8 + (4 * C if want_grad else 0) + (4 if want_wtarget else 0)))
+    _call("focal_loss.grad" if want_grad else "focal_loss", "la_focal_loss", _stream(target), _ptr(logits),
+          target.data_ptr(), _ptr(class_w), _ptr(grad_scale), _ptr(loss), _ptr(grad), _ptr(wt), _ptr(ws), B, C, P,
+          float(gamma), int(ignore_index), 1 if mean else 0)
+    return loss, grad, wt

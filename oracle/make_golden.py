@@ -1,7 +1,7 @@
 """Generate the committed golden fixtures under tests/golden/ from the UNMODIFIED reference.
 
 TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference); the fixtures it writes are
-what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512] [metrics]
+what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512] [metrics] [loss]
 
 Every fixture stores: the oracle `cfg`, the inputs, the reference outputs and either the full state dict
 (tiny models) or the synthetic-weight seed (real-size models; weights are a pure function of
@@ -278,8 +278,42 @@ def metrics_f4(models):
     print("metrics_f4.pt", [tuple(c["logits"].shape) for c in cases])
 
 
+def loss_f1(models):
+    """Focal loss + class weighting: values and autograd gradients of the UNMODIFIED
+    label_anything.loss.LabelAnythingLoss / get_weight_matrix_from_labels on seeded inputs."""
+    from label_anything.loss import LabelAnythingLoss
+    from label_anything.loss.utils import get_weight_matrix_from_labels
+
+    g = torch.Generator().manual_seed(9)
+    cases = []
+    for B, C, H, W, gamma, weighting, ignore, comp_w in [
+        (2, 3, 7, 9, 2.0, True, True, 1.0),        # odd sizes (scalar path), MAE-L training classes
+        (2, 6, 16, 12, 2.0, True, True, 0.5),      # 5-way + background, component weight != 1 (applied twice)
+        (1, 6, 8, 8, 2.0, True, False, 1.0),       # no ignored pixels: the other branch of the weight function
+        (2, 11, 8, 12, 1.5, True, True, 1.0),      # more planes than the register window, non-integer gamma
+        (2, 4, 8, 8, 2.0, False, True, 1.0),       # no class weighting
+    ]:
+        logits = (torch.randn(B, C, H, W, generator=g) * 3).requires_grad_(True)
+        target = torch.randint(0, C, (B, H, W), generator=g)
+        target[target == C - 1] = 0 if C > 4 else C - 1                                    # an absent class for C > 4
+        if ignore:
+            target[:, -2:, :] = -100
+        with torch.no_grad():
+            logits[0, 1 if target[0, 0, 0] != 1 else 2, 0, 0] = float("-inf")              # padded-pixel style -inf
+        loss = LabelAnythingLoss({"focal": {"weight": comp_w, "gamma": gamma}}, class_weighting=weighting)
+        out = loss(logits, target)
+        out["value"].backward()
+        wt, cw = get_weight_matrix_from_labels(target, C)
+        cases.append({"logits": logits.detach().clone(), "target": target, "gamma": gamma, "class_weighting": weighting,
+                      "component_weight": comp_w, "value": out["value"].detach().clone(),
+                      "component": out["components"]["focal"], "grad": logits.grad.clone(), "wtarget": wt,
+                      "class_weights": cw})
+    torch.save({"meta": _meta(), "cases": cases}, GOLD / "loss_f1.pt")
+    print("loss_f1.pt", [(tuple(c["logits"].shape), float(c["value"])) for c in cases])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tiny", "mae256", "samvit", "metrics"]
+    which = sys.argv[1:] or ["tiny", "mae256", "samvit", "metrics", "loss"]
     models = ref_import.import_reference()
     torch.set_num_threads(8)
     if "tiny" in which:
@@ -293,3 +327,5 @@ if __name__ == "__main__":
         sam512(models)
     if "metrics" in which:
         metrics_f4(models)
+    if "loss" in which:
+        loss_f1(models)
