@@ -537,8 +537,9 @@ int la_build_src(void* stream, const float* feat, const float* m16, const unsign
   p.lead = feat_lead;
   const int tpr = d / 4;
   int threads = tpr >= 256 ? tpr : (256 / tpr) * tpr;
-  // row chunks per sequence: enough CTAs to fill the machine even for few sequences
-  long long chunks = (4ll * sm_count() + n_seq - 1) / n_seq;
+  // row chunks per sequence: enough CTAs for >= 16 waves of the 2 resident CTAs per SM, so that the ragged last
+  // wave costs a few percent (one CTA per sequence left a 5th wave of 16 CTAs behind 4 full ones: 20 %)
+  long long chunks = (32ll * sm_count() + n_seq - 1) / n_seq;
   const long long max_chunks = (tokens + 63) / 64;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
