@@ -277,7 +277,9 @@ extern "C" int la_focal_loss(void* stream, const float* logits, const long long*
   const bool vec4 = pixels % 4 == 0 && al(logits) && al(target) && al(grad_out) && al(wtarget_out);
   const long long groups = static_cast<long long>(batch) * (vec4 ? pixels / 4 : pixels);
   long long ctas = (groups + LOSS_THREADS - 1) / LOSS_THREADS;
-  const long long cap = static_cast<long long>(sm_count()) * 8 < LOSS_MAX_CTAS ? static_cast<long long>(sm_count()) * 8 : LOSS_MAX_CTAS;
+  // one resident wave: 4 CTAs per SM at 64 registers (value), 2 at 118 (gradient)
+  long long cap = static_cast<long long>(sm_count()) * (grad_out ? 2 : 4);
+  if (cap > LOSS_MAX_CTAS) cap = LOSS_MAX_CTAS;
   if (ctas > cap) ctas = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned g = static_cast<unsigned>(ctas);

@@ -53,7 +53,16 @@ def reference_ops():
 
 px = B * H * W
 res = {}
-for name, wp, wg in (("confmat only", False, False), ("confmat + global label maps", True, True)):
+# segmentation-like labels: 32x32-pixel blocks of one class, predictions agreeing with them on ~90 % of the blocks
+blocks = torch.randint(0, C, (B, H // 32, W // 32), device="cuda")
+gt_seg = blocks.repeat_interleave(32, 1).repeat_interleave(32, 2).contiguous()
+pred_blocks = torch.where(torch.rand(blocks.shape, device="cuda") < 0.9, blocks, torch.randint_like(blocks, C))
+logits_seg = (torch.randn(B, C, H, W, device="cuda") * 0.1
+              + 4.0 * torch.nn.functional.one_hot(pred_blocks.repeat_interleave(32, 1).repeat_interleave(32, 2), C).permute(0, 3, 1, 2)).contiguous()
+ms = timed(lambda: ops.label_confusion(logits_seg, None, gt_seg, table, conf, bad, want_preds=True, want_gt=True))
+res["segmentation-like labels, confmat + global label maps"] = {"ms": ms, "GB/s": px * (4 * C + 24) / ms / 1e6,
+                                                                 "algorithmic_bytes": px * (4 * C + 24)}
+for name, wp, wg in (("random labels, confmat only", False, False), ("random labels, confmat + global label maps", True, True)):
     ms = timed(lambda: ops.label_confusion(logits, None, gt, table, conf, bad, want_preds=wp, want_gt=wg))
     nbytes = px * (4 * C + 8 + (16 if wp else 0))
     res[name] = {"ms": ms, "GB/s": nbytes / ms / 1e6, "algorithmic_bytes": nbytes}
