@@ -286,7 +286,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 // cycles, so 1 KB rows (the prompt encoder's bf16 image tokens) must be moved several at a time to reach HBM speed.
 // rpc = 1 when rows are remapped (window partition).  POOL: the mean-pool variant -- CTA = (sequence, slice), nothing
 // but per-CTA column sums of y is written (prompt_encoder.py:733-735).
-template <int NVT, bool POOL, bool HAS_X, bool HAS_D>
+template <int NVT, bool POOL, bool HAS_X, bool HAS_D, bool HAS_D2 = false>
 __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddLnParams p, const int stages, const int rpc) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31;
@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
   const int tail = (p.d & 127) >> 2;
   const uint32_t xbytes = HAS_X ? static_cast<uint32_t>(p.d) * 4 : 0;
   const uint32_t dbytes = HAS_D ? static_cast<uint32_t>(p.d) * 2 : 0;
-  const uint32_t slot_bytes = (static_cast<uint32_t>(rpc) * (xbytes + dbytes) + 127) & ~127u;
+  const uint32_t d2bytes = HAS_D2 ? static_cast<uint32_t>(p.d) * 2 : 0;   // second bf16 stream (delta2)
+  const uint32_t slot_bytes = (static_cast<uint32_t>(rpc) * (xbytes + dbytes + d2bytes) + 127) & ~127u;
   uint8_t* ring = ln_smem + static_cast<size_t>(warp) * stages * slot_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(8) * stages * slot_bytes) + warp * LN_MAX_STAGES;
   if (lane == 0) {
@@ -352,9 +353,10 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
     if (pad) return;
     const uint32_t n = static_cast<uint32_t>(row_end - row0 < rpc ? row_end - row0 : rpc);
     uint8_t* dst = ring + static_cast<size_t>(slot) * slot_bytes;
-    mbar_arrive_expect_tx(&bars[slot], n * (xbytes + dbytes));
+    mbar_arrive_expect_tx(&bars[slot], n * (xbytes + dbytes + d2bytes));
     if constexpr (HAS_X) bulk_load(dst, p.x_in + src * p.d, n * xbytes, &bars[slot]);
     if constexpr (HAS_D) bulk_load(dst + rpc * xbytes, p.delta + src * p.d, n * dbytes, &bars[slot]);
+    if constexpr (HAS_D2) bulk_load(dst + rpc * (xbytes + dbytes), p.delta2 + src * p.d, n * d2bytes, &bars[slot]);
   };
 
   if (lane == 0) {
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
         const long long row = row0 + rr, src = src0 + rr;
         const float4* xs = reinterpret_cast<const float4*>(buf + static_cast<size_t>(rr) * xbytes);
         const uint2* ds = reinterpret_cast<const uint2*>(buf + static_cast<size_t>(rpc) * xbytes + static_cast<size_t>(rr) * dbytes);
+        [[maybe_unused]] const uint2* ds2 = reinterpret_cast<const uint2*>(buf + static_cast<size_t>(rpc) * (xbytes + dbytes) + static_cast<size_t>(rr) * d2bytes);
         if (p.seq_add) {
           const long long sq_ = src / p.seq_rows;
           if (sq_ != sa_seq) {   // warp-uniform
@@ -423,6 +426,15 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
             if constexpr (HAS_X) a = xs[idx];
             if constexpr (HAS_D) {
               const uint2 dv = ds[idx];
+              const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
+              const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
+              a.x += __low2float(d01);
+              a.y += __high2float(d01);
+              a.z += __low2float(d23);
+              a.w += __high2float(d23);
+            }
+            if constexpr (HAS_D2) {
+              const uint2 dv = ds2[idx];
               const __nv_bfloat162 d01 = *reinterpret_cast<const __nv_bfloat162*>(&dv.x);
               const __nv_bfloat162 d23 = *reinterpret_cast<const __nv_bfloat162*>(&dv.y);
               a.x += __low2float(d01);
@@ -548,6 +560,9 @@ static int launch_staged(cudaStream_t st, const AddLnParams& p, int grid, const 
     LA_CHECK_CUDA(cudaGetLastError());
     return LA_OK;
   };
+  if constexpr (POOL) {   // the mean-pool of the prompt encoder adds two bf16 streams (image tokens + last MLP output)
+    if (p.delta2) return go(add_layernorm_staged_kernel<NVT, POOL, false, true, true>);
+  }
   if (p.x_in && p.delta) return go(add_layernorm_staged_kernel<NVT, POOL, true, true>);
   if (p.x_in) return go(add_layernorm_staged_kernel<NVT, POOL, true, false>);
   return go(add_layernorm_staged_kernel<NVT, POOL, false, true>);
@@ -763,8 +778,8 @@ int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta
   const int need = (d + 127) / 128;
   const int grid = static_cast<int>(n_seq * slices);
   // big problems: the staged (bulk-copy ring) variant
-  if (!delta2 && need <= 4 && d % 32 == 0 && p.rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr) {
-    const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0)), 8, smem);
+  if ((!delta2 || (!x_in && delta)) && need <= 4 && d % 32 == 0 && p.rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr) {
+    const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0) + (delta2 ? 2 : 0)), 8, smem);
     if (ring.stages >= 2) {
       int rc;
       if (need <= 2) rc = launch_staged<2, true>(st, p, grid, ring);

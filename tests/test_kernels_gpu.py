@@ -279,6 +279,11 @@ def test_add_layernorm_modes():
     _close(y6b, r6, 2 ** -8, 2e-3, "LN staged seq_add bf16")
     pooled = ops.add_layernorm_meanpool(None, k16, gm, bt, 1e-5, S, T, D, seq_add=sa)
     _close(pooled, r6.view(S, T, D).mean(1), 1e-5, 1e-5, "LN staged meanpool")
+    # ... and with the second bf16 stream (image tokens + last MLP output), the prompt encoder's final norm4
+    d26 = torch.randn(S * T, D, device="cuda", generator=g).to(torch.bfloat16)
+    r7 = F.layer_norm(k16.float() + d26.float() + sa.repeat_interleave(T, 0), (D,), gm, bt, 1e-5)
+    pooled = ops.add_layernorm_meanpool(None, k16, gm, bt, 1e-5, S, T, D, delta2=d26, seq_add=sa)
+    _close(pooled, r7.view(S, T, D).mean(1), 1e-5, 1e-5, "LN staged meanpool, two bf16 streams")
 
 
 def test_layout_and_index_kernels_are_exact():
