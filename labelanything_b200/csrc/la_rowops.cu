@@ -504,8 +504,10 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
   }
   if constexpr (POOL) {
     // deterministic reduction: lanes own disjoint channels; the CTA's warps are summed in a fixed order through
-    // shared memory (behind the ring and its barriers); one partial row per (sequence, slice)
-    float4* red = reinterpret_cast<float4*>(ln_smem + static_cast<size_t>(8) * stages * slot_bytes + 8 * LN_MAX_STAGES * 8);
+    // shared memory; one partial row per (sequence, slice).  The scratch aliases the ring: every issued chunk has been
+    // consumed by now, the barrier makes sure all warps are done with theirs.
+    __syncthreads();
+    float4* red = reinterpret_cast<float4*>(ln_smem);
     const int dv = p.d >> 2;
 #pragma unroll
     for (int i = 0; i < NVT; ++i) {
@@ -535,7 +537,7 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
 struct LnRing {
   int stages, rpc, smem;
 };
-static inline LnRing ln_ring_for(uint32_t row_bytes, int max_rpc, size_t extra) {
+static inline LnRing ln_ring_for(uint32_t row_bytes, int max_rpc, size_t extra, int min_stages = 3) {
   LnRing r;
   r.rpc = static_cast<int>(6144 / row_bytes);
   if (r.rpc > max_rpc) r.rpc = max_rpc;
@@ -545,7 +547,7 @@ static inline LnRing ln_ring_for(uint32_t row_bytes, int max_rpc, size_t extra) 
   for (;; --r.rpc) {   // at least 3 chunks in flight per warp (2 if even a single row is that large)
     slot = (static_cast<uint32_t>(r.rpc) * row_bytes + 127) & ~127u;
     r.stages = static_cast<int>((112 * 1024 - extra - 8 * LN_MAX_STAGES * 8) / (8 * static_cast<size_t>(slot)));
-    if (r.stages >= 3 || r.rpc == 1) break;
+    if (r.stages >= min_stages || r.rpc == 1) break;
   }
   if (r.stages > LN_MAX_STAGES) r.stages = LN_MAX_STAGES;
   r.smem = 8 * r.stages * static_cast<int>(slot) + 8 * LN_MAX_STAGES * 8 + static_cast<int>(extra);
@@ -779,9 +781,12 @@ int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta
   const int grid = static_cast<int>(n_seq * slices);
   // big problems: the staged (bulk-copy ring) variant
   if ((!delta2 || (!x_in && delta)) && need <= 4 && d % 32 == 0 && p.rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr) {
-    const LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0) + (delta2 ? 2 : 0)), 8, smem);
+    // two chunks in flight per warp are enough here (16 warps x 2 x 6 KB per SM), so the ring prefers large bulk
+    // copies over depth; the reduction scratch aliases the ring
+    LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0) + (delta2 ? 2 : 0)), 8, 0, 2);
     if (ring.stages >= 2) {
       int rc;
+      if (ring.smem < static_cast<int>(smem)) ring.smem = static_cast<int>(smem);   // reduction scratch (aliases the ring)
       if (need <= 2) rc = launch_staged<2, true>(st, p, grid, ring);
       else rc = launch_staged<4, true>(st, p, grid, ring);
       if (rc) return rc;
