@@ -17,6 +17,7 @@
 //                        pad to the batch maximum with -inf (background channel: 0), absent classes -> -inf.
 //                        label_anything/models/lam.py:383-453, 92-93
 #include "la_common.cuh"
+#include <cstdlib>
 
 namespace la {
 
@@ -271,6 +272,125 @@ __global__ void __launch_bounds__(256) build_src_kernel(const BuildSrcParams p) 
           *reinterpret_cast<uint2*>(out_seq + static_cast<long long>(t) * p.D) = pk;
         }
       }
+    }
+  }
+}
+
+// Tensor-core variant (D % 64 == 0, D <= 512).  The 16 -> D projection is a K = 16 matrix product: as FFMA2 it costs 85
+// instructions per warp-row and the kernel is issue bound at 1.8 TB/s (profiles/r01_ncu_prompt_v4.txt); as
+// mma.m16n8k8 TF32 (10-bit mantissas, fp32 accumulation: error 2^-11 per product, below the bf16 rounding of the
+// output) it is 16 MMAs per 16 rows x 64 channels.  A warp owns 64 channels, a CTA's D / 64 warps walk the same
+// 16-row tiles.  The column index n of an MMA tile is free, so tile j's column n stands for channel
+// 64 w + 16 (n >> 1) + 2 j + (n & 1): a lane's accumulators (columns 2t, 2t+1 of 8 tiles) are then 16 CONTIGUOUS
+// channels -- the fp32 feature rows are loaded straight into the accumulators as four 16-byte loads and the bf16 row
+// leaves as two 16-byte stores.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) build_src_mma_kernel(const BuildSrcParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const long long s = blockIdx.y;
+  const int chunks = gridDim.x;
+  const int per = (((p.T + chunks - 1) / chunks) + 15) & ~15;   // whole 16-row tiles per chunk
+  const int t_begin = blockIdx.x * per;
+  const int t_end = min(p.T, t_begin + per);
+  if (t_begin >= t_end) return;
+  const int c = static_cast<int>(s % p.C);
+  const long long bm_seq = s / p.C;
+  const long long bm = (bm_seq / p.M) * (p.M + p.lead) + p.lead + bm_seq % p.M;
+  const bool has_map = p.m16 != nullptr && (p.mflag == nullptr || p.mflag[s] != 0);
+  const int col0 = warp * 64 + t * 16;   // this lane's 16 contiguous channels
+
+  float base[16];
+  {
+    const float* vec = p.m16 == nullptr ? p.no_mask : (has_map ? p.b6 : p.not_a_mask);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(vec + col0) + i);
+      if (p.code) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(p.code + static_cast<long long>(c) * p.D + col0) + i);
+        v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+      }
+      base[4 * i] = v.x; base[4 * i + 1] = v.y; base[4 * i + 2] = v.z; base[4 * i + 3] = v.w;
+    }
+  }
+  // B fragments: tile j, k-step q: b0 = W[k = 8q + t][n = g], b1 = W[k = 8q + t + 4][n = g], W[k][n] = w6[channel(j, n)][k]
+  uint32_t bf[8][2][2];
+  if (has_map) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wrow = p.w6 + static_cast<long long>(warp * 64 + (g >> 1) * 16 + 2 * j + (g & 1)) * 16;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        bf[j][q][0] = to_tf32(__ldg(wrow + 8 * q + t));
+        bf[j][q][1] = to_tf32(__ldg(wrow + 8 * q + t + 4));
+      }
+    }
+  }
+  const float* feat_seq = p.feat + bm * p.T * static_cast<long long>(p.D) + col0;
+  __nv_bfloat16* out_seq = p.out + s * p.T * static_cast<long long>(p.D) + col0;
+  const float* m16_seq = p.m16 != nullptr ? p.m16 + s * p.T * 16 : nullptr;
+
+  for (int tile0 = t_begin; tile0 < t_end; tile0 += 16) {
+    const int r_lo = tile0 + g, r_hi = tile0 + g + 8;
+    const bool v_lo = r_lo < t_end, v_hi = r_hi < t_end;
+    // acc[j][e] = row g, channel col0 + 2j + e;  acc[j][2 + e] = row g + 8, same channel
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v_lo) lo = __ldg(reinterpret_cast<const float4*>(feat_seq + static_cast<long long>(r_lo) * p.D) + i);
+      if (v_hi) hi = __ldg(reinterpret_cast<const float4*>(feat_seq + static_cast<long long>(r_hi) * p.D) + i);
+      acc[2 * i][0] = lo.x + base[4 * i];
+      acc[2 * i][1] = lo.y + base[4 * i + 1];
+      acc[2 * i + 1][0] = lo.z + base[4 * i + 2];
+      acc[2 * i + 1][1] = lo.w + base[4 * i + 3];
+      acc[2 * i][2] = hi.x + base[4 * i];
+      acc[2 * i][3] = hi.y + base[4 * i + 1];
+      acc[2 * i + 1][2] = hi.z + base[4 * i + 2];
+      acc[2 * i + 1][3] = hi.w + base[4 * i + 3];
+    }
+    if (has_map) {
+      // A fragments: a0 = (row g, k = t), a1 = (row g + 8, k = t), a2 = (row g, k = t + 4), a3 = (row g + 8, k = t + 4)
+      uint32_t a[2][4];
+      const float* m_lo = m16_seq + static_cast<long long>(r_lo) * 16;
+      const float* m_hi = m16_seq + static_cast<long long>(r_hi) * 16;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        a[q][0] = v_lo ? to_tf32(__ldg(m_lo + 8 * q + t)) : 0u;
+        a[q][1] = v_hi ? to_tf32(__ldg(m_hi + 8 * q + t)) : 0u;
+        a[q][2] = v_lo ? to_tf32(__ldg(m_lo + 8 * q + t + 4)) : 0u;
+        a[q][3] = v_hi ? to_tf32(__ldg(m_hi + 8 * q + t + 4)) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mma_tf32_16x8x8(acc[j], a[0], bf[j][0][0], bf[j][0][1]);
+        mma_tf32_16x8x8(acc[j], a[1], bf[j][1][0], bf[j][1][1]);
+      }
+    }
+    if (v_lo) {
+      uint4* dst = reinterpret_cast<uint4*>(out_seq + static_cast<long long>(r_lo) * p.D);
+      dst[0] = make_uint4(pack_bf16(acc[0][0], acc[0][1]), pack_bf16(acc[1][0], acc[1][1]),
+                          pack_bf16(acc[2][0], acc[2][1]), pack_bf16(acc[3][0], acc[3][1]));
+      dst[1] = make_uint4(pack_bf16(acc[4][0], acc[4][1]), pack_bf16(acc[5][0], acc[5][1]),
+                          pack_bf16(acc[6][0], acc[6][1]), pack_bf16(acc[7][0], acc[7][1]));
+    }
+    if (v_hi) {
+      uint4* dst = reinterpret_cast<uint4*>(out_seq + static_cast<long long>(r_hi) * p.D);
+      dst[0] = make_uint4(pack_bf16(acc[0][2], acc[0][3]), pack_bf16(acc[1][2], acc[1][3]),
+                          pack_bf16(acc[2][2], acc[2][3]), pack_bf16(acc[3][2], acc[3][3]));
+      dst[1] = make_uint4(pack_bf16(acc[4][2], acc[4][3]), pack_bf16(acc[5][2], acc[5][3]),
+                          pack_bf16(acc[6][2], acc[6][3]), pack_bf16(acc[7][2], acc[7][3]));
     }
   }
 }
@@ -545,6 +665,12 @@ int la_build_src(void* stream, const float* feat, const float* m16, const unsign
   if (chunks < 1) chunks = 1;
   LA_CHECK_ARG(n_seq <= 65535, "la_build_src: more than 65535 sequences per call (chunk the call)");
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(n_seq));
+  // tensor-core variant: one warp per 64 channels (LA_BUILD_SRC_FMA=1 keeps the FFMA2 kernel)
+  if (d % 64 == 0 && d <= 512 && getenv("LA_BUILD_SRC_FMA") == nullptr) {
+    build_src_mma_kernel<<<grid, d / 2, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    LA_CHECK_CUDA(cudaGetLastError());
+    return LA_OK;
+  }
   build_src_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
