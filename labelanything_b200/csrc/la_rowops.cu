@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
   float4 acc[POOL ? NVT : 1];
 #pragma unroll
   for (int i = 0; i < (POOL ? NVT : 1); ++i) acc[i] = make_float4(0, 0, 0, 0);
+  [[maybe_unused]] float pool_c = 0.f, pool_n = 0.f;   // POOL: sum of rstd_r * mean_r, rows seen by this warp
   int slot = 0;
   for (long long chunk = c_first; chunk < n_chunks; chunk += c_step) {
     const long long row0 = base + chunk * rpc;
@@ -466,7 +467,21 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         const float rstd = rsqrtf(sq * inv_d + p.eps);
-        uint8_t* yrow = POOL ? nullptr : static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(row) * p.d * ebytes;
+        if constexpr (POOL) {
+          // mean over rows of (x - mean_r) rstd_r gamma + beta = gamma (sum_r rstd_r x_r - sum_r rstd_r mean_r) / T + beta:
+          // one FMA per element here, gamma / beta once per warp after the loop
+          pool_c = fmaf(rstd, mean, pool_c);
+          pool_n += 1.0f;
+#pragma unroll
+          for (int i = 0; i < NVT; ++i) {
+            acc[i].x = fmaf(v[i].x, rstd, acc[i].x);
+            acc[i].y = fmaf(v[i].y, rstd, acc[i].y);
+            acc[i].z = fmaf(v[i].z, rstd, acc[i].z);
+            acc[i].w = fmaf(v[i].w, rstd, acc[i].w);
+          }
+          continue;
+        }
+        uint8_t* yrow = static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(row) * p.d * ebytes;
 #pragma unroll
         for (int i = 0; i < NVT; ++i) {
           const bool on = (i < nv) || (i == nv && lane < tail);
@@ -512,7 +527,15 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
 #pragma unroll
     for (int i = 0; i < NVT; ++i) {
       const bool on = (i < nv) || (i == nv && lane < tail);
-      if (on) red[warp * dv + i * 32 + lane] = acc[i];
+      if (on) {
+        const float4 g = gmv[i], b = btv[i];
+        float4 a = acc[i];
+        a.x = fmaf(g.x, a.x - pool_c, b.x * pool_n);
+        a.y = fmaf(g.y, a.y - pool_c, b.y * pool_n);
+        a.z = fmaf(g.z, a.z - pool_c, b.z * pool_n);
+        a.w = fmaf(g.w, a.w - pool_c, b.w * pool_n);
+        red[warp * dv + i * 32 + lane] = a;
+      }
     }
     __syncthreads();
     float4* dstp = reinterpret_cast<float4*>(p.pool_out + static_cast<long long>(blockIdx.x) * p.d);
