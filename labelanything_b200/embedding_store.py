@@ -4,7 +4,7 @@
 label_anything/data/coco.py:251-275,490-505 (`load_file` per image, then `torch.stack`).
 
 Same files, byte for byte (the safetensors container: u64 header length, compact JSON header padded with spaces to
-8 bytes, tensors ordered by descending element size then name, raw little-endian data), but batched:
+8 bytes, tensors ordered by descending dtype rank then name, raw little-endian data), but batched:
   * load: headers parsed once, every file's payload is read by a thread pool STRAIGHT into its slot of one pinned
     [n, C, h, w] staging buffer (no per-file tensors, no torch.stack copy), then one asynchronous host-to-device copy;
   * save: one device-to-host copy of the whole batch into pinned memory, files written by the pool.
@@ -27,6 +27,9 @@ _DTYPES = {"F64": torch.float64, "F32": torch.float32, "F16": torch.float16, "BF
            "I64": torch.int64, "I32": torch.int32, "I16": torch.int16, "I8": torch.int8, "U8": torch.uint8,
            "BOOL": torch.bool}
 _NAMES = {v: k for k, v in _DTYPES.items()}
+# file order of the safetensors writer: descending position in its dtype enumeration (BOOL < U8 < I8 < I16 < F16 < BF16
+# < I32 < F32 < F64 < I64), then by name
+_RANK = {n: i for i, n in enumerate(["BOOL", "U8", "I8", "I16", "F16", "BF16", "I32", "F32", "F64", "I64"])}
 
 
 def _header_bytes(entries: list[tuple[str, torch.dtype, tuple, int]], metadata: Optional[dict] = None) -> bytes:
@@ -44,7 +47,7 @@ def _header_bytes(entries: list[tuple[str, torch.dtype, tuple, int]], metadata: 
 
 def write_safetensors(path: str, tensors: dict, metadata: Optional[dict] = None) -> None:
     """Byte-identical to safetensors.torch.save_file(tensors, path, metadata) for contiguous CPU tensors."""
-    items = sorted(tensors.items(), key=lambda kv: (-kv[1].element_size(), kv[0]))
+    items = sorted(tensors.items(), key=lambda kv: (-_RANK[_NAMES[kv[1].dtype]], kv[0]))
     entries = [(k, v.dtype, tuple(v.shape), v.numel() * v.element_size()) for k, v in items]
     head = _header_bytes(entries, metadata)
     with open(path, "wb") as f:
@@ -53,7 +56,7 @@ def write_safetensors(path: str, tensors: dict, metadata: Optional[dict] = None)
         for _, v in items:
             if not (v.device.type == "cpu" and v.is_contiguous()):
                 raise ValueError("write_safetensors: tensors must be contiguous CPU tensors")
-            f.write(v.view(torch.uint8).numpy().tobytes() if v.dtype == torch.bfloat16 else v.numpy().tobytes())
+            f.write(v.reshape(-1).view(torch.uint8).numpy().tobytes() if v.dtype == torch.bfloat16 else v.numpy().tobytes())
 
 
 def read_safetensors_header(path: str) -> tuple[dict, int]:

@@ -60,3 +60,20 @@ def test_save_round_trip_and_errors(tmp_path):
         store.load([10], device="cpu")
     with pytest.raises(FileNotFoundError):
         store.load([77], device="cpu")
+
+
+def test_writer_matches_safetensors_on_random_tensor_sets(tmp_path):
+    g = torch.Generator().manual_seed(5)
+    dtypes = [torch.float32, torch.float16, torch.bfloat16, torch.int64, torch.int32, torch.uint8, torch.bool,
+              torch.float64, torch.int16, torch.int8]
+    for trial in range(25):
+        tensors = {}
+        for k in range(int(torch.randint(1, 5, (1,), generator=g))):
+            dt = dtypes[int(torch.randint(0, len(dtypes), (1,), generator=g))]
+            shape = tuple(int(v) for v in torch.randint(0, 5, (int(torch.randint(0, 4, (1,), generator=g)),), generator=g))
+            base = torch.randint(0, 100, shape, generator=g)
+            tensors[f"t{trial}_{k}" if k else "embedding"] = base.to(dt)
+        a, b = tmp_path / "a.safetensors", tmp_path / "b.safetensors"
+        save_file(tensors, str(a))
+        write_safetensors(str(b), tensors)
+        assert a.read_bytes() == b.read_bytes(), {k: (v.dtype, tuple(v.shape)) for k, v in tensors.items()}

@@ -49,3 +49,23 @@ def test_loss_module_mirrors_the_reference_constructor():
         LabelAnythingLoss({"dice": {"weight": 1.0}})
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         loss(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int64))
+
+
+def test_oracle_matches_torch_autograd_on_random_inputs():
+    """Independent of the fixture: the same formula written with torch ops (F.cross_entropy, exp, pow, mean) and
+    differentiated by autograd, on random shapes / gammas / ignore patterns."""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(3)
+    for B, C, H, W, gamma in [(1, 2, 5, 7, 2.0), (3, 7, 4, 4, 1.0), (2, 9, 6, 5, 2.5), (1, 21, 3, 3, 2.0)]:
+        x = (torch.randn(B, C, H, W, generator=g) * 2).requires_grad_(True)
+        t = torch.randint(0, C, (B, H, W), generator=g)
+        t[0, 0, :2] = -100
+        wt_np, _ = lo.get_weight_matrix_from_labels(t.numpy().copy(), C)
+        wt = torch.from_numpy(wt_np)
+        ce = F.cross_entropy(x, t, reduction="none")
+        loss = torch.mean(torch.pow(1 - torch.exp(-ce), gamma) * wt * ce)
+        loss.backward()
+        assert abs(float(lo.focal_loss(x.detach().numpy(), t.numpy(), gamma, wt_np)) - float(loss)) <= 1e-5 * abs(float(loss))
+        np.testing.assert_allclose(lo.focal_loss_grad(x.detach().numpy(), t.numpy(), gamma, wt_np), x.grad.numpy(),
+                                   rtol=2e-4, atol=1e-7)

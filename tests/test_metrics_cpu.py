@@ -113,3 +113,25 @@ def test_two_rank_state_reduction():
     assert conf == [[15, 3, 0], [0, 12, 6], [3, 0, 9]]
     want = mo.strict_mean_iou(np.array(conf), -100)
     assert abs(value - float(want)) < 1e-6
+
+
+def test_chained_table_equals_sequential_substitution_on_random_episodes():
+    """Property check against the oracle's literal restatement of data/utils.py:583-589 (itself pinned by the
+    reference fixture): random category sets, random class lists (with repeats and several examples), both `compact`
+    settings, labels that include untouched values."""
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        n_cat = int(rng.integers(2, 25))
+        cat_ids = sorted(rng.choice(np.arange(1, 91), size=n_cat, replace=False).tolist())
+        categories = {int(k): {} for k in cat_ids}
+        B = int(rng.integers(1, 4))
+        classes = [[rng.choice(cat_ids, size=int(rng.integers(1, min(6, n_cat) + 1)), replace=False).tolist()
+                    for _ in range(int(rng.integers(1, 4)))] for _ in range(B)]
+        compact = bool(trial % 2)
+        labels = rng.integers(-1, 9, size=(B, 5, 6)).astype(np.int64)
+        labels[:, 0, 0] = -100
+        want = mo.to_global_multiclass(classes, categories, labels, compact=compact)[0]
+        table = chain_label_map(classes, categories, compact=compact, map_len=32).numpy()
+        inside = (labels >= 0) & (labels < table.shape[1])
+        got = np.where(inside, table[np.arange(B)[:, None, None], np.clip(labels, 0, table.shape[1] - 1)], labels)
+        assert np.array_equal(got, want), (classes, cat_ids, compact)
