@@ -101,7 +101,7 @@ int la_attention_window_bf16(void* stream, const void* q, long long ld_q, int q_
 /* Diagnostics: when device_buffer != NULL, CTA (0,0,0) of every following la_attention_bf16 launch records clock64()
  * stamps into it: int64 [5 roles (MMA issuers, softmax A / B first warp, softmax A / B last warp)][192 tiles]
  * [4 events]; NULL switches it off. */
-int la_attention_set_trace(void* device_buffer);
+int la_attention_set_trace(void* device_buffer);   /* LA_ERR_UNSUPPORTED unless built with -DLA_ATT_TRACE */
 
 /* ---- streaming row kernels ----------------------------------------------------------------------- */
 /* x = x_in[(row % x_mod) if x_mod > 0 else row] + delta[row]  (fp32 + bf16); optionally stored to x_out (may

@@ -7,6 +7,7 @@ string-match it (label_anything/experiment/run.py:339-355, experiment/utils.py:2
 from __future__ import annotations
 
 import ctypes
+import os
 import re
 from pathlib import Path
 
@@ -58,12 +59,15 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = LIB_PATH
+    if os.environ.get("LA_B200_LIB"):   # experiment builds of tools/ (build.build_variant); never set by the product
+        path = Path(os.environ["LA_B200_LIB"])
+    if not path.exists():
         raise RuntimeError(
-            f"labelanything_b200: native library {LIB_PATH} is missing. Build it with "
+            f"labelanything_b200: native library {path} is missing. Build it with "
             "`python -m labelanything_b200.build` (or __graft_entry__.build()). There is no CPU/eager fallback."
         )
-    cdll = ctypes.CDLL(str(LIB_PATH))
+    cdll = ctypes.CDLL(str(path))
     for name, (ret, types) in declared_functions().items():
         fn = getattr(cdll, name)  # AttributeError if the header and the library disagree
         fn.restype = {"const char*": ctypes.c_char_p, "long long": ctypes.c_longlong}.get(ret, ctypes.c_int)

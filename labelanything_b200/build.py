@@ -88,5 +88,37 @@ def build(force: bool = False, verbose: bool = True) -> Path:
     return LIB_PATH
 
 
+def build_variant(tag: str, defines: list[str], sources: tuple[str, ...] = ("la_attention.cu",)) -> Path:
+    """Experiment builds: recompile `sources` with extra -D flags, link them with the regular objects of the other
+    sources into _variants/liblabelanything_b200_<tag>.so.  Loaded instead of the product library when the environment
+    variable LA_B200_LIB points at it (tools/ only; the product path never sets it)."""
+    nvcc = _nvcc()
+    build()
+    vdir = PKG_DIR / "_variants"
+    vdir.mkdir(exist_ok=True)
+    objs = []
+    for src in _sources():
+        if src.name in sources:
+            obj = vdir / f"{src.stem}_{tag}.o"
+            cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(src), "-o", str(obj)]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            (vdir / f"{src.stem}_{tag}.log").write_text(res.stdout + res.stderr)
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed for variant {tag}:\n{res.stdout}\n{res.stderr}")
+            objs.append(obj)
+        else:
+            objs.append(BUILD_DIR / (src.stem + ".o"))
+    out = vdir / f"liblabelanything_b200_{tag}.so"
+    cmd = [nvcc, "-shared", "-o", str(out), *map(str, objs), "-cudart", "static",
+           "-gencode", "arch=compute_100a,code=sm_100a"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":   # python -m labelanything_b200.build --variant tag D1=1 D2=0
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        print(build(force="--force" in sys.argv))

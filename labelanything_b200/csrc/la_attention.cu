@@ -31,22 +31,49 @@
 #include "la_common.cuh"
 #include <type_traits>
 #include <cuda_fp16.h>
-#include <cstdlib>
 
 namespace la {
 
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_D = 64;
-// every ATT_POLY_EXP-th pair of scores of the 64-key modes takes the polynomial exp2 (0 = never)
-#ifndef ATT_POLY_EXP
-#define ATT_POLY_EXP 4
+// ATT_POLY_NUM of every ATT_POLY_DEN pairs of scores of the 64-key modes take the polynomial exp2 (evenly spread)
+#ifndef ATT_POLY_NUM
+#define ATT_POLY_NUM 1
+#endif
+#ifndef ATT_POLY_DEN
+#define ATT_POLY_DEN 4
 #endif
 // ... and of the 112-key window mode (0: measured no gain there -- that kernel is bound by its per-item latency chain)
-#ifndef ATT_POLY_EXP_WIN
-#define ATT_POLY_EXP_WIN 0
+#ifndef ATT_POLY_NUM_WIN
+#define ATT_POLY_NUM_WIN 0
 #endif
 #ifndef ATT_TS_OPERANDS
 #define ATT_TS_OPERANDS 1
+#endif
+// 64-key modes: the softmax threads fetch score tile g+1 into a second register set right after the exponentials of
+// tile g: the barrier wait and the TMEM load latency run under the P store / fence / arrive of tile g.
+#ifndef ATT_PIPE
+#define ATT_PIPE 0
+#endif
+// 64-key modes: the exponential passes of the two Q tiles' softmax warps take turns (FlashAttention-3/4 style
+// ping-pong).  Warp 4+q (tile A) and warp 8+q (tile B) share scheduler q and its MUFU unit; left alone they run in
+// lockstep (both wait, both take the maximum, both compete for the MUFU: ~940 cycles of exponentials per tile for
+// 2 x 384 cycles of MUFU work, with the unit idle during the other ~500 cycles of every tile period).  A pair of
+// named barriers per scheduler hands the exponential pass back and forth, so one warp's barrier waits, TMEM loads
+// and maximum run under the other's exponentials.
+// element type of P (the A operand of the PV product): 1 = fp16, 0 = bf16
+#ifndef ATT_P_F16
+#define ATT_P_F16 0
+#endif
+// timing diagnostics (WRONG results; experiment builds only): skip the rel_w fold MMAs / the MUFU exponentials
+#ifndef ATT_DIAG_NOFOLD
+#define ATT_DIAG_NOFOLD 0
+#endif
+#ifndef ATT_DIAG_NOEXP
+#define ATT_DIAG_NOEXP 0
+#endif
+#ifndef ATT_PINGPONG
+#define ATT_PINGPONG 2
 #endif
 constexpr int ATT_STG_STRIDE = 272;     // bytes per row of the table staging area (68 floats: conflict-free STS.128)
 // setmaxnreg budget: 256 softmax threads + 128 control threads share 384 x 168 = 64512 registers (launch allocation).
@@ -54,8 +81,8 @@ constexpr int ATT_STG_STRIDE = 272;     // bytes per row of the table staging ar
 // everything the softmax threads can get.
 template <int KV_TILE>
 struct AttRegs {
-  static constexpr int SOFTMAX = KV_TILE <= 64 ? 200 : 216;
-  static constexpr int CONTROL = KV_TILE <= 64 ? 104 : 72;
+  static constexpr int SOFTMAX = KV_TILE <= 64 ? 216 : 216;
+  static constexpr int CONTROL = KV_TILE <= 64 ? 72 : 72;
   static_assert(256 * SOFTMAX + 128 * CONTROL <= ATT_THREADS * 168,
                 "setmaxnreg.inc can only hand out what the CTA was launched with (168 registers x 384 threads)");
 };
@@ -78,17 +105,26 @@ struct AttParams {
   long long ld_out;
   int out_mode;  // 0: row = seq*seq_len + t ; 1: window unpartition
   int win, nwin, img_hw;  // out_mode 1: window size, windows per side, un-padded grid side
-  long long* trace;       // diagnostics (la_attention_set_trace): clock64 stamps of CTA (0,0,0), else nullptr
-  int debug;              // diagnostics (LA_ATT_DEBUG env): bit0 always rescale, bit1 never skip the O wait
+  long long* trace;       // -DLA_ATT_TRACE builds: clock64 stamps of CTA (0,0,0) (la_attention_set_trace), else nullptr
 };
 
 // trace layout: [role][tile][event] int64; roles: 0 = MMA issuers (P seen / next S issued, per Q tile), 1 / 2 = softmax
 // A / B first warp (wait S, got S, max done, P delivered), 3 / 4 = the same warps' item boundaries, indexed by item
 // (O ready, epilogue stores issued, window tables ready, prologue done)
 constexpr int ATT_TRACE_TILES = 192, ATT_TRACE_EVENTS = 4;   // the first three items of a 64-tile-per-item run
-__device__ __forceinline__ void att_trace(const AttParams& p, bool on, int role, int tile, int ev) {
+// Compiled in only with -DLA_ATT_TRACE (experiment builds, labelanything_b200/build.py::build_variant): the product
+// library has no trace state and no environment lookups on the launch path.
+__device__ __forceinline__ void att_trace([[maybe_unused]] const AttParams& p, [[maybe_unused]] bool on,
+                                          [[maybe_unused]] int role, [[maybe_unused]] int tile,
+                                          [[maybe_unused]] int ev) {
+#ifdef LA_ATT_TRACE
   if (on && tile < ATT_TRACE_TILES) p.trace[(role * ATT_TRACE_TILES + tile) * ATT_TRACE_EVENTS + ev] = clock64();
+#endif
 }
+// diagnostics (compile time): bit0 always rescale, bit1 never skip the O wait
+#ifndef LA_ATT_DEBUG_FLAGS
+#define LA_ATT_DEBUG_FLAGS 0
+#endif
 
 template <int KV_TILE, int BIAS>
 struct AttSmem {
@@ -118,6 +154,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+// named barriers 1..15 (0 is __syncthreads): `count` threads in total, bar_sync-ers and bar_arrive-rs together
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
@@ -375,7 +419,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // (M128 x N64 x K16), so descriptor arithmetic between them is what starves it.  All descriptors are
       // base + small offset on pre-shifted 32-bit low words (the high word is a constant), one elect per tile.
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, KV_TILE, 0, 0);  // S = Q K^T   (both K-major, smem)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_D, 0, 1);    // O += P V    (P in TMEM, V MN-major)
+      // O += P V  (P in TMEM, V MN-major).  ATT_P_F16: P travels as fp16 (A format field 0) against the bf16 V --
+      // P <= 2^8 by the lazy rescale, so fp16's 11 significant bits apply (bf16: 8) and the product is exact in fp32
+      constexpr uint32_t idesc_o = ATT_P_F16 ? (umma_idesc_bf16(128, ATT_D, 0, 1) & ~(7u << 7))
+                                             : umma_idesc_bf16(128, ATT_D, 0, 1);
       // S += A_w I/scale: fp16 operands (A/B format fields 0) -- 11 significant bits for the bias instead of 8
       constexpr uint32_t idesc_w = umma_idesc_bf16(128, KV_TILE, 0, 0) & ~((7u << 7) | (7u << 10));
       constexpr uint32_t LA = NBUF;
@@ -436,7 +483,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_ts_lo(d, tq + ks * 8, bk + 2 * ks, idesc_s, ks > 0);
-          if constexpr (FOLD_W) {
+          if constexpr (FOLD_W && !ATT_DIAG_NOFOLD) {
             // S += A_w x I / scale : adds rel_w[q, kw] to column kw of every key tile (KV_TILE == 64 == grid width)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) umma_ts_lo(d, tq + 32 + ks * 8, lo_id + 2 * ks, idesc_w, true);
@@ -603,6 +650,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
     }
 
+    // score tile gq of this CTA's tile sequence (TMEM -> registers); the caller awaits it with tmem_ld_wait()
+    auto fetch_scores = [&](const uint32_t gq, uint32_t* dst) {
+      const uint32_t bq = gq % NBUF;
+      mbar_wait(&bar_s[3 * x + bq], (gq / NBUF) & 1);
+      tc_fence_after();
+      const uint32_t ts = t_s0 + bq * KV_TILE;
+#pragma unroll
+      for (int c = 0; c + 32 <= KV_TILE; c += 32) tmem_ld_x32(ts + c, dst + c);
+      if constexpr (KV_TILE % 32 != 0) tmem_ld_x16(ts + (KV_TILE / 32) * 32, dst + (KV_TILE / 32) * 32);
+    };
+    constexpr bool PF = DB && (ATT_PIPE != 0);
+    // measured (profiles/r02_exp_attention.txt): +14 % on the HF ViT shape (901 tokens, no bias), -4 % on the 64x64
+    // rel-pos mode, whose tile period is set by the two exponential passes either way -> 2 = bias-free mode only
+    constexpr bool PP = DB && (ATT_PINGPONG == 1 || (ATT_PINGPONG == 2 && BIAS == ATT_BIAS_NONE));
+    if constexpr (PP) {
+      // tile A goes first: tile B's warp pre-arrives on A's barrier (only if there is work at all)
+      if (x == 1 && static_cast<int>(blockIdx.x) < n_items) named_bar_arrive(1 + 2 * quarter, 64);
+    }
+    uint32_t sva[KV_TILE];
+    if constexpr (PF) {
+      if (static_cast<int>(blockIdx.x) < n_items) {
+        fetch_scores(0, sva);
+        tmem_ld_wait();
+      }
+    }
+
     int it = 0;
     uint32_t g0 = 0;
     // window mode: one 256-row pair per sequence, so a thread's token and its position in the window never change
@@ -660,7 +733,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       BT rh_next = BT(0.0f);   // 64x64 mode: rel_h term of the next key tile (= key-grid row), fetched one tile ahead
       if constexpr (FOLD_W) rh_next = rh_pre;
 
-      for (int j = 0; j < NT; ++j) {
+      // one key tile: `sv` holds (PF) or receives (!PF) the scores of tile j; with PF the next tile of this CTA -- of
+      // this item or the first one of the next item -- is fetched into `svn` while tile j is being processed
+      auto do_tile = [&](const int j, uint32_t* sv, uint32_t* svn) {
         const uint32_t g = g0 + j;
         const int valid = p.seq_len - j * KV_TILE;  // keys of this tile that exist (may exceed KV_TILE)
         // rel_h terms of the NG key-grid rows of this tile
@@ -679,16 +754,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t buf = g % NBUF;
         const uint32_t t_s = t_s0 + buf * KV_TILE;
         att_trace(p, tr, tr_role, g, 0);
-        mbar_wait(&bar_s[3 * x + buf], (g / NBUF) & 1);
-        tc_fence_after();
+        [[maybe_unused]] bool has_next = false;
+        if constexpr (PF) {
+          has_next = (j + 1 < NT) || (w + static_cast<int>(gridDim.x) < n_items);
+        } else {
+          // ---- the whole score row into registers: ONE pass over TMEM ----
+          fetch_scores(g, sv);
+          tmem_ld_wait();
+        }
         att_trace(p, tr, tr_role, g, 1);
-
-        // ---- the whole score row into registers: ONE pass over TMEM ----
-        uint32_t sv[KV_TILE];
-#pragma unroll
-        for (int c = 0; c + 32 <= KV_TILE; c += 32) tmem_ld_x32(t_s + c, sv + c);
-        if constexpr (KV_TILE % 32 != 0) tmem_ld_x16(t_s + (KV_TILE / 32) * 32, sv + (KV_TILE / 32) * 32);
-        tmem_ld_wait();
         if constexpr (WIN) {
           // 196 keys = 112 + 84: the second tile's last 28 columns are beyond the window (compile-time positions)
           if (j == 1) {
@@ -742,7 +816,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         bool need = false;
         if (j == 0) {
           m_used = mx;
-        } else if (mx > m_used + 8.0f || (p.debug & 1)) {
+        } else if (mx > m_used + 8.0f || (LA_ATT_DEBUG_FLAGS & 1)) {
           alpha = ex2_approx(m_used - mx);
           m_used = mx;
           need = true;
@@ -769,6 +843,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
         for (int gi = 0; gi < NG; ++gi) offg[gi] = rh2[gi] - m_used;
         float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
+        if constexpr (PP) named_bar_sync(1 + 2 * quarter + x, 64);   // my turn on this scheduler's MUFU
 #pragma unroll
         for (int c0 = 0; c0 < KV_TILE; c0 += 32) {
           const int width = (KV_TILE - c0 >= 32) ? 32 : 16;
@@ -784,30 +859,49 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 ffma2(a0, a1, __uint_as_float(sv[col]), __uint_as_float(sv[col + 1]), sl2, offg[0]);
               }
               float e0, e1;
-              constexpr int POLY = WIN ? ATT_POLY_EXP_WIN : ATT_POLY_EXP;
-              if (POLY > 0 && ((col >> 1) % POLY) == POLY - 1) {
+              constexpr int PNUM = WIN ? ATT_POLY_NUM_WIN : ATT_POLY_NUM;
+              if (((col >> 1) * PNUM) % ATT_POLY_DEN < PNUM) {
                 e0 = a0;
                 e1 = a1;
                 exp2_poly_x2(e0, e1);
+              } else if (ATT_DIAG_NOEXP) {
+                e0 = a0;
+                e1 = a1;
               } else {
                 e0 = ex2_approx(a0);
                 e1 = ex2_approx(a1);
               }
               if ((i & 2) == 0) fadd2_acc(l0, l1, e0, e1);
               else fadd2_acc(l2, l3, e0, e1);
-              pk[i >> 1] = pack_bf16(e0, e1);
+              pk[i >> 1] = ATT_P_F16 ? pack_f16(e0, e1) : pack_bf16(e0, e1);
             }
           }
           if (width == 32) tmem_st_32x32b_x16(t_s + (c0 >> 1), pk);
           else tmem_st_32x32b_x8(t_s + (c0 >> 1), pk);
         }
+        if constexpr (PP) {
+          // hand the MUFU to the other Q tile's warp (not after this CTA's very last tile: nobody would wait for it)
+          if (x == 0 || j + 1 < NT || w + static_cast<int>(gridDim.x) < n_items)
+            named_bar_arrive(1 + 2 * quarter + (x ^ 1), 64);
+        }
         l_sum += (l0 + l1) + (l2 + l3);
+        if constexpr (PF) {
+          // S(g+1) was issued when P(g-1) arrived, a whole tile ago: fetch it now, so that its barrier wait and TMEM
+          // load latency run under the P store / fence / arrive of this tile instead of opening the next one.
+          // (Any earlier and the score tile is not there yet: its buffer held P(g-1) until PV(g-1) had read it.)
+          if (has_next) fetch_scores(g + 1, svn);
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[3 * x + buf]);
+        if constexpr (PF) {
+          if (has_next) tmem_ld_wait();   // svn is valid from here on
+        }
         att_trace(p, tr, tr_role, g, 3);
-      }
+      };
+      // PF: all scores of tile j are consumed when the next tile is fetched, so one register set serves both
+      for (int j = 0; j < NT; ++j) do_tile(j, sva, sva);
 
       if constexpr (FOLD_W) {
         if (w + static_cast<int>(gridDim.x) < n_items) {
@@ -897,11 +991,20 @@ static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, 
 
 }  // namespace la
 
-static long long* g_att_trace = nullptr;
+#ifdef LA_ATT_TRACE
+static long long* g_att_trace = nullptr;   // experiment builds only
+#endif
 
 extern "C" int la_attention_set_trace(void* device_buffer) {
+#ifdef LA_ATT_TRACE
   g_att_trace = static_cast<long long*>(device_buffer);
   return LA_OK;
+#else
+  (void)device_buffer;
+  la::set_last_error("la_attention_set_trace: this library was built without -DLA_ATT_TRACE (the product library keeps "
+                     "no trace state)");
+  return LA_ERR_UNSUPPORTED;
+#endif
 }
 
 static int attention_dispatch(const char* fn, void* stream, const void* q, long long ld_q, int q_off, const void* kv,
@@ -941,8 +1044,11 @@ static int attention_dispatch(const char* fn, void* stream, const void* q, long 
   p.win = grid_hw;
   p.nwin = nwin;
   p.img_hw = img_hw;
+#ifdef LA_ATT_TRACE
   p.trace = g_att_trace;
-  { const char* e = getenv("LA_ATT_DEBUG"); p.debug = e ? atoi(e) : 0; }
+#else
+  p.trace = nullptr;
+#endif
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (rel_table != nullptr) {
     LA_CHECK_ARG(grid_hw == 14 && seq_len == 196 && rel_pad == 32,

@@ -165,6 +165,9 @@ def test_fused_attention_matches_torch(mode, n_seq, L, gsz, qscale):
     g = _gen(L + n_seq)
     qkv = torch.randn(n_seq * L, 3 * heads * 64, device="cuda", generator=g)
     qkv[:, : heads * 64] *= qscale
+    # V = 1 + N(0, 1/4): every output element is O(1) in every parametrization (a softmax average of N(0, 1) values
+    # over thousands of keys would be ~0.03, and an absolute tolerance would then hide any error)
+    qkv[:, 2 * heads * 64:] = 1.0 + 0.5 * qkv[:, 2 * heads * 64:]
     qkv = qkv.to(torch.bfloat16)
     rel_h = rel_w = bh = bw = None
     if gsz:
@@ -182,9 +185,16 @@ def test_fused_attention_matches_torch(mode, n_seq, L, gsz, qscale):
             bh, bw = _rev_bias(ops, qh, rel_h, 128, td), _rev_bias(ops, qh, rel_w, 128, td)
         ops.attention(qkv, qkv, n_seq, L, heads, 0.125, out, 0, heads * 64, 2 * heads * 64, bh, bw, grid_hw=gsz)
     ref = _ref_attention(qkv, n_seq, L, heads, 0.125, rel_h, rel_w, gsz)
-    # P and the output are rounded to bf16 (2^-9 each, P errors average over the keys): 1e-2 relative + 1e-2 absolute
-    # of outputs that are O(0.1-1) — the bound the torch sdpa bf16 kernels meet on the same inputs
-    _close(out, ref, 2e-2, 2e-2, f"attention {mode}")
+    assert float(ref.abs().mean()) > 0.5      # the outputs are O(1): the absolute term below is 0.2 % of the signal
+    # kernel tolerance on identical bf16 inputs vs torch fp32.  Two bf16 roundings sit on the path, each with a
+    # worst-case relative error of 2^-8 (half an ulp at the bottom of a binade): P before the PV product and the
+    # output.  With ordinary logits (qscale 1) hundreds of keys carry weight and the P errors average out: bound =
+    # 2^-8 (output rounding) + 2e-3 absolute.  With 4x logits (qscale 4: softmax dominated by one or two keys, the
+    # lazy-rescale path) the P error of the dominant key reaches the output unaveraged: bound = 2^-7 + 2e-3.
+    _close(out, ref, 2 ** -8 if qscale == 1.0 else 2 ** -7, 2e-3, f"attention {mode}")
+    err = (out.float() - ref).abs()
+    print(f"attention {mode} L={L} qscale={qscale}: max_abs_err {err.max().item():.3e} mean {err.mean().item():.3e} "
+          f"(|ref| mean {ref.abs().mean().item():.3f})")
 
 
 def test_window_attention_unpartition_drops_padding():
