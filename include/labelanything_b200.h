@@ -260,8 +260,8 @@ int la_label_class_weights(void* stream, const long long* labels, long long n, i
  *   grad_out (optional, [batch, classes, pixels]) = grad_scale[0] * d loss / d logits (grad_scale NULL = 1)
  *   wtarget_out (optional, [batch, pixels]) = class_w[target] (0 where ignored): the reference's weight matrix.
  *     (logits may be NULL when only wtarget_out is requested.)
- * workspace: la_focal_loss_workspace_bytes() bytes, zero-initialised once by the caller, reusable across calls on
- * one stream.  Replaces label_anything/loss/focal.py:8-25 and the focal branch of LabelAnythingLoss.logits_loss
+ * workspace: la_focal_loss_workspace_bytes() bytes of 8-byte aligned scratch, no initialisation required (the entry
+ * point zeroes its own counter on the stream); one workspace per call in flight.  Replaces label_anything/loss/focal.py:8-25 and the focal branch of LabelAnythingLoss.logits_loss
  * (label_anything/loss/__init__.py:67-92). */
 long long la_focal_loss_workspace_bytes(void);
 int la_focal_loss(void* stream, const float* logits, const long long* target, const float* class_w,

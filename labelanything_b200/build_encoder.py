@@ -30,6 +30,14 @@ vit_configs = dict(  # build_encoder.py:9-28
 def _build_vit(encoder_embed_dim, encoder_depth, encoder_num_heads, encoder_global_attn_indexes, checkpoint=None,
                use_sam_checkpoint=False, project_last_hidden=True):
     """build_encoder.py:43-80"""
+    if encoder_embed_dim % encoder_num_heads or encoder_embed_dim // encoder_num_heads != 64:
+        # ViT-H: 1280 / 16 = head_dim 80.  The tcgen05 attention kernels stage 64-element (128-byte, one swizzle atom)
+        # head slices; there is no head_dim-80 path, and none is faked: fail here, before a multi-GB checkpoint load,
+        # like every other out-of-scope option of the reference (DESIGN.md §1).
+        raise NotImplementedError(
+            f"labelanything_b200: SAM ViT with head_dim {encoder_embed_dim // max(encoder_num_heads, 1)} "
+            f"(embed_dim {encoder_embed_dim}, {encoder_num_heads} heads) is not supported; the native attention kernels "
+            "are built for head_dim 64 (vit_b, vit_l)")
     vit = ImageEncoderViT(depth=encoder_depth, embed_dim=encoder_embed_dim, img_size=1024, mlp_ratio=4,
                           norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_heads=encoder_num_heads,
                           patch_size=16, qkv_bias=True, use_rel_pos=True,
@@ -63,6 +71,8 @@ class ViTModelWrapper(ViTModel):
     # -- packed-weight cache (same contract as common.NativeModule, which we cannot inherit from) ----------
     _cache = NativeModule._cache
     packed = NativeModule.packed
+    _packed_eager = NativeModule._packed_eager
+    _packed_checked = NativeModule._packed_checked
 
     def __getstate__(self):
         state = self.__dict__.copy()
@@ -83,6 +93,11 @@ class ViTModelWrapper(ViTModel):
         cfg = self.config
         d, heads = cfg.hidden_size, cfg.num_attention_heads
         assert gh == gw, "native HF-ViT path expects square inputs"
+        if getattr(cfg, "hidden_act", "gelu") != "gelu":
+            raise NotImplementedError(f"labelanything_b200: HF ViT hidden_act={cfg.hidden_act!r}; the native MLP epilogue "
+                                      "is the exact-erf GELU ('gelu') of the ViT / ViT-MAE checkpoints")
+        if d != heads * 64:
+            raise NotImplementedError(f"labelanything_b200: HF ViT head_dim {d // heads}; native attention is head_dim 64")
         blocks = []
         for i, layer in enumerate(self.encoder.layer):
             att = layer.attention.attention

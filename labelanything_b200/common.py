@@ -28,7 +28,24 @@ class NativeModule(nn.Module):
         return c
 
     def packed(self, key: str, build: Callable[[], object], *deps: torch.Tensor):
-        """Return cache[key], rebuilding it when any tensor in `deps` changed (in-place update, .to(), load)."""
+        """Return cache[key], rebuilding it when any tensor in `deps` changed (in-place update, .to(), load).
+
+        Under torch.compile tracing an existing entry is used as is (a graph constant guarded by dynamo) -- the
+        (data_ptr, _version) signature cannot be evaluated on traced tensors; a compiled model therefore assumes frozen
+        weights between recompilations, like any weight-prepacking backend.  Missing entries are built outside the
+        graph."""
+        if torch.compiler.is_compiling():
+            hit = self._cache().get(key)
+            if hit is not None:
+                return hit[1]
+            return self._packed_eager(key, build, deps)
+        return self._packed_checked(key, build, deps)
+
+    @torch.compiler.disable
+    def _packed_eager(self, key, build, deps):
+        return self._packed_checked(key, build, deps)
+
+    def _packed_checked(self, key, build, deps):
         sig = tuple((d.data_ptr(), d._version, str(d.device), d.dtype) for d in deps)
         c = self._cache()
         hit = c.get(key)

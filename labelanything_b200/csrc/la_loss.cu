@@ -283,6 +283,9 @@ extern "C" int la_focal_loss(void* stream, const float* logits, const long long*
   if (ctas > cap) ctas = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned g = static_cast<unsigned>(ctas);
+  // the "CTAs done" counter starts at zero on every launch: the workspace needs no initialisation by the caller and a
+  // launch that was aborted (or raced on the same scratch) cannot leave it in a state where the last-CTA branch never fires
+  if (p.counter != nullptr) LA_CHECK_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
   if (vec4) {
     if (grad_out) focal_loss_kernel<4, true><<<g, LOSS_THREADS, 0, st>>>(p);
     else focal_loss_kernel<4, false><<<g, LOSS_THREADS, 0, st>>>(p);

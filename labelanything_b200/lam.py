@@ -108,7 +108,7 @@ class Lam(NativeModule):
         pe_result = self.prompt_encoder.encode(feats, B, M, points, boxes, masks, flag_examples, feat_lead=1)
         q32, q16 = ops.copy_slabs(feats, B, T, N * T, 0, want_f32=True, want_bf16=True)
         seg = self.mask_decoder.decode(q32, q16, self.prompt_encoder.dense_pe_tokens(),
-                                       pe_result[ResultDict.CLASS_EMBS], B, g, g)
+                                       pe_result[ResultDict.CLASS_EMBS], B, g, g, pe_cached=True)
         return seg, pe_result
 
     def forward(self, batched_input: Dict[str, Any]) -> Dict[str, torch.Tensor]:
@@ -134,7 +134,7 @@ class Lam(NativeModule):
         T = g * g
         q32, q16 = ops.copy_slabs(feats, B, T, N * T, 0, want_f32=True, want_bf16=True)
         ce = class_embeddings[ResultDict.CLASS_EMBS]
-        seg = self.mask_decoder.decode(q32, q16, self.prompt_encoder.dense_pe_tokens(), ce, B, g, g)
+        seg = self.mask_decoder.decode(q32, q16, self.prompt_encoder.dense_pe_tokens(), ce, B, g, g, pe_cached=True)
         return self.postprocess_masks(seg, batched_input["dims"].unsqueeze(1))
 
     def postprocess_masks(self, masks: torch.Tensor, original_sizes: torch.Tensor,

@@ -41,7 +41,8 @@ def get_weight_matrix_from_labels(labels: torch.Tensor, num_classes: int, ignore
 class _FocalFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, target, class_w, gamma, ignore_index, mean):
-        xc = x.contiguous()
+        ctx.in_dtype = x.dtype
+        xc = x.float().contiguous()       # autocast / bf16 logits: the kernel computes in fp32 like the reference's CE
         loss, _, _ = ops.focal_loss(xc, target, class_w, gamma, ignore_index, mean)
         ctx.save_for_backward(xc, target, class_w if class_w is not None else torch.empty(0, device=x.device))
         ctx.cfg = (gamma, ignore_index, mean, class_w is not None)
@@ -53,7 +54,7 @@ class _FocalFn(torch.autograd.Function):
         gamma, ignore_index, mean, has_w = ctx.cfg
         _, grad, _ = ops.focal_loss(xc, target, class_w if has_w else None, gamma, ignore_index, mean, want_loss=False,
                                     want_grad=True, grad_scale=grad_out.float().contiguous())
-        return grad, None, None, None, None, None
+        return grad.to(ctx.in_dtype), None, None, None, None, None
 
 
 class FocalLoss(nn.Module):

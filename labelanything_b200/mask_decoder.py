@@ -105,7 +105,7 @@ class MaskDecoderLam(NativeModule):
 
     # ------------------------------------------------------------------ native forward
     def decode(self, q32: torch.Tensor, q16: torch.Tensor, pe: torch.Tensor, class_embeddings: torch.Tensor,
-               B: int, h: int, w: int) -> torch.Tensor:
+               B: int, h: int, w: int, pe_cached: bool = False) -> torch.Tensor:
         """q32 / q16: query-image features, token-major fp32 / bf16 [B*h*w, D]; pe fp32 [h*w, D];
         class_embeddings fp32 [B, C, D] -> low-resolution logits fp32 [B, C, 4h, 4w]."""
         assert h == w, "the native pixel-shuffle kernels expect square feature maps"
@@ -114,7 +114,8 @@ class MaskDecoderLam(NativeModule):
         C = class_embeddings.shape[1]
         assert isinstance(self.transformer, TwoWayTransformer), "only TwoWayTransformer has a native path"
         tokens = class_embeddings.float().contiguous().view(B * C, D)
-        queries, keys16, _ = run_two_way(self.transformer, q16, q32, pe, tokens, B, T, C, want_queries=True)
+        queries, keys16, _ = run_two_way(self.transformer, q16, q32, pe, tokens, B, T, C, want_queries=True,
+                                         pe_cached=pe_cached)
         cls = self.class_mlp.run(queries)                                # [B*C, D/8] fp32
 
         up = self.output_upscaling

@@ -1,7 +1,9 @@
-"""Thin torch-tensor wrappers over the C ABI (include/labelanything_b200.h).
+"""Thin torch-tensor wrappers over the C ABI (include/labelanything_b200.h), registered as torch custom ops.
 
 PyTorch is used for device memory and the current stream only; every function here validates shapes/dtypes,
 hands raw pointers to the native library and raises RuntimeError on failure.  Nothing falls back to torch math.
+Each entry point is also a `torch.library` custom op with a fake implementation (`torch.ops.labelanything_b200.la_*`),
+which is what `torch.compile(model)` records (label_anything/experiment/run.py:167-169 compiles the model on request).
 """
 from __future__ import annotations
 
@@ -12,10 +14,6 @@ from . import _native
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 DT_BF16, DT_F32, DT_F16 = 0, 1, 2
 _DTC = {torch.bfloat16: DT_BF16, torch.float32: DT_F32, torch.float16: DT_F16}
-
-
-def _stream(t: torch.Tensor) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
 
 
 class OpProfiler:
@@ -58,24 +56,115 @@ class profile:
 
 def _cost(flops: float = 0.0, nbytes: float = 0.0) -> None:
     global _COST
-    _COST = (float(flops), float(nbytes))
+    if _PROF is not None:
+        _COST = (float(flops), float(nbytes))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The C ABI as torch custom ops.
+#
+# Every `int la_xxx(void* stream, ...)` entry point of include/labelanything_b200.h is registered as the custom op
+# `labelanything_b200::la_xxx` (torch.library): pointer parameters become `Tensor?` arguments (non-const pointers are
+# declared as mutated, `Tensor(a!)?`), integers / floats stay scalars, the stream parameter disappears (it is torch's
+# current stream on the device of the first CUDA tensor argument).  All outputs are allocated by the Python wrappers
+# below and mutated in place, so every op returns nothing and its fake (meta) implementation is a no-op: FakeTensor
+# tracing, `torch.compile` (dynamo + AOT functionalisation re-inplaces the mutable ops) and `torch.export` see the
+# launch sequence as ordinary graph nodes instead of opaque ctypes calls.  The schema is derived from the header, so the
+# header stays the single source of truth for the boundary.
+# ------------------------------------------------------------------------------------------------------------------
+_OPS_NS = "labelanything_b200"
+_OP_PARAMS: dict = {}     # op name -> [(kind, c type)], kind in {"tensor", "int", "float"}; stream parameter dropped
+_op_lib = None
+
+
+def _schema_of(name: str, types: list) -> tuple:
+    params, parts, alias = [], [], 0
+    for i, t in enumerate(types[1:]):          # types[0] is `void* stream`
+        if "*" in t:
+            if t.startswith("const"):
+                parts.append(f"Tensor? a{i}")
+            else:
+                parts.append(f"Tensor({chr(ord('a') + alias)}!)? a{i}")
+                alias += 1
+            params.append(("tensor", t))
+        elif t == "float":
+            parts.append(f"float a{i}")
+            params.append(("float", t))
+        else:
+            parts.append(f"int a{i}")
+            params.append(("int", t))
+    return f"{name}({', '.join(parts)}) -> ()", params
+
+
+def _launch(name: str, args) -> int:
+    """Raw launch: tensors -> device pointers, torch's current stream of the first CUDA tensor's device, that device made
+    current for the call (the C ABI launches on, and queries, the calling thread's current device)."""
+    fn = getattr(_native.lib(), name)
+    dev = None
+    cargs = []
+    for (kind, _), a in zip(_OP_PARAMS[name], args):
+        if kind == "tensor":
+            if a is None:
+                cargs.append(None)
+            else:
+                if dev is None and a.is_cuda:
+                    dev = a.device
+                cargs.append(a.data_ptr())
+        else:
+            cargs.append(a)
+    if dev is None:
+        raise RuntimeError(f"labelanything_b200.{name}: no CUDA tensor among the arguments; there is no CPU fallback")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if dev.index != torch.cuda.current_device():
+        # tensors on a device that is not the thread's current one (model.to("cuda:1") in a single process): the stream
+        # handle belongs to that device, so the launch, sm_count() and cudaFuncSetAttribute must run there too
+        with torch.cuda.device(dev):
+            return fn(stream, *cargs)
+    return fn(stream, *cargs)
+
+
+def _register_ops() -> None:
+    global _op_lib
+    if _op_lib is not None:
+        return
+    lib = torch.library.Library(_OPS_NS, "DEF")
+    for name, (ret, types) in _native.declared_functions().items():
+        if ret != "int" or not types or types[0] != "void*" or name == "la_attention_set_trace":
+            continue                            # queries (la_version, *_workspace_bytes, la_last_error) are not launches
+        schema, params = _schema_of(name, types)
+        _OP_PARAMS[name] = params
+        lib.define(schema)
+
+        def impl(*args, _name=name):
+            _native.check(_launch(_name, args), _name)
+
+        lib.impl(name, impl, "CompositeExplicitAutograd")
+        torch.library.register_fake(f"{_OPS_NS}::{name}", lambda *args: None, lib=lib)
+    _op_lib = lib
+
+
+_register_ops()
 
 
 def _call(what: str, fn: str, *args) -> None:
-    """Invoke one C-ABI entry point; raise RuntimeError with the library's message on failure."""
+    """Invoke one C-ABI entry point (see the block comment above); raise RuntimeError with the library's message on
+    failure.  Eager calls go straight to the launch; under torch.compile tracing the registered custom op is called, so
+    the launch becomes a graph node."""
     global _COST
-    f = getattr(_native.lib(), fn)
+    if torch.compiler.is_compiling():
+        getattr(getattr(torch.ops, _OPS_NS), fn)(*args)
+        return
     prof = _PROF
     if prof is None:
-        rc = f(*args)
+        rc = _launch(fn, args)
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = f(*args)
+        rc = _launch(fn, args)
         e1.record()
         prof.records.append((what, _COST[0], _COST[1], e0, e1))
         prof.launches += 1
-    _COST = (0.0, 0.0)
+        _COST = (0.0, 0.0)
     _native.check(rc, what)
 
 
@@ -103,19 +192,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     _cost(2.0 * M * N * K, 2.0 * (M * K + N * K) + M * N * out.element_size())
-    _call(f"gemm.n{N}.k{K}" if _PROF is not None else "gemm", "la_gemm_bf16", _stream(a), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0),
-        bias.data_ptr() if bias is not None else None, out.data_ptr(), out.stride(0),
+    _call(f"gemm.n{N}.k{K}" if _PROF is not None else "gemm", "la_gemm_bf16", a, a.stride(0), w, w.stride(0),
+        bias if bias is not None else None, out, out.stride(0),
         _DTC[out.dtype], M, N, K, act)
     return out
 
 
-def _ptr(t):
-    return t.data_ptr() if t is not None else None
+_NO_GEMM_ACCUMULATE = bool(__import__("os").environ.get("LA_NO_GEMM_ACCUMULATE"))   # experiment switch
 
 
 def gemm_accumulate_supported(m: int, n: int) -> bool:
-    import os
-    return m >= 2048 and n >= 256 and n % 8 == 0 and not os.environ.get("LA_NO_GEMM_ACCUMULATE")
+    return m >= 2048 and n >= 256 and n % 8 == 0 and not _NO_GEMM_ACCUMULATE
 
 
 def gemm_accumulate(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, x: torch.Tensor) -> torch.Tensor:
@@ -128,8 +215,8 @@ def gemm_accumulate(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None,
     assert x.dtype == torch.float32 and x.shape == (M, N) and x.stride(1) == 1 and gemm_accumulate_supported(M, N)
     assert bias is None or (bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous())
     _cost(2.0 * M * N * K, 2.0 * (M * K + N * K) + 8.0 * M * N)
-    _call(f"gemm_acc.n{N}.k{K}" if _PROF is not None else "gemm", "la_gemm_bf16_accumulate", _stream(a), a.data_ptr(),
-          a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), x.data_ptr(), x.stride(0), M, N, K)
+    _call(f"gemm_acc.n{N}.k{K}" if _PROF is not None else "gemm", "la_gemm_bf16_accumulate", a,
+          a.stride(0), w, w.stride(0), bias, x, x.stride(0), M, N, K)
     return x
 
 
@@ -151,8 +238,8 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, n_img: 
     out = torch.empty((n_img * h * wd, N), dtype=out_dtype, device=x.device)
     M = n_img * h * wd
     _cost(2.0 * M * N * 9 * c, 2.0 * (M * c + N * 9 * c) + M * N * out.element_size())
-    _call(f"conv3x3.n{N}.c{c}" if _PROF is not None else "conv3x3", "la_conv3x3_bf16", _stream(x), x.data_ptr(), n_img, h,
-          wd, c, w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(), out.stride(0), _DTC[out.dtype], N, act)
+    _call(f"conv3x3.n{N}.c{c}" if _PROF is not None else "conv3x3", "la_conv3x3_bf16", x, n_img, h,
+          wd, c, w, w.stride(0), bias, out, out.stride(0), _DTC[out.dtype], N, act)
     return out
 
 
@@ -169,9 +256,9 @@ def attention_window(q: torch.Tensor, kv: torch.Tensor, n_seq: int, n_heads: int
     L = 196
     _cost(4.0 * n_seq * n_heads * L * L * 64 + 2.0 * n_seq * n_heads * L * 64 * 2 * rel_pad,
           2.0 * 4 * n_seq * L * n_heads * 64)
-    _call(f"attention.L{L}" if _PROF is not None else "attention", "la_attention_window_bf16", _stream(q), q.data_ptr(),
-          q.stride(0), q_off, kv.data_ptr(), kv.stride(0), k_off, v_off, q.shape[0], n_seq, n_heads, float(scale),
-          rel_table.data_ptr(), rel_pad, out.data_ptr(), out.stride(0), out_mode, nwin, img_hw)
+    _call(f"attention.L{L}" if _PROF is not None else "attention", "la_attention_window_bf16", q,
+          q.stride(0), q_off, kv, kv.stride(0), k_off, v_off, q.shape[0], n_seq, n_heads, float(scale),
+          rel_table, rel_pad, out, out.stride(0), out_mode, nwin, img_hw)
     return out
 
 
@@ -193,9 +280,9 @@ def attention(q: torch.Tensor, kv: torch.Tensor, n_seq: int, seq_len: int, n_hea
         ldb = bias_h.stride(1)
         assert bias_h.stride(0) == ldb * n_heads
     _cost(4.0 * n_seq * n_heads * seq_len * seq_len * 64, 2.0 * 4 * n_seq * seq_len * n_heads * 64)
-    _call(f"attention.L{seq_len}" if _PROF is not None else "attention", "la_attention_bf16", _stream(q), q.data_ptr(), q.stride(0), q_off, kv.data_ptr(), kv.stride(0), k_off, v_off, q.shape[0], n_seq,
-        seq_len, n_heads, float(scale), _ptr(bias_h), _ptr(bias_w),
-        _DTC[bias_h.dtype] if bias_h is not None else DT_F32, ldb, grid_hw, out.data_ptr(), out.stride(0),
+    _call(f"attention.L{seq_len}" if _PROF is not None else "attention", "la_attention_bf16", q, q.stride(0), q_off, kv, kv.stride(0), k_off, v_off, q.shape[0], n_seq,
+        seq_len, n_heads, float(scale), bias_h, bias_w,
+        _DTC[bias_h.dtype] if bias_h is not None else DT_F32, ldb, grid_hw, out, out.stride(0),
         out_mode, nwin, img_hw)
     return out
 
@@ -223,10 +310,10 @@ def add_layernorm(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: 
     _cost(0.0, float(rows) * d * sum(sz for t, sz in ((x_in, 4 if x_mod == 0 else 0), (delta, 2), (delta2, 2), (x_out, 4),
                                                         (y_out, y_out.element_size() if y_out is not None else 0),
                                                         (y2_out, 4), (ype_out, 2)) if t is not None))
-    _call(f"add_layernorm.d{d}.map{map_mode}" if _PROF is not None else "add_layernorm", "la_add_layernorm", _stream(ref), _ptr(x_in), x_mod, _ptr(delta), _ptr(delta2), _ptr(seq_add), seq_rows, _ptr(x_out),
-        _ptr(gamma), _ptr(beta), float(eps), act, _ptr(y_out),
-        DT_F32 if (y_out is not None and y_out.dtype == torch.float32) else DT_BF16, _ptr(y2_out), _ptr(pe), pe_mod,
-        _ptr(ype_out), rows, d, map_mode, seq_len, win, nwin, hw)
+    _call(f"add_layernorm.d{d}.map{map_mode}" if _PROF is not None else "add_layernorm", "la_add_layernorm", x_in, x_mod, delta, delta2, seq_add, seq_rows, x_out,
+        gamma, beta, float(eps), act, y_out,
+        DT_F32 if (y_out is not None and y_out.dtype == torch.float32) else DT_BF16, y2_out, pe, pe_mod,
+        ype_out, rows, d, map_mode, seq_len, win, nwin, hw)
 
 
 def add_layernorm_meanpool(x_in: torch.Tensor | None, delta: torch.Tensor | None, gamma: torch.Tensor,
@@ -244,9 +331,9 @@ def add_layernorm_meanpool(x_in: torch.Tensor | None, delta: torch.Tensor | None
     out = torch.empty((n_seq, d), dtype=torch.float32, device=ref.device)
     _cost(0.0, float(n_seq) * rows_per_seq * d * ((4 if x_in is not None else 0) + (2 if delta is not None else 0) +
                                                     (2 if delta2 is not None else 0)))
-    _call("add_layernorm_meanpool", "la_add_layernorm_meanpool", _stream(ref), _ptr(x_in), _ptr(delta), _ptr(delta2), _ptr(seq_add),
-                                                 gamma.data_ptr(), beta.data_ptr(), float(eps), n_seq, rows_per_seq,
-                                                 d, ws.data_ptr(), slices, out.data_ptr())
+    _call("add_layernorm_meanpool", "la_add_layernorm_meanpool", x_in, delta, delta2, seq_add,
+                                                 gamma, beta, float(eps), n_seq, rows_per_seq,
+                                                 d, ws, slices, out)
     return out
 
 
@@ -254,7 +341,7 @@ def embed_tokens(patch: torch.Tensor, cls: torch.Tensor | None, pos: torch.Tenso
                  n_img: int, tokens_per_img: int, n_cls: int, d: int) -> torch.Tensor:
     _require_cuda(patch, cls, pos, x)
     assert patch.dtype == torch.bfloat16 and patch.is_contiguous() and x.dtype == torch.float32 and x.is_contiguous()
-    _call("embed_tokens", "la_embed_tokens", _stream(x), patch.data_ptr(), _ptr(cls), _ptr(pos), x.data_ptr(), n_img,
+    _call("embed_tokens", "la_embed_tokens", patch, cls, pos, x, n_img,
                                        tokens_per_img, n_cls, d)
     return x
 
@@ -268,7 +355,7 @@ def im2col_patch16(images: torch.Tensor, out: torch.Tensor | None = None) -> tor
     if out is None:
         out = torch.empty((I * (S // 16) ** 2, C * 256), dtype=torch.bfloat16, device=images.device)
     _cost(0.0, float(I) * C * S * S * 6)
-    _call("im2col_patch16", "la_im2col_patch16", _stream(images), images.data_ptr(), out.data_ptr(), I, C, S)
+    _call("im2col_patch16", "la_im2col_patch16", images, out, I, C, S)
     return out
 
 
@@ -279,8 +366,18 @@ def im2col_3x3(x: torch.Tensor, n_img: int, h: int, w: int, c: int, out: torch.T
     if out is None:
         out = torch.empty((n_img * h * w, 9 * c), dtype=torch.bfloat16, device=x.device)
     _cost(0.0, float(n_img) * h * w * c * 2 * 10)
-    _call("im2col_3x3", "la_im2col_3x3", _stream(x), x.data_ptr(), out.data_ptr(), n_img, h, w, c)
+    _call("im2col_3x3", "la_im2col_3x3", x, out, n_img, h, w, c)
     return out
+
+
+@torch.compiler.assume_constant_result
+def _attention_tokens_workspace_bytes(n_seq: int, nq: int, nk: int, n_heads: int, head_dim: int) -> int:
+    return int(_native.lib().la_attention_tokens_workspace_bytes(n_seq, nq, nk, n_heads, head_dim))
+
+
+@torch.compiler.assume_constant_result
+def _focal_loss_workspace_bytes() -> int:
+    return int(_native.lib().la_focal_loss_workspace_bytes())
 
 
 def attention_tokens(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: int, nq: int, nk: int, n_heads: int,
@@ -297,13 +394,12 @@ def attention_tokens(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: i
     if out is None:
         out = torch.empty((n_seq * nq, w), dtype=torch.bfloat16, device=q.device)
     assert out.dtype == torch.bfloat16 and out.shape == (n_seq * nq, w) and out.stride(1) == 1
-    lib = _native.lib()
-    ws_bytes = lib.la_attention_tokens_workspace_bytes(n_seq, nq, nk, n_heads, head_dim)
+    ws_bytes = _attention_tokens_workspace_bytes(n_seq, nq, nk, n_heads, head_dim)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes > 0 else None
     _cost(4.0 * n_seq * nq * nk * w, 2.0 * n_seq * (2 * nq + 2 * nk) * w)
-    _call("attention_tokens", "la_attention_tokens", _stream(q), q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _ptr(q_add),
-        q_add.stride(0) if q_add is not None else 0, _ptr(k_add), k_add.stride(0) if k_add is not None else 0,
-        out.data_ptr(), out.stride(0), n_seq, nq, nk, n_heads, head_dim, head_dim ** -0.5, _ptr(ws))
+    _call("attention_tokens", "la_attention_tokens", q, q.stride(0), k, k.stride(0), v, v.stride(0), q_add,
+        q_add.stride(0) if q_add is not None else 0, k_add, k_add.stride(0) if k_add is not None else 0,
+        out, out.stride(0), n_seq, nq, nk, n_heads, head_dim, head_dim ** -0.5, ws)
     return out
 
 
@@ -318,9 +414,9 @@ def mask_downscale(masks: torch.Tensor, host_weights: dict) -> torch.Tensor:
         assert hw[k].device.type == "cpu" and hw[k].dtype == torch.float32 and hw[k].is_contiguous()
     assert hw["w0"].numel() == 16 and hw["w3"].numel() == 256, "mask_downscaling is built for mask_in_chans = 16"
     _cost(0.0, float(S) * H * W * 4 * 2)
-    _call("mask_downscale", "la_mask_downscale", _stream(masks), masks.data_ptr(), out.data_ptr(), S, H, W, hw["w0"].data_ptr(), hw["b0"].data_ptr(),
-        hw["g1"].data_ptr(), hw["be1"].data_ptr(), float(hw["eps1"]), hw["w3"].data_ptr(), hw["b3"].data_ptr(),
-        hw["g2"].data_ptr(), hw["be2"].data_ptr(), float(hw["eps2"]))
+    _call("mask_downscale", "la_mask_downscale", masks, out, S, H, W, hw["w0"], hw["b0"],
+        hw["g1"], hw["be1"], float(hw["eps1"]), hw["w3"], hw["b3"],
+        hw["g2"], hw["be2"], float(hw["eps2"]))
     return out
 
 
@@ -330,7 +426,7 @@ def resize_bilinear(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
     n, h, w, c = x.shape
     out = torch.empty((n, out_h, out_w, c), dtype=torch.float32, device=x.device)
-    _call("resize_bilinear", "la_resize_bilinear", _stream(x), x.data_ptr(), out.data_ptr(), n, h, w, out_h, out_w, c)
+    _call("resize_bilinear", "la_resize_bilinear", x, out, n, h, w, out_h, out_w, c)
     return out
 
 
@@ -352,8 +448,8 @@ def build_src(feat: torch.Tensor, m16: torch.Tensor | None, mask_flags: torch.Te
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
     out = torch.empty((n_seq * tokens, d), dtype=torch.bfloat16, device=feat.device)
     _cost(0.0, float(n_seq) * tokens * (d * 2 + (64 if m16 is not None else 0)) + float(n_seq // n_classes) * tokens * d * 4)
-    _call("build_src", "la_build_src", _stream(feat), feat.data_ptr(), _ptr(m16), _ptr(mask_flags), _ptr(w6), _ptr(b6),
-                                    _ptr(not_a_mask), _ptr(no_mask), _ptr(code), out.data_ptr(), n_seq, tokens, d,
+    _call("build_src", "la_build_src", feat, m16, mask_flags, w6, b6,
+                                    not_a_mask, no_mask, code, out, n_seq, tokens, d,
                                     n_classes, examples, feat_lead)
     return out
 
@@ -368,9 +464,9 @@ def embed_sparse(points, point_labels, boxes, box_flags, gauss, not_a_point, pe_
     Bx = boxes.shape[1] if boxes is not None else 0
     n = (P + (0 if boxes is not None else 1) if points is not None else 0) + 2 * Bx
     out = torch.empty((n_seq, n, d), dtype=torch.float32, device=gauss.device)
-    _call("embed_sparse", "la_embed_sparse", _stream(gauss), _ptr(points), _ptr(point_labels), P, _ptr(boxes),
-                                       _ptr(box_flags), Bx, gauss.data_ptr(), not_a_point.data_ptr(),
-                                       pe_table.data_ptr(), out.data_ptr(), n_seq, d, image_w, image_h)
+    _call("embed_sparse", "la_embed_sparse", points, point_labels, P, boxes,
+                                       box_flags, Bx, gauss, not_a_point,
+                                       pe_table, out, n_seq, d, image_w, image_h)
     return out
 
 
@@ -381,7 +477,7 @@ def masked_mean(emb: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
     B, M, C, D = emb.shape
     assert flags.shape == (B, M, C)
     out = torch.empty((B, C, D), dtype=torch.float32, device=emb.device)
-    _call("masked_mean", "la_masked_mean", _stream(emb), emb.data_ptr(), flags.data_ptr(), out.data_ptr(), B, M, C, D)
+    _call("masked_mean", "la_masked_mean", emb, flags, out, B, M, C, D)
     return out
 
 
@@ -393,7 +489,7 @@ def classify(x: torch.Tensor, cls: torch.Tensor, batch: int, pixels: int) -> tor
     assert x.shape == (batch * pixels, dk) and cls.shape[0] == batch
     out = torch.empty((batch, C, pixels), dtype=torch.float32, device=x.device)
     _cost(2.0 * batch * pixels * C * dk, float(batch) * pixels * (dk * 2 + C * 4))
-    _call("classify", "la_classify", _stream(x), x.data_ptr(), cls.data_ptr(), out.data_ptr(), batch, pixels, C, dk)
+    _call("classify", "la_classify", x, cls, out, batch, pixels, C, dk)
     return out
 
 
@@ -407,8 +503,8 @@ def postprocess_masks(logits: torch.Tensor, sizes: torch.Tensor, flag_gts: torch
     B, C, lh, lw = logits.shape
     out = torch.empty((B, C, out_h, out_w), dtype=torch.float32, device=logits.device)
     _cost(0.0, float(B) * C * (out_h * out_w + lh * lw) * 4)
-    _call("postprocess_masks", "la_postprocess_masks", _stream(logits), logits.data_ptr(), out.data_ptr(), sizes.data_ptr(),
-                                            _ptr(flag_gts), B, C, lh, lw, image_size, out_h, out_w)
+    _call("postprocess_masks", "la_postprocess_masks", logits, out, sizes,
+                                            flag_gts, B, C, lh, lw, image_size, out_h, out_w)
     return out
 
 
@@ -421,9 +517,9 @@ def nchw_to_tokens(x: torch.Tensor, want_f32: bool = True, want_bf16: bool = Fal
     o16 = torch.empty((n * h * w, C), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     for s in range(0, n, 32768):
         m = min(32768, n - s)
-        _call("nchw_to_tokens", "la_nchw_to_tokens", _stream(x), x[s:].data_ptr(),
-                                             o32[s * h * w:].data_ptr() if want_f32 else None,
-                                             o16[s * h * w:].data_ptr() if want_bf16 else None, m, C, h * w)
+        _call("nchw_to_tokens", "la_nchw_to_tokens", x[s:],
+                                             o32[s * h * w:] if want_f32 else None,
+                                             o16[s * h * w:] if want_bf16 else None, m, C, h * w)
     return o32, o16
 
 
@@ -435,7 +531,7 @@ def tokens_to_nchw(x: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
     out = torch.empty((n, C, h, w), dtype=torch.float32, device=x.device)
     for s in range(0, n, 32768):
         m = min(32768, n - s)
-        _call("tokens_to_nchw", "la_tokens_to_nchw", _stream(x), x[s * h * w:].data_ptr(), out[s:].data_ptr(), m, C, h * w)
+        _call("tokens_to_nchw", "la_tokens_to_nchw", x[s * h * w:], out[s:], m, C, h * w)
     return out
 
 
@@ -448,7 +544,7 @@ def copy_slabs(x: torch.Tensor, n_slabs: int, slab_rows: int, stride_rows: int, 
     assert (n_slabs - 1) * stride_rows + offset_rows + slab_rows <= x.shape[0]
     o32 = torch.empty((n_slabs * slab_rows, d), dtype=torch.float32, device=x.device) if want_f32 else None
     o16 = torch.empty((n_slabs * slab_rows, d), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    _call("copy_slabs", "la_copy_slabs", _stream(x), x.data_ptr(), stride_rows, offset_rows, _ptr(o32), _ptr(o16),
+    _call("copy_slabs", "la_copy_slabs", x, stride_rows, offset_rows, o32, o16,
                                      n_slabs, slab_rows, d)
     return o32, o16
 
@@ -459,7 +555,7 @@ def add_bcast(a: torch.Tensor, b: torch.Tensor, row_div: int, b_mod: int) -> tor
     assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
     assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1] and b.shape[0] >= b_mod
     out = torch.empty_like(a)
-    _call("add_bcast", "la_add_bcast", _stream(a), a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], a.shape[1],
+    _call("add_bcast", "la_add_bcast", a, b, out, a.shape[0], a.shape[1],
                                     row_div, b_mod)
     return out
 
@@ -469,7 +565,7 @@ def permute_rows(x: torch.Tensor, outer: int, na: int, nb: int) -> torch.Tensor:
     _require_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.shape[0] == outer * na * nb
     out = torch.empty_like(x)
-    _call("permute_rows", "la_permute_rows", _stream(x), x.data_ptr(), out.data_ptr(), outer, na, nb, x.shape[1])
+    _call("permute_rows", "la_permute_rows", x, out, outer, na, nb, x.shape[1])
     return out
 
 
@@ -504,23 +600,16 @@ def label_confusion(logits: torch.Tensor | None, preds: torch.Tensor | None, gt:
     gt_out = torch.empty((B,) + spatial, dtype=torch.int64, device=ref.device) if (want_gt and gt is not None) else None
     _cost(0.0, float(B) * P * (4 * C + (8 if preds is not None else 0) + (8 if gt is not None else 0)
                                + (8 if preds_out is not None else 0) + (8 if gt_out is not None else 0)))
-    _call("label_confusion", "la_label_confusion", _stream(ref), _ptr(logits), _ptr(preds), _ptr(gt), _ptr(label_map),
-          _ptr(preds_out), _ptr(gt_out), _ptr(confmat), _ptr(invalid), B, C, P,
+    _call("label_confusion", "la_label_confusion", logits, preds, gt, label_map,
+          preds_out, gt_out, confmat, invalid, B, C, P,
           label_map.shape[1] if label_map is not None else 0, G, int(ignore_index))
     return preds_out, gt_out
 
 
-_LOSS_WS: dict = {}
-
-
 def _loss_workspace(device: torch.device) -> torch.Tensor:
-    """Zero-initialised scratch of la_focal_loss (per device and stream; the kernel leaves it reusable)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _LOSS_WS.get(key)
-    if ws is None:
-        ws = torch.zeros(_native.lib().la_focal_loss_workspace_bytes() // 8 + 1, dtype=torch.float64, device=device)
-        _LOSS_WS[key] = ws
-    return ws
+    """Scratch of la_focal_loss (per-CTA partial sums + a counter the entry point zeroes itself): a fresh stream-ordered
+    allocation per call -- nothing cached per stream, nothing to leak."""
+    return torch.empty(_focal_loss_workspace_bytes() // 8 + 1, dtype=torch.float64, device=device)
 
 
 def label_class_weights(labels: torch.Tensor, classes: int, ignore_index: int = -100):
@@ -530,8 +619,8 @@ def label_class_weights(labels: torch.Tensor, classes: int, ignore_index: int = 
     hist = torch.empty(classes + 2, dtype=torch.int64, device=labels.device)
     w = torch.empty(classes, dtype=torch.float32, device=labels.device)
     _cost(0.0, 8.0 * labels.numel())
-    _call("label_class_weights", "la_label_class_weights", _stream(labels), labels.data_ptr(), labels.numel(), classes,
-          int(ignore_index), hist.data_ptr(), w.data_ptr())
+    _call("label_class_weights", "la_label_class_weights", labels, labels.numel(), classes,
+          int(ignore_index), hist, w)
     return w, hist
 
 
@@ -555,7 +644,7 @@ def focal_loss(logits: torch.Tensor, target: torch.Tensor, class_w: torch.Tensor
     wt = torch.empty(target.shape, dtype=torch.float32, device=target.device) if want_wtarget else None
     ws = _loss_workspace(target.device) if want_loss else None
     _cost(0.0, float(B) * P * (4 * C + 8 + (4 * C if want_grad else 0) + (4 if want_wtarget else 0)))
-    _call("focal_loss.grad" if want_grad else "focal_loss", "la_focal_loss", _stream(target), _ptr(logits),
-          target.data_ptr(), _ptr(class_w), _ptr(grad_scale), _ptr(loss), _ptr(grad), _ptr(wt), _ptr(ws), B, C, P,
+    _call("focal_loss.grad" if want_grad else "focal_loss", "la_focal_loss", logits,
+          target, class_w, grad_scale, loss, grad, wt, ws, B, C, P,
           float(gamma), int(ignore_index), 1 if mean else 0)
     return loss, grad, wt

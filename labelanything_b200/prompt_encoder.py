@@ -247,7 +247,7 @@ class PromptImageEncoder(PromptEncoder):
                                 None if mflags is None else mflags[s0:s0 + ns], w6, b6, nam, nom, code, ns, T, D, C, M,
                                 feat_lead=feat_lead, seq_offset=s0)
             _, _, p = run_two_way(self.transformer, src, None, pe, sparse[s0 * n:(s0 + ns) * n], ns, T, n,
-                                  want_queries=False, pool=True)
+                                  want_queries=False, pool=True, pe_cached=True)
             pooled.append(p)
             del src
         emb = pooled[0] if len(pooled) == 1 else torch.cat(pooled)       # [S, D] = [B, M, C, D]

@@ -108,12 +108,18 @@ def _b(att: Attention, name: str) -> torch.Tensor:
     return f32(att, name + ".b", getattr(att, name + "_proj").bias)
 
 
-def _pe_table(att: Attention, name: str, pe: torch.Tensor) -> torch.Tensor:
+def _pe_table(att: Attention, name: str, pe: torch.Tensor, cached: bool) -> torch.Tensor:
     """pe [T, D] fp32 -> pe @ W_name^T  [T, internal_dim] fp32 (bias stays in the projection GEMM).  Constant per
-    (model, resolution): computed once at weight-packing time."""
+    (model, resolution) on the native `Lam` path, whose `pe` is the prompt encoder's cached `dense_pe_tokens()` tensor
+    (`cached=True`): computed once at weight-packing time.  A transient `pe` (the reference-signature `forward`
+    methods build one per call) is NOT cached: the allocator may hand the same address to a different positional
+    encoding, which a (data_ptr, _version) key could not tell apart."""
     w = getattr(att, name + "_proj").weight
-    return att.packed(f"pe:{name}:{pe.shape[0]}", lambda: (pe.double() @ w.detach().double().t()).float().contiguous(),
-                      w, pe)
+    make = lambda: (pe.double() @ w.detach().double().t()).float().contiguous()   # noqa: E731
+    if not cached:
+        with torch.no_grad():
+            return make()
+    return att.packed(f"pe:{name}:{pe.shape[0]}", make, w, pe)
 
 
 def _ln(mod: NativeModule, name: str, ln: nn.LayerNorm):
@@ -170,9 +176,10 @@ def run_attention_mlp_block(blk: AttentionMLPBlock, x: torch.Tensor, n_seq: int,
 # ------------------------------------------------------------------------------------------------------------
 def run_two_way(tw: TwoWayTransformer, keys16: torch.Tensor, keys32: Optional[torch.Tensor], pe: torch.Tensor,
                 tokens: torch.Tensor, S: int, T: int, n: int, *, want_queries: bool, pool: bool = False,
-                want_keys_f32: bool = False):
+                want_keys_f32: bool = False, pe_cached: bool = False):
     """keys16 bf16 [S*T, D] (the image tokens; keys32 = the same in fp32 when available), pe fp32 [T, D] (dense
-    positional encoding, shared by all sequences), tokens fp32 [S*n, D] (also the tokens' positional encoding).
+    positional encoding, shared by all sequences; pe_cached: it is the model's cached dense_pe_tokens() tensor, so the
+    tables projected from it may be cached too), tokens fp32 [S*n, D] (also the tokens' positional encoding).
 
     Returns (queries fp32 [S*n, D] | None, keys, pooled):
       pool=True  -> keys is None and pooled = mean over the T image tokens of the last layer's output [S, D] fp32
@@ -234,7 +241,7 @@ def run_two_way(tw: TwoWayTransformer, keys16: torch.Tensor, keys32: Optional[to
         # ---- (2) tokens attend to the image ----------------------------------------------------------------
         tq = ops.gemm(tokpe16, _w(t2i, "q"), _b(t2i, "q"))
         o = ops.attention_tokens(tq, proj[:, :Dc], proj[:, Dc:2 * Dc], S, n, T, H, Dc // H,
-                                 k_add=_pe_table(t2i, "k", pe))
+                                 k_add=_pe_table(t2i, "k", pe, pe_cached))
         o = ops.gemm(o, _w(t2i, "out"), _b(t2i, "out"))
         g2, b2, e2 = _ln(layer, "norm2", layer.norm2)
         tok32n, tok16 = _empty(R, D, torch.float32, dev), _empty(R, D, torch.bfloat16, dev)
@@ -257,7 +264,7 @@ def run_two_way(tw: TwoWayTransformer, keys16: torch.Tensor, keys32: Optional[to
         delta = seq_add = None
         if need_q:
             tk = ops.gemm(tokpe16, _w(i2t, "k"), _b(i2t, "k"))
-            o = ops.attention_tokens(proj[:, 2 * Dc:], tk, tv, S, T, n, H, Dc // H, q_add=_pe_table(i2t, "q", pe))
+            o = ops.attention_tokens(proj[:, 2 * Dc:], tk, tv, S, T, n, H, Dc // H, q_add=_pe_table(i2t, "q", pe, pe_cached))
             delta = ops.gemm(o, _w(i2t, "out"), _b(i2t, "out"))    # [S*T, D] bf16
             del o
         else:
@@ -287,7 +294,7 @@ def run_two_way(tw: TwoWayTransformer, keys16: torch.Tensor, keys32: Optional[to
         Df = fa.internal_dim
         kv = ops.gemm(keys16, _cat_w(fa, ("k", "v")), _cat_b(fa, ("k", "v")))
         tq = ops.gemm(tokpe16, _w(fa, "q"), _b(fa, "q"))
-        o = ops.attention_tokens(tq, kv[:, :Df], kv[:, Df:], S, n, T, H, Df // H, k_add=_pe_table(fa, "k", pe))
+        o = ops.attention_tokens(tq, kv[:, :Df], kv[:, Df:], S, n, T, H, Df // H, k_add=_pe_table(fa, "k", pe, pe_cached))
         o = ops.gemm(o, _w(fa, "out"), _b(fa, "out"))
         gf, bf, ef = _ln(tw, "norm_final", tw.norm_final_attn)
         queries = _empty(R, D, torch.float32, dev)

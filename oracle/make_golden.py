@@ -1,7 +1,8 @@
 """Generate the committed golden fixtures under tests/golden/ from the UNMODIFIED reference.
 
 TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference); the fixtures it writes are
-what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512] [metrics] [loss]
+what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512] [mael256] [sam20w] [samragged] [samneck]
+        [metrics] [loss]
 
 Every fixture stores: the oracle `cfg`, the inputs, the reference outputs and either the full state dict
 (tiny models) or the synthetic-weight seed (real-size models; weights are a pure function of
@@ -246,6 +247,111 @@ def sam512(models):
     print("sam512_5w5s.pt", out["logits"].shape)
 
 
+MAEL256_CFG = {"image_size": 480, "image_embedding_size": (30, 30), "has_neck": True, "spatial_convs": 3,
+               "class_attention": False, "example_attention": False, "example_class_attention": True,
+               "custom_preprocess": False, "encoder": {"kind": "hf", "num_heads": 16, "depth": 24}}
+
+
+def mael256(models):
+    """BASELINE config 4's model forward: MAE-L-256 (HF ViT-L 1024/24/16/4096, 480 px, embed 256, NO class encoder;
+    parameters/trainval/coco/mael.yaml:42-51), 2-way 5-shot, B=1 through the `images` key, plus the ViT-L encoder output
+    of the query image."""
+    from label_anything.models.build_lam import _build_lam
+
+    lam = _build_lam(build_vit=lambda project_last_hidden: _hf_wrapper(1024, 24, 16, 4096, 224),
+                     image_embed_dim=1024, embed_dim=256, image_size=480, spatial_convs=3, class_attention=False,
+                     example_attention=False, example_class_attention=True, custom_preprocess=False).eval()
+    load_synth_weights(lam, seed=0)
+    ep = make_episode(1, 2, 5, 480, seed=4)
+    t0 = time.time()
+    with torch.no_grad():
+        out = lam(ep)
+        enc = lam.image_encoder(ep["images"][0, :1])
+    print(f"mael256 reference forward {time.time() - t0:.1f}s")
+    torch.save({"meta": _meta(), "cfg": MAEL256_CFG, "weights_seed": 0,
+                "episode_args": dict(batch=1, n_ways=2, k_shots=5, image_size=480, seed=4), "class_rows": None,
+                "logits_sub3": out["logits"][..., ::3, ::3].clone(),
+                "class_examples_embeddings": out["class_examples_embeddings"],
+                "encoder_out_sub": enc[0, ::16].clone(),
+                "shapes": {k: tuple(v.shape) for k, v in lam.state_dict().items()}}, GOLD / "mael256_2w5s.pt")
+    print("mael256_2w5s.pt", out["logits"].shape)
+
+
+def sam20w(models):
+    """BASELINE config 5's episode shape at B=1 -- 20-way 5-shot: M = 100 support images, C = 21 classes, S = 2100
+    prompt sequences -- through the `embeddings` key of the SAM-512 head (neck 768 -> 512, example_attention,
+    RandomMatrixEncoder with 21 pinned rows).  The reference materialises S x D x T fp32 tensors (17.6 GB each at
+    T = 4096, SURVEY.md H5): the fixture uses a 512-px model (T = 32 x 32), which the reference fits in host memory;
+    the native test lowers max_rows_per_pass so that the prompt encoder's chunking is exercised all the same."""
+    from label_anything.models.build_lam import build_lam_no_vit
+
+    lam = build_lam_no_vit(image_embed_dim=768, embed_dim=512, image_size=512, spatial_convs=3, class_attention=False,
+                           example_attention=True, example_class_attention=False,
+                           class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 512},
+                           custom_preprocess=True).eval()
+    load_synth_weights(lam, seed=0)
+    rows = torch.arange(21)
+    _pin_rows(lam, rows)
+    ep = make_episode(1, 20, 5, 512, seed=5, embeddings=(768, 32))
+    t0 = time.time()
+    with torch.no_grad():
+        out = lam(ep)
+    print(f"sam 20-way 5-shot reference forward {time.time() - t0:.1f}s")
+    cfg = dict(SAM512_CFG, image_size=512, image_embedding_size=(32, 32))
+    cfg.pop("encoder")
+    torch.save({"meta": _meta(), "cfg": cfg, "weights_seed": 0,
+                "model_args": dict(image_embed_dim=768, embed_dim=512, image_size=512, spatial_convs=3,
+                                   class_attention=False, example_attention=True, example_class_attention=False,
+                                   class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 512},
+                                   custom_preprocess=True),
+                "episode_args": dict(batch=1, n_ways=20, k_shots=5, image_size=512, seed=5, embeddings=(768, 32)),
+                "class_rows": rows, "logits_sub4": out["logits"][..., ::4, ::4].clone(),
+                "class_examples_embeddings": out["class_examples_embeddings"]}, GOLD / "sam512head_20w5s.pt")
+    print("sam512head_20w5s.pt", out["logits"].shape)
+
+
+def samragged(models):
+    """SAM-512, 1-way 1-shot, B = 2 through the `images` key with RAGGED original sizes (custom_preprocess crop +
+    per-item resize + -inf padding to the batch maximum, lam.py:383-453)."""
+    lam = _sam512(models)
+    rows = torch.arange(2)
+    _pin_rows(lam, rows)
+    ep = make_episode(2, 1, 1, 1024, seed=6)
+    ep["dims"] = torch.tensor([[[683, 1024], [1024, 1024]], [[960, 771], [500, 375]]], dtype=torch.int64)
+    t0 = time.time()
+    with torch.no_grad():
+        out = lam(ep)
+    print(f"sam ragged B=2 reference forward {time.time() - t0:.1f}s")
+    torch.save({"meta": _meta(), "cfg": SAM512_CFG, "weights_seed": 0,
+                "episode_args": dict(batch=2, n_ways=1, k_shots=1, image_size=1024, seed=6), "dims": ep["dims"],
+                "class_rows": rows, "logits_sub4": out["logits"][..., ::4, ::4].clone(),
+                "logits_shape": tuple(out["logits"].shape),
+                "class_examples_embeddings": out["class_examples_embeddings"]}, GOLD / "sam512_b2_ragged.pt")
+    print("sam512_b2_ragged.pt", out["logits"].shape)
+
+
+def samneck(models):
+    """SAM ViT-B with its own neck (project_last_hidden=True, out_chans 256) and return_last_block_state=True
+    (image_encoder.py:110-131; used by preprocess.py:160-162)."""
+    from label_anything.models.build_encoder import build_vit_b
+
+    vit = build_vit_b(project_last_hidden=True).eval()
+    load_synth_weights(vit, seed=0)
+    img = make_episode(1, 1, 1, 1024, seed=0)["images"][0, :1]
+    t0 = time.time()
+    with torch.no_grad():
+        out = vit(img, return_last_block_state=True)
+        plain = vit(img)
+    print(f"sam vit + neck reference forward {time.time() - t0:.1f}s", {k: tuple(v.shape) for k, v in out.items()})
+    assert torch.equal(plain, out["last_hidden_state"])
+    torch.save({"meta": _meta(), "weights_seed": 0,
+                "episode_args": dict(batch=1, n_ways=1, k_shots=1, image_size=1024, seed=0),
+                "keys": sorted(str(getattr(k, "value", k)) for k in out.keys()), "last_hidden_state_sub": out["last_hidden_state"][0, ::8].clone(),
+                "last_block_state_sub": out["last_block_state"][0, ::16].clone(),
+                "shapes": {k: tuple(v.shape) for k, v in vit.state_dict().items()}}, GOLD / "sam_vit_neck_1img.pt")
+    print("sam_vit_neck_1img.pt")
+
+
 def metrics_f4(models):
     """Post-logits step: torch.argmax + the reference's own to_global_multiclass on seeded
     inputs with ties, -inf planes, NaNs and ignore_index targets; the confusion matrix is torch.bincount of the
@@ -325,6 +431,14 @@ if __name__ == "__main__":
         samvit(models)
     if "sam512" in which:
         sam512(models)
+    if "mael256" in which:
+        mael256(models)
+    if "sam20w" in which:
+        sam20w(models)
+    if "samragged" in which:
+        samragged(models)
+    if "samneck" in which:
+        samneck(models)
     if "metrics" in which:
         metrics_f4(models)
     if "loss" in which:

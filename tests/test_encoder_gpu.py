@@ -1,5 +1,10 @@
 """GPU parity of the native image encoders against golden tensors produced by the unmodified reference
-(tests/golden/sam512_vit_1img.pt, mae256_1w1s.pt; weights are the deterministic synthetic ones)."""
+(tests/golden/sam512_vit_1img.pt, sam_vit_neck_1img.pt, mae256_1w1s.pt, mael256_2w5s.pt; weights are the deterministic
+synthetic ones).  The native path computes with bf16 operands / fp32 accumulation against an fp32 reference, so the
+bounds are END-TO-END drift bounds, stated relative to the standard deviation of the reference tensor: max |err| <=
+MAX_REL * std, mean |err| <= MEAN_REL * std (bf16 carries 8 significant bits: 0.4 % per rounding, a dozen roundings per
+block, 12-24 blocks).  Per-kernel parity at kernel tolerance lives in tests/test_kernels_gpu.py; the bf16-matched oracle
+comparison at 1e-3 in tests/test_lam_gpu.py."""
 from pathlib import Path
 
 import pytest
@@ -9,9 +14,19 @@ GOLD = Path(__file__).resolve().parent / "golden"
 pytestmark = pytest.mark.gpu
 
 
-def _stats(a, b):
-    err = (a.float() - b.float()).abs()
-    return err.max().item(), err.mean().item(), b.float().abs().mean().item()
+MAX_REL, MEAN_REL = 0.10, 0.012
+
+
+def _check(name, a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    assert bool(torch.isfinite(a).all()), f"{name}: non-finite output"
+    err = (a - b).abs()
+    std = b.std().item()
+    mx, mean = err.max().item() / std, err.mean().item() / std
+    print(f"{name}: max_abs_err={err.max().item():.4f} mean_abs_err={err.mean().item():.5f} ref_std={std:.4f} "
+          f"-> max/std={mx:.4f} mean/std={mean:.5f}")
+    assert mx < MAX_REL and mean < MEAN_REL, f"{name}: max/std {mx:.4f} (< {MAX_REL}), mean/std {mean:.5f} (< {MEAN_REL})"
 
 
 def test_sam_vit_b_1024_matches_reference_golden():
@@ -28,10 +43,7 @@ def test_sam_vit_b_1024_matches_reference_golden():
     with torch.no_grad():
         out = vit(img)
     assert out.shape == (1, 768, 64, 64)
-    mx, mean, ref_mag = _stats(out[0, ::16].cpu(), g["encoder_out_sub"])
-    print(f"SAM ViT-B encoder: max_abs_err={mx:.4f} mean_abs_err={mean:.5f} ref_mean_abs={ref_mag:.4f}")
-    # bf16 operands / fp32 accumulate through 12 blocks against an fp32 reference: end-to-end drift bound
-    assert mean < 0.02 * max(ref_mag, 1e-3) + 2e-3 and mx < 0.25
+    _check("SAM ViT-B encoder", out[0, ::16], g["encoder_out_sub"])
 
 
 def test_hf_vit_b_480_matches_reference_golden():
@@ -47,6 +59,43 @@ def test_hf_vit_b_480_matches_reference_golden():
     with torch.no_grad():
         out = vit(img)
     assert out.shape == (1, 768, 30, 30)
-    mx, mean, ref_mag = _stats(out[0, ::16].cpu(), g["encoder_out_sub"])
-    print(f"HF ViT-B encoder: max_abs_err={mx:.4f} mean_abs_err={mean:.5f} ref_mean_abs={ref_mag:.4f}")
-    assert mean < 0.02 * max(ref_mag, 1e-3) + 2e-3 and mx < 0.25
+    _check("HF ViT-B encoder", out[0, ::16], g["encoder_out_sub"])
+
+
+def test_hf_vit_l_480_matches_reference_golden():
+    """The encoder of BASELINE config 4 (MAE-L: 1024 wide, 24 layers, 16 heads, MLP 4096)."""
+    from labelanything_b200.build_encoder import build_vit_from_config
+    from labelanything_b200.synthetic import make_episode, synth_tensor
+
+    g = torch.load(GOLD / "mael256_2w5s.pt", weights_only=False)
+    vit = build_vit_from_config(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096)
+    sd = vit.state_dict()
+    vit.load_state_dict({k: synth_tensor("image_encoder." + k, tuple(v.shape), 0) for k, v in sd.items()})
+    vit = vit.cuda()
+    img = make_episode(**g["episode_args"])["images"][0, :1].cuda()
+    with torch.no_grad():
+        out = vit(img)
+    assert out.shape == (1, 1024, 30, 30)
+    _check("HF ViT-L encoder", out[0, ::16], g["encoder_out_sub"])
+
+
+def test_sam_vit_with_neck_and_last_block_state_matches_reference_golden():
+    """`forward(x, return_last_block_state=True)` of the SAM encoder built with its own neck: the dict the embedding
+    extraction writes (label_anything/preprocess.py:160-162, image_encoder.py:120-131)."""
+    from labelanything_b200.build_encoder import build_vit_b
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    g = torch.load(GOLD / "sam_vit_neck_1img.pt", weights_only=False)
+    vit = build_vit_b(project_last_hidden=True)
+    assert {k: tuple(v.shape) for k, v in vit.state_dict().items()} == g["shapes"]
+    load_synth_weights(vit, seed=g["weights_seed"])
+    vit = vit.cuda()
+    img = make_episode(**g["episode_args"])["images"][0, :1].cuda()
+    with torch.no_grad():
+        out = vit(img, return_last_block_state=True)
+        plain = vit(img)
+    assert sorted(out.keys()) == g["keys"] == ["last_block_state", "last_hidden_state"]
+    assert out["last_hidden_state"].shape == (1, 256, 64, 64) and out["last_block_state"].shape == (1, 768, 64, 64)
+    assert torch.equal(plain, out["last_hidden_state"])
+    _check("SAM ViT-B last_block_state", out["last_block_state"][0, ::16], g["last_block_state_sub"])
+    _check("SAM ViT-B + neck last_hidden_state", out["last_hidden_state"][0, ::8], g["last_hidden_state_sub"])

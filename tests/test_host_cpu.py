@@ -45,6 +45,28 @@ def test_registry_and_submodule_attributes():
     assert tuple(lam.get_dense_pe().shape) == (1, 256, 16, 16)
 
 
+def test_vit_h_is_refused_at_build_time():
+    """ViT-H has head_dim 80; the native attention kernels are head_dim 64.  The registry keeps the reference's keys,
+    but building must fail loudly (before any checkpoint is loaded), not at the first forward."""
+    import pytest
+
+    with pytest.raises(NotImplementedError, match="head_dim 80"):
+        models.model_registry["vit_h"]()
+    with pytest.raises(NotImplementedError, match="head_dim 80"):
+        models.model_registry["lam_h"]()
+
+
+def test_hf_vit_with_another_activation_is_refused():
+    import pytest
+    from transformers import ViTConfig
+
+    vit = models.ViTModelWrapper(ViTConfig(hidden_size=64, num_hidden_layers=1, num_attention_heads=1,
+                                           intermediate_size=128, image_size=32, patch_size=16,
+                                           hidden_act="gelu_new"))
+    with pytest.raises(NotImplementedError, match="hidden_act"):
+        vit._spec(2, 2)
+
+
 def test_labelanything_wrapper_captures_config_and_pickles():
     m = models.LabelAnything(encoder=lambda project_last_hidden: build_vit_from_config(), image_embed_dim=768,
                              embed_dim=256, image_size=480, spatial_convs=3, custom_preprocess=False)

@@ -99,6 +99,97 @@ def test_sam512_5w5s_matches_reference_golden():
     assert mx < MAX_REL and mean < MEAN_REL
 
 
+def test_mael256_2w5s_matches_reference_golden():
+    """BASELINE config 4's model forward: MAE-L-256 (HF ViT-L 480 px, embed 256, no class encoder), 2-way 5-shot."""
+    from labelanything_b200.build_encoder import build_vit_from_config
+    from labelanything_b200.build_lam import build_lam
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    g = torch.load(GOLD / "mael256_2w5s.pt", weights_only=False)
+    lam = build_lam(build_vit=lambda project_last_hidden: build_vit_from_config(
+        hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096),
+        image_embed_dim=1024, embed_dim=256, image_size=480, spatial_convs=3, class_attention=False,
+        example_attention=False, example_class_attention=True, custom_preprocess=False)
+    assert {k: tuple(v.shape) for k, v in lam.state_dict().items()} == g["shapes"]
+    load_synth_weights(lam, seed=g["weights_seed"])
+    lam = lam.cuda()
+    ep = _to_cuda(make_episode(**g["episode_args"]))
+    with torch.no_grad():
+        out = lam(ep)
+    assert out["logits"].shape == (1, 3, 480, 480)
+    mx, mean, _ = _report("mael256 class_examples_embeddings", out["class_examples_embeddings"],
+                          g["class_examples_embeddings"])
+    assert mx < MAX_REL and mean < MEAN_REL
+    mx, mean, _ = _report("mael256 logits", out["logits"][..., ::3, ::3], g["logits_sub3"])
+    assert mx < MAX_REL and mean < MEAN_REL
+
+
+def test_sam512_head_20way_5shot_matches_reference_golden():
+    """BASELINE config 5's episode shape at B=1: 20-way 5-shot (M = 100, C = 21, S = 2100 prompt sequences) through the
+    `embeddings` key of the SAM-512 head (fixture at T = 32 x 32, see oracle/make_golden.py::sam20w)."""
+    from labelanything_b200.build_lam import build_lam_no_vit
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    g = torch.load(GOLD / "sam512head_20w5s.pt", weights_only=False)
+    lam = build_lam_no_vit(**g["model_args"])
+    load_synth_weights(lam, seed=g["weights_seed"])
+    lam.prompt_encoder.class_encoder.fixed_rows = g["class_rows"]
+    lam = lam.cuda()
+    ep = _to_cuda(make_episode(**g["episode_args"]))
+    with torch.no_grad():
+        out = lam(ep)
+    assert out["logits"].shape == (1, 21, 512, 512) and out["class_examples_embeddings"].shape == (1, 100, 21, 512)
+    mx, mean, _ = _report("20w5s class_examples_embeddings", out["class_examples_embeddings"],
+                          g["class_examples_embeddings"])
+    assert mx < MAX_REL and mean < MEAN_REL
+    mx, mean, _ = _report("20w5s logits", out["logits"][..., ::4, ::4], g["logits_sub4"])
+    assert mx < MAX_REL and mean < MEAN_REL
+
+
+def test_prompt_encoder_passes_are_invisible():
+    """The prompt encoder processes whole episodes per pass up to `max_rows_per_pass` image-token rows; the split must
+    not change a bit (every sequence is independent until the per-episode merge)."""
+    from labelanything_b200.build_lam import build_lam_no_vit
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    lam = build_lam_no_vit(image_embed_dim=384, embed_dim=256, image_size=256, spatial_convs=3, example_attention=True,
+                           class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 256})
+    load_synth_weights(lam, seed=2)
+    lam.prompt_encoder.class_encoder.fixed_rows = torch.arange(21)
+    lam = lam.cuda()
+    ep = _to_cuda(make_episode(3, 20, 2, 256, seed=3, embeddings=(384, 16)))       # 3 episodes x 840 sequences
+    with torch.no_grad():
+        one = lam(ep)
+        lam.prompt_encoder.max_rows_per_pass = 840 * 256                           # -> one episode per pass
+        three = lam(ep)
+    assert torch.equal(one["logits"], three["logits"])
+    assert torch.equal(one["class_examples_embeddings"], three["class_examples_embeddings"])
+
+
+def test_sam512_b2_ragged_dims_matches_reference_golden():
+    """SAM-512, B = 2 through the `images` key with ragged original sizes: crop of the un-padded region, per-item resize,
+    -inf padding to the batch maximum (background: 0) -- pattern compared exactly, values at the drift bound."""
+    from labelanything_b200.build_lam import build_lam_vit_b
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    g = torch.load(GOLD / "sam512_b2_ragged.pt", weights_only=False)
+    lam = build_lam_vit_b(image_embed_dim=768, embed_dim=512, image_size=1024, use_vit_sam_neck=False,
+                          spatial_convs=3, class_attention=False, example_attention=True,
+                          example_class_attention=False,
+                          class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 512},
+                          custom_preprocess=True)
+    load_synth_weights(lam, seed=g["weights_seed"])
+    lam.prompt_encoder.class_encoder.fixed_rows = g["class_rows"]
+    lam = lam.cuda()
+    ep = make_episode(**g["episode_args"])
+    ep["dims"] = g["dims"]
+    with torch.no_grad():
+        out = lam(_to_cuda(ep))
+    assert tuple(out["logits"].shape) == g["logits_shape"] == (2, 2, 1024, 1024)   # batch max incl. the support dims
+    mx, mean, _ = _report("ragged B=2 logits", out["logits"][..., ::4, ::4], g["logits_sub4"])   # incl. exact -inf pattern
+    assert mx < MAX_REL and mean < MEAN_REL
+
+
 @pytest.mark.parametrize("variant", ["mixed_all_attn", "masks_only", "points_only"])
 def test_lam_no_vit_matches_oracle(variant):
     """Prompt encoder + decoder + postprocess on precomputed `embeddings` against the CPU oracle: mixed prompts
