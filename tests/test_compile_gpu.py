@@ -41,7 +41,9 @@ def test_opcheck_schema_and_fake_registration():
     torch.library.opcheck(torch.ops.labelanything_b200.la_add_layernorm.default,
                           (x, 0, None, None, None, 0, None, gm, gm, 1e-6, 0, y, ops.DT_BF16, None, None, 0, None, 64, 256,
                            0, 0, 0, 0, 0), test_utils=("test_schema", "test_faketensor"))
-    # the op called through the dispatcher == the wrapper's direct launch
+    # the op called through the dispatcher == the wrapper's direct launch (opcheck itself works on clones)
+    torch.ops.labelanything_b200.la_gemm_bf16(a, a.stride(0), w, w.stride(0), b, out, out.stride(0), ops.DT_F32, 300, 256,
+                                               128, ops.ACT_NONE)
     ref = ops.gemm(a, w, b, out_dtype=torch.float32)
     assert torch.equal(ref, out)
 
@@ -97,7 +99,7 @@ load_synth_weights(lam, seed=1 + rank)        # different weights per rank: DDP 
 wm = WrapperModule(lam, LabelAnythingLoss({"focal": {"weight": 1.0, "gamma": 2.0}}, class_weighting=True)).cuda()
 ddp = torch.nn.parallel.DistributedDataParallel(wm, device_ids=[0], find_unused_parameters=True)
 ep = {k: v.cuda() for k, v in make_episode(1, 2, 1, 256, seed=5, prompts="mixed", embeddings=(384, 16)).items()}
-gt = torch.randint(0, 3, (1, 256, 256), device="cuda")
+gt = torch.randint(0, 3, (1, 256, 256), generator=torch.Generator().manual_seed(3)).cuda()
 with torch.no_grad():
     out = ddp(ep, gt)
 vals = [torch.zeros(2) for _ in range(2)]

@@ -3,8 +3,8 @@
 synthetic ones).  The native path computes with bf16 operands / fp32 accumulation against an fp32 reference, so the
 bounds are END-TO-END drift bounds, stated relative to the standard deviation of the reference tensor: max |err| <=
 MAX_REL * std, mean |err| <= MEAN_REL * std (bf16 carries 8 significant bits: 0.4 % per rounding, a dozen roundings per
-block, 12-24 blocks).  Per-kernel parity at kernel tolerance lives in tests/test_kernels_gpu.py; the bf16-matched oracle
-comparison at 1e-3 in tests/test_lam_gpu.py."""
+block, 12-24 blocks).  Per-kernel parity at kernel tolerance lives in tests/test_kernels_gpu.py; the comparison with
+the bf16-matched oracle in tests/test_lam_gpu.py."""
 from pathlib import Path
 
 import pytest
@@ -14,7 +14,7 @@ GOLD = Path(__file__).resolve().parent / "golden"
 pytestmark = pytest.mark.gpu
 
 
-MAX_REL, MEAN_REL = 0.10, 0.012
+MAX_REL, MEAN_REL = 0.06, 0.009     # measured (round 2): 0.023-0.039 / 0.0042-0.0061
 
 
 def _check(name, a, b):

@@ -191,7 +191,10 @@ def test_fused_attention_matches_torch(mode, n_seq, L, gsz, qscale):
     # output.  With ordinary logits (qscale 1) hundreds of keys carry weight and the P errors average out: bound =
     # 2^-8 (output rounding) + 2e-3 absolute.  With 4x logits (qscale 4: softmax dominated by one or two keys, the
     # lazy-rescale path) the P error of the dominant key reaches the output unaveraged: bound = 2^-7 + 2e-3.
-    _close(out, ref, 2 ** -8 if qscale == 1.0 else 2 ** -7, 2e-3, f"attention {mode}")
+    # The rel-pos modes add the fp16 rounding of the table products (|bias| up to ~3 -> 1.5e-3 absolute in the logit,
+    # i.e. 1.5e-3 relative in P, twice: rel_h and rel_w): + 2^-8 on the sharp cases.
+    rtol = 2 ** -8 if qscale == 1.0 else (2 ** -7 + (2 ** -8 if gsz else 0.0))
+    _close(out, ref, rtol, 2e-3, f"attention {mode}")
     err = (out.float() - ref).abs()
     print(f"attention {mode} L={L} qscale={qscale}: max_abs_err {err.max().item():.3e} mean {err.mean().item():.3e} "
           f"(|ref| mean {ref.abs().mean().item():.3f})")

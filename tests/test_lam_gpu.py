@@ -27,6 +27,42 @@ def _oracle():
     return lam_oracle
 
 
+def _oracle_bf16():
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import lam_oracle_bf16
+
+    return lam_oracle_bf16
+
+
+# The bf16-matched oracle (oracle/lam_oracle_bf16.py: the reference algorithm with bf16 operands at the native rounding
+# points, pinned to the unmodified reference with the roundings switched off by tests/test_oracle_golden.py) separates
+# "wrong algorithm" from "bf16 operands": the native path must be CLOSER to it than to the fp32 reference, and within
+# MATCHED_REL of the logit spread.  It cannot be held to 1e-3 max-abs end to end, and no pair of bf16 evaluations of this
+# network can: two evaluations that differ by as little as the fp32 summation order round a few intermediate values to
+# different bf16 neighbours (0.4-0.8 % each), every such flip perturbs the next layer's inputs, and after a handful of
+# GEMM -> round stages the two are a full bf16 rounding noise apart (DESIGN.md §4 has the recurrence and the measured
+# numbers).  1e-3 is held where it is meaningful: per kernel on identical inputs (tests/test_kernels_gpu.py).
+MATCHED_REL_MAX, MATCHED_REL_MEAN = 0.08, 0.012
+
+
+def _matched(name, a, b, fp32_ref=None):
+    a, b = a.float().cpu(), b.float().cpu()
+    fin = torch.isfinite(b)
+    assert torch.equal(torch.isfinite(a), fin), f"{name}: -inf pattern differs"
+    err = (a[fin] - b[fin]).abs()
+    std = b[fin].std().item()
+    msg = (f"{name} [native vs bf16-matched oracle]: max_abs_err={err.max().item():.5f} mean_abs_err={err.mean().item():.6f} "
+           f"ref_std={std:.4f} -> max/std={err.max().item() / std:.4f} mean/std={err.mean().item() / std:.5f}")
+    if fp32_ref is not None:
+        f = fp32_ref.float().cpu()
+        d_native, d_matched = (a[fin] - f[fin]).abs().mean().item(), (b[fin] - f[fin]).abs().mean().item()
+        msg += f" | mean |native - fp32| {d_native:.6f}, mean |matched - fp32| {d_matched:.6f}"
+    print(msg)
+    assert err.max().item() <= MATCHED_REL_MAX * std and err.mean().item() <= MATCHED_REL_MEAN * std, msg
+    if fp32_ref is not None:
+        assert err.mean().item() <= 1.1 * d_native, msg     # at least as close to the matched oracle as to the fp32 one
+
+
 def _report(name, a, b):
     a, b = a.float().cpu(), b.float().cpu()
     fin = torch.isfinite(b)
@@ -190,6 +226,59 @@ def test_sam512_b2_ragged_dims_matches_reference_golden():
     assert mx < MAX_REL and mean < MEAN_REL
 
 
+def test_mae256_1w1s_against_the_bf16_matched_oracle():
+    """Full `images` path of BASELINE config 1/2's model (HF ViT-B 480 px -> neck -> prompt encoder -> decoder ->
+    postprocess) against the bf16-matched oracle."""
+    from labelanything_b200.build_encoder import build_vit_from_config
+    from labelanything_b200.build_lam import build_lam
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    g = torch.load(GOLD / "mae256_1w1s.pt", weights_only=False)
+    lam = build_lam(build_vit=lambda project_last_hidden: build_vit_from_config(), image_embed_dim=768,
+                    embed_dim=256, image_size=480, spatial_convs=3, class_attention=False, example_attention=False,
+                    example_class_attention=True,
+                    class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 256},
+                    custom_preprocess=False)
+    load_synth_weights(lam, seed=g["weights_seed"])
+    lam.prompt_encoder.class_encoder.fixed_rows = g["class_rows"]
+    sd = {k: v.clone() for k, v in lam.state_dict().items()}
+    ep = make_episode(**g["episode_args"])
+    with torch.no_grad():
+        matched = _oracle_bf16().lam_forward(sd, g["cfg"], dict(ep), class_rows=g["class_rows"])
+        out = lam.cuda()(_to_cuda(ep))
+    _matched("mae256 logits", out["logits"][..., ::3, ::3], matched["logits"][..., ::3, ::3], g["logits_sub3"])
+    _report("mae256 logits [bf16-matched oracle vs fp32 reference golden]", matched["logits"][..., ::3, ::3], g["logits_sub3"])
+
+
+def test_sam512_1w1s_against_the_bf16_matched_oracle():
+    """Full `images` path of BASELINE config 3's model (SAM ViT-B 1024 px with windowed + global rel-pos attention ->
+    neck 768 -> 512 -> prompt encoder -> decoder -> postprocess), 1-way 1-shot, against the bf16-matched oracle."""
+    from labelanything_b200.build_lam import build_lam_vit_b
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+
+    lam = build_lam_vit_b(image_embed_dim=768, embed_dim=512, image_size=1024, use_vit_sam_neck=False,
+                          spatial_convs=3, class_attention=False, example_attention=True,
+                          example_class_attention=False,
+                          class_encoder={"name": "RandomMatrixEncoder", "bank_size": 100, "embed_dim": 512},
+                          custom_preprocess=True)
+    load_synth_weights(lam, seed=0)
+    rows = torch.arange(2)
+    lam.prompt_encoder.class_encoder.fixed_rows = rows
+    sd = {k: v.clone() for k, v in lam.state_dict().items()}
+    cfg = {"image_size": 1024, "image_embedding_size": (64, 64), "has_neck": True, "spatial_convs": 3,
+           "class_attention": False, "example_attention": True, "example_class_attention": False,
+           "custom_preprocess": True,
+           "encoder": {"kind": "sam", "num_heads": 12, "depth": 12, "global_attn": [2, 5, 8, 11], "window": 14}}
+    ep = make_episode(1, 1, 1, 1024, seed=11)
+    ep["dims"] = torch.tensor([[[768, 1024], [1024, 1024]]], dtype=torch.int64)
+    with torch.no_grad():
+        matched = _oracle_bf16().lam_forward(sd, cfg, dict(ep), class_rows=rows)
+        ref = _oracle().lam_forward(sd, cfg, dict(ep), class_rows=rows)
+        out = lam.cuda()(_to_cuda(ep))
+    _matched("sam512 1w1s logits", out["logits"], matched["logits"], ref["logits"])
+    _report("sam512 1w1s logits [bf16-matched oracle vs fp32 oracle]", matched["logits"], ref["logits"])
+
+
 @pytest.mark.parametrize("variant", ["mixed_all_attn", "masks_only", "points_only"])
 def test_lam_no_vit_matches_oracle(variant):
     """Prompt encoder + decoder + postprocess on precomputed `embeddings` against the CPU oracle: mixed prompts
@@ -253,6 +342,11 @@ def test_lam_no_vit_matches_oracle(variant):
             yard = O.lam_forward(sd, cfg, dict(ep), class_rows=rows)
         out = lam.cuda()(_to_cuda(ep))
     assert out["logits"].shape == ref["logits"].shape
+    with torch.no_grad():
+        matched = _oracle_bf16().lam_forward(sd, cfg, dict(ep), class_rows=rows)
+    _matched(f"{variant} logits", out["logits"], matched["logits"], ref["logits"])
+    _matched(f"{variant} class_examples_embeddings", out["class_examples_embeddings"],
+             matched["class_examples_embeddings"], ref["class_examples_embeddings"])
     for key in ("class_examples_embeddings", "logits"):
         ymx, ymean, _ = _report(f"{variant} {key} [reference bf16-autocast vs fp32]", yard[key].float(), ref[key])
         mx, mean, _ = _report(f"{variant} {key} [native vs fp32 oracle]", out[key], ref[key])

@@ -61,3 +61,29 @@ def test_prepare_prompts_drops_all_zero_types():
 def test_missing_inputs_raise_like_reference():
     with pytest.raises(ValueError, match="Either 'images' or 'embeddings'"):
         O.lam_forward({}, {"image_size": 64}, {"dims": torch.zeros(1, 1, 2)})
+
+
+@pytest.mark.parametrize("name", ["tiny_sam_lam.pt", "tiny_sam_lam_masks_only.pt", "tiny_mae_lam.pt"])
+def test_bf16_matched_oracle_is_the_same_algorithm(name):
+    """oracle/lam_oracle_bf16.py restates the path with the native rounding points (and the native path's exact
+    re-associations: positional tables projected separately, the 1x1 mask conv after the resize, the single-key
+    softmax).  With the roundings switched off it must BE the reference algorithm: pinned against the same fixtures of
+    the unmodified reference, at fp32 re-association tolerance.  With them on, it must stay within bf16 drift of it."""
+    import lam_oracle_bf16 as OB
+
+    g = _load(name)
+    OB.EXACT = True
+    try:
+        with torch.no_grad():
+            out = OB.lam_forward(g["state_dict"], g["cfg"], dict(g["episode"]), class_rows=g["class_rows"])
+    finally:
+        OB.EXACT = False
+    _cmp(out["class_examples_embeddings"], g["class_examples_embeddings"], 5e-5)
+    _cmp(out["logits"], g["logits"], 1e-4)
+    with torch.no_grad():
+        rounded = OB.lam_forward(g["state_dict"], g["cfg"], dict(g["episode"]), class_rows=g["class_rows"])
+    fin = torch.isfinite(g["logits"])
+    assert torch.equal(torch.isfinite(rounded["logits"]), fin)
+    err = (rounded["logits"][fin] - g["logits"][fin]).abs()
+    std = g["logits"][fin].std()
+    assert 0 < err.max() < 0.35 * std and err.mean() < 0.03 * std, (err.max().item(), err.mean().item(), std.item())
