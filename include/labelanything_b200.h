@@ -268,6 +268,28 @@ int la_focal_loss(void* stream, const float* logits, const long long* target, co
                   const float* grad_scale, float* loss_out, float* grad_out, float* wtarget_out, void* workspace,
                   int batch, int classes, long long pixels, float gamma, long long ignore_index, int mean);
 
+/* ---- input preprocessing (the step right before Lam.forward) ----------------------------------------------- */
+/* One image: uint8 HWC [H, W, 3] -> fp32 CHW [3, S, S] = zero_pad((resize_bilinear_PIL(img, new_h, new_w) / 255 - mean)
+ * / std), bit-identical to CustomResize -> ToTensor -> CustomNormalize (label_anything/data/transforms.py:14-46; the
+ * non-custom Resize((S, S)) -> ToTensor -> Normalize of data/__init__.py:33-61 is new_h = new_w = S).  The resize is
+ * Pillow's 8-bit antialiased triangle resample (Resample.c): bounds_* int32 [new, 2] = (first source index, count),
+ * kk_* int32 [new, ksize_*] = 22-bit fixed-point coefficients, computed by the caller exactly as Pillow does
+ * (labelanything_b200/transforms.py::pil_bilinear_coeffs); NULL tables for an axis whose size does not change.
+ * tmp: uint8 scratch [H, new_w, 3] (horizontal pass output), required when bounds_x != NULL. */
+int la_preprocess_image_u8(void* stream, const void* src, int H, int W, int new_h, int new_w, int S,
+                           const int* bounds_x, const int* kk_x, int ksize_x, const int* bounds_y, const int* kk_y,
+                           int ksize_y, void* tmp, float mean0, float mean1, float mean2, float std0, float std1,
+                           float std2, float* out);
+/* PromptsProcessor.apply_masks (transforms.py:196-224): OR of n uint8 instance masks [n, H, W], nearest resize to
+ * (new_h, new_w), zero pad to long_side, nearest resize to out_side (new_h = new_w = 0: straight nearest resize, the
+ * non-custom pipeline) -> out fp32 [out_side, out_side] in {0, 1}; *flag (uint8, optional) is set to 1 when any output
+ * pixel is set (flag_masks, data/utils.py:218-224) and left untouched otherwise.  n = 0 -> zeros. */
+int la_rasterize_masks_u8(void* stream, const void* masks, int n, int H, int W, int new_h, int new_w, int long_side,
+                          int out_side, float* out, void* flag);
+/* PromptsProcessor.apply_coords / apply_boxes (transforms.py:159-194): n (x, y) pairs in float64, x * sx and y * sy in
+ * double, rounded once to fp32 (the reference assigns the float64 result into a float32 tensor). */
+int la_scale_coords_f64(void* stream, const void* coords, long long n, double sx, double sy, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ _CTYPE = {
     "int": ctypes.c_int,
     "long long": ctypes.c_longlong,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
 }
 
 

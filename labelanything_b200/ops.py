@@ -87,7 +87,7 @@ def _schema_of(name: str, types: list) -> tuple:
                 parts.append(f"Tensor({chr(ord('a') + alias)}!)? a{i}")
                 alias += 1
             params.append(("tensor", t))
-        elif t == "float":
+        elif t in ("float", "double"):
             parts.append(f"float a{i}")
             params.append(("float", t))
         else:
@@ -648,3 +648,44 @@ def focal_loss(logits: torch.Tensor, target: torch.Tensor, class_w: torch.Tensor
           target, class_w, grad_scale, loss, grad, wt, ws, B, C, P,
           float(gamma), int(ignore_index), 1 if mean else 0)
     return loss, grad, wt
+
+
+# ---------------------------------------------------------------------------------------------- input preprocessing
+def preprocess_image_u8(src: torch.Tensor, new_h: int, new_w: int, size: int, bounds_x, kk_x, ksize_x: int, bounds_y,
+                        kk_y, ksize_y: int, tmp, mean, std, out: torch.Tensor) -> torch.Tensor:
+    """uint8 HWC [H, W, 3] -> fp32 CHW [3, size, size] (Pillow-exact bilinear resize, /255, (x - mean) / std, zero pad)."""
+    _require_cuda(src, bounds_x, kk_x, bounds_y, kk_y, tmp, out)
+    assert src.dtype == torch.uint8 and src.is_contiguous() and src.dim() == 3 and src.shape[2] == 3
+    H, W = int(src.shape[0]), int(src.shape[1])
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (3, size, size)
+    for b, k, ks, n in ((bounds_x, kk_x, ksize_x, new_w), (bounds_y, kk_y, ksize_y, new_h)):
+        assert (b is None) == (k is None)
+        if b is not None:
+            assert b.dtype == torch.int32 and k.dtype == torch.int32 and b.is_contiguous() and k.is_contiguous()
+            assert tuple(b.shape) == (n, 2) and tuple(k.shape) == (n, ks)
+    assert tmp is None or (tmp.dtype == torch.uint8 and tmp.is_contiguous() and tmp.numel() >= H * new_w * 3)
+    _cost(0.0, float(H) * W * 3 + 12.0 * size * size)
+    _call("preprocess_image", "la_preprocess_image_u8", src, H, W, new_h, new_w, size, bounds_x, kk_x, ksize_x, bounds_y,
+          kk_y, ksize_y, tmp, float(mean[0]), float(mean[1]), float(mean[2]), float(std[0]), float(std[1]), float(std[2]),
+          out)
+    return out
+
+
+def rasterize_masks_u8(masks, n: int, H: int, W: int, new_h: int, new_w: int, long_side: int, out_side: int,
+                       out: torch.Tensor, flag=None) -> torch.Tensor:
+    """OR of n uint8 masks [n, H, W] -> nearest / pad / nearest -> fp32 {0, 1} [out_side, out_side] (+ presence flag)."""
+    _require_cuda(masks, out, flag)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == out_side * out_side
+    assert masks is None or (masks.dtype == torch.uint8 and masks.is_contiguous() and masks.numel() == n * H * W)
+    assert flag is None or (flag.dtype == torch.uint8 and flag.numel() == 1)
+    _call("rasterize_masks", "la_rasterize_masks_u8", masks, n, H, W, new_h, new_w, long_side, out_side, out, flag)
+    return out
+
+
+def scale_coords_f64(coords: torch.Tensor, sx: float, sy: float, out: torch.Tensor) -> torch.Tensor:
+    """(x, y) float64 pairs * (sx, sy) in double -> fp32."""
+    _require_cuda(coords, out)
+    assert coords.dtype == torch.float64 and coords.is_contiguous() and coords.shape[-1] == 2
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == coords.shape
+    _call("scale_coords", "la_scale_coords_f64", coords, coords.numel() // 2, float(sx), float(sy), out)
+    return out

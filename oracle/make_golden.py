@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference); the fixtures it writes are
 what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512] [mael256] [sam20w] [samragged] [samneck]
-        [metrics] [loss]
+        [preprocess] [metrics] [loss]
 
 Every fixture stores: the oracle `cfg`, the inputs, the reference outputs and either the full state dict
 (tiny models) or the synthetic-weight seed (real-size models; weights are a pure function of
@@ -352,6 +352,56 @@ def samneck(models):
     print("sam_vit_neck_1img.pt")
 
 
+def preprocess_f3(models):
+    """Input preprocessing through the reference's OWN classes: CustomResize + ToTensor + CustomNormalize
+    (and the non-custom Resize + ToTensor + Normalize) on PIL images, PromptsProcessor.apply_masks / apply_coords /
+    apply_boxes.  Inputs are seeded uint8 arrays; outputs are stored whole or strided."""
+    import numpy as np
+    from PIL import Image
+    from torchvision.transforms import Compose, Resize, ToTensor
+
+    from label_anything.data.transforms import CustomNormalize, CustomResize, Normalize, PromptsProcessor
+
+    rng = np.random.default_rng(12)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    images = []
+    for (h, w, size, custom, stride) in [(300, 200, 256, True, 1), (123, 457, 256, True, 1), (256, 256, 256, True, 1),
+                                         (97, 64, 128, False, 1), (420, 630, 384, True, 1), (120, 160, 512, True, 2)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        # smooth half of the image so the fixture is not pure noise (gradients exercise the rounding differently)
+        yy, xx = np.mgrid[0:h, 0:w]
+        img[: h // 2] = np.stack([(xx[: h // 2] * 255 // max(w - 1, 1)), (yy[: h // 2] * 255 // max(h - 1, 1)),
+                                  ((xx[: h // 2] + yy[: h // 2]) % 256)], axis=-1).astype(np.uint8)
+        tf = (Compose([CustomResize(size), ToTensor(), CustomNormalize(size, mean, std)]) if custom
+              else Compose([Resize(size=(size, size)), ToTensor(), Normalize(mean, std)]))
+        out = tf(Image.fromarray(img))
+        images.append({"image": torch.from_numpy(img), "size": size, "custom_preprocess": custom, "stride": stride,
+                       "out": out[:, ::stride, ::stride].clone(), "out_shape": tuple(out.shape),
+                       "out_sum": out.double().sum().item()})
+    prompts = []
+    for (n, h, w, custom) in [(3, 300, 200, True), (1, 123, 457, True), (2, 640, 480, False), (0, 50, 60, True),
+                              (2, 420, 630, True)]:
+        pp = PromptsProcessor(long_side_length=1024, masks_side_length=256, custom_preprocess=custom)
+        masks = np.zeros((n, h, w), dtype=np.uint8)
+        for i in range(n):
+            y0, x0 = rng.integers(0, h // 2), rng.integers(0, w // 2)
+            masks[i, y0:y0 + rng.integers(1, h // 2), x0:x0 + rng.integers(1, w // 2)] = 1
+            masks[i] |= (rng.random((h, w)) > 0.97).astype(np.uint8)                 # isolated pixels: nearest sampling
+        out_mask = torch.as_tensor(np.asarray(pp.apply_masks(masks if n else np.array([]))))
+        pts = rng.random((4, 2)) * np.array([w, h])
+        boxes = np.concatenate([rng.random((3, 2)) * np.array([w, h]) / 2, rng.random((3, 2)) * np.array([w, h]) / 2 + np.array([w, h]) / 2], axis=1)
+        prompts.append({"masks": torch.from_numpy(masks), "custom_preprocess": custom, "mask_out": out_mask.reshape(256, 256),
+                        "points": torch.from_numpy(pts), "points_out": torch.from_numpy(pp.apply_coords(pts, (h, w))),
+                        "boxes": torch.from_numpy(boxes), "boxes_out": torch.from_numpy(pp.apply_boxes(boxes, (h, w))),
+                        "original_size": (h, w)})
+    import PIL
+    import torchvision
+
+    meta = dict(_meta(), pillow=PIL.__version__, torchvision=torchvision.__version__)
+    torch.save({"meta": meta, "mean": mean, "std": std, "images": images, "prompts": prompts}, GOLD / "preprocess_f3.pt")
+    print("preprocess_f3.pt", [tuple(i["out"].shape) for i in images], [tuple(p["mask_out"].shape) for p in prompts])
+
+
 def metrics_f4(models):
     """Post-logits step: torch.argmax + the reference's own to_global_multiclass on seeded
     inputs with ties, -inf planes, NaNs and ignore_index targets; the confusion matrix is torch.bincount of the
@@ -439,6 +489,8 @@ if __name__ == "__main__":
         samragged(models)
     if "samneck" in which:
         samneck(models)
+    if "preprocess" in which:
+        preprocess_f3(models)
     if "metrics" in which:
         metrics_f4(models)
     if "loss" in which:
