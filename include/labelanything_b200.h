@@ -268,6 +268,18 @@ int la_focal_loss(void* stream, const float* logits, const long long* target, co
                   const float* grad_scale, float* loss_out, float* grad_out, float* wtarget_out, void* workspace,
                   int batch, int classes, long long pixels, float gamma, long long ignore_index, int mean);
 
+/* Corrective prompt points of the iterative-prompting loop: `generate_points_from_errors`
+ * (label_anything/experiment/substitution.py:17-96) + the coordinate scaling of Substitutor.generate_new_points
+ * (substitution.py:161-171).  logits [batch, classes, height, width] fp32, gt [batch, height, width] int64 (ignore_index
+ * counts as background, :33).  For every (b, c): the pixels where exactly one of argmax(logits) == c, gt == c holds
+ * are its errors, in row-major order; point i is error number (|rnd[b, c, i]| mod count): points[b, c, i] = (x * sx[b],
+ * y * sy[b]) in fp32, labels[b, c, i] = +1 (gt == c: false negative) / -1 (false positive), 0 for class 0 and for
+ * classes without errors (whose point is (0, 0)).  workspace: la_error_points_workspace_bytes(batch, classes, height). */
+long long la_error_points_workspace_bytes(int batch, int classes, int height);
+int la_error_points(void* stream, const float* logits, const long long* gt, int batch, int classes, int height,
+                    int width, long long ignore_index, const long long* rnd, int n_points, const float* sx,
+                    const float* sy, void* workspace, float* points, float* labels);
+
 /* ---- input preprocessing (the step right before Lam.forward) ----------------------------------------------- */
 /* One image: uint8 HWC [H, W, 3] -> fp32 CHW [3, S, S] = zero_pad((resize_bilinear_PIL(img, new_h, new_w) / 255 - mean)
  * / std), bit-identical to CustomResize -> ToTensor -> CustomNormalize (label_anything/data/transforms.py:14-46; the

@@ -228,3 +228,171 @@ extern "C" int la_label_confusion(void* stream, const float* logits, const long 
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Iterative prompting (second half): `generate_points_from_errors`
+// (label_anything/experiment/substitution.py:17-96) -- one corrective point per (episode, class) sampled from the
+// pixels where the prediction is wrong: errors = one_hot(gt) - one_hot(argmax(logits)) is +1 at a false negative of the
+// class (-> positive point) and -1 at a false positive (-> negative point); `torch.nonzero` lists them in (b, c, h, w)
+// order and the reference draws `num_points` indices per (b, c) group with torch.randint.  The reference materialises
+// two one-hot [B, C, H, W] int64 tensors, their difference and the full nonzero list (~100 bytes per pixel per class);
+// here: one pass counts the errors per (b, c, row), and one block per (b, c) scans the H row counts, finds the row of
+// the k-th error and selects the pixel inside it with ballots -- the logits are read twice, nothing is materialised.
+// The random draw is an INPUT (rand[b, c, n], any non-negative integers; k = rand mod count), so the caller owns the
+// RNG and the result is reproducible; classes without an error get the reference's (0, 0) / label 0 entry; the
+// background class keeps its coordinates but gets label 0 (substitution.py:94-95).  Coordinates leave as (x, y) scaled
+// per episode like PromptsProcessor.torch_apply_coords (fp32 * fp32, substitution.py:166-171).
+// ------------------------------------------------------------------------------------------------------------------
+namespace la {
+
+struct ErrParams {
+  const float* logits;      // [B, C, H, W]
+  const long long* gt;      // [B, H, W]
+  int* rowcnt;              // [B, C, H] workspace
+  const long long* rnd;     // [B, C, n]
+  const float* sx;          // [B] new_w / old_w as fp32
+  const float* sy;          // [B]
+  float* points;            // [B, C, n, 2] (x, y)
+  float* labels;            // [B, C, n]
+  int B, C, H, W, n;
+  long long ignore_index;
+};
+
+__device__ __forceinline__ int pixel_pred(const ErrParams& p, int b, int h, int w) {
+  float best = -INFINITY;
+  int arg = 0;
+  const float* src = p.logits + ((static_cast<long long>(b) * p.C) * p.H + h) * p.W + w;
+  for (int c = 0; c < p.C; ++c) argmax_step(__ldg(src + static_cast<long long>(c) * p.H * p.W), c, best, arg);
+  return arg;
+}
+
+__device__ __forceinline__ int pixel_target(const ErrParams& p, int b, int h, int w) {
+  const long long t = __ldg(p.gt + (static_cast<long long>(b) * p.H + h) * p.W + w);
+  return t == p.ignore_index ? 0 : static_cast<int>(t);     // substitution.py:33
+}
+
+// one warp per image row: rowcnt[b, c, h] = errors of class c in row h (a wrong pixel is an error of BOTH its classes)
+__global__ void __launch_bounds__(256) error_row_count_kernel(const ErrParams p) {
+  extern __shared__ int s_cnt[];                      // [warps][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* cnt = s_cnt + warp * p.C;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  const bool live = row < static_cast<long long>(p.B) * p.H;
+  for (int c = lane; c < p.C; c += 32) cnt[c] = 0;
+  __syncwarp();
+  if (live) {
+    const int b = static_cast<int>(row / p.H), h = static_cast<int>(row % p.H);
+    for (int w = lane; w < p.W; w += 32) {
+      const int pr = pixel_pred(p, b, h, w), t = pixel_target(p, b, h, w);
+      if (pr != t) {
+        if (t >= 0 && t < p.C) atomicAdd(cnt + t, 1);
+        atomicAdd(cnt + pr, 1);
+      }
+    }
+    __syncwarp();
+    for (int c = lane; c < p.C; c += 32) p.rowcnt[(static_cast<long long>(b) * p.C + c) * p.H + h] = cnt[c];
+  }
+}
+
+// one block per (b, c): scan the row counts, then one warp per requested point
+__global__ void __launch_bounds__(128) error_point_select_kernel(const ErrParams p) {
+  extern __shared__ int s_pre[];                      // [H + 1] exclusive prefix of the row counts
+  const int b = blockIdx.x / p.C, c = blockIdx.x % p.C;
+  const int* rc = p.rowcnt + (static_cast<long long>(b) * p.C + c) * p.H;
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int h = 0; h < p.H; ++h) {
+      s_pre[h] = run;
+      run += rc[h];
+    }
+    s_pre[p.H] = run;
+  }
+  __syncthreads();
+  const int total = s_pre[p.H];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < p.n; i += blockDim.x >> 5) {
+    const long long o = (static_cast<long long>(b) * p.C + c) * p.n + i;
+    float x = 0.f, y = 0.f, lab = 0.f;
+    if (total > 0) {
+      const long long r = __ldg(p.rnd + o);
+      int k = static_cast<int>((r < 0 ? -r : r) % total);
+      int lo = 0, hi = p.H - 1;                       // last row whose prefix <= k
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_pre[mid] <= k) lo = mid; else hi = mid - 1;
+      }
+      const int h = lo;
+      k -= s_pre[h];
+      int found_w = -1, found_lab = 0;
+      for (int w0 = 0; w0 < p.W && found_w < 0; w0 += 32) {
+        const int w = w0 + lane;
+        bool err = false;
+        int t = 0;
+        if (w < p.W) {
+          const int pr = pixel_pred(p, b, h, w);
+          t = pixel_target(p, b, h, w);
+          err = pr != t && (pr == c || t == c);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, err);
+        const int here = __popc(m);
+        if (k < here) {
+          // the k-th set bit of m
+          unsigned mm = m;
+          for (int j = 0; j < k; ++j) mm &= mm - 1;
+          const int src_lane = __ffs(mm) - 1;
+          found_w = w0 + src_lane;
+          found_lab = __shfl_sync(0xffffffffu, t == c ? 1 : -1, src_lane);
+        } else {
+          k -= here;
+        }
+      }
+      if (found_w >= 0) {
+        x = __fmul_rn(static_cast<float>(found_w), __ldg(p.sx + b));
+        y = __fmul_rn(static_cast<float>(h), __ldg(p.sy + b));
+        lab = c == 0 ? 0.f : static_cast<float>(found_lab);
+      }
+    }
+    if (lane == 0) {
+      p.points[2 * o] = x;
+      p.points[2 * o + 1] = y;
+      p.labels[o] = lab;
+    }
+  }
+}
+
+}  // namespace la
+
+extern "C" long long la_error_points_workspace_bytes(int batch, int classes, int height) {
+  return static_cast<long long>(batch) * classes * height * static_cast<long long>(sizeof(int));
+}
+
+extern "C" int la_error_points(void* stream, const float* logits, const long long* gt, int batch, int classes, int height,
+                               int width, long long ignore_index, const long long* rnd, int n_points, const float* sx,
+                               const float* sy, void* workspace, float* points, float* labels) {
+  using namespace la;
+  LA_CHECK_ARG(logits && gt && rnd && sx && sy && workspace && points && labels, "la_error_points: null pointer");
+  LA_CHECK_ARG(batch > 0 && classes > 0 && height > 0 && width > 0 && n_points > 0, "la_error_points: empty problem");
+  LA_CHECK_ARG(classes <= 1024 && height <= 8192, "la_error_points: at most 1024 classes and 8192 rows");
+  ErrParams p;
+  p.logits = logits;
+  p.gt = gt;
+  p.rowcnt = static_cast<int*>(workspace);
+  p.rnd = rnd;
+  p.sx = sx;
+  p.sy = sy;
+  p.points = points;
+  p.labels = labels;
+  p.B = batch;
+  p.C = classes;
+  p.H = height;
+  p.W = width;
+  p.n = n_points;
+  p.ignore_index = ignore_index;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long rows = static_cast<long long>(batch) * height;
+  error_row_count_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 8 * classes * sizeof(int), st>>>(p);
+  LA_CHECK_CUDA(cudaGetLastError());
+  error_point_select_kernel<<<batch * classes, 128, (height + 1) * sizeof(int), st>>>(p);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}

@@ -689,3 +689,27 @@ def scale_coords_f64(coords: torch.Tensor, sx: float, sy: float, out: torch.Tens
     assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == coords.shape
     _call("scale_coords", "la_scale_coords_f64", coords, coords.numel() // 2, float(sx), float(sy), out)
     return out
+
+
+@torch.compiler.assume_constant_result
+def _error_points_workspace_bytes(batch: int, classes: int, height: int) -> int:
+    return int(_native.lib().la_error_points_workspace_bytes(batch, classes, height))
+
+
+def error_points(logits: torch.Tensor, gt: torch.Tensor, rand: torch.Tensor, sx: torch.Tensor, sy: torch.Tensor,
+                 ignore_index: int = -100):
+    """-> (points fp32 [B, C, n, 2] (x, y) scaled by (sx[b], sy[b]), labels fp32 [B, C, n]); see la_error_points."""
+    _require_cuda(logits, gt, rand, sx, sy)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and logits.dim() == 4
+    B, C, H, W = logits.shape
+    assert gt.dtype == torch.int64 and gt.is_contiguous() and tuple(gt.shape) == (B, H, W)
+    assert rand.dtype == torch.int64 and rand.is_contiguous() and rand.shape[:2] == (B, C)
+    n = rand.shape[2]
+    for t in (sx, sy):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == B
+    ws = torch.empty(_error_points_workspace_bytes(B, C, H), dtype=torch.uint8, device=logits.device)
+    points = torch.empty((B, C, n, 2), dtype=torch.float32, device=logits.device)
+    labels = torch.empty((B, C, n), dtype=torch.float32, device=logits.device)
+    _cost(0.0, 2.0 * B * H * W * (4 * C + 8))
+    _call("error_points", "la_error_points", logits, gt, B, C, H, W, int(ignore_index), rand, n, sx, sy, ws, points, labels)
+    return points, labels

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference); the fixtures it writes are
 what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512] [mael256] [sam20w] [samragged] [samneck]
-        [preprocess] [metrics] [loss]
+        [preprocess] [points] [metrics] [loss]
 
 Every fixture stores: the oracle `cfg`, the inputs, the reference outputs and either the full state dict
 (tiny models) or the synthetic-weight seed (real-size models; weights are a pure function of
@@ -402,6 +402,53 @@ def preprocess_f3(models):
     print("preprocess_f3.pt", [tuple(i["out"].shape) for i in images], [tuple(p["mask_out"].shape) for p in prompts])
 
 
+def points_f4(models):
+    """Iterative prompting: the reference's own generate_points_from_errors with torch.randint replaced,
+    for the duration of the call, by a recorded stand-in (index = fixed draw mod count) -- the same device the rows of
+    RandomMatrixEncoder are pinned with.  B = 1 and C <= B cases only: for C > B the reference's `argsort(b * B + c)` has
+    duplicate keys and an unstable sort decides the row order."""
+    import label_anything.experiment.substitution as sub
+
+    g = torch.Generator().manual_seed(6)
+    cases = []
+    for B, C, H, W, n in [(1, 4, 37, 53, 1), (1, 6, 64, 48, 1), (3, 3, 40, 40, 1), (1, 3, 32, 32, 1), (1, 5, 24, 24, 1)]:
+        logits = torch.randn(B, C, H, W, generator=g)
+        gt = torch.randint(0, C, (B, H, W), generator=g)
+        gt[:, -3:, :] = -100
+        if C == 3 and B == 1:                      # a class with no error at all -> the padding row
+            gt[gt == 2] = 0
+            logits[:, 2] = -50.0
+        if C == 5:                                 # perfect prediction: the early-return branch
+            gt = logits.argmax(dim=1)
+        draws = torch.randint(0, 2 ** 31 - 1, (B, C, n), generator=g)
+        order = iter(draws.flatten().tolist())
+
+        def fake_randint(low, high, size, device=None, _order=None):
+            raise RuntimeError
+
+        real = torch.randint
+        # groups are visited in sorted (b, c) order; classes without errors are skipped by the reference
+        pred = logits.argmax(dim=1)
+        t = gt.clone()
+        t[t == -100] = 0
+        has_err = [[bool(((t[b] == c).long() - (pred[b] == c).long()).abs().sum() > 0) for c in range(C)] for b in range(B)]
+        seq = [int(draws[b, c, i]) for b in range(B) for c in range(C) if has_err[b][c] for i in range(n)]
+        it = iter(seq)
+
+        def pinned_randint(low, high, size, device=None, **kw):
+            return torch.tensor([next(it) % int(high) for _ in range(size[0])], dtype=torch.int64)
+
+        torch.randint = pinned_randint
+        try:
+            pts, labels = sub.generate_points_from_errors(logits, gt, n)
+        finally:
+            torch.randint = real
+        cases.append({"logits": logits, "gt": gt, "rand": draws, "points": pts.float(), "labels": labels.float(),
+                      "num_points": n})
+    torch.save({"meta": _meta(), "cases": cases}, GOLD / "points_f4.pt")
+    print("points_f4.pt", [tuple(c["points"].shape) for c in cases])
+
+
 def metrics_f4(models):
     """Post-logits step: torch.argmax + the reference's own to_global_multiclass on seeded
     inputs with ties, -inf planes, NaNs and ignore_index targets; the confusion matrix is torch.bincount of the
@@ -491,6 +538,8 @@ if __name__ == "__main__":
         samneck(models)
     if "preprocess" in which:
         preprocess_f3(models)
+    if "points" in which:
+        points_f4(models)
     if "metrics" in which:
         metrics_f4(models)
     if "loss" in which:

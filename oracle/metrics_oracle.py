@@ -73,3 +73,34 @@ def strict_mean_iou(confmat: np.ndarray, ignore_index=None) -> np.float32:
     c = confmat.astype(np.float32)
     bg = c[0, 0] / (c[0, 0] + c[0, 1:].sum() + c[1:, 0].sum())
     return np.float32((metric * n - bg) / (n - 1))
+
+
+def generate_points_from_errors(logits: np.ndarray, gt: np.ndarray, rand: np.ndarray, ignore_index: int = -100,
+                                scale_xy=None):
+    """label_anything/experiment/substitution.py:17-96 with the random draw made explicit: rand int64 [B, C, n] stands
+    in for `torch.randint(0, count, (n,))` of each (b, c) group (index = rand mod count), rows in the intended (b, c)
+    order (the reference's `argsort(b * B + c)` agrees whenever its keys are unique).  scale_xy = (sx [B], sy [B]) fp32
+    is PromptsProcessor.torch_apply_coords of Substitutor.generate_new_points (:166-171).
+    -> points fp32 [B, C, n, 2] (x, y), labels fp32 [B, C, n]."""
+    B, C, H, W = logits.shape
+    n = rand.shape[2]
+    t = np.where(gt == ignore_index, 0, gt)
+    pred = argmax_dim1(logits)
+    points = np.zeros((B, C, n, 2), dtype=np.float32)
+    labels = np.zeros((B, C, n), dtype=np.float32)
+    for b in range(B):
+        for c in range(C):
+            err = (t[b] == c).astype(np.int64) - (pred[b] == c).astype(np.int64)      # one_hot(gt) - one_hot(pred)
+            ys, xs = np.nonzero(err)                                                     # row-major, like torch.nonzero
+            if len(ys) == 0:
+                continue                                                                 # the (0, 0) / label 0 padding row
+            for i in range(n):
+                k = int(abs(int(rand[b, c, i])) % len(ys))
+                points[b, c, i] = (xs[k], ys[k])                                         # x / y swapped (:66-68)
+                labels[b, c, i] = err[ys[k], xs[k]]
+    labels[:, 0] = 0                                                                     # ignore background (:94-95)
+    if scale_xy is not None:
+        sx, sy = (np.asarray(v, dtype=np.float32) for v in scale_xy)
+        points[..., 0] = points[..., 0] * sx[:, None, None]
+        points[..., 1] = points[..., 1] * sy[:, None, None]
+    return points, labels

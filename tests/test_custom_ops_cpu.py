@@ -24,7 +24,7 @@ def test_every_launch_entry_point_is_a_custom_op_with_the_header_schema():
                 mutated = arg.alias_info is not None and arg.alias_info.is_write
                 assert mutated == (not ctype.startswith("const")), (name, arg.name, ctype)
             else:
-                assert str(arg.type) == ("float" if ctype == "float" else "int"), (name, arg.name)
+                assert str(arg.type) == ("float" if ctype in ("float", "double") else "int"), (name, arg.name)
         assert len(schema.returns) == 0                             # outputs are caller-allocated, mutated in place
 
 

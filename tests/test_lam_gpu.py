@@ -45,7 +45,7 @@ def _oracle_bf16():
 # next roundings (u = 2^-8), which perturbs the following layer by ~sqrt(u d): d -> sqrt(u d) reaches u itself after
 # about five GEMM -> round stages, whatever d started at.  What the matched oracle CAN certify, and what
 # is asserted here: the native drift from the fp32 reference is no larger than that of an independent bf16 evaluation at
-# the same rounding points (x1.5), and N is as close to M as M is to F (x1.5) -- i.e. there is no error component beyond
+# the same rounding points (x1.5), and N - M is what two independent noise realisations give (x1.25) -- i.e. there is no error component beyond
 # bf16 rounding noise.  north_star's 1e-3 is held where it is meaningful: per kernel, on identical inputs
 # (tests/test_kernels_gpu.py).
 def _matched(name, a, b, fp32_ref):
@@ -59,7 +59,9 @@ def _matched(name, a, b, fp32_ref):
            f"{nm.max().item():.5f}  (ref std {std:.4f})")
     print(msg)
     assert nf.mean().item() <= 1.5 * mf.mean().item() + 1e-4 * std, "native drifts more than a bf16 evaluation does: " + msg
-    assert nm.mean().item() <= 1.5 * mf.mean().item() + 1e-4 * std, "native is not a bf16 evaluation of this algorithm: " + msg
+    # two independent noise realisations around F are sqrt(nf^2 + mf^2) apart; a systematic error would push N - M beyond it
+    indep = (nf.mean().item() ** 2 + mf.mean().item() ** 2) ** 0.5
+    assert nm.mean().item() <= 1.25 * indep + 1e-4 * std, "native is not a bf16 evaluation of this algorithm: " + msg
     assert nm.max().item() <= 0.15 * std, msg
 
 

@@ -135,3 +135,37 @@ def test_chained_table_equals_sequential_substitution_on_random_episodes():
         inside = (labels >= 0) & (labels < table.shape[1])
         got = np.where(inside, table[np.arange(B)[:, None, None], np.clip(labels, 0, table.shape[1] - 1)], labels)
         assert np.array_equal(got, want), (classes, cat_ids, compact)
+
+
+def test_error_points_oracle_matches_the_reference_fixture():
+    """generate_points_from_errors (substitution.py:17-96): the oracle with the recorded draws reproduces the UNMODIFIED
+    reference function (whose torch.randint was pinned to the same draws) exactly -- coordinates, labels, padding rows,
+    the all-correct early return."""
+    import torch
+
+    g = torch.load(ROOT / "tests" / "golden" / "points_f4.pt", weights_only=False)
+    for c in g["cases"]:
+        pts, labels = mo.generate_points_from_errors(c["logits"].numpy(), c["gt"].numpy(), c["rand"].numpy())
+        assert np.array_equal(pts, c["points"].numpy()), tuple(c["logits"].shape)
+        assert np.array_equal(labels, c["labels"].numpy())
+
+
+def test_macro_jaccard_known_answer_from_the_torchmetrics_documentation():
+    """torchmetrics is not installed here, so its reduce is restated; this pins it to the worked example of the
+    MulticlassJaccardIndex docstring of torchmetrics 1.7.1 (the version of the reference's uv.lock:2672-2673):
+        target = [2, 1, 0, 0], preds = [2, 1, 0, 1], num_classes = 3  ->  tensor(0.6667)
+    (IoU per class 1/2, 1/2, 1) and to the absent-class rule of `_jaccard_index_reduce` (a class with no prediction and
+    no target gets weight 0 in the macro average)."""
+    target, preds = np.array([2, 1, 0, 0]), np.array([2, 1, 0, 1])
+    conf = mo.confusion_matrix(preds, target, 3) if hasattr(mo, "confusion_matrix") else None
+    if conf is None:
+        conf = np.zeros((3, 3), dtype=np.int64)
+        for t, p in zip(target, preds):
+            conf[t, p] += 1
+    val = MeanIoU._macro_jaccard(torch.from_numpy(conf), None)
+    assert abs(float(val) - 2.0 / 3.0) < 1e-6 and f"{float(val):.4f}" == "0.6667"
+    conf4 = np.zeros((4, 4), dtype=np.int64)
+    conf4[:3, :3] = conf                                               # class 3 never appears
+    assert abs(float(MeanIoU._macro_jaccard(torch.from_numpy(conf4), None)) - 2.0 / 3.0) < 1e-6
+    # ignore_index inside the class range: that class is dropped from the average
+    assert abs(float(MeanIoU._macro_jaccard(torch.from_numpy(conf), 2)) - 0.5) < 1e-6

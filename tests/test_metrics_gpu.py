@@ -104,3 +104,47 @@ def test_full_size_checksum_properties():
         b1 = 3 if b0 == 0 else B
         ops.label_confusion(logits[b0:b1], None, gt[b0:b1], None, parts, bad, want_preds=False, want_gt=False)
     assert torch.equal(parts, conf)
+
+
+def test_error_points_match_the_reference_fixture_and_the_oracle():
+    """la_error_points (generate_points_from_errors, substitution.py:17-96) through the C ABI: exact coordinates and
+    labels against the fixture of the unmodified reference (same pinned draws), against the oracle on a large ragged
+    case with several points per class, and the Substitutor glue."""
+    from labelanything_b200.substitution import Substitutor, generate_points_from_errors
+
+    g = torch.load(ROOT / "tests" / "golden" / "points_f4.pt", weights_only=False)
+    for c in g["cases"]:
+        pts, labels = generate_points_from_errors(c["logits"].cuda(), c["gt"].cuda(), c["num_points"],
+                                                  rand=c["rand"].cuda())
+        assert torch.equal(pts.cpu(), c["points"]) and torch.equal(labels.cpu(), c["labels"])
+    gen = torch.Generator().manual_seed(1)
+    B, C, H, W, n = 4, 21, 300, 517, 3
+    logits = torch.randn(B, C, H, W, generator=gen)
+    logits[:, :, : H // 2] = torch.round(logits[:, :, : H // 2])           # ties -> first maximum
+    gt = torch.randint(0, C, (B, H, W), generator=gen)
+    gt[:, -5:] = -100
+    gt[0][gt[0] == 7] = 0
+    logits[0, 7] = -60.0                                                    # class 7 of episode 0: no error -> padding
+    rand = torch.randint(0, 2 ** 31 - 1, (B, C, n), generator=gen)
+    sx, sy = torch.rand(B, generator=gen) + 0.5, torch.rand(B, generator=gen) + 0.5
+    pts, labels = generate_points_from_errors(logits.cuda(), gt.cuda(), n, rand=rand.cuda(), scale_xy=(sx, sy))
+    mo = _mo()
+    rp, rl = mo.generate_points_from_errors(logits.numpy(), gt.numpy(), rand.numpy(), scale_xy=(sx.numpy(), sy.numpy()))
+    assert np.array_equal(pts.cpu().numpy(), rp) and np.array_equal(labels.cpu().numpy(), rl)
+    assert float(labels[0, 7].abs().sum()) == 0 and float(pts[0, 7].abs().sum()) == 0 and float(labels[:, 0].abs().sum()) == 0
+    # Substitutor.generate_new_points: one more point slot on the query example, zero padding on the others
+    from labelanything_b200.utils import BatchKeys
+
+    M, P = 3, 2
+    batch = {BatchKeys.PROMPT_POINTS: torch.rand(B, M, C, P, 2).cuda(), BatchKeys.FLAG_POINTS: torch.ones(B, M, C, P).cuda(),
+             BatchKeys.DIMS: torch.tensor([[[H, W]] * M] * B)}
+    sub = Substitutor(num_points=1, long_side_length=1024)
+    sub.reset((batch, None))
+    sub.generate_new_points(logits.cuda(), gt.cuda(), rand=rand[:, :, :1].contiguous().cuda())
+    assert batch[BatchKeys.PROMPT_POINTS].shape == (B, M, C, P + 1, 2) and batch[BatchKeys.FLAG_POINTS].shape == (B, M, C, P + 1)
+    assert float(batch[BatchKeys.FLAG_POINTS][:, 1:, :, P:].abs().sum()) == 0
+    sxs, sys_ = sub._scales(batch[BatchKeys.DIMS])
+    rp1, rl1 = mo.generate_points_from_errors(logits.numpy(), gt.numpy(), rand[:, :, :1].numpy(),
+                                              scale_xy=(sxs.numpy(), sys_.numpy()))
+    assert np.array_equal(batch[BatchKeys.PROMPT_POINTS][:, 0, :, P:].cpu().numpy(), rp1)
+    assert np.array_equal(batch[BatchKeys.FLAG_POINTS][:, 0, :, P:].cpu().numpy(), rl1)
