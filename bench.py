@@ -304,6 +304,12 @@ def secondary_measurements(lam, steps: int = 3) -> dict:
         ce = lam.generate_class_embeddings(sup_in)
         t0[1].record()
         torch.cuda.synchronize()
+        from labelanything_b200.utils import ResultDict
+
+        # the same cached class embeddings serve every query of the step (lam.py:362-381 decodes B queries against
+        # class_embeddings[B, C, D])
+        ce = dict(ce)
+        ce[ResultDict.CLASS_EMBS] = ce[ResultDict.CLASS_EMBS].expand(B, -1, -1).contiguous()
         q = {"images": torch.randn(B, 1, 3, IMAGE_SIZE, IMAGE_SIZE, device="cuda"),
              "dims": torch.full((B, 2), IMAGE_SIZE, dtype=torch.int64, device="cuda")}
         ms = _timed(lambda: lam.predict(q, ce), steps)
