@@ -713,3 +713,37 @@ def error_points(logits: torch.Tensor, gt: torch.Tensor, rand: torch.Tensor, sx:
     _cost(0.0, 2.0 * B * H * W * (4 * C + 8))
     _call("error_points", "la_error_points", logits, gt, B, C, H, W, int(ignore_index), rand, n, sx, sy, ws, points, labels)
     return points, labels
+
+
+# ---------------------------------------------------------------------------------------------- pooled attention
+def attention_pooled_supported(n_query: int, n_heads: int, d: int, tokens: int) -> bool:
+    """Shapes la_attention_pooled_bf16 is built for (everything else keeps the projected k / v path)."""
+    return n_query * n_heads <= 8 and d in (64, 128, 256, 512) and tokens >= 1 and not _NO_POOLED_ATTENTION
+
+
+_NO_POOLED_ATTENTION = bool(__import__("os").environ.get("LA_NO_POOLED_ATTENTION"))   # experiment switch
+
+
+def attention_pooled(x: torch.Tensor, u: torch.Tensor, e: torch.Tensor | None, scale: float, n_seq: int, tokens: int,
+                     rows: int) -> torch.Tensor:
+    """y[s, r] = sum_t softmax_t(scale (u[s, r] . x[s, t] + e[s, r, t])) x[s, t]; x bf16 [n_seq*tokens, d] read once."""
+    _require_cuda(x, u, e)
+    d = x.shape[1]
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == n_seq * tokens
+    assert u.dtype == torch.bfloat16 and u.is_contiguous() and tuple(u.shape) == (n_seq * rows, d)
+    assert e is None or (e.dtype == torch.float32 and e.is_contiguous() and tuple(e.shape) == (n_seq * rows, tokens))
+    y = torch.empty((n_seq * rows, d), dtype=torch.bfloat16, device=x.device)
+    _cost(4.0 * n_seq * rows * tokens * d, 2.0 * n_seq * tokens * d + (4.0 * n_seq * rows * tokens if e is not None else 0))
+    _call("attention_pooled", "la_attention_pooled_bf16", x, x.stride(0), u, e, float(scale), y, n_seq, tokens, rows, d)
+    return y
+
+
+def head_rows(t: torch.Tensor, n_seq: int, heads: int, head_dim: int, expand: bool) -> torch.Tensor:
+    """expand: bf16 [n_seq, H*dh] -> [n_seq*H, H*dh] with row (s, h) keeping only head h's columns;
+    gather: [n_seq*H, H*dh] -> [n_seq, H*dh] taking head h's columns from row (s, h)."""
+    _require_cuda(t)
+    w = heads * head_dim
+    assert t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape) == ((n_seq if expand else n_seq * heads), w)
+    out = torch.empty(((n_seq * heads if expand else n_seq), w), dtype=torch.bfloat16, device=t.device)
+    _call("head_rows", "la_head_rows_bf16", t, out, n_seq, heads, head_dim, 0 if expand else 1)
+    return out

@@ -17,7 +17,10 @@ Exact simplifications used (no approximation):
     exactly 1, so that attention's output is out_proj(v_proj(token)) for every image position: a per-sequence
     vector folded into the following add+LayerNorm (no image-side q projection, no [S*T, D] branch tensor);
   * the prompt encoder only consumes the image-token output (prompt_encoder.py:681-685), so the final
-    token->image attention (transformer.py:245-250) is skipped there (`want_queries=False`).
+    token->image attention (transformer.py:245-250) is skipped there (`want_queries=False`);
+  * with a single token per sequence the token->image attention needs no projection of the image tokens: by
+    associativity the k / v projections move to the query side (`_pooled_token_to_image`, csrc/la_poolattn.cu) and the
+    S*T image tokens are read once instead of projected (2.6 TFLOP, 10 GB per layer), written and read again.
 """
 from __future__ import annotations
 
@@ -120,6 +123,26 @@ def _pe_table(att: Attention, name: str, pe: torch.Tensor, cached: bool) -> torc
         with torch.no_grad():
             return make()
     return att.packed(f"pe:{name}:{pe.shape[0]}", make, w, pe)
+
+
+def _pooled_token_to_image(att: Attention, tq: torch.Tensor, keys16: torch.Tensor, pe: torch.Tensor, pe_cached: bool,
+                           S: int, T: int, H: int, Dc: int) -> torch.Tensor:
+    """Attention(q = tokens + pe_q, k = keys + pe, v = keys) for ONE query token per sequence (transformer.py:311-318,
+    common.py:97-148) without projecting the S*T image tokens:
+        q_h . k_{h,t} = u_h . x_t + u_h . pe_t + q_h . b_k[h],   u_h = W_k[h]^T q_h       (the last term is constant
+        o_h = W_v[h] (sum_t p_{h,t} x_t) + b_v[h]                                          over t: gone in the softmax)
+    tq bf16 [S, Dc] (projected query incl. bias) -> bf16 [S, Dc] (input of out_proj).  Every product is a la_gemm_bf16
+    over S*H rows; the image tokens are touched only by la_attention_pooled_bf16."""
+    dh = Dc // H
+    wk_t = att.packed("wk_t", lambda: att.k_proj.weight.detach().t().to(torch.bfloat16).contiguous(), att.k_proj.weight)
+    make_pe16 = lambda: pe.to(torch.bfloat16).contiguous()   # noqa: E731
+    pe16 = att.packed(f"pe16:{pe.shape[0]}", make_pe16, pe) if pe_cached else make_pe16()
+    qb = ops.head_rows(tq, S, H, dh, expand=True)                          # [S*H, Dc], row (s, h) = q_h in its columns
+    u = ops.gemm(qb, wk_t, None)                                           # [S*H, D]   u_h = W_k[h]^T q_h
+    e = ops.gemm(u, pe16, None, out_dtype=torch.float32)                   # [S*H, T]   u_h . pe_t
+    y = ops.attention_pooled(keys16, u, e, dh ** -0.5, S, T, H)            # [S*H, D]   sum_t p x_t
+    ov = ops.gemm(y, _w(att, "v"), _b(att, "v"))                           # [S*H, Dc]  W_v y_h + b_v (all head blocks)
+    return ops.head_rows(ov, S, H, dh, expand=False)                       # [S, Dc]    head h's block of row (s, h)
 
 
 def _ln(mod: NativeModule, name: str, ln: nn.LayerNorm):
@@ -228,7 +251,13 @@ def run_two_way(tw: TwoWayTransformer, keys16: torch.Tensor, keys32: Optional[to
         Dc = t2i.internal_dim
         assert i2t.internal_dim == Dc
         need_q = n > 1
-        if need_q:
+        # One query token per sequence (mask-only prompts): no image-side projection at all -- the k / v projections
+        # are moved to the query side by associativity and the image tokens are read once, as they are
+        # (csrc/la_poolattn.cu).
+        pooled = (not need_q) and ops.attention_pooled_supported(n, H, D, T)
+        if pooled:
+            proj = None
+        elif need_q:
             w_img = layer.packed("w_img3", lambda: torch.cat([t2i.k_proj.weight, t2i.v_proj.weight, i2t.q_proj.weight])
                                  .detach().to(torch.bfloat16).contiguous(),
                                  t2i.k_proj.weight, t2i.v_proj.weight, i2t.q_proj.weight)
@@ -236,12 +265,16 @@ def run_two_way(tw: TwoWayTransformer, keys16: torch.Tensor, keys32: Optional[to
                                  .detach().float().contiguous(), t2i.k_proj.bias, t2i.v_proj.bias, i2t.q_proj.bias)
         else:
             w_img, b_img = _cat_w(t2i, ("k", "v")), _cat_b(t2i, ("k", "v"))
-        proj = ops.gemm(keys16, w_img, b_img)                      # [S*T, 2Dc | 3Dc] bf16
+        if not pooled:
+            proj = ops.gemm(keys16, w_img, b_img)                  # [S*T, 2Dc | 3Dc] bf16
 
         # ---- (2) tokens attend to the image ----------------------------------------------------------------
         tq = ops.gemm(tokpe16, _w(t2i, "q"), _b(t2i, "q"))
-        o = ops.attention_tokens(tq, proj[:, :Dc], proj[:, Dc:2 * Dc], S, n, T, H, Dc // H,
-                                 k_add=_pe_table(t2i, "k", pe, pe_cached))
+        if pooled:
+            o = _pooled_token_to_image(t2i, tq, keys16, pe, pe_cached, S, T, H, Dc)
+        else:
+            o = ops.attention_tokens(tq, proj[:, :Dc], proj[:, Dc:2 * Dc], S, n, T, H, Dc // H,
+                                     k_add=_pe_table(t2i, "k", pe, pe_cached))
         o = ops.gemm(o, _w(t2i, "out"), _b(t2i, "out"))
         g2, b2, e2 = _ln(layer, "norm2", layer.norm2)
         tok32n, tok16 = _empty(R, D, torch.float32, dev), _empty(R, D, torch.bfloat16, dev)
@@ -269,7 +302,7 @@ def run_two_way(tw: TwoWayTransformer, keys16: torch.Tensor, keys32: Optional[to
             del o
         else:
             seq_add = ops.gemm(tv, _w(i2t, "out"), _b(i2t, "out"), out_dtype=torch.float32)   # [S, D]
-        del proj
+        proj = None
         g4, b4, e4 = _ln(layer, "norm4", layer.norm4)
         x_in, d1, d2 = (keys32, delta, None) if keys32 is not None else (None, keys16, delta)
         if last and pool:

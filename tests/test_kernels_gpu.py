@@ -457,3 +457,66 @@ def test_classify_and_postprocess_match_torch():
         fin = torch.isfinite(ref)
         assert torch.equal(torch.isfinite(out), fin) and torch.equal(out[~fin], ref[~fin])
         _close(out[fin], ref[fin], 1e-5, 2e-5, "postprocess")
+
+
+# ---------------------------------------------------------------------------------------------- pooled attention
+@pytest.mark.parametrize("S,T,rows,D", [(5, 4096, 8, 512), (3, 900, 8, 256), (2, 70, 3, 128), (4, 64, 1, 64),
+                                        (2, 1000, 8, 512)])
+def test_pooled_attention_matches_torch(S, T, rows, D):
+    """y = softmax(scale (u x^T + e)) x with x as key AND value (la_attention_pooled_bf16): identical bf16 inputs vs
+    torch fp32; ragged last tile (T % 64 != 0), fewer than 8 query rows, every supported width."""
+    ops = _ops()
+    g = _gen(S + T + rows + D)
+    x = (0.5 * torch.randn(S * T, D, device="cuda", generator=g) + 0.25).to(torch.bfloat16)
+    u = (torch.randn(S * rows, D, device="cuda", generator=g) * (4.0 / math.sqrt(D))).to(torch.bfloat16)
+    e = torch.randn(S * rows, T, device="cuda", generator=g)
+    scale = 0.7
+    y = ops.attention_pooled(x, u, e, scale, S, T, rows)
+    xf, uf = x.float().view(S, T, D), u.float().view(S, rows, D)
+    p = torch.softmax((uf @ xf.transpose(1, 2) + e.view(S, rows, T)) * scale, dim=-1)
+    ref = (p @ xf).reshape(S * rows, D)
+    # bf16 rounding of P (averaged over the tokens carrying weight) and of the output: 2^-8 relative + 2e-3 absolute
+    _close(y, ref, 2 ** -8, 2e-3, "pooled attention")
+    y0 = ops.attention_pooled(x, u, None, scale, S, T, rows)
+    ref0 = (torch.softmax(uf @ xf.transpose(1, 2) * scale, dim=-1) @ xf).reshape(S * rows, D)
+    _close(y0, ref0, 2 ** -8, 2e-3, "pooled attention, no positional scores")
+
+
+def test_head_rows_expand_and_gather_are_exact():
+    ops = _ops()
+    S, H, dh = 7, 8, 32
+    t = torch.randn(S, H * dh, device="cuda").to(torch.bfloat16)
+    ex = ops.head_rows(t, S, H, dh, expand=True)
+    ref = torch.zeros(S, H, H, dh, device="cuda", dtype=torch.bfloat16)
+    for h in range(H):
+        ref[:, h, h] = t.view(S, H, dh)[:, h]
+    assert torch.equal(ex, ref.view(S * H, H * dh))
+    assert torch.equal(ops.head_rows(ex, S, H, dh, expand=False), t)
+
+
+def test_pooled_token_to_image_equals_the_projected_path():
+    """The associativity rewrite of the single-query token->image attention against the k / v projection path it
+    replaces (same module, same inputs): equal up to bf16 rounding of the intermediates."""
+    from labelanything_b200 import ops as O
+    from labelanything_b200 import transformer as TR
+    from labelanything_b200.synthetic import load_synth_weights
+
+    D, H, S, T = 256, 8, 6, 900
+    tw = TR.TwoWayTransformer(depth=2, embedding_dim=D, num_heads=H, mlp_dim=512)
+    load_synth_weights(tw, seed=3)
+    tw = tw.cuda()
+    g = _gen(11)
+    keys16 = torch.randn(S * T, D, device="cuda", generator=g).to(torch.bfloat16)
+    pe = torch.randn(T, D, device="cuda", generator=g)
+    tok = torch.randn(S, D, device="cuda", generator=g)
+    with torch.no_grad():
+        _, _, pooled_new = TR.run_two_way(tw, keys16, None, pe, tok, S, T, 1, want_queries=False, pool=True)
+        O._NO_POOLED_ATTENTION = True
+        try:
+            _, _, pooled_old = TR.run_two_way(tw, keys16, None, pe, tok, S, T, 1, want_queries=False, pool=True)
+        finally:
+            O._NO_POOLED_ATTENTION = False
+    err = (pooled_new - pooled_old).abs()
+    print(f"pooled vs projected path: max {err.max().item():.4e} mean {err.mean().item():.4e} "
+          f"(|ref| mean {pooled_old.abs().mean().item():.3f})")
+    assert err.max().item() < 2e-2 and err.mean().item() < 2e-3
