@@ -106,12 +106,12 @@ int la_attention_set_trace(void* device_buffer);   /* LA_ERR_UNSUPPORTED unless 
 /* Token -> image attention WITHOUT materialised k / v projections (few query rows against many image tokens):
  *   y[s, r, :] = sum_t softmax_t(scale * (u[s, r] . x[s, t] + e[s, r, t])) x[s, t, :]      r < rows <= 8
  * x bf16 [n_seq * tokens, d] (row stride ldx) is BOTH the key and the value operand and is read exactly once;
- * u bf16 [n_seq * rows, d]; e fp32 [n_seq * rows, tokens] or NULL; y bf16 [n_seq * rows, d]; d in {64, 128, 256, 512}.
+ * u bf16 [n_seq * rows, d]; e fp32 [n_seq * rows, >= tokens] (row stride lde) or NULL; y bf16 [n_seq * rows, d]; d in {64, 128, 256, 512}.
  * With u_h = W_k[h]^T q_h, e = u . pe^T and o_h = W_v[h] y_h + b_v[h] this is exactly Attention(q, k = keys + pe,
  * v = keys) of label_anything/models/transformer.py:311-318 / common.py:97-148 (the k bias is constant over t and
  * drops out of the softmax); the small projections around it are la_gemm_bf16 calls. */
-int la_attention_pooled_bf16(void* stream, const void* x, long long ldx, const void* u, const float* e, float scale,
-                             void* y, long long n_seq, int tokens, int rows, int d);
+int la_attention_pooled_bf16(void* stream, const void* x, long long ldx, const void* u, const float* e, long long lde,
+                             float scale, void* y, long long n_seq, int tokens, int rows, int d);
 /* mode 0: out[(s, h), c] = in[s, c] if c / head_dim == h else 0   (bf16 [n_seq, H*dh] -> [n_seq*H, H*dh]);
  * mode 1: out[s, h*dh + j] = in[(s, h), h*dh + j]                 (bf16 [n_seq*H, H*dh] -> [n_seq, H*dh]). */
 int la_head_rows_bf16(void* stream, const void* in, void* out, long long n_seq, int heads, int head_dim, int mode);

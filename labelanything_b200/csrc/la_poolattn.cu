@@ -53,7 +53,8 @@ __device__ __forceinline__ float pa_ex2(float x) {
 
 struct PoolAttnParams {
   const __nv_bfloat16* u;   // [n_seq * rows, d]
-  const float* e;           // [n_seq * rows, tokens] or nullptr
+  const float* e;           // [n_seq * rows, lde] or nullptr
+  long long lde;            // row stride of e (>= tokens)
   __nv_bfloat16* y;         // [n_seq * rows, d]
   long long n_seq;
   int tokens, rows, d;
@@ -103,7 +104,7 @@ pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttn
       ua2[kk] = live ? __ldg(reinterpret_cast<const uint32_t*>(ur + 16 * kk + 8)) : 0u;
     }
   }
-  const float* erow = (p.e != nullptr && g < p.rows) ? p.e + (seq * p.rows + g) * p.tokens : nullptr;
+  const float* erow = (p.e != nullptr && g < p.rows) ? p.e + (seq * p.rows + g) * p.lde : nullptr;
 
   float yacc[8][4];
 #pragma unroll
@@ -238,7 +239,8 @@ static int launch_pooled(cudaStream_t st, const CUtensorMap& tm, const PoolAttnP
 }  // namespace la
 
 extern "C" int la_attention_pooled_bf16(void* stream, const void* x, long long ldx, const void* u, const float* e,
-                                        float scale, void* y, long long n_seq, int tokens, int rows, int d) {
+                                        long long lde, float scale, void* y, long long n_seq, int tokens, int rows,
+                                        int d) {
   using namespace la;
   LA_CHECK_ARG(x && u && y, "la_attention_pooled_bf16: null pointer");
   LA_CHECK_ARG(n_seq > 0 && n_seq < (1ll << 31) && tokens > 0, "la_attention_pooled_bf16: empty problem");
@@ -246,6 +248,7 @@ extern "C" int la_attention_pooled_bf16(void* stream, const void* x, long long l
   LA_CHECK_ARG(d % 64 == 0 && d >= 64 && d <= 512 && (d / 64 == 1 || d / 64 == 2 || d / 64 == 4 || d / 64 == 8),
                "la_attention_pooled_bf16: d must be 64, 128, 256 or 512 (got %d)", d);
   LA_CHECK_ARG(ldx >= d && ldx % 8 == 0, "la_attention_pooled_bf16: bad row stride");
+  LA_CHECK_ARG(e == nullptr || lde >= tokens, "la_attention_pooled_bf16: lde must be >= tokens");
   LA_CHECK_ARG(n_seq * tokens < (1ll << 31), "la_attention_pooled_bf16: too many rows for TMA coordinates");
   LA_CHECK_ARG(scale > 0.f, "la_attention_pooled_bf16: the softmax scale must be positive");
   CUtensorMap tm;
@@ -256,6 +259,7 @@ extern "C" int la_attention_pooled_bf16(void* stream, const void* x, long long l
   PoolAttnParams p;
   p.u = static_cast<const __nv_bfloat16*>(u);
   p.e = e;
+  p.lde = lde;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.n_seq = n_seq;
   p.tokens = tokens;

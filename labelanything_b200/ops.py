@@ -731,10 +731,12 @@ def attention_pooled(x: torch.Tensor, u: torch.Tensor, e: torch.Tensor | None, s
     d = x.shape[1]
     assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == n_seq * tokens
     assert u.dtype == torch.bfloat16 and u.is_contiguous() and tuple(u.shape) == (n_seq * rows, d)
-    assert e is None or (e.dtype == torch.float32 and e.is_contiguous() and tuple(e.shape) == (n_seq * rows, tokens))
+    assert e is None or (e.dtype == torch.float32 and e.dim() == 2 and e.stride(1) == 1 and e.shape[0] == n_seq * rows
+                         and e.shape[1] >= tokens)
     y = torch.empty((n_seq * rows, d), dtype=torch.bfloat16, device=x.device)
     _cost(4.0 * n_seq * rows * tokens * d, 2.0 * n_seq * tokens * d + (4.0 * n_seq * rows * tokens if e is not None else 0))
-    _call("attention_pooled", "la_attention_pooled_bf16", x, x.stride(0), u, e, float(scale), y, n_seq, tokens, rows, d)
+    _call("attention_pooled", "la_attention_pooled_bf16", x, x.stride(0), u, e, e.stride(0) if e is not None else 0,
+          float(scale), y, n_seq, tokens, rows, d)
     return y
 
 

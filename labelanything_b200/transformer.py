@@ -135,7 +135,11 @@ def _pooled_token_to_image(att: Attention, tq: torch.Tensor, keys16: torch.Tenso
     over S*H rows; the image tokens are touched only by la_attention_pooled_bf16."""
     dh = Dc // H
     wk_t = att.packed("wk_t", lambda: att.k_proj.weight.detach().t().to(torch.bfloat16).contiguous(), att.k_proj.weight)
-    make_pe16 = lambda: pe.to(torch.bfloat16).contiguous()   # noqa: E731
+    def make_pe16():   # rows padded to a multiple of 8 (the GEMM's N granularity; 900 tokens at 480 px): the extra
+        t = torch.zeros(((pe.shape[0] + 7) // 8 * 8, pe.shape[1]), dtype=torch.bfloat16, device=pe.device)   # columns
+        t[:pe.shape[0]] = pe.to(torch.bfloat16)                                                      # of e are never read
+        return t
+
     pe16 = att.packed(f"pe16:{pe.shape[0]}", make_pe16, pe) if pe_cached else make_pe16()
     qb = ops.head_rows(tq, S, H, dh, expand=True)                          # [S*H, Dc], row (s, h) = q_h in its columns
     u = ops.gemm(qb, wk_t, None)                                           # [S*H, D]   u_h = W_k[h]^T q_h
