@@ -69,9 +69,10 @@ __global__ void __launch_bounds__(NW * 32)
 pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // [stage][warp] slabs | partial scores [warp][64 tokens][8 rows] fp32 | P [warp][8 rows][72] bf16 | mbarriers
+  // [stage][warp] slabs | partial scores [warp][64 tokens][8 rows] fp32 | totals [64][8] | P [warp][8 rows][72] bf16 | mbarriers
   float* red = reinterpret_cast<float*>(smem + PA_STAGES * NW * PA_SLAB);
-  __nv_bfloat16* pbuf_all = reinterpret_cast<__nv_bfloat16*>(red + NW * PA_TILE * 8);
+  float* tot = red + NW * PA_TILE * 8;                                   // summed scores [64 tokens][8 rows]
+  __nv_bfloat16* pbuf_all = reinterpret_cast<__nv_bfloat16*>(tot + PA_TILE * 8);
   uint64_t* bars = reinterpret_cast<uint64_t*>(pbuf_all + NW * 8 * PA_P_STRIDE);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,22 +134,14 @@ pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttn
   for (int c = 0; c < 4; ++c) yacc[c][0] = yacc[c][1] = yacc[c][2] = yacc[c][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int i = 0; i < n_tiles; ++i) {
-    // positional scores of this tile (fetched a tile ago); start the next tile's fetch: its latency hides under the MMAs
-    float ev[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) ev[k] = e_next[k];
-    if (i + 1 < n_tiles) load_e(i + 1, e_next);
-
-    const int st = i % PA_STAGES;
-    mbar_wait(&bars[st * NW + warp], (i / PA_STAGES) & 1);
+  // partial scores of tile `tile` over this warp's 64 channels: S[64 tokens x 8 rows] = X_w[64 x 64] U_w^T
+  auto score_mmas = [&](int tile, float (&sp)[4][4]) {
+    const int st = tile % PA_STAGES;
+    mbar_wait(&bars[st * NW + warp], (tile / PA_STAGES) & 1);
     const uint32_t slab = smem_u32(smem + (st * NW + warp) * PA_SLAB);
-
-    // ---- partial scores over this warp's 64 channels: S[64 tokens x 8 rows] = X_w[64 x 64] U_w^T ----
-    float s[4][4];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-      s[mt][0] = s[mt][1] = s[mt][2] = s[mt][3] = 0.f;
+      sp[mt][0] = sp[mt][1] = sp[mt][2] = sp[mt][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         // A = X: matrices (tokens 0-7, k lo) (tokens 8-15, k lo) (tokens 0-7, k hi) (tokens 8-15, k hi)
@@ -157,50 +150,67 @@ pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttn
         const int chunk = 2 * kk + (mi >> 1);
         uint32_t a[4];
         ldmatrix_x4(a, slab + tok * 128 + ((chunk ^ (tok & 7)) << 4));
-        mma_16816(s[mt], a, ub0[kk], ub1[kk]);
+        mma_16816(sp[mt], a, ub0[kk], ub1[kk]);
       }
     }
-    // ---- sum the partials of all warps ----
-    {
-      float* mine = red + (warp * PA_TILE + g) * 8 + 2 * q;
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        *reinterpret_cast<float2*>(mine + (16 * mt) * 8) = make_float2(s[mt][0], s[mt][1]);
-        *reinterpret_cast<float2*>(mine + (16 * mt + 8) * 8) = make_float2(s[mt][2], s[mt][3]);
-      }
-    }
-    __syncthreads();
+  };
+  auto store_partials = [&](const float (&sp)[4][4]) {
+    float* mine = red + (warp * PA_TILE + g) * 8 + 2 * q;
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int w2 = 0; w2 < NW; ++w2) {
-        const float* src = red + (w2 * PA_TILE + 16 * mt + g) * 8 + 2 * q;
-        const float2 lo = *reinterpret_cast<const float2*>(src);
-        const float2 hi = *reinterpret_cast<const float2*>(src + 64);
-        a0 += lo.x;
-        a1 += lo.y;
-        a2 += hi.x;
-        a3 += hi.y;
-      }
-      s[mt][0] = a0;
-      s[mt][1] = a1;
-      s[mt][2] = a2;
-      s[mt][3] = a3;
+      *reinterpret_cast<float2*>(mine + (16 * mt) * 8) = make_float2(sp[mt][0], sp[mt][1]);
+      *reinterpret_cast<float2*>(mine + (16 * mt + 8) * 8) = make_float2(sp[mt][2], sp[mt][3]);
     }
-    __syncthreads();   // `red` is rewritten by the next tile
+  };
 
-    // ---- positional scores, scale, tail mask, online softmax per query row (every warp: the same statistics) ----
+  // Software pipeline: the score MMAs of tile i + 1 are issued BEFORE the softmax of tile i, so the tensor pipe works
+  // through them (and then through the value MMAs of tile i) while the ALUs do the reduction and the exponentials.
+  float s_next[4][4];
+  score_mmas(0, s_next);
+  store_partials(s_next);
+  __syncthreads();
+
+  for (int i = 0; i < n_tiles; ++i) {
+    float ev[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ev[k] = e_next[k];
+    if (i + 1 < n_tiles) load_e(i + 1, e_next);   // consumed a tile later: the load latency hides under this tile
+
+    // ---- (a) every warp sums the partials of ITS 64 / NW tokens (all 8 rows) and publishes the totals ----
+    {
+      constexpr int TPW = PA_TILE / NW;            // tokens per warp
+#pragma unroll
+      for (int unit = lane; unit < TPW * 4; unit += 32) {
+        const int tok = warp * TPW + (unit >> 2), rp = unit & 3;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; ++w2) {
+          const float2 v = *reinterpret_cast<const float2*>(red + (w2 * PA_TILE + tok) * 8 + 2 * rp);
+          a0 += v.x;
+          a1 += v.y;
+        }
+        *reinterpret_cast<float2*>(tot + tok * 8 + 2 * rp) = make_float2(a0, a1);
+      }
+    }
+    __syncthreads();   // totals complete; `red` may be rewritten
+
+    // ---- (b) score MMAs of the next tile (results are only needed at the end of this iteration) ----
+    if (i + 1 < n_tiles) score_mmas(i + 1, s_next);
+
+    // ---- (c) totals + positional scores, scale, tail mask, online softmax per query row ----
+    float s[4][4];
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        const bool in = i * PA_TILE + 16 * mt + 8 * hh + g < p.tokens;
-        float& v0 = s[mt][2 * hh];
-        float& v1 = s[mt][2 * hh + 1];
-        v0 = in ? (v0 + ev[4 * mt + 2 * hh]) * p.scale_log2 : -INFINITY;
-        v1 = in ? (v1 + ev[4 * mt + 2 * hh + 1]) * p.scale_log2 : -INFINITY;
+        const int tok = 16 * mt + 8 * hh + g;
+        const float2 v = *reinterpret_cast<const float2*>(tot + tok * 8 + 2 * q);
+        const bool in = i * PA_TILE + tok < p.tokens;
+        const float v0 = in ? (v.x + ev[4 * mt + 2 * hh]) * p.scale_log2 : -INFINITY;
+        const float v1 = in ? (v.y + ev[4 * mt + 2 * hh + 1]) * p.scale_log2 : -INFINITY;
+        s[mt][2 * hh] = v0;
+        s[mt][2 * hh + 1] = v1;
         mx0 = fmaxf(mx0, v0);
         mx1 = fmaxf(mx1, v1);
       }
@@ -243,7 +253,8 @@ pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttn
     }
     __syncwarp();   // P of this warp is complete in its buffer
 
-    // ---- Y^T[64 channels x 8 rows] += X_w^T[64 channels x 64 tokens] P[64 tokens x 8 rows] ----
+    // ---- (d) Y^T[64 channels x 8 rows] += X_w^T[64 channels x 64 tokens] P[64 tokens x 8 rows] ----
+    const uint32_t slab = smem_u32(smem + ((i % PA_STAGES) * NW + warp) * PA_SLAB);
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
       // B = P: b0 = P[tokens 16kt + 2q, +1][row g], b1 = tokens + 8
@@ -262,12 +273,15 @@ pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttn
       }
     }
 
-    // ---- this warp is done with its slab (and its P buffer): refill the slab with tile i + STAGES ----
+    // ---- (e) this warp is done with the slab of tile i (and its P buffer): refill it with tile i + STAGES ----
     __syncwarp();
     if (lane == 0 && i + PA_STAGES < n_tiles) {
       fence_proxy_async_smem();
       issue(i + PA_STAGES);
     }
+    // ---- (f) publish the next tile's partial scores ----
+    if (i + 1 < n_tiles) store_partials(s_next);
+    __syncthreads();   // partials of tile i + 1 complete; every warp has read the totals of tile i
   }
 
   // y[seq, row, 64 warp + 16 ct + g (+8)] for rows 2q, 2q + 1
@@ -289,7 +303,7 @@ pooled_attention_kernel(const __grid_constant__ CUtensorMap tm_x, const PoolAttn
 
 template <int NW>
 static int launch_pooled(cudaStream_t st, const CUtensorMap& tm, const PoolAttnParams& p) {
-  const int smem = PA_STAGES * NW * PA_SLAB + NW * PA_TILE * 8 * static_cast<int>(sizeof(float)) +
+  const int smem = PA_STAGES * NW * PA_SLAB + (NW + 1) * PA_TILE * 8 * static_cast<int>(sizeof(float)) +
                    NW * 8 * PA_P_STRIDE * 2 + PA_STAGES * NW * 8 + 1024;
   auto kern = pooled_attention_kernel<NW>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
