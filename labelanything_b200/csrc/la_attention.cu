@@ -29,6 +29,7 @@
 //     so the softmax threads see scores that already contain it -- no per-element bias arithmetic, no 64-register
 //     rel_w row (the MUFU/issue-bound softmax loop is the limiter of this kernel, the tensor pipe has slack).
 #include "la_common.cuh"
+#include "la_attn_math.cuh"
 #include <type_traits>
 #include <cuda_fp16.h>
 
@@ -149,114 +150,6 @@ struct AttSmem {
   static constexpr int TOTAL = OFF_BAR + 512 + 1024;
   static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 };
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-// named barriers 1..15 (0 is __syncthreads): `count` threads in total, bar_sync-ers and bar_arrive-rs together
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  __half2 v = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// sm_100 packed-pair / three-input forms: half the issue slots of the scalar instructions (FMNMX3, FFMA2, FADD2)
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-// (d0, d1) = (a0, a1) * (b, b) + (c, c)
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
-  asm("{\n\t"
-      ".reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\t"
-      "mov.b64 rb, {%4, %4};\n\t"
-      "mov.b64 rc, {%5, %5};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t"
-      "}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b), "f"(c));
-}
-// 2^a for two arguments on the FMA pipe instead of the MUFU: a = n + f, n = round(a), |f| <= 1/2 (magic-number rounding),
-// 2^f by a degree-3 minimax polynomial (relative error 7.5e-5 -- far below the bf16 rounding of P), 2^n by adding
-// n to the exponent field.  MUFU.EX2 issues at a quarter of the FMA rate, and the exponentials are what bounds the
-// softmax warps at head_dim 64, so a fraction of every score row takes this path (the FlashAttention-4 trick).
-// Arguments are clamped at -126 (result ~1e-38 instead of 0 for masked keys); the caller guarantees a <= 8.
-__device__ __forceinline__ void exp2_poly_x2(float& a0, float& a1) {
-  const float x0 = fmaxf(a0, -126.0f), x1 = fmaxf(a1, -126.0f);
-  uint32_t t0, t1, p0, p1;
-  asm("{\n\t"
-      ".reg .b64 x, t, r, f, p, c;\n\t"
-      "mov.b64 x, {%4, %5};\n\t"
-      "mov.b64 c, {%6, %6};\n\t"
-      "add.rn.f32x2 t, x, c;\n\t"          // t = x + 1.5 * 2^23: round(x) in the low mantissa bits
-      "mov.b64 c, {%7, %7};\n\t"
-      "add.rn.f32x2 r, t, c;\n\t"          // r = round(x)
-      "mov.b64 c, {%8, %8};\n\t"
-      "fma.rn.f32x2 f, r, c, x;\n\t"       // f = x - r
-      "mov.b64 p, {%9, %9};\n\t"
-      "mov.b64 c, {%10, %10};\n\t"
-      "fma.rn.f32x2 p, p, f, c;\n\t"
-      "mov.b64 c, {%11, %11};\n\t"
-      "fma.rn.f32x2 p, p, f, c;\n\t"
-      "mov.b64 c, {%12, %12};\n\t"
-      "fma.rn.f32x2 p, p, f, c;\n\t"
-      "mov.b64 {%0, %1}, t;\n\t"
-      "mov.b64 {%2, %3}, p;\n\t"
-      "}"
-      : "=r"(t0), "=r"(t1), "=r"(p0), "=r"(p1)
-      : "f"(x0), "f"(x1), "f"(12582912.0f), "f"(-12582912.0f), "f"(-1.0f), "f"(0.0551716685f), "f"(0.2426111251f),
-        "f"(0.6932609677f), "f"(0.9999280572f));
-  a0 = __uint_as_float(p0 + (t0 << 23));
-  a1 = __uint_as_float(p1 + (t1 << 23));
-}
-// (d0, d1) = (a0, a1) * (b, b) + (c0, c1)
-__device__ __forceinline__ void ffma2v(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
-  asm("{\n\t"
-      ".reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\t"
-      "mov.b64 rb, {%4, %4};\n\t"
-      "mov.b64 rc, {%5, %6};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t"
-      "}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
-}
-// (d0, d1) = (a0, a1) + (b, b)
-__device__ __forceinline__ void fadd2s(float& d0, float& d1, float a0, float a1, float b) {
-  asm("{\n\t"
-      ".reg .b64 ra, rb, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\t"
-      "mov.b64 rb, {%4, %4};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t"
-      "}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b));
-}
-// (d0, d1) += (a0, a1)
-__device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float a1) {
-  asm("{\n\t"
-      ".reg .b64 ra, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\t"
-      "mov.b64 rd, {%0, %1};\n\t"
-      "add.rn.f32x2 rd, rd, ra;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t"
-      "}"
-      : "+f"(d0), "+f"(d1)
-      : "f"(a0), "f"(a1));
-}
 
 template <int KV_TILE, int BIAS, bool TF16 = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -1088,12 +981,35 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
                             nwin, img_hw);
 }
 
+// second-generation window kernel (la_attention_win.cu): one N = 208 score accumulator per Q tile
+int la_attention_window_v2(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
+                           int k_off, int v_off, long long rows_total, int n_seq, int n_heads, float scale,
+                           const void* rel_table, int rel_pad, void* out, long long ld_out, int out_mode, int nwin,
+                           int img_hw);
+#ifndef LA_WINDOW_V1
+#define LA_WINDOW_V1 0      // 1: the first-generation 112-key-tile mode of attention_fwd_kernel (experiment builds)
+#endif
+
 extern "C" int la_attention_window_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv,
                                         long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq,
                                         int n_heads, float scale, const void* rel_table, int rel_pad, void* out,
                                         long long ld_out, int out_mode, int nwin, int img_hw) {
   using namespace la;
   LA_CHECK_ARG(rel_table != nullptr, "la_attention_window_bf16: rel_table is required");
+  if (!LA_WINDOW_V1) {
+    LA_CHECK_ARG(q && kv && out && n_seq > 0 && n_heads > 0 && scale > 0.0f, "la_attention_window_bf16: bad arguments");
+    LA_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+                 "la_attention_window_bf16: strides/offsets must be multiples of 8 elements");
+    LA_CHECK_ARG(rows_total >= static_cast<long long>(n_seq) * 196 && rows_total < (1ll << 31),
+                 "la_attention_window_bf16: rows_total out of range");
+    LA_CHECK_ARG(rel_pad == 32 && (reinterpret_cast<uintptr_t>(rel_table) & 15) == 0,
+                 "la_attention_window_bf16: rel_table is the 16-byte aligned [64][64] operand with rel_pad 32");
+    LA_CHECK_ARG(out_mode == 0 || (nwin > 0 && img_hw > 0 && n_seq % (nwin * nwin) == 0),
+                 "la_attention_window_bf16: bad window-unpartition parameters");
+    LA_CHECK_ARG(static_cast<long long>(n_seq) * n_heads < (1ll << 31), "la_attention_window_bf16: too many work items");
+    return la_attention_window_v2(stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total, n_seq, n_heads, scale,
+                                  rel_table, rel_pad, out, ld_out, out_mode, nwin, img_hw);
+  }
   return attention_dispatch("la_attention_window_bf16", stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total,
                             n_seq, 196, n_heads, scale, nullptr, nullptr, LA_DTYPE_F32, 0, rel_table, rel_pad, 14, out, ld_out,
                             out_mode, nwin, img_hw);

@@ -1,0 +1,420 @@
+// labelanything_b200 — 14x14-window attention of the SAM ViT blocks, second generation (sm_100a).
+//
+// Replaces label_anything/models/image_encoder.py:239-255 (Attention.forward), 258-304 (window partition /
+// unpartition, folded into the output row mapping) and 319-376 (decomposed rel-pos bias, formed in-kernel) for the
+// windowed blocks: 196 queries x 196 keys x head_dim 64 per (window, head) item.
+//
+// The first-generation window mode (la_attention.cu, 112-key tiles) walks every item through a chain of four tensor-
+// pipe round trips (T -> S0 -> [P0 -> PV0, S1] -> [P1 -> PV1] -> O), ~9.6 K cycles per item even with no exponential at
+// all against an MUFU floor of 3.6 K (profiles/r02_exp_attention.txt).  Here ALL 196 keys of a Q tile are one score
+// accumulator (one M128 x N208 product per Q tile, 208 = 196 rounded up to the MMA's N granularity), so an item is
+//     [T, S] -> softmax over the whole key row -> P -> ONE PV (K = 208) -> O
+// i.e. two round trips, no running maximum and no O rescale:
+//   * TMEM (512 columns): S_A [0, 208), S_B [208, 416), T [416, 480) shared by the two Q tiles in turn (A(i), B(i),
+//     A(i+1), ...).  P (bf16) overlays columns [0, 104) of its score region, O columns [104, 168) -- free once the
+//     softmax has consumed the scores, and PV is only issued after the whole P row is delivered.
+//   * softmax: one thread per query row, two passes over its 196 scores in 28-column chunks (two key-grid rows each),
+//     the next chunk's TMEM load in flight while the current one is processed: pass 1 takes the row maximum of
+//     scale * s + rel_w + rel_h, pass 2 forms P = exp2(. - max) -> bf16 -> TMEM.  The decomposed rel-pos products
+//     T = Q x rel^T come from one extra MMA per Q tile; every thread parks its T row (fp16, 128 B) in its own -- by
+//     then consumed -- Q row in shared memory and reads the 2 x 14 entries at its (qh, qw) shift back.
+//   * loads: Q (2 x 128 rows), K and V (208 rows each: the 12 rows past the window are the next window's, finite,
+//     and are masked / multiplied by P = 0) through a 2-stage ring.
+//   warp 0: TMA producer; warps 1 / 3: MMA issuers of Q tile A / B; warp 2: TMEM allocation;
+//   warps 4-7 / 8-11: softmax + epilogue of Q tile A / B.
+#include "la_common.cuh"
+#include "la_attn_math.cuh"
+
+namespace la {
+
+constexpr int WA_THREADS = 384;
+constexpr int WA_KEYS = 196, WA_N = 208, WA_GW = 14;
+constexpr int WA_Q_BYTES = 2 * 128 * 128;         // two Q tiles
+constexpr int WA_KV_BYTES = WA_N * 128;           // one K or V tile (208 rows)
+constexpr int WA_STAGE = WA_Q_BYTES + 2 * WA_KV_BYTES;
+constexpr int WA_OFF_REL = 2 * WA_STAGE;
+constexpr int WA_OFF_BAR = WA_OFF_REL + 8192;
+constexpr int WA_SMEM = WA_OFF_BAR + 512 + 1024;
+constexpr int WA_SOFTMAX_REGS = 208, WA_CONTROL_REGS = 88;
+static_assert(256 * WA_SOFTMAX_REGS + 128 * WA_CONTROL_REGS <= WA_THREADS * 168, "setmaxnreg budget");
+static_assert(WA_SMEM <= 232448, "shared memory budget");
+// share of the exponentials on the FMA pipe: WA_POLY_NUM of every 7 score pairs
+#ifndef WA_POLY_NUM
+#define WA_POLY_NUM 2
+#endif
+
+struct WinParams {
+  int n_seq, n_heads;
+  int q_off, k_off, v_off;
+  float scale_log2;
+  int rel_pad;
+  __nv_bfloat16* out;
+  long long ld_out;
+  int out_mode, nwin, img_hw;
+};
+
+// 28 consecutive TMEM columns of this thread's lane -> registers (x16 + x8 + x4)
+__device__ __forceinline__ void tmem_ld_28(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+               : "r"(taddr + 16) : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]) : "r"(taddr + 24) : "memory");
+}
+// 14 registers -> 14 consecutive TMEM columns (x8 + x4 + x2)
+__device__ __forceinline__ void tmem_st_14(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr + 8), "r"(r[8]), "r"(r[9]),
+               "r"(r[10]), "r"(r[11]) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr + 12), "r"(r[12]), "r"(r[13])
+               : "memory");
+}
+
+__global__ void __launch_bounds__(WA_THREADS, 1)
+window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                        const __grid_constant__ CUtensorMap tm_rel, const WinParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WA_OFF_BAR);
+  uint64_t* full = bars;              // [stage]  Q + K + V landed
+  uint64_t* stage_free = full + 2;    // [stage]  both PV products of the item completed (two commits)
+  uint64_t* bar_t = stage_free + 2;   // [tile]   T ready
+  uint64_t* bar_s = bar_t + 2;        // [tile]   S ready
+  uint64_t* bar_p = bar_s + 2;        // [tile]   P delivered (4 warps)
+  uint64_t* bar_o = bar_p + 2;        // [tile]   O ready
+  uint64_t* o_free = bar_o + 2;       // [tile]   O read by the epilogue (4 warps): the score region may be overwritten
+  uint64_t* t_done = o_free + 2;      // [tile]   T read by the prologue (4 warps): the T columns may be overwritten
+  uint64_t* rel_full = t_done + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rel_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.n_seq * p.n_heads;          // item = (window sequence, head), head fastest
+  const int n_my = (n_items > static_cast<int>(blockIdx.x))
+                       ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                       : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    tma_prefetch_desc(&tm_rel);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&stage_free[s], 2);
+      mbar_init(&bar_t[s], 1);
+      mbar_init(&bar_s[s], 1);
+      mbar_init(&bar_p[s], 4);
+      mbar_init(&bar_o[s], 1);
+      mbar_init(&o_free[s], 4);
+      mbar_init(&t_done[s], 4);
+    }
+    mbar_init(rel_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t TM_T = 416, TM_O_IN_S = 104;
+
+  if (warp < 4) {
+    setmaxnreg_dec<WA_CONTROL_REGS>();
+    if (warp == 0) {
+      // ------------------------------------ TMA producer ------------------------------------
+      if (lane == 0) {
+        mbar_arrive_expect_tx(rel_full, 8192);
+        tma_load_2d(smem + WA_OFF_REL, &tm_rel, rel_full, 0, 0);
+        for (int it = 0; it < n_my; ++it) {
+          const int w = blockIdx.x + it * gridDim.x;
+          const int head = w % p.n_heads, seq = w / p.n_heads;
+          const int row0 = seq * WA_KEYS;
+          const int st = it & 1;
+          mbar_wait(&stage_free[st], ((it >> 1) & 1) ^ 1);
+          uint8_t* base = smem + st * WA_STAGE;
+          mbar_arrive_expect_tx(&full[st], WA_STAGE);
+          tma_load_2d(base, &tm_q, &full[st], p.q_off + head * 64, row0);
+          tma_load_2d(base + 16384, &tm_q, &full[st], p.q_off + head * 64, row0 + 128);
+          tma_load_2d(base + WA_Q_BYTES, &tm_kv, &full[st], p.k_off + head * 64, row0);
+          tma_load_2d(base + WA_Q_BYTES + WA_KV_BYTES, &tm_kv, &full[st], p.v_off + head * 64, row0);
+        }
+      }
+    } else if (warp == 1 || warp == 3) {
+      // ------------------------------------ MMA issuers -------------------------------------
+      // Per item and Q tile x: T_x = Q_x rel^T and S_x = Q_x K^T as soon as the loads are there, the T columns have
+      // been released by the other tile's prologue and the previous item's O_x (which overlays S_x) has been read;
+      // then, when the softmax warps have delivered the whole P row,  O_x = P_x V  (K = 208).
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, WA_N, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);     // P from TMEM, V MN-major
+      const int x = warp == 1 ? 0 : 1;
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t lo_rel = desc_lo(smem_base + WA_OFF_REL);
+      const uint32_t tm_s = tm + x * WA_N;
+      for (int it = 0; it < n_my; ++it) {
+        const int st = it & 1;
+        const uint32_t lo_q = desc_lo(smem_base + st * WA_STAGE + x * 16384);
+        const uint32_t lo_k = desc_lo(smem_base + st * WA_STAGE + WA_Q_BYTES);
+        const uint32_t lo_v = desc_lo(smem_base + st * WA_STAGE + WA_Q_BYTES + WA_KV_BYTES);
+        mbar_wait(&full[st], (it >> 1) & 1);
+        if (it == 0) mbar_wait(rel_full, 0);
+        // T columns: users in the order A(0), B(0), A(1), B(1), ...
+        if (x == 0) {
+          if (it > 0) mbar_wait(&t_done[1], (it - 1) & 1);
+        } else {
+          mbar_wait(&t_done[0], it & 1);
+        }
+        if (it > 0) mbar_wait(&o_free[x], (it - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_ss_lo(tm + TM_T, lo_q + 2 * ks, lo_rel + 2 * ks, idesc_t, ks > 0);
+          umma_commit(&bar_t[x]);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_ss_lo(tm_s, lo_q + 2 * ks, lo_k + 2 * ks, idesc_s, ks > 0);
+          umma_commit(&bar_s[x]);
+        }
+        __syncwarp();
+        mbar_wait(&bar_p[x], it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < WA_N / 16; ++ks)
+            umma_ts_lo(tm_s + TM_O_IN_S, tm_s + ks * 8, lo_v + ks * (2048 >> 4), idesc_o, ks > 0);
+          umma_commit(&bar_o[x]);
+          umma_commit(&stage_free[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================== softmax warpgroups =====================================
+    setmaxnreg_inc<WA_SOFTMAX_REGS>();
+    const int x = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                 // row inside the Q tile
+    const int t = x * 128 + r;                         // token inside the window
+    const bool row_valid = t < WA_KEYS;
+    const int ty = t / WA_GW, tx = t - ty * WA_GW;
+    const int qh = row_valid ? ty : 0, qw = row_valid ? tx : 0;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + x * WA_N;
+    const uint32_t t_t = tmem_base + lane_addr + TM_T;
+    const float sl2 = p.scale_log2;
+    constexpr float LOG2E = 1.4426950408889634f;
+    // a whole warp without a valid row (rows 224..255 of tile B) only keeps the barriers moving
+    const bool warp_live = x * 128 + quarter * 32 < WA_KEYS;
+
+    for (int it = 0; it < n_my; ++it) {
+      const int w = blockIdx.x + it * gridDim.x;
+      const int head = w % p.n_heads, seq = w / p.n_heads;
+      const int st = it & 1;
+      const uint32_t par = it & 1;
+
+      // ---- rel-pos prologue: T row -> fp16 -> own (consumed) Q row in shared memory -> the 2 x 14 shifted entries ----
+      mbar_wait(&bar_t[x], par);
+      mbar_wait(&bar_s[x], par);          // S complete as well: no MMA reads this tile's Q rows any more
+      tc_fence_after();
+      float rw2[WA_GW], rh2[WA_GW];
+      {
+        uint32_t tb[64];
+        tmem_ld_x32(t_t, tb);
+        tmem_ld_x32(t_t + 32, tb + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_done[x]);
+        uint8_t* qrow = smem + st * WA_STAGE + x * 16384 + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 v;
+          v.x = pack_f16(__uint_as_float(tb[8 * c + 0]), __uint_as_float(tb[8 * c + 1]));
+          v.y = pack_f16(__uint_as_float(tb[8 * c + 2]), __uint_as_float(tb[8 * c + 3]));
+          v.z = pack_f16(__uint_as_float(tb[8 * c + 4]), __uint_as_float(tb[8 * c + 5]));
+          v.w = pack_f16(__uint_as_float(tb[8 * c + 6]), __uint_as_float(tb[8 * c + 7]));
+          *reinterpret_cast<uint4*>(qrow + ((c ^ (r & 7)) << 4)) = v;
+        }
+        __syncwarp();   // (own row only: this is the compiler-level ordering of the stores above and the loads below)
+        // bias of key (kh, kw) for a query at (qh, qw): T[13 - qh + kh] + T[rel_pad + 13 - qw + kw]
+        auto entry = [&](int e) -> float {
+          return __half2float(*reinterpret_cast<const __half*>(qrow + (((e >> 3) ^ (r & 7)) << 4) + (e & 7) * 2));
+        };
+#pragma unroll
+        for (int i = 0; i < WA_GW; ++i) {
+          rh2[i] = entry(WA_GW - 1 - qh + i) * LOG2E;
+          rw2[i] = entry(p.rel_pad + WA_GW - 1 - qw + i) * LOG2E;
+        }
+        fence_proxy_async_smem();   // these generic accesses precede the next TMA fill of the stage
+      }
+
+      float inv_l = 0.f;
+      if (warp_live) {
+        // ---- pass 1: row maximum of  scale * s + rel_w + rel_h  over the 196 keys, 28 columns (2 key rows) at a time ----
+        uint32_t ca[28], cb[28];
+        float mx = -INFINITY;
+        tmem_ld_28(t_s, ca);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+          uint32_t* cur = (c & 1) ? cb : ca;
+          uint32_t* nxt = (c & 1) ? ca : cb;
+          if (c + 1 < 7) tmem_ld_28(t_s + 28 * (c + 1), nxt);
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < WA_GW; i += 2) {
+              float a0, a1;
+              ffma2v(a0, a1, __uint_as_float(cur[gi * WA_GW + i]), __uint_as_float(cur[gi * WA_GW + i + 1]), sl2, rw2[i],
+                     rw2[i + 1]);
+              if (i & 2) m1 = max3(m1, a0, a1);
+              else m0 = max3(m0, a0, a1);
+            }
+            mx = fmaxf(mx, fmaxf(m0, m1) + rh2[2 * c + gi]);
+          }
+          if (c + 1 < 7) tmem_ld_wait();
+        }
+        // ---- pass 2: P = exp2(. - max) -> bf16 -> TMEM over the consumed score columns; row sum in fp32 ----
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        tmem_ld_28(t_s, ca);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+          uint32_t* cur = (c & 1) ? cb : ca;
+          uint32_t* nxt = (c & 1) ? ca : cb;
+          if (c + 1 < 7) tmem_ld_28(t_s + 28 * (c + 1), nxt);
+          uint32_t pk[14];
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            const float off = rh2[2 * c + gi] - mx;
+#pragma unroll
+            for (int i = 0; i < WA_GW; i += 2) {
+              float a0, a1;
+              ffma2v(a0, a1, __uint_as_float(cur[gi * WA_GW + i]), __uint_as_float(cur[gi * WA_GW + i + 1]), sl2, rw2[i],
+                     rw2[i + 1]);
+              fadd2s(a0, a1, a0, a1, off);
+              float e0, e1;
+              if ((i >> 1) < WA_POLY_NUM) {
+                e0 = a0;
+                e1 = a1;
+                exp2_poly_x2(e0, e1);
+              } else {
+                e0 = ex2_approx(a0);
+                e1 = ex2_approx(a1);
+              }
+              if (i & 2) fadd2_acc(l2, l3, e0, e1);
+              else fadd2_acc(l0, l1, e0, e1);
+              pk[(gi * WA_GW + i) >> 1] = pack_bf16(e0, e1);
+            }
+          }
+          if (c + 1 < 7) tmem_ld_wait();        // the next chunk is in registers before its columns are overwritten below
+          tmem_st_14(t_s + 14 * c, pk);          // columns [14c, 14c+14) <= 28c: already consumed
+        }
+        inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
+      }
+      {
+        // keys 196..207 (the next window's rows) get P = 0: columns 98..103.  (Rows without a query -- a whole warp of
+        // tile B -- keep whatever their lanes hold: rows are independent in the PV product and theirs are never stored.)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t_s + 98), "r"(0u), "r"(0u),
+                     "r"(0u), "r"(0u) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t_s + 102), "r"(0u), "r"(0u) : "memory");
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[x]);
+
+      // ---- epilogue: O / l -> bf16 -> global (window un-partition folded into the row mapping) ----
+      mbar_wait(&bar_o[x], par);
+      tc_fence_after();
+      uint32_t ov[64];
+      tmem_ld_x32(t_s + TM_O_IN_S, ov);
+      tmem_ld_x32(t_s + TM_O_IN_S + 32, ov + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[x]);
+      long long out_row = -1;
+      if (row_valid) {
+        if (p.out_mode == 0) {
+          out_row = static_cast<long long>(seq) * WA_KEYS + t;
+        } else {
+          const int per_img = p.nwin * p.nwin;
+          const int img = seq / per_img, wi = seq - img * per_img;
+          const int wy = wi / p.nwin;
+          const int y = wy * WA_GW + ty;
+          const int xx = (wi - wy * p.nwin) * WA_GW + tx;
+          if (y < p.img_hw && xx < p.img_hw) out_row = (static_cast<long long>(img) * p.img_hw + y) * p.img_hw + xx;
+        }
+      }
+      if (out_row >= 0) {
+        __nv_bfloat16* dst = p.out + out_row * p.ld_out + head * 64;
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq) {
+          uint4 pk4;
+          pk4.x = pack_bf16(__uint_as_float(ov[gq * 8 + 0]) * inv_l, __uint_as_float(ov[gq * 8 + 1]) * inv_l);
+          pk4.y = pack_bf16(__uint_as_float(ov[gq * 8 + 2]) * inv_l, __uint_as_float(ov[gq * 8 + 3]) * inv_l);
+          pk4.z = pack_bf16(__uint_as_float(ov[gq * 8 + 4]) * inv_l, __uint_as_float(ov[gq * 8 + 5]) * inv_l);
+          pk4.w = pack_bf16(__uint_as_float(ov[gq * 8 + 6]) * inv_l, __uint_as_float(ov[gq * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + gq * 8) = pk4;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace la
+
+// Second-generation entry behind la_attention_window_bf16 (same contract, see the public header).
+int la_attention_window_v2(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
+                           int k_off, int v_off, long long rows_total, int n_seq, int n_heads, float scale,
+                           const void* rel_table, int rel_pad, void* out, long long ld_out, int out_mode, int nwin,
+                           int img_hw) {
+  using namespace la;
+  CUtensorMap tm_q, tm_kv, tm_rel;
+  int rc = make_tensor_map_2d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_q, (uint64_t)rows_total,
+                              (uint64_t)ld_q * 2, 64, 128, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_kv, kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_kv, (uint64_t)rows_total,
+                          (uint64_t)ld_kv * 2, 64, WA_N, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_rel, rel_table, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64, 64, 128, 64, 64, Swizzle::B128);
+  if (rc) return rc;
+  WinParams p;
+  p.n_seq = n_seq;
+  p.n_heads = n_heads;
+  p.q_off = q_off;
+  p.k_off = k_off;
+  p.v_off = v_off;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.rel_pad = rel_pad;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ld_out = ld_out;
+  p.out_mode = out_mode;
+  p.nwin = nwin;
+  p.img_hw = img_hw;
+  LA_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+  const long long items = static_cast<long long>(n_seq) * n_heads;
+  const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
+  window_attention_kernel<<<grid, WA_THREADS, WA_SMEM, static_cast<cudaStream_t>(stream)>>>(tm_q, tm_kv, tm_rel, p);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
