@@ -35,8 +35,20 @@
 
 namespace la {
 
-constexpr int ATT_THREADS = 384;
 constexpr int ATT_D = 64;
+// Threads per query row of the 64-key modes (template parameter SPLIT of the kernel): 1 = one softmax thread per row
+// (8 softmax warps, 2 per scheduler), 2 = the 64 score columns of a tile are split between two threads of different
+// warps (16 softmax warps, 4 per scheduler).  The softmax warps bound the 64x64 mode (in-order issue at IPC ~0.55 with
+// two warps per scheduler, profiles/r02_ncu_attention_global_v1.txt); twice the warps hide each other's MUFU / TMEM /
+// barrier latencies.  See the SPLIT == 2 softmax block for how the two threads of a row agree on the running maximum.
+#ifndef ATT_SPLIT
+#define ATT_SPLIT 1
+#endif
+// SPLIT == 2, 64x64 rel-pos mode: 1 = rel_w through the extra score MMAs (as with SPLIT == 1), 0 = added by the threads
+#ifndef ATT_SPLIT_FOLD
+#define ATT_SPLIT_FOLD 0
+#endif
+constexpr int att_threads(int split) { return 128 + 256 * split; }
 // ATT_POLY_NUM of every ATT_POLY_DEN pairs of scores of the 64-key modes take the polynomial exp2 (evenly spread)
 #ifndef ATT_POLY_NUM
 #define ATT_POLY_NUM 1
@@ -76,16 +88,22 @@ constexpr int ATT_D = 64;
 #ifndef ATT_PINGPONG
 #define ATT_PINGPONG 2
 #endif
+// 64-key modes: the tile maximum is taken on every ATT_MAX_EVERY-th key tile (see pass 1 of the softmax warps)
+#ifndef ATT_MAX_EVERY
+#define ATT_MAX_EVERY 1
+#endif
 constexpr int ATT_STG_STRIDE = 272;     // bytes per row of the table staging area (68 floats: conflict-free STS.128)
 // setmaxnreg budget: 256 softmax threads + 128 control threads share 384 x 168 = 64512 registers (launch allocation).
 // 64-key tiles keep 64 score registers per thread and leave the control warps 104; the 112-key window tiles need
 // everything the softmax threads can get.
-template <int KV_TILE>
+template <int KV_TILE, int SPLIT = 1>
 struct AttRegs {
-  static constexpr int SOFTMAX = KV_TILE <= 64 ? 216 : 216;
-  static constexpr int CONTROL = KV_TILE <= 64 ? 72 : 72;
-  static_assert(256 * SOFTMAX + 128 * CONTROL <= ATT_THREADS * 168,
-                "setmaxnreg.inc can only hand out what the CTA was launched with (168 registers x 384 threads)");
+  // launch allocation: 168 registers x 384 threads, 96 x 640 threads (SPLIT == 2: 32 score registers per thread)
+  static constexpr int LAUNCH = SPLIT == 2 ? 96 : 168;
+  static constexpr int SOFTMAX = SPLIT == 2 ? 104 : 216;
+  static constexpr int CONTROL = SPLIT == 2 ? 56 : 72;
+  static_assert(256 * SPLIT * SOFTMAX + 128 * CONTROL <= att_threads(SPLIT) * LAUNCH,
+                "setmaxnreg.inc can only hand out what the CTA was launched with");
 };
 
 enum AttBias : int { ATT_BIAS_NONE = 0, ATT_BIAS_GLOBAL64 = 1, ATT_BIAS_WINDOW14 = 2 };
@@ -127,9 +145,9 @@ __device__ __forceinline__ void att_trace([[maybe_unused]] const AttParams& p, [
 #define LA_ATT_DEBUG_FLAGS 0
 #endif
 
-template <int KV_TILE, int BIAS>
+template <int KV_TILE, int BIAS, int SPLIT = 1>
 struct AttSmem {
-  static constexpr int STAGES = KV_TILE <= 64 ? (BIAS == 1 ? 5 : 6) : 3;   // K / V ring depth
+  static constexpr int STAGES = KV_TILE <= 64 ? (BIAS == 1 ? (SPLIT == 2 ? 4 : 5) : 6) : 3;   // K / V ring depth
   static constexpr int Q_BYTES = 2 * 128 * 128;             // two Q tiles, 128 rows x 128 B
   static constexpr int KV_BYTES = KV_TILE * 128;            // one K or V tile
   static constexpr int KV_SLOT = ((KV_BYTES + 1023) / 1024) * 1024;
@@ -146,16 +164,23 @@ struct AttSmem {
   static constexpr int REL_BYTES = BIAS == 2 ? 8192 : 0;
   static constexpr int OFF_STG = OFF_REL + REL_BYTES;
   static constexpr int STG_BYTES = BIAS == 2 ? 256 * ATT_STG_STRIDE : 0;
-  static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
+  // SPLIT == 2: per-row half-tile maxima [4 tile slots][Q tile][half][128 rows] and row-sum exchange [Q tile][half][128]
+  static constexpr int OFF_HM = OFF_STG + STG_BYTES;
+  static constexpr int HM_BYTES = SPLIT == 2 ? 4 * 2 * 2 * 128 * 4 : 0;
+  static constexpr int OFF_LX = OFF_HM + HM_BYTES;
+  static constexpr int LX_BYTES = SPLIT == 2 ? 2 * 2 * 128 * 4 : 0;
+  static constexpr int OFF_BAR = OFF_LX + LX_BYTES;
   static constexpr int TOTAL = OFF_BAR + 512 + 1024;
   static_assert(TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
-template <int KV_TILE, int BIAS, bool TF16 = false>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int KV_TILE, int BIAS, bool TF16 = false, int SPLIT = 1>
+__global__ void __launch_bounds__(att_threads(SPLIT), 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_rel, const AttParams p) {
-  using S = AttSmem<KV_TILE, BIAS>;
+  using S = AttSmem<KV_TILE, BIAS, SPLIT>;
+  static_assert(SPLIT == 1 || (SPLIT == 2 && KV_TILE == 64 && ATT_TS_OPERANDS),
+                "two threads per row: 64-key tiles with two score buffers per Q tile");
   constexpr int ST = S::STAGES;
   // bias(q, k) = rel_w[q][k % GW] + rel_h[q][k / GW]: a KV tile holds NG key-grid rows of GW keys
   constexpr int GW = BIAS == ATT_BIAS_GLOBAL64 ? 64 : (BIAS == ATT_BIAS_WINDOW14 ? 14 : KV_TILE);
@@ -170,7 +195,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   // both chains queued) off the softmax warps' critical path; two buffers leave room for Q / A_w in tensor memory.
   constexpr uint32_t NBUF = DB ? (TSQ ? 2 : 3) : 1;
   // 64x64 rel-pos mode: rel_w enters the scores through an extra MMA (see the header comment)
-  constexpr bool FOLD_W = BIAS == ATT_BIAS_GLOBAL64;
+  // SPLIT == 2 (ATT_SPLIT_FOLD 0): the softmax threads add rel_w themselves -- with four softmax warps per scheduler they
+  // have the issue slots, and the tensor pipe (12 instead of 8 MMAs per Q tile and key tile) is what is short
+  constexpr bool FOLD_W = BIAS == ATT_BIAS_GLOBAL64 && (SPLIT == 1 || ATT_SPLIT_FOLD);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -222,10 +249,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     for (int x = 0; x < 2; ++x) {
       for (int b = 0; b < 3; ++b) {
         mbar_init(&bar_s[3 * x + b], 1);
-        mbar_init(&bar_p[3 * x + b], 4);
+        mbar_init(&bar_p[3 * x + b], 4 * SPLIT);
         mbar_init(&bar_pv[3 * x + b], 1);
       }
-      mbar_init(&o_empty[x], 4);
+      mbar_init(&o_empty[x], 4 * SPLIT);
       mbar_init(&aw_full[x], 1);
       mbar_init(&aw_full[2 + x], 1);
       mbar_init(&bar_t[x], 1);
@@ -266,7 +293,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
   if (warp < 4) {
     // ===================================== control warpgroup =====================================
-    setmaxnreg_dec<AttRegs<KV_TILE>::CONTROL>();
+    setmaxnreg_dec<AttRegs<KV_TILE, SPLIT>::CONTROL>();
     if (warp == 0) {
       // ------------------------------------ TMA producer ------------------------------------
       if (lane == 0) {
@@ -430,8 +457,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           const uint32_t a_p = tm_s + buf * KV_TILE;
           const uint32_t bv = lo_v + vslot * (S::KV_SLOT >> 4);
 #pragma unroll
-          for (int ks = 0; ks < KV_TILE / 16; ++ks)
-            umma_ts_lo(tm_o, a_p + ks * 8, bv + ks * (2048 >> 4), idesc_o, pc.j > 0 || ks > 0);
+          for (int ks = 0; ks < KV_TILE / 16; ++ks) {
+            // SPLIT == 2: each half of the row delivers its 32 keys of P over the first 16 of its OWN 32 score columns
+            const uint32_t pa = SPLIT == 2 ? a_p + (ks >> 1) * 32 + (ks & 1) * 8 : a_p + ks * 8;
+            umma_ts_lo(tm_o, pa, bv + ks * (2048 >> 4), idesc_o, pc.j > 0 || ks > 0);
+          }
           umma_commit(&bar_pv[3 * x + buf]);
           umma_commit(&empty_v[vslot]);
           if (more) mma_s(sc);
@@ -503,9 +533,279 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
       }
     }
+  } else if constexpr (SPLIT == 2) {
+    // ============================ softmax warps, two threads per query row ============================
+    // Warp 4 + 8 * half + 4 * x + quarter owns rows [32 * quarter, +32) of Q tile x (TMEM lane quarter = warp % 4)
+    // and score columns [32 * half, +32) of every key tile; it writes its 32 keys of P over the first 16 of its own
+    // columns and accumulates the row sum of its half.  The two threads of a row must scale a tile by the SAME
+    // running maximum m (they feed one PV product), but m need not be the exact maximum: P is bf16 (8 exponent
+    // bits) and O / l are fp32, so any m within ~2^100 of the true one costs no precision.  Protocol:
+    //   * every tile each thread publishes the maximum of its half (log2 units, rel_h included) in shared memory,
+    //     slot g % 4, BEFORE it arrives on the tile's P barrier;
+    //   * tile 0 of an item: exact -- the pair meets at a named barrier and takes the larger half maximum;
+    //   * tile j >= 2: candidate = larger half maximum of tile j - 2.  It is visible without any extra
+    //     synchronisation: S(j) is only issued once all eight warps have delivered P(j - 2).  m moves to the
+    //     candidate when it exceeds m by more than 2^8 (lazy rescale, as before); both threads see the same two
+    //     numbers and take the same decision.
+    // The half maximum of a tile is off the critical path (nothing in the tile depends on it), so the maximum pass,
+    // the exponentials and the P stores of the four warps of a scheduler interleave freely.
+    setmaxnreg_inc<AttRegs<KV_TILE, SPLIT>::SOFTMAX>();
+    const int sw = warp - 4;
+    const int quarter = warp & 3;
+    const int x = (sw >> 2) & 1;
+    const int half = sw >> 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s0 = tmem_base + lane_addr + TM_S + x * S_SPAN + half * 32;   // my columns of score buffer 0
+    const uint32_t t_o = tmem_base + lane_addr + TM_O + x * 64 + half * 32;        // my 32 channels of O
+    const int pair_bar = 1 + x * 4 + quarter;                                       // named barrier of the row pair
+    float* const hm = reinterpret_cast<float*>(smem + S::OFF_HM);                   // [slot][x][half][row]
+    float* const lx = reinterpret_cast<float*>(smem + S::OFF_LX);                   // [x][half][row]
+    auto hm_at = [&](uint32_t slot, int hf) -> float* { return hm + (((slot * 2 + x) * 2 + hf) * 128 + r); };
+    const float sl2 = p.scale_log2;
+    constexpr float LOG2E = 1.4426950408889634f;
+    using BT = typename std::conditional<TF16, __half, float>::type;
+    auto tab_f32 = [](BT v) -> float {
+      if constexpr (TF16) return __half2float(v); else return v;
+    };
+    auto bh_row_of = [&](int w2) -> const BT* {
+      const int qpair2 = w2 % n_qp;
+      const int head2 = (w2 / n_qp) % p.n_heads;
+      const long long row0 = static_cast<long long>(w2 / (n_qp * p.n_heads)) * p.seq_len;
+      const int t2 = qpair2 * 256 + x * 128 + r;
+      const int tt = t2 < p.seq_len ? t2 : 0;
+      return static_cast<const BT*>(p.bias_h) + ((row0 + tt) * p.n_heads + head2) * p.ldb + (GW - 1 - tt / GW);
+    };
+    constexpr bool REL64 = BIAS == ATT_BIAS_GLOBAL64;
+    constexpr bool RWR = REL64 && !FOLD_W;   // rel_w of my 32 key columns in registers
+    const BT* bh_row_pre = nullptr;
+    BT rh_pre = BT(0.0f);
+    if constexpr (REL64) {
+      if (static_cast<int>(blockIdx.x) < n_items) {
+        bh_row_pre = bh_row_of(blockIdx.x);
+        rh_pre = __ldg(bh_row_pre);
+      }
+    }
+    const bool tr = tr0 && quarter == 0 && half == 0;
+
+    int it = 0;
+    uint32_t g0 = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it, g0 += NT) {
+      const int qpair = w % n_qp;
+      const int head = (w / n_qp) % p.n_heads;
+      const int seq = w / (n_qp * p.n_heads);
+      const int t = qpair * 256 + x * 128 + r;
+      const bool row_valid = t < p.seq_len;
+      const BT* bh_row = bh_row_pre;
+      BT rh_next = rh_pre;
+      // rel_w[q, kw] of my columns kw = 32 * half + i (log2 units): entry (63 - qw + kw) of the query's table row
+      float rw[RWR ? 32 : 2];
+      if constexpr (RWR) {
+        const int tt = row_valid ? t : 0;
+#ifdef ATT_DIAG_RW0
+        const long long e = (63 - (tt & 63)) + half * 32;   // timing diagnostic (WRONG results): every row reads table row 0
+#else
+        const long long e = ((static_cast<long long>(seq) * p.seq_len + tt) * p.n_heads + head) * p.ldb + (63 - (tt & 63)) +
+                            half * 32;
+#endif
+        if constexpr (TF16) {
+          // the 32 entries start at a 2-byte aligned offset: fetch the aligned 32-bit words around them and funnel
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<const __half*>(p.bias_w) + (e & ~1ll));
+          const bool odd = (e & 1) != 0;
+          uint32_t wv[17];
+#pragma unroll
+          for (int i = 0; i < 17; ++i) wv[i] = __ldg(src + i);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t pr = odd ? __byte_perm(wv[i], wv[i + 1], 0x5432) : wv[i];
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pr));
+            rw[2 * i] = f.x * LOG2E;
+            rw[2 * i + 1] = f.y * LOG2E;
+          }
+        } else {
+          const float* src = static_cast<const float*>(p.bias_w) + e;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rw[i] = __ldg(src + i) * LOG2E;
+        }
+      }
+      float m_used = 0.0f;
+      float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
+
+#pragma unroll 1
+      for (int j = 0; j < NT; ++j) {
+        const uint32_t g = g0 + j;
+        const uint32_t buf = g % NBUF;
+        float rh2 = 0.0f;
+        if constexpr (REL64) {
+          rh2 = tab_f32(rh_next) * LOG2E;
+          if (j + 1 < NT) rh_next = __ldg(bh_row + j + 1);
+        }
+        att_trace(p, tr, 1 + x, g, 0);
+        mbar_wait(&bar_s[3 * x + buf], (g / NBUF) & 1);
+        tc_fence_after();
+        const uint32_t t_s = t_s0 + buf * KV_TILE;
+        // My 32 score columns travel in two chunks of 16 (one register set: with rel_w in registers a whole half row
+        // does not fit next to it, and a spilled rel_h prefetch stalls every tile for a full global-load latency).
+        // P of chunk c goes to columns [8c, 8c + 8) of my region: score columns consumed by then.
+        uint32_t sv[16];
+        auto load_chunk = [&](const int c) {
+          tmem_ld_x16(t_s + 16 * c, sv);
+          tmem_ld_wait();
+          if constexpr (BIAS == ATT_BIAS_NONE) {
+            const int valid = p.seq_len - j * KV_TILE - half * 32 - 16 * c;   // keys of this chunk that exist
+            if (valid < 16) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i >= valid) sv[i] = 0xff800000u;
+            }
+          }
+        };
+        att_trace(p, tr, 1 + x, g, 1);
+
+        // ---- the tile's m ----
+        float alpha = 1.0f;
+        bool need = false;
+        if (j == 0) {
+          // exact: one extra pass over the scores (once per item)
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            load_chunk(c);
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              if constexpr (RWR) {
+                float a0, a1;
+                ffma2v(a0, a1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), sl2, rw[16 * c + i], rw[16 * c + i + 1]);
+                if (i & 2) m1 = max3(m1, a0, a1);
+                else m0 = max3(m0, a0, a1);
+              } else {
+                if (i & 2) m1 = max3(m1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+                else m0 = max3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+              }
+            }
+          }
+          const float mine = RWR ? fmaxf(m0, m1) + rh2 : fmaf(fmaxf(m0, m1), sl2, rh2);
+          *hm_at(g & 3, half) = mine;
+          named_bar_sync(pair_bar, 64);
+          m_used = fmaxf(mine, *hm_at(g & 3, half ^ 1));
+        } else if (j >= 2) {
+          const float cand = fmaxf(*hm_at((g - 2) & 3, 0), *hm_at((g - 2) & 3, 1));
+          if (cand > m_used + 8.0f || ((LA_ATT_DEBUG_FLAGS & 1) && cand > m_used)) {
+            alpha = ex2_approx(m_used - cand);
+            m_used = cand;
+            need = true;
+          }
+        }
+        att_trace(p, tr, 1 + x, g, 2);
+        if (__any_sync(0xffffffffu, need)) {
+          // O must hold everything up to the previous tile before it is rescaled (my 32 channels)
+          mbar_wait(&bar_pv[3 * x + (g - 1) % NBUF], ((g - 1) / NBUF) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int hs = 0; hs < 2; ++hs) {
+            uint32_t ov[16];
+            tmem_ld_x16(t_o + 16 * hs, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x32b_x16(t_o + 16 * hs, ov);
+          }
+          l0 *= alpha;
+          l1 *= alpha;
+          l2 *= alpha;
+          l3 *= alpha;
+        }
+
+        // ---- P = exp2(s * scale + rel_h - m) -> bf16 -> TMEM; the half maximum of THIS tile for tile j + 2 ----
+        const float off = rh2 - m_used;
+        float x0 = -INFINITY, x1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          load_chunk(c);
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float a0, a1;
+            if constexpr (RWR) {
+              // a = s * scale + rel_w + (rel_h - m); the half maximum is taken on a (it differs from the logit by -m)
+              float c0f, c1f;
+              fadd2s(c0f, c1f, rw[16 * c + i], rw[16 * c + i + 1], off);
+              ffma2v(a0, a1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), sl2, c0f, c1f);
+              if (i & 2) x1 = max3(x1, a0, a1);
+              else x0 = max3(x0, a0, a1);
+            } else {
+              ffma2(a0, a1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), sl2, off);
+              if (i & 2) x1 = max3(x1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+              else x0 = max3(x0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+            }
+            float e0, e1;
+            if ((((16 * c + i) >> 1) * ATT_POLY_NUM) % ATT_POLY_DEN < ATT_POLY_NUM) {
+              e0 = a0;
+              e1 = a1;
+              exp2_poly_x2(e0, e1);
+            } else if (ATT_DIAG_NOEXP) {
+              e0 = a0;
+              e1 = a1;
+            } else {
+              e0 = ex2_approx(a0);
+              e1 = ex2_approx(a1);
+            }
+            if ((i & 2) == 0) fadd2_acc(l0, l1, e0, e1);
+            else fadd2_acc(l2, l3, e0, e1);
+            pk[i >> 1] = pack_bf16(e0, e1);
+          }
+          tmem_st_32x32b_x8(t_s + 8 * c, pk);
+        }
+        *hm_at(g & 3, half) = RWR ? fmaxf(x0, x1) + m_used : fmaf(fmaxf(x0, x1), sl2, rh2);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[3 * x + buf]);
+        att_trace(p, tr, 1 + x, g, 3);
+      }
+
+      if constexpr (REL64) {
+        if (w + static_cast<int>(gridDim.x) < n_items) {
+          bh_row_pre = bh_row_of(w + gridDim.x);
+          rh_pre = __ldg(bh_row_pre);
+        }
+      }
+
+      // ---- epilogue: the pair adds its row sums, each thread normalises and stores its 32 channels ----
+      const float l_mine = (l0 + l1) + (l2 + l3);
+      lx[(x * 2 + half) * 128 + r] = l_mine;
+      {
+        const uint32_t gl = g0 + NT - 1;   // last tile of the item
+        mbar_wait(&bar_pv[3 * x + gl % NBUF], (gl / NBUF) & 1);
+      }
+      tc_fence_after();
+      att_trace(p, tr, 3 + x, it, 0);
+      uint32_t ov[32];
+      tmem_ld_x32(t_o, ov);
+      named_bar_sync(pair_bar, 64);
+      const float inv_l = 1.0f / (l_mine + lx[(x * 2 + (half ^ 1)) * 128 + r]);
+      tmem_ld_wait();
+      // O is in registers: hand the accumulator back to the MMA warp before the global stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[x]);
+      if (row_valid) {
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(seq) * p.seq_len + t) * p.ld_out + head * ATT_D + half * 32;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          uint4 pk4;
+          pk4.x = pack_bf16(__uint_as_float(ov[gq * 8 + 0]) * inv_l, __uint_as_float(ov[gq * 8 + 1]) * inv_l);
+          pk4.y = pack_bf16(__uint_as_float(ov[gq * 8 + 2]) * inv_l, __uint_as_float(ov[gq * 8 + 3]) * inv_l);
+          pk4.z = pack_bf16(__uint_as_float(ov[gq * 8 + 4]) * inv_l, __uint_as_float(ov[gq * 8 + 5]) * inv_l);
+          pk4.w = pack_bf16(__uint_as_float(ov[gq * 8 + 6]) * inv_l, __uint_as_float(ov[gq * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + gq * 8) = pk4;
+        }
+      }
+      att_trace(p, tr, 3 + x, it, 1);
+    }
   } else {
     // ===================================== softmax warpgroups =====================================
-    setmaxnreg_inc<AttRegs<KV_TILE>::SOFTMAX>();
+    setmaxnreg_inc<AttRegs<KV_TILE, SPLIT>::SOFTMAX>();
     const int x = (warp - 4) >> 2;     // Q tile: 0 = A, 1 = B
     const int quarter = warp & 3;      // TMEM lane quarter
     const int r = quarter * 32 + lane;  // row inside the Q tile
@@ -692,15 +992,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         } else {
           // raw scores (rel_w already inside them in the 64x64 mode): max first, scale once (scale > 0)
           static_assert(WIN || KV_TILE % 8 == 0, "max tree works on groups of 8");
-          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          // The running maximum is only a scaling reference: P is bf16 (8 exponent bits) and O / l are fp32, so a
+          // stale m costs no precision as long as the scores stay within ~2^100 of it.  ATT_MAX_EVERY > 1 takes the
+          // tile maximum on every n-th tile only (always on tile 0).  Measured (profiles/r02_exp_attention.txt): no
+          // gain (756 / 765 TF with n = 4 / 8 against 777 with n = 1), so the product takes it on every tile.
+          if (j % ATT_MAX_EVERY == 0) {
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < KV_TILE; i += 8) {
-            m0 = max3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
-            m1 = max3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
-            m2 = max3(m2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
-            m3 = max3(m3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+            for (int i = 0; i < KV_TILE; i += 8) {
+              m0 = max3(m0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+              m1 = max3(m1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+              m2 = max3(m2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+              m3 = max3(m3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+            }
+            mx = fmaf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), sl2, rh2[0]);
+          } else {
+            mx = m_used;
           }
-          mx = fmaf(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)), sl2, rh2[0]);
         }
 
         att_trace(p, tr, tr_role, g, 2);
@@ -857,10 +1165,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
 }
 
-template <int KV_TILE, int BIAS, bool TF16 = false>
+template <int KV_TILE, int BIAS, bool TF16 = false, int SPLIT = 1>
 static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, const void* kv, long long ld_kv,
                             const AttParams& p, const void* rel = nullptr) {
-  using S = AttSmem<KV_TILE, BIAS>;
+  using S = AttSmem<KV_TILE, BIAS, SPLIT>;
   CUtensorMap tm_q, tm_kv, tm_rel;
   int rc = make_tensor_map_2d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_q, (uint64_t)p.rows_total,
                               (uint64_t)ld_q * 2, 64, 128, Swizzle::B128);
@@ -868,7 +1176,7 @@ static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, 
   rc = make_tensor_map_2d(&tm_kv, kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_kv, (uint64_t)p.rows_total,
                           (uint64_t)ld_kv * 2, 64, KV_TILE, Swizzle::B128);
   if (rc) return rc;
-  auto kern = attention_fwd_kernel<KV_TILE, BIAS, TF16>;
+  auto kern = attention_fwd_kernel<KV_TILE, BIAS, TF16, SPLIT>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   const long long items = static_cast<long long>((p.seq_len + 255) / 256) * p.n_heads * p.n_seq;
   const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
@@ -877,7 +1185,7 @@ static int launch_attention(cudaStream_t stream, const void* q, long long ld_q, 
     rc = make_tensor_map_2d(&tm_rel, rel, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64, 64, 128, 64, 64, Swizzle::B128);
     if (rc) return rc;
   }
-  kern<<<grid, ATT_THREADS, S::TOTAL, stream>>>(tm_q, tm_kv, tm_rel, p);
+  kern<<<grid, att_threads(SPLIT), S::TOTAL, stream>>>(tm_q, tm_kv, tm_rel, p);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
@@ -953,7 +1261,7 @@ static int attention_dispatch(const char* fn, void* stream, const void* q, long 
   }
   if (!has_bias) {
     LA_CHECK_ARG(out_mode == 0, "%s: window output mapping needs the window mode", fn);
-    return launch_attention<64, ATT_BIAS_NONE>(st, q, ld_q, kv, ld_kv, p);
+    return launch_attention<64, ATT_BIAS_NONE, false, ATT_SPLIT>(st, q, ld_q, kv, ld_kv, p);
   }
   if (grid_hw == 64) {
     LA_CHECK_ARG(seq_len == 4096 && ldb >= 127 && out_mode == 0, "%s: 64x64 rel-pos mode expects seq_len 4096, ldb >= 127",
@@ -962,9 +1270,9 @@ static int attention_dispatch(const char* fn, void* stream, const void* q, long 
     if (bias_dtype == LA_DTYPE_F16) {
       LA_CHECK_ARG(ldb % 2 == 0 && (reinterpret_cast<uintptr_t>(bias_w) & 3) == 0 && ldb >= 128,
                    "%s: fp16 tables need an even ldb >= 128 and 4-byte aligned rows", fn);
-      return launch_attention<64, ATT_BIAS_GLOBAL64, true>(st, q, ld_q, kv, ld_kv, p);
+      return launch_attention<64, ATT_BIAS_GLOBAL64, true, ATT_SPLIT>(st, q, ld_q, kv, ld_kv, p);
     }
-    return launch_attention<64, ATT_BIAS_GLOBAL64>(st, q, ld_q, kv, ld_kv, p);
+    return launch_attention<64, ATT_BIAS_GLOBAL64, false, ATT_SPLIT>(st, q, ld_q, kv, ld_kv, p);
   }
   set_last_error("%s: unsupported rel-pos grid %d (fp32 tables: 64; 14x14 windows go through la_attention_window_bf16)",
                  fn, grid_hw);
@@ -985,7 +1293,7 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
 int la_attention_window_v2(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
                            int k_off, int v_off, long long rows_total, int n_seq, int n_heads, float scale,
                            const void* rel_table, int rel_pad, void* out, long long ld_out, int out_mode, int nwin,
-                           int img_hw);
+                           int img_hw, long long* trace);
 #ifndef LA_WINDOW_V1
 #define LA_WINDOW_V1 0      // 1: the first-generation 112-key-tile mode of attention_fwd_kernel (experiment builds)
 #endif
@@ -1007,8 +1315,13 @@ extern "C" int la_attention_window_bf16(void* stream, const void* q, long long l
     LA_CHECK_ARG(out_mode == 0 || (nwin > 0 && img_hw > 0 && n_seq % (nwin * nwin) == 0),
                  "la_attention_window_bf16: bad window-unpartition parameters");
     LA_CHECK_ARG(static_cast<long long>(n_seq) * n_heads < (1ll << 31), "la_attention_window_bf16: too many work items");
+#ifdef LA_ATT_TRACE
+    long long* const trace = g_att_trace;
+#else
+    long long* const trace = nullptr;
+#endif
     return la_attention_window_v2(stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total, n_seq, n_heads, scale,
-                                  rel_table, rel_pad, out, ld_out, out_mode, nwin, img_hw);
+                                  rel_table, rel_pad, out, ld_out, out_mode, nwin, img_hw, trace);
   }
   return attention_dispatch("la_attention_window_bf16", stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total,
                             n_seq, 196, n_heads, scale, nullptr, nullptr, LA_DTYPE_F32, 0, rel_table, rel_pad, 14, out, ld_out,

@@ -103,6 +103,18 @@ __device__ __forceinline__ void fadd2s(float& d0, float& d1, float a0, float a1,
       : "=f"(d0), "=f"(d1)
       : "f"(a0), "f"(a1), "f"(b));
 }
+// (d0, d1) = (a0, a1) * (b, b)
+__device__ __forceinline__ void fmul2s(float& d0, float& d1, float a0, float a1, float b) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %4};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b));
+}
 // (d0, d1) += (a0, a1)
 __device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float a1) {
   asm("{\n\t"

@@ -106,7 +106,7 @@ if __name__ == "__main__":
             env = dict(os.environ, EXP_CHILD="1", EXP_TAG=tag)
             if tag != "product":
                 env["LA_B200_LIB"] = str(ROOT / "labelanything_b200" / "_variants" / f"liblabelanything_b200_{tag}.so")
-            r = subprocess.run([sys.executable, __file__], env=env, capture_output=True, text=True, timeout=600)
+            r = subprocess.run([sys.executable, __file__], env=env, capture_output=True, text=True, timeout=200)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else f"{tag}: FAILED rc={r.returncode} {r.stderr[-800:]}"
             print(line, flush=True)
             log.write(line + "\n")
