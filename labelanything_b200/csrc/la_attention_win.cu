@@ -20,6 +20,11 @@
 //     T = Q x rel^T come from one extra MMA per Q tile; every thread parks its T row (fp16, 128 B) in a staging row
 //     in shared memory and reads the 2 x 14 entries at its (qh, qw) shift back as aligned 32-bit words (+ one byte
 //     permute each for an odd shift).  The prologue only needs T, so it runs under the S product.
+//   * output: every thread writes its normalised bf16 row (128 B) over its -- long consumed -- Q row in shared memory
+//     (the 128B-swizzled image of a [196 tokens][64 channels] box) and the producer warp sends the item out with ONE
+//     4-D TMA store (channels, x, y, image; box 64 x 14 x 14 x 1: the window un-partition is the tensor map, rows and
+//     columns past the image are dropped by the copy engine) before it refills the stage.  The first version stored
+//     from the softmax threads: 1200-1900 cycles per item between O ready and the next prologue.
 //   * loads: Q (2 x 128 rows), K and V (208 rows each: the 12 rows past the window are the next window's, finite,
 //     and are masked / multiplied by P = 0) through a 2-stage ring.
 //   warp 0: TMA producer; warps 1 / 3: MMA issuers of Q tile A / B; warp 2: TMEM allocation;
@@ -60,10 +65,6 @@ struct WinParams {
   __nv_bfloat16* out;
   long long ld_out;
   int out_mode, nwin, img_hw;
-  // n / d = umulhi(n, magic) for n * d < 2^32 (window index -> image, window row): no division sequences (two
-  // MUFU.RCP + conversions each, on the pipe the exponentials need) in the per-item path
-  uint32_t magic_per_img, magic_nwin;
-  int wide_store;     // output rows are 32-byte aligned: 256-bit stores
   long long* trace;   // -DLA_ATT_TRACE builds: clock64 stamps of CTA 0, [role][item][event]; else nullptr
 };
 
@@ -102,7 +103,8 @@ __device__ __forceinline__ void tmem_st_14(uint32_t taddr, const uint32_t* r) {
 
 __global__ void __launch_bounds__(WA_THREADS, 1)
 window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                        const __grid_constant__ CUtensorMap tm_rel, const WinParams p) {
+                        const __grid_constant__ CUtensorMap tm_rel, const __grid_constant__ CUtensorMap tm_out,
+                        const WinParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WA_OFF_BAR);
@@ -115,7 +117,8 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint64_t* bar_o = bar_p2 + 2;       // [tile]   O ready
   uint64_t* o_free = bar_o + 2;       // [tile]   O read by the epilogue (4 warps): the score region may be overwritten
   uint64_t* t_done = o_free + 2;      // [tile]   T read by the prologue (4 warps): the T columns may be overwritten
-  uint64_t* rel_full = t_done + 2;
+  uint64_t* out_full = t_done + 2;    // [stage]  the item's output rows are written over its Q rows (8 warps)
+  uint64_t* rel_full = out_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rel_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,6 +131,7 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
     tma_prefetch_desc(&tm_rel);
+    tma_prefetch_desc(&tm_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -140,6 +144,7 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_init(&bar_o[s], 1);
       mbar_init(&o_free[s], 4);
       mbar_init(&t_done[s], 4);
+      mbar_init(&out_full[s], 8);
     }
     mbar_init(rel_full, 1);
     fence_barrier_init();
@@ -161,12 +166,32 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       if (lane == 0) {
         mbar_arrive_expect_tx(rel_full, 8192);
         tma_load_2d(smem + WA_OFF_REL, &tm_rel, rel_full, 0, 0);
+        // item j's output rows (written over its Q rows by the softmax warps) -> global memory
+        auto store_item = [&](const int j) {
+          const int w = blockIdx.x + j * gridDim.x;
+          const int head = w % p.n_heads, seq = w / p.n_heads;
+          mbar_wait(&out_full[j & 1], (j >> 1) & 1);
+          const uint8_t* src = smem + (j & 1) * WA_STAGE;
+          if (p.out_mode == 0) {
+            tma_store_4d(&tm_out, src, head * 64, 0, seq, 0);
+          } else {
+            const int per_img = p.nwin * p.nwin;
+            const int img = seq / per_img, wi = seq - img * per_img;
+            const int wy = wi / p.nwin;
+            tma_store_4d(&tm_out, src, head * 64, (wi - wy * p.nwin) * WA_GW, wy * WA_GW, img);
+          }
+          tma_store_commit();
+        };
         for (int it = 0; it < n_my; ++it) {
           const int w = blockIdx.x + it * gridDim.x;
           const int head = w % p.n_heads, seq = w / p.n_heads;
           const int row0 = seq * WA_KEYS;
           const int st = it & 1;
           mbar_wait(&stage_free[st], ((it >> 1) & 1) ^ 1);
+          if (it >= 2) {
+            store_item(it - 2);
+            tma_store_wait_read<0>();   // the copy engine has read the stage: it may be refilled
+          }
           uint8_t* base = smem + st * WA_STAGE;
           mbar_arrive_expect_tx(&full[st], WA_STAGE);
           tma_load_2d(base, &tm_q, &full[st], p.q_off + head * 64, row0);
@@ -174,6 +199,8 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           tma_load_2d(base + WA_Q_BYTES, &tm_kv, &full[st], p.k_off + head * 64, row0);
           tma_load_2d(base + WA_Q_BYTES + WA_KV_BYTES, &tm_kv, &full[st], p.v_off + head * 64, row0);
         }
+        for (int j = n_my > 2 ? n_my - 2 : 0; j < n_my; ++j) store_item(j);
+        tma_store_wait_read<0>();
       }
     } else if (warp == 1 || warp == 3) {
       // ------------------------------------ MMA issuers -------------------------------------
@@ -412,41 +439,23 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[x]);
-      long long out_row = -1;
-      if (row_valid) {
-        if (p.out_mode == 0) {
-          out_row = static_cast<long long>(seq) * WA_KEYS + t;
-        } else {
-          const int per_img = p.nwin * p.nwin;
-          const int img = p.magic_per_img ? static_cast<int>(__umulhi(static_cast<uint32_t>(seq), p.magic_per_img)) : seq;
-          const int wi = seq - img * per_img;
-          const int wy = static_cast<int>(__umulhi(static_cast<uint32_t>(wi), p.magic_nwin));
-          const int y = wy * WA_GW + ty;
-          const int xx = (wi - wy * p.nwin) * WA_GW + tx;
-          if (y < p.img_hw && xx < p.img_hw) out_row = (static_cast<long long>(img) * p.img_hw + y) * p.img_hw + xx;
-        }
-      }
-      if (out_row >= 0) {
-        __nv_bfloat16* dst = p.out + out_row * p.ld_out + head * 64;
-        // (first version: 64 scalar multiplies + eight 16-byte stores per row, 1900 cycles per item in the trace build)
-        uint32_t pk[32];
+      // my row, normalised, as bf16 over my Q row of this item's stage (128B-swizzled like the load that filled it):
+      // Q was last read by the S product, and the stage is only refilled after the producer has stored these rows
+      {
+        uint8_t* orow = smem + st * WA_STAGE + x * 16384 + r * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float o0, o1;
-          fmul2s(o0, o1, __uint_as_float(ov[2 * i]), __uint_as_float(ov[2 * i + 1]), inv_l);
-          pk[i] = pack_bf16(o0, o1);
+        for (int c = 0; c < 8; ++c) {
+          float o0, o1, o2, o3, o4, o5, o6, o7;
+          fmul2s(o0, o1, __uint_as_float(ov[8 * c + 0]), __uint_as_float(ov[8 * c + 1]), inv_l);
+          fmul2s(o2, o3, __uint_as_float(ov[8 * c + 2]), __uint_as_float(ov[8 * c + 3]), inv_l);
+          fmul2s(o4, o5, __uint_as_float(ov[8 * c + 4]), __uint_as_float(ov[8 * c + 5]), inv_l);
+          fmul2s(o6, o7, __uint_as_float(ov[8 * c + 6]), __uint_as_float(ov[8 * c + 7]), inv_l);
+          *reinterpret_cast<uint4*>(orow + ((c ^ (r & 7)) << 4)) =
+              make_uint4(pack_bf16(o0, o1), pack_bf16(o2, o3), pack_bf16(o4, o5), pack_bf16(o6, o7));
         }
-        if (p.wide_store) {
-#pragma unroll
-          for (int gq = 0; gq < 4; ++gq)
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + gq * 16), "r"(pk[8 * gq]),
-                         "r"(pk[8 * gq + 1]), "r"(pk[8 * gq + 2]), "r"(pk[8 * gq + 3]), "r"(pk[8 * gq + 4]),
-                         "r"(pk[8 * gq + 5]), "r"(pk[8 * gq + 6]), "r"(pk[8 * gq + 7]) : "memory");
-        } else {
-#pragma unroll
-          for (int gq = 0; gq < 8; ++gq)
-            *reinterpret_cast<uint4*>(dst + gq * 8) = make_uint4(pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
-        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&out_full[st]);
       }
       wa_trace(p, trs, 2 + x, it, 5);
       head += d_head;
@@ -496,18 +505,31 @@ int la_attention_window_v2(void* stream, const void* q, long long ld_q, int q_of
   p.out_mode = out_mode;
   p.nwin = nwin;
   p.img_hw = img_hw;
-  // magic = floor(2^32 / d) + 1: exact quotient for n * d < 2^32 (n < 2^31 / 196 window sequences, d <= nwin^2)
-  const uint32_t per_img = static_cast<uint32_t>(nwin > 0 ? nwin * nwin : 1);
-  p.magic_per_img = per_img > 1 ? static_cast<uint32_t>((1ull << 32) / per_img) + 1u : 0u;
-  p.magic_nwin = nwin > 1 ? static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(nwin)) + 1u : 0u;
-  LA_CHECK_ARG(out_mode == 0 || static_cast<unsigned long long>(n_seq) * per_img < (1ull << 32),
-               "la_attention_window_bf16: window-unpartition needs n_seq * nwin^2 < 2^32");
-  p.wide_store = (ld_out % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) ? 1 : 0;
   p.trace = trace;
+  // the output as (channel, x, y, image) [window un-partition] or (channel, token, window sequence, 1): one box per item
+  CUtensorMap tm_out;
+  {
+    const uint64_t row_bytes = static_cast<uint64_t>(ld_out) * 2;
+    uint64_t dims[4], strides[3];
+    uint32_t box[4];
+    if (out_mode == 0) {
+      dims[0] = static_cast<uint64_t>(ld_out), dims[1] = WA_KEYS, dims[2] = static_cast<uint64_t>(n_seq), dims[3] = 1;
+      strides[0] = row_bytes, strides[1] = row_bytes * WA_KEYS, strides[2] = row_bytes * WA_KEYS * n_seq;
+      box[0] = 64, box[1] = WA_KEYS, box[2] = 1, box[3] = 1;
+    } else {
+      const uint64_t hw = static_cast<uint64_t>(img_hw);
+      dims[0] = static_cast<uint64_t>(ld_out), dims[1] = hw, dims[2] = hw, dims[3] = static_cast<uint64_t>(n_seq / (nwin * nwin));
+      strides[0] = row_bytes, strides[1] = row_bytes * hw, strides[2] = row_bytes * hw * hw;
+      box[0] = 64, box[1] = WA_GW, box[2] = WA_GW, box[3] = 1;
+    }
+    rc = make_tensor_map_4d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dims, strides, box, Swizzle::B128);
+    if (rc) return rc;
+  }
   LA_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
   const long long items = static_cast<long long>(n_seq) * n_heads;
   const int grid = items < sm_count() ? static_cast<int>(items) : sm_count();
-  window_attention_kernel<<<grid, WA_THREADS, WA_SMEM, static_cast<cudaStream_t>(stream)>>>(tm_q, tm_kv, tm_rel, p);
+  window_attention_kernel<<<grid, WA_THREADS, WA_SMEM, static_cast<cudaStream_t>(stream)>>>(tm_q, tm_kv, tm_rel, tm_out,
+                                                                                            p);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
