@@ -58,6 +58,28 @@ int sm_count();
 // ----------------------------------------------------------------------------------------
 // small utilities
 // ----------------------------------------------------------------------------------------
+// n / d for n < 2^31 and a run-time d without the ~25-instruction division sequence (MUFU.RCP + conversions):
+// mul = ceil(2^(31 + s) / d), s = ceil(log2 d); n / d = umulhi(n, mul) >> (s - 1)   (d = 1: identity)
+struct FastDiv {
+  uint32_t mul, shift, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.mul = 0;
+  f.shift = 0;
+  if (d > 1) {
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    f.mul = static_cast<uint32_t>(((1ull << (31 + s)) + d - 1) / d);
+    f.shift = s - 1;
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+  return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shift);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -18,6 +18,14 @@
 // The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps
 // the mainloop of tile i+1.
 #include "la_common.cuh"
+// experiment switches (compile time, labelanything_b200/build.py::build_variant): the product library reads no
+// environment variables on the launch path
+#ifndef LA_GEMM_1CTA
+#define LA_GEMM_1CTA 0          // 1: never use CTA pairs
+#endif
+#ifndef LA_GEMM_ACC_MODE
+#define LA_GEMM_ACC_MODE 0      // 1 / 2: force the in-place / prefetching residual epilogue
+#endif
 #include <cstdlib>
 #include <type_traits>
 #include <cuda_fp16.h>
@@ -452,7 +460,7 @@ extern "C" int la_gemm_bf16(void* stream, const void* a, long long lda, const vo
 
   const int block_n = N >= 256 ? 256 : (N > 64 ? 128 : 64);
   // big problems run on CTA pairs (W boxes of 128 rows: each CTA loads half of the 256-wide tile)
-  const bool pair = block_n == 256 && M >= 2048 && getenv("LA_GEMM_1CTA") == nullptr;
+  const bool pair = block_n == 256 && M >= 2048 && !LA_GEMM_1CTA;
   CUtensorMap tm_a, tm_w, tm_out;
   int rc = make_tensor_map_2d(&tm_a, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)M,
                               (uint64_t)lda * 2, GEMM_BLOCK_K, GEMM_BLOCK_M, Swizzle::B128);
@@ -549,8 +557,7 @@ extern "C" int la_gemm_bf16_accumulate(void* stream, const void* a, long long ld
   if (rc) return rc;
   // long-K GEMMs hide the residual chunk's load behind their own tile; short-K ones get the prefetching epilogue
   // (one pipeline stage less, a second staging buffer per epilogue warp)
-  const char* e = getenv("LA_GEMM_ACC_MODE");
-  const int mode = e ? atoi(e) : (K >= 2048 ? 1 : 2);
+  const int mode = LA_GEMM_ACC_MODE ? LA_GEMM_ACC_MODE : (K >= 2048 ? 1 : 2);
   if (mode == 2) return launch_gemm_2cta<float, false, 2>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE);
   return launch_gemm_2cta<float, false, 1>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE);
 }

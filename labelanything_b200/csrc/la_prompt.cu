@@ -17,6 +17,9 @@
 //                        pad to the batch maximum with -inf (background channel: 0), absent classes -> -inf.
 //                        label_anything/models/lam.py:383-453, 92-93
 #include "la_common.cuh"
+#ifndef LA_BUILD_SRC_FMA
+#define LA_BUILD_SRC_FMA 0      // experiment builds: 1 = FFMA2 kernel for every width
+#endif
 #include <cstdlib>
 
 namespace la {
@@ -665,8 +668,8 @@ int la_build_src(void* stream, const float* feat, const float* m16, const unsign
   if (chunks < 1) chunks = 1;
   LA_CHECK_ARG(n_seq <= 65535, "la_build_src: more than 65535 sequences per call (chunk the call)");
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(n_seq));
-  // tensor-core variant: one warp per 64 channels (LA_BUILD_SRC_FMA=1 keeps the FFMA2 kernel)
-  if (d % 64 == 0 && d <= 512 && getenv("LA_BUILD_SRC_FMA") == nullptr) {
+  // tensor-core variant: one warp per 64 channels (-DLA_BUILD_SRC_FMA=1 builds keep the FFMA2 kernel)
+  if (d % 64 == 0 && d <= 512 && !LA_BUILD_SRC_FMA) {
     build_src_mma_kernel<<<grid, d / 2, 0, static_cast<cudaStream_t>(stream)>>>(p);
     LA_CHECK_CUDA(cudaGetLastError());
     return LA_OK;

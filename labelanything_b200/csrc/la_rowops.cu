@@ -14,6 +14,9 @@
 // All are pure streaming kernels: 16-byte vectorised, coalesced along the channel dimension, grid sized in
 // multiples of the SM count; the roofline that bounds them is HBM bandwidth.
 #include "la_common.cuh"
+#ifndef LA_LN_UNSTAGED
+#define LA_LN_UNSTAGED 0        // experiment builds: 1 = register-load kernels only (tools/diag_ln.py)
+#endif
 #include <cstdlib>
 
 namespace la {
@@ -47,6 +50,7 @@ struct AddLnParams {
                                 // 3 pixel shuffle: src row = (img, y, x, ky, kx) -> dst row (img, 2y+ky, 2x+kx)
   int seq_len;                  // map 2
   int win, nwin, hw;            // map 1
+  FastDiv fd_w2, fd_per_img, fd_nwin, fd_win;   // map 1: divisions by win^2, nwin^2, nwin, win (rows < 2^31)
 };
 
 // NVT: float4 slots per lane (compile time, >= ceil(d / 128)); POOL: the mean-pooling variant (keeps per-lane column sums).
@@ -331,14 +335,16 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
     pad = false;
     if (p.map_mode == 1) {
       // 32-bit index arithmetic (the launcher guarantees rows < 2^31): these divisions sit on the refill path
+      // (multiply-high divisions: the plain ones -- four MUFU.RCP sequences per chunk on the refill path and again
+      //  in the consumer -- held this mode at 0.60 of the copy peak against 0.82 for the identity mapping)
       const uint32_t r32 = static_cast<uint32_t>(row);
       const uint32_t w2 = p.win * p.win;
-      const uint32_t widx = r32 / w2;
+      const uint32_t widx = fast_div(r32, p.fd_w2);
       const uint32_t tin = r32 - widx * w2;
       const uint32_t per_img = p.nwin * p.nwin;
-      const uint32_t img = widx / per_img;
+      const uint32_t img = fast_div(widx, p.fd_per_img);
       const uint32_t wi = widx - img * per_img;
-      const uint32_t wy = wi / p.nwin, ty = tin / p.win;
+      const uint32_t wy = fast_div(wi, p.fd_nwin), ty = fast_div(tin, p.fd_win);
       const uint32_t y = wy * p.win + ty;
       const uint32_t x = (wi - wy * p.nwin) * p.win + (tin - ty * p.win);
       pad = (y >= static_cast<uint32_t>(p.hw)) || (x >= static_cast<uint32_t>(p.hw));
@@ -746,13 +752,18 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   p.win = win;
   p.nwin = nwin;
   p.hw = hw;
+  if (map_mode == 1) {
+    p.fd_w2 = make_fastdiv(static_cast<uint32_t>(win) * win);
+    p.fd_per_img = make_fastdiv(static_cast<uint32_t>(nwin) * nwin);
+    p.fd_nwin = make_fastdiv(static_cast<uint32_t>(nwin));
+    p.fd_win = make_fastdiv(static_cast<uint32_t>(win));
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int need = (d + 127) / 128;
   // the ViT block case goes through the staged kernel (bulk async row copies, 3 rows in flight per warp)
   const bool staged = x_mod == 0 && !delta2 && !y2_out && !ype_out && act == LA_ACT_NONE && gamma && y_out &&
                       rows < (1ll << 31) &&
-                      (map_mode == 0 || map_mode == 1) && need <= 6 && d % 32 == 0 && rows >= 4096 &&
-                      getenv("LA_LN_UNSTAGED") == nullptr;
+                      (map_mode == 0 || map_mode == 1) && need <= 6 && d % 32 == 0 && rows >= 4096 && !LA_LN_UNSTAGED;
   if (staged) {
     // window partition: pairs of rows (tx, tx + 1) with tx even share a window row and their padding status when the
     // window side and the grid side are even
@@ -803,7 +814,7 @@ int la_add_layernorm_meanpool(void* stream, const float* x_in, const void* delta
   const int need = (d + 127) / 128;
   const int grid = static_cast<int>(n_seq * slices);
   // big problems: the staged (bulk-copy ring) variant
-  if ((!delta2 || (!x_in && delta)) && need <= 4 && d % 32 == 0 && p.rows >= 4096 && getenv("LA_LN_UNSTAGED") == nullptr) {
+  if ((!delta2 || (!x_in && delta)) && need <= 4 && d % 32 == 0 && p.rows >= 4096 && !LA_LN_UNSTAGED) {
     // two chunks in flight per warp are enough here (16 warps x 2 x 6 KB per SM), so the ring prefers large bulk
     // copies over depth; the reduction scratch aliases the ring
     LnRing ring = ln_ring_for(static_cast<uint32_t>(d) * ((x_in ? 4 : 0) + (delta ? 2 : 0) + (delta2 ? 2 : 0)), 8, 0, 2);

@@ -24,7 +24,9 @@ def timeit(f, iters=10):
 
 
 def main():
-    tag = "unstaged" if os.environ.get("LA_LN_UNSTAGED") else "staged"
+    # A/B against the register-load kernels: build a variant with -DLA_LN_UNSTAGED=1 (sources=("la_rowops.cu",)) and
+    # point LA_B200_LIB at it
+    tag = os.environ.get("LA_B200_LIB", "product").rsplit("_", 1)[-1]
     g = torch.Generator(device="cuda").manual_seed(0)
     # (a) ViT block: x += delta; y = LN(x) bf16
     rows, d = 131072, 768
