@@ -91,7 +91,9 @@ int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, co
  * REVERSED rel_pos_h table (row i = rel_pos_h[26 - i]), rows [rel_pad, rel_pad + 27) = the reversed rel_pos_w table,
  * all other rows zero.  Per work item one extra tcgen05.mma forms T = Q_tile x rel_table^T in tensor memory and the
  * bias of key (kh, kw) for a query at (qh, qw) is T[13 - qh + kh] + T[rel_pad + 13 - qw + kw] -- same arithmetic as
- * the fp32 tables of la_attention_bf16 without their HBM round trip.  out_mode / nwin / img_hw as above.
+ * the fp32 tables of la_attention_bf16 without their HBM round trip.  out_mode / nwin / img_hw as above.  The output
+ * leaves through one 4-D TMA store per (window, head) -- (channel, x, y, image) for out_mode 1, whose box drops the
+ * rows and columns past the image -- so `out` must be 16-byte aligned (ld_out % 8 == 0 as everywhere).
  *   label_anything/models/image_encoder.py:239-255,258-304,319-376 */
 int la_attention_window_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
                              int k_off, int v_off, long long rows_total, int n_seq, int n_heads, float scale,
