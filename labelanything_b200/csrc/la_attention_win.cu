@@ -25,6 +25,10 @@
 //     4-D TMA store (channels, x, y, image; box 64 x 14 x 14 x 1: the window un-partition is the tensor map, rows and
 //     columns past the image are dropped by the copy engine) before it refills the stage.  The first version stored
 //     from the softmax threads: 1200-1900 cycles per item between O ready and the next prologue.
+//   * row sums on the tensor core: next to every K step of PV the issuer queues  L += P x ones  (M128 x N16, 8 cycles)
+//     into 16 spare TMEM columns per Q tile, so the softmax threads do no fp32 accumulation of their own (98 packed
+//     adds per row: a fifth of the dispatch cycles of the exponential pass, which is what bounds an item) and the
+//     normaliser is the sum of exactly the bf16 P values the numerator uses.
 //   * loads: Q (2 x 128 rows), K and V (208 rows each: the 12 rows past the window are the next window's, finite,
 //     and are masked / multiplied by P = 0) through a 2-stage ring.
 //   warp 0: TMA producer; warps 1 / 3: MMA issuers of Q tile A / B; warp 2: TMEM allocation;
@@ -43,7 +47,9 @@ constexpr int WA_OFF_REL = 2 * WA_STAGE;
 // staging rows of the rel-pos products T (64 fp16 entries per query row; 144-byte stride: conflict-free 16-byte stores)
 constexpr int WA_STG_STRIDE = 144;
 constexpr int WA_OFF_STG = WA_OFF_REL + 8192;
-constexpr int WA_OFF_BAR = WA_OFF_STG + 256 * WA_STG_STRIDE;
+// sixteen 128-byte rows of bf16 ones: the B operand of the row-sum product (every K step reads the same block)
+constexpr int WA_OFF_ONES = WA_OFF_STG + 256 * WA_STG_STRIDE;
+constexpr int WA_OFF_BAR = WA_OFF_ONES + 2048;
 constexpr int WA_SMEM = WA_OFF_BAR + 512 + 1024;
 constexpr int WA_SOFTMAX_REGS = 208, WA_CONTROL_REGS = 88;
 // O = P V is issued in two parts: K steps [0, WA_PV_SPLIT) (keys 0..127) after score chunk WA_P_EARLY_CHUNK
@@ -153,11 +159,13 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < 2048 / 4; i += WA_THREADS) reinterpret_cast<uint32_t*>(smem + WA_OFF_ONES)[i] = 0x3f803f80u;
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t TM_T = 416, TM_O_IN_S = 104;
+  constexpr uint32_t TM_T = 416, TM_O_IN_S = 104, TM_L = 480;   // L_A [480, 496), L_B [496, 512)
 
   if (warp < 4) {
     setmaxnreg_dec<WA_CONTROL_REGS>();
@@ -210,11 +218,14 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, WA_N, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);     // P from TMEM, V MN-major
+      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 16, 0, 1);     // P from TMEM, ones (MN-major, any 16 rows)
       const int x = warp == 1 ? 0 : 1;
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t lo_rel = desc_lo(smem_base + WA_OFF_REL);
       const uint32_t tm_s = tm + x * WA_N;
+      const uint32_t tm_l = tm + TM_L + x * 16;
+      const uint32_t lo_ones = desc_lo(smem_base + WA_OFF_ONES);
       const bool tri = p.trace != nullptr && blockIdx.x == 0 && lane == 0;
       for (int it = 0; it < n_my; ++it) {
         const int st = it & 1;
@@ -250,16 +261,20 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         wa_trace(p, tri, x, it, 2);
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < WA_PV_SPLIT; ++ks)
+          for (int ks = 0; ks < WA_PV_SPLIT; ++ks) {
             umma_ts_lo(tm_s + TM_O_IN_S, tm_s + ks * 8, lo_v + ks * (2048 >> 4), idesc_o, ks > 0);
+            umma_ts_lo(tm_l, tm_s + ks * 8, lo_ones, idesc_l, ks > 0);
+          }
         }
         __syncwarp();
         mbar_wait(&bar_p2[x], it & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int ks = WA_PV_SPLIT; ks < WA_N / 16; ++ks)
+          for (int ks = WA_PV_SPLIT; ks < WA_N / 16; ++ks) {
             umma_ts_lo(tm_s + TM_O_IN_S, tm_s + ks * 8, lo_v + ks * (2048 >> 4), idesc_o, true);
+            umma_ts_lo(tm_l, tm_s + ks * 8, lo_ones, idesc_l, true);
+          }
           umma_commit(&bar_o[x]);
           umma_commit(&stage_free[st]);
         }
@@ -280,6 +295,7 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t t_s = tmem_base + lane_addr + x * WA_N;
     const uint32_t t_t = tmem_base + lane_addr + TM_T;
+    const uint32_t t_l = tmem_base + lane_addr + TM_L + x * 16;
     const float sl2 = p.scale_log2;
     constexpr float LOG2E = 1.4426950408889634f;
     // a whole warp without a valid row (rows 224..255 of tile B) only keeps the barriers moving
@@ -340,7 +356,6 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_wait(&bar_s[x], par);
       tc_fence_after();
       wa_trace(p, trs, 2 + x, it, 1);
-      float inv_l = 0.f;
       if (warp_live) {
         // ---- pass 1: row maximum of  scale * s + rel_w + rel_h  over the 196 keys, 28 columns (2 key rows) at a time ----
         uint32_t ca[28], cb[28];
@@ -368,8 +383,7 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           if (c + 1 < 7) tmem_ld_wait();
         }
         wa_trace(p, trs, 2 + x, it, 2);
-        // ---- pass 2: P = exp2(. - max) -> bf16 -> TMEM over the consumed score columns; row sum in fp32 ----
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        // ---- pass 2: P = exp2(. - max) -> bf16 -> TMEM over the consumed score columns (row sum: tensor core) ----
         tmem_ld_28(t_s, ca);
         tmem_ld_wait();
 #pragma unroll
@@ -396,8 +410,6 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 e0 = ex2_approx(a0);
                 e1 = ex2_approx(a1);
               }
-              if (i & 2) fadd2_acc(l2, l3, e0, e1);
-              else fadd2_acc(l0, l1, e0, e1);
               pk[(gi * WA_GW + i) >> 1] = pack_bf16(e0, e1);
             }
           }
@@ -411,7 +423,6 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             if (lane == 0) mbar_arrive(&bar_p[x]);
           }
         }
-        inv_l = 1.0f / ((l0 + l1) + (l2 + l3));
       } else {
         if (lane == 0) mbar_arrive(&bar_p[x]);   // a warp without rows keeps the barriers moving
       }
@@ -433,9 +444,12 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       tc_fence_after();
       wa_trace(p, trs, 2 + x, it, 4);
       uint32_t ov[64];
+      uint32_t lsum;
       tmem_ld_x32(t_s + TM_O_IN_S, ov);
       tmem_ld_x32(t_s + TM_O_IN_S + 32, ov + 32);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(lsum) : "r"(t_l) : "memory");
       tmem_ld_wait();
+      const float inv_l = 1.0f / __uint_as_float(lsum);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[x]);
