@@ -14,6 +14,9 @@
 // All are pure streaming kernels: 16-byte vectorised, coalesced along the channel dimension, grid sized in
 // multiples of the SM count; the roofline that bounds them is HBM bandwidth.
 #include "la_common.cuh"
+#ifndef LA_LN_FULL_MAXV
+#define LA_LN_FULL_MAXV 6       // widest row (in 128-channel slots) that takes the lean staged row loop
+#endif
 #ifndef LA_LN_UNSTAGED
 #define LA_LN_UNSTAGED 0        // experiment builds: 1 = register-load kernels only (tools/diag_ln.py)
 #endif
@@ -50,6 +53,7 @@ struct AddLnParams {
                                 // 3 pixel shuffle: src row = (img, y, x, ky, kx) -> dst row (img, 2y+ky, 2x+kx)
   int seq_len;                  // map 2
   int win, nwin, hw;            // map 1
+  FastDiv fd_seq;               // division by seq_rows (staged kernels: rows < 2^31)
   FastDiv fd_w2, fd_per_img, fd_nwin, fd_win;   // map 1: divisions by win^2, nwin^2, nwin, win (rows < 2^31)
 };
 
@@ -290,7 +294,11 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 // cycles, so 1 KB rows (the prompt encoder's bf16 image tokens) must be moved several at a time to reach HBM speed.
 // rpc = 1 when rows are remapped (window partition).  POOL: the mean-pool variant -- CTA = (sequence, slice), nothing
 // but per-CTA column sums of y is written (prompt_encoder.py:733-735).
-template <int NVT, bool POOL, bool HAS_X, bool HAS_D, bool HAS_D2 = false>
+// FULL: d == NVT * 128 (every lane slot is live): the lean row loop -- no slot predicates, the per-sequence vector
+// looked up with a multiply-high division (or once per CTA when pooling), pointers advanced instead of recomputed.
+// The general loop issued 348 warp instructions per 512-channel row in the mean-pool case, 68 % issue-active at
+// 2.3 TB/s (profiles/r01_ncu_meanpool_v4.txt): instruction-bound on an HBM-bound operation.
+template <int NVT, bool POOL, bool HAS_X, bool HAS_D, bool HAS_D2 = false, bool FULL = false>
 __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddLnParams p, const int stages, const int rpc) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31;
@@ -385,6 +393,14 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
     sav[i] = make_float4(0, 0, 0, 0);
   }
   long long sa_seq = -1;
+  if constexpr (FULL && POOL) {
+    if (p.seq_add) {   // one sequence per CTA
+      sa_seq = blockIdx.x / p.pool_slices;
+      const float4* sadd = reinterpret_cast<const float4*>(p.seq_add + sa_seq * p.d);
+#pragma unroll
+      for (int i = 0; i < NVT; ++i) sav[i] = __ldg(sadd + i * 32 + lane);
+    }
+  }
   float4 acc[POOL ? NVT : 1];
 #pragma unroll
   for (int i = 0; i < (POOL ? NVT : 1); ++i) acc[i] = make_float4(0, 0, 0, 0);
@@ -407,6 +423,104 @@ __global__ void __launch_bounds__(256, 2) add_layernorm_staged_kernel(const AddL
       const uint8_t* buf = ring + static_cast<size_t>(slot) * slot_bytes;
       mbar_wait(&bars[slot], (phases >> slot) & 1);
       phases ^= 1u << slot;
+      if constexpr (FULL) {
+        const uint8_t* xrow = buf + lane * 16;                                  // + i * 512 + rr * xbytes
+        const uint8_t* drow = buf + static_cast<size_t>(rpc) * xbytes + lane * 8;   // + i * 256 + rr * dbytes
+        const uint8_t* d2row = buf + static_cast<size_t>(rpc) * (xbytes + dbytes) + lane * 8;
+        float* xo = p.x_out ? p.x_out + src0 * p.d + lane * 4 : nullptr;
+        uint8_t* yrow = POOL ? nullptr : static_cast<uint8_t*>(p.y_out) + static_cast<size_t>(row0) * p.d * ebytes;
+        uint32_t sq_cur = 0, sq_left = 0;   // sequence of the current row, rows left in it
+        if (!POOL && p.seq_add) {
+          sq_cur = fast_div(static_cast<uint32_t>(src0), p.fd_seq);
+          const long long left = (static_cast<long long>(sq_cur) + 1) * p.seq_rows - src0;
+          sq_left = left < 0xffffffffll ? static_cast<uint32_t>(left) : 0xffffffffu;
+        }
+#pragma unroll 1
+        for (int rr = 0; rr < n; ++rr) {
+          if (!POOL && p.seq_add) {
+            if (static_cast<long long>(sq_cur) != sa_seq) {   // warp-uniform; once per sequence
+              sa_seq = sq_cur;
+              const float4* sadd = reinterpret_cast<const float4*>(p.seq_add + static_cast<long long>(sq_cur) * p.d);
+#pragma unroll
+              for (int i = 0; i < NVT; ++i) sav[i] = __ldg(sadd + i * 32 + lane);
+            }
+            if (--sq_left == 0) {
+              ++sq_cur;
+              sq_left = p.seq_rows < 0xffffffffll ? static_cast<uint32_t>(p.seq_rows) : 0xffffffffu;
+            }
+          }
+          float4 v[NVT];
+#pragma unroll
+          for (int i = 0; i < NVT; ++i) {
+            float4 a;
+            if constexpr (HAS_X) a = *reinterpret_cast<const float4*>(xrow + i * 512);
+            if constexpr (HAS_D) {
+              const uint2 dv = *reinterpret_cast<const uint2*>(drow + i * 256);
+              const float d0 = __uint_as_float(dv.x << 16), d1 = __uint_as_float(dv.x & 0xffff0000u);
+              const float d2 = __uint_as_float(dv.y << 16), d3 = __uint_as_float(dv.y & 0xffff0000u);
+              if constexpr (HAS_X) {
+                a.x += d0, a.y += d1, a.z += d2, a.w += d3;
+              } else {
+                a = make_float4(d0, d1, d2, d3);
+              }
+            }
+            if constexpr (HAS_D2) {
+              const uint2 dv = *reinterpret_cast<const uint2*>(d2row + i * 256);
+              a.x += __uint_as_float(dv.x << 16), a.y += __uint_as_float(dv.x & 0xffff0000u);
+              a.z += __uint_as_float(dv.y << 16), a.w += __uint_as_float(dv.y & 0xffff0000u);
+            }
+            if (p.seq_add) a.x += sav[i].x, a.y += sav[i].y, a.z += sav[i].z, a.w += sav[i].w;
+            if (xo) *reinterpret_cast<float4*>(xo + i * 128) = a;
+            v[i] = a;
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < NVT; ++i) sum += v[i].x + v[i].y + v[i].z + v[i].w;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float mean = sum * inv_d;
+          float sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < NVT; ++i) {
+            const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+            sq += dx * dx + dy * dy + dz * dz + dw * dw;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          const float rstd = rsqrtf(sq * inv_d + p.eps);
+          if constexpr (POOL) {
+            pool_c = fmaf(rstd, mean, pool_c);
+            pool_n += 1.0f;
+#pragma unroll
+            for (int i = 0; i < NVT; ++i) {
+              acc[i].x = fmaf(v[i].x, rstd, acc[i].x);
+              acc[i].y = fmaf(v[i].y, rstd, acc[i].y);
+              acc[i].z = fmaf(v[i].z, rstd, acc[i].z);
+              acc[i].w = fmaf(v[i].w, rstd, acc[i].w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < NVT; ++i) {
+              const float4 g = gmv[i], b = btv[i];
+              float4 o;   // same arithmetic as the general loop: the two paths give identical bits
+              o.x = (v[i].x - mean) * rstd * g.x + b.x;
+              o.y = (v[i].y - mean) * rstd * g.y + b.y;
+              o.z = (v[i].z - mean) * rstd * g.z + b.z;
+              o.w = (v[i].w - mean) * rstd * g.w + b.w;
+              if (p.y_f32) {
+                reinterpret_cast<float4*>(yrow)[i * 32 + lane] = o;
+              } else {
+                reinterpret_cast<uint2*>(yrow)[i * 32 + lane] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+              }
+            }
+            yrow += static_cast<size_t>(p.d) * ebytes;
+          }
+          xrow += xbytes;
+          drow += dbytes;
+          d2row += d2bytes;
+          if (xo) xo += p.d;
+        }
+      } else
       for (int rr = 0; rr < n; ++rr) {
         const long long row = row0 + rr, src = src0 + rr;
         const float4* xs = reinterpret_cast<const float4*>(buf + static_cast<size_t>(rr) * xbytes);
@@ -591,6 +705,17 @@ static int launch_staged(cudaStream_t st, const AddLnParams& p, int grid, const 
     LA_CHECK_CUDA(cudaGetLastError());
     return LA_OK;
   };
+  // Every lane slot live: the lean row loop -- where the general one is instruction-bound, i.e. for bf16-only rows
+  // (norm4 of the prompt encoder 4.2 -> 5.7 TB/s, its mean-pool 2.5 -> 4.2 TB/s) and the window partition of an fp32
+  // stream (5.3 -> 5.8 TB/s).  With an fp32 stream in identity order the general loop, which the compiler unrolls
+  // across rows, is already at 0.89-0.95 of the copy peak and the lean one is 6-12 % slower (same-box A/B).
+  if (p.d == NVT * 128 && p.rows < (1ll << 31) && NVT <= LA_LN_FULL_MAXV) {
+    if constexpr (POOL) {
+      if (p.delta2) return go(add_layernorm_staged_kernel<NVT, POOL, false, true, true, true>);
+    }
+    if (!p.x_in) return go(add_layernorm_staged_kernel<NVT, POOL, false, true, false, true>);
+    if (p.map_mode == 1 && !p.delta) return go(add_layernorm_staged_kernel<NVT, POOL, true, false, false, true>);
+  }
   if constexpr (POOL) {   // the mean-pool of the prompt encoder adds two bf16 streams (image tokens + last MLP output)
     if (p.delta2) return go(add_layernorm_staged_kernel<NVT, POOL, false, true, true>);
   }
@@ -752,6 +877,8 @@ int la_add_layernorm(void* stream, const float* x_in, long long x_mod, const voi
   p.win = win;
   p.nwin = nwin;
   p.hw = hw;
+  // (a sequence longer than the staged kernels' 2^31 rows never ends inside them: any divisor above the row count does)
+  p.fd_seq = make_fastdiv(seq_rows <= 0 ? 1u : (seq_rows >= (1ll << 31) ? 0x7fffffffu : static_cast<uint32_t>(seq_rows)));
   if (map_mode == 1) {
     p.fd_w2 = make_fastdiv(static_cast<uint32_t>(win) * win);
     p.fd_per_img = make_fastdiv(static_cast<uint32_t>(nwin) * nwin);
