@@ -772,6 +772,37 @@ embed_tokens_kernel(const __nv_bfloat16* __restrict__ patch, const float* __rest
   }
 }
 
+// the same with 32-bit indices and multiply-high divisions (two 64-bit divisions per 16 bytes in the kernel above)
+__global__ void __launch_bounds__(256)
+embed_tokens_fast_kernel(const __nv_bfloat16* __restrict__ patch, const float* __restrict__ cls,
+                         const float* __restrict__ pos, float* __restrict__ x, uint32_t total, int T, int n_cls, int d,
+                         FastDiv f_dv, FastDiv f_t) {
+  const uint32_t dv = static_cast<uint32_t>(d) >> 2;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t rt = fast_div(i, f_dv);
+    const uint32_t c4 = i - rt * dv;
+    const uint32_t img = fast_div(rt, f_t);
+    const int tok = static_cast<int>(rt - img * T);
+    float4 a;
+    if (tok < n_cls) {
+      a = __ldg(reinterpret_cast<const float4*>(cls) + c4);
+    } else {
+      const uint2 pv = reinterpret_cast<const uint2*>(
+          patch + (static_cast<long long>(img) * (T - n_cls) + tok - n_cls) * static_cast<long long>(d))[c4];
+      a = make_float4(__uint_as_float(pv.x << 16), __uint_as_float(pv.x & 0xffff0000u), __uint_as_float(pv.y << 16),
+                      __uint_as_float(pv.y & 0xffff0000u));
+    }
+    if (pos) {
+      const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(tok) * d) + c4);
+      a.x += pe.x;
+      a.y += pe.y;
+      a.z += pe.z;
+      a.w += pe.w;
+    }
+    reinterpret_cast<float4*>(x)[i] = a;
+  }
+}
+
 // images [I, C, S, S] fp32 -> rows [I * (S/P)^2, C*P*P] bf16, column = c*P*P + ky*P + kx   (P == 16)
 __global__ void __launch_bounds__(256)
 im2col_patch16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, long long n_img, int C, int S) {
@@ -819,6 +850,29 @@ im2col_3x3_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restric
     uint4 v = make_uint4(0, 0, 0, 0);
     if (yy >= 0 && yy < H && xx >= 0 && xx < W)
       v = __ldg(reinterpret_cast<const uint4*>(in + ((im * H + yy) * W + xx) * static_cast<long long>(C)) + c8);
+    reinterpret_cast<uint4*>(out)[i] = v;
+  }
+}
+
+// the same with 32-bit indices and multiply-high divisions (five 64-bit divisions per 16 bytes above)
+__global__ void __launch_bounds__(256)
+im2col_3x3_fast_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, uint32_t total, int H,
+                       int W, int C, FastDiv f_cv, FastDiv f_w, FastDiv f_h) {
+  const uint32_t cv = static_cast<uint32_t>(C) >> 3;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t r0 = fast_div(i, f_cv);
+    const uint32_t c8 = i - r0 * cv;
+    const uint32_t r1 = r0 / 9u;
+    const int tap = static_cast<int>(r0 - r1 * 9u);
+    const uint32_t r2 = fast_div(r1, f_w);
+    const int x = static_cast<int>(r1 - r2 * W);
+    const uint32_t im = fast_div(r2, f_h);
+    const int y = static_cast<int>(r2 - im * H);
+    const int ty = tap / 3;
+    const int yy = y + ty - 1, xx = x + (tap - ty * 3) - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(im) * H + yy) * W + xx) * static_cast<long long>(C)) + c8);
     reinterpret_cast<uint4*>(out)[i] = v;
   }
 }
@@ -974,6 +1028,13 @@ int la_embed_tokens(void* stream, const void* patch, const float* cls, const flo
   LA_CHECK_ARG(patch && x && n_img > 0 && tokens_per_img > n_cls && d % 4 == 0, "la_embed_tokens: bad arguments");
   LA_CHECK_ARG(n_cls == 0 || cls, "la_embed_tokens: cls token missing");
   const long long total = n_img * tokens_per_img * (d / 4);
+  if (total < (1ll << 31)) {
+    embed_tokens_fast_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(patch), cls, pos, x, static_cast<uint32_t>(total), tokens_per_img, n_cls, d,
+        make_fastdiv(static_cast<uint32_t>(d / 4)), make_fastdiv(static_cast<uint32_t>(tokens_per_img)));
+    LA_CHECK_CUDA(cudaGetLastError());
+    return LA_OK;
+  }
   embed_tokens_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(patch), cls, pos, x, n_img, tokens_per_img, n_cls, d);
   LA_CHECK_CUDA(cudaGetLastError());
@@ -994,6 +1055,14 @@ int la_im2col_3x3(void* stream, const void* in, void* out, long long n_img, int 
   using namespace la;
   LA_CHECK_ARG(in && out && n_img > 0 && height > 0 && width > 0 && channels % 8 == 0, "la_im2col_3x3: bad arguments");
   const long long total = n_img * height * width * 9 * (channels / 8);
+  if (total < (1ll << 31)) {
+    im2col_3x3_fast_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), static_cast<uint32_t>(total), height,
+        width, channels, make_fastdiv(static_cast<uint32_t>(channels / 8)), make_fastdiv(static_cast<uint32_t>(width)),
+        make_fastdiv(static_cast<uint32_t>(height)));
+    LA_CHECK_CUDA(cudaGetLastError());
+    return LA_OK;
+  }
   im2col_3x3_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n_img, height, width, channels);
   LA_CHECK_CUDA(cudaGetLastError());
