@@ -51,6 +51,16 @@ int la_device_check(void); /* LA_OK iff the current device is sm_100 */
 int la_gemm_bf16(void* stream, const void* a, long long lda, const void* w, long long ldw, const float* bias,
                  void* out, long long ldo, int out_dtype, int M, int N, int K, int act);
 
+/* The same product stored into a PADDED GRID: the M rows of `a` are the pixels (image, y, x) of M / grid^2 square
+ * grid x grid token maps; `out` (bf16, row stride ldo) is [M / grid^2][padded][padded][ldo] and receives row
+ * (image, y, x) at position (image, y, x) of the padded grid (4-D TMA stores), while the padded^2 - grid^2 positions
+ * outside get the bias row -- what the reference's zero padding after norm1 projects to
+ * (label_anything/models/image_encoder.py:183-192,271-275: F.pad, then qkv = Linear(x)).  With it the windowed ViT
+ * blocks project 64 x 64 instead of 70 x 70 tokens per image and la_attention_window_bf16 (in_pad > 0) fetches each
+ * window from the padded grid.  grid % 32 == 0. */
+int la_gemm_bf16_to_grid(void* stream, const void* a, long long lda, const void* w, long long ldw, const float* bias,
+                         void* out, long long ldo, int M, int N, int K, int grid, int padded);
+
 /* x[M,N] (fp32, row stride ldx) += a @ w^T + bias: the residual add of the ViT blocks done in the epilogue of the
  * GEMM that produces the branch, in fp32 on the fp32 accumulator (each epilogue warp TMA-loads its chunk of x into the
  * staging buffer it stores from).  CTA-pair kernel only: M >= 2048, N >= 256.
@@ -91,14 +101,17 @@ int la_attention_bf16(void* stream, const void* q, long long ld_q, int q_off, co
  * REVERSED rel_pos_h table (row i = rel_pos_h[26 - i]), rows [rel_pad, rel_pad + 27) = the reversed rel_pos_w table,
  * all other rows zero.  Per work item one extra tcgen05.mma forms T = Q_tile x rel_table^T in tensor memory and the
  * bias of key (kh, kw) for a query at (qh, qw) is T[13 - qh + kh] + T[rel_pad + 13 - qw + kw] -- same arithmetic as
- * the fp32 tables of la_attention_bf16 without their HBM round trip.  out_mode / nwin / img_hw as above.  The output
- * leaves through one 4-D TMA store per (window, head) -- (channel, x, y, image) for out_mode 1, whose box drops the
+ * the fp32 tables of la_attention_bf16 without their HBM round trip.  out_mode / nwin / img_hw as above.
+ * in_pad = 0: q / kv hold window-partitioned rows (sequence * 196 + token).  in_pad > 0: q / kv are padded-grid
+ * tensors [image][in_pad][in_pad][ld] written by la_gemm_bf16_to_grid (padding positions = bias row) and window
+ * (wy, wx) of an image is fetched as one 4-D TMA box at (x, y) = (14 wx, 14 wy); sequence = image * nwin^2 + wy * nwin + wx.
+ * The output leaves through one 4-D TMA store per (window, head) -- (channel, x, y, image) for out_mode 1, whose box drops the
  * rows and columns past the image -- so `out` must be 16-byte aligned (ld_out % 8 == 0 as everywhere).
  *   label_anything/models/image_encoder.py:239-255,258-304,319-376 */
 int la_attention_window_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
                              int k_off, int v_off, long long rows_total, int n_seq, int n_heads, float scale,
                              const void* rel_table, int rel_pad, void* out, long long ld_out, int out_mode, int nwin,
-                             int img_hw);
+                             int img_hw, int in_pad);
 
 /* Diagnostics: when device_buffer != NULL, CTA (0,0,0) of every following la_attention_bf16 launch records clock64()
  * stamps into it: int64 [5 roles (MMA issuers, softmax A / B first warp, softmax A / B last warp)][192 tiles]

@@ -1316,7 +1316,7 @@ extern "C" int la_attention_bf16(void* stream, const void* q, long long ld_q, in
 int la_attention_window_v2(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
                            int k_off, int v_off, long long rows_total, int n_seq, int n_heads, float scale,
                            const void* rel_table, int rel_pad, void* out, long long ld_out, int out_mode, int nwin,
-                           int img_hw, long long* trace);
+                           int img_hw, int in_pad, long long* trace);
 #ifndef LA_WINDOW_V1
 #define LA_WINDOW_V1 0      // 1: the first-generation 112-key-tile mode of attention_fwd_kernel (experiment builds)
 #endif
@@ -1324,15 +1324,22 @@ int la_attention_window_v2(void* stream, const void* q, long long ld_q, int q_of
 extern "C" int la_attention_window_bf16(void* stream, const void* q, long long ld_q, int q_off, const void* kv,
                                         long long ld_kv, int k_off, int v_off, long long rows_total, int n_seq,
                                         int n_heads, float scale, const void* rel_table, int rel_pad, void* out,
-                                        long long ld_out, int out_mode, int nwin, int img_hw) {
+                                        long long ld_out, int out_mode, int nwin, int img_hw, int in_pad) {
   using namespace la;
   LA_CHECK_ARG(rel_table != nullptr, "la_attention_window_bf16: rel_table is required");
   if (!LA_WINDOW_V1) {
     LA_CHECK_ARG(q && kv && out && n_seq > 0 && n_heads > 0 && scale > 0.0f, "la_attention_window_bf16: bad arguments");
     LA_CHECK_ARG(ld_q % 8 == 0 && ld_kv % 8 == 0 && ld_out % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
                  "la_attention_window_bf16: strides/offsets must be multiples of 8 elements");
-    LA_CHECK_ARG(rows_total >= static_cast<long long>(n_seq) * 196 && rows_total < (1ll << 31),
-                 "la_attention_window_bf16: rows_total out of range");
+    if (in_pad > 0) {
+      LA_CHECK_ARG(nwin > 0 && n_seq % (nwin * nwin) == 0 && in_pad >= nwin * 14 &&
+                       rows_total >= static_cast<long long>(n_seq / (nwin * nwin)) * in_pad * in_pad,
+                   "la_attention_window_bf16: padded-grid input needs nwin, in_pad >= 14 nwin and "
+                   "rows_total >= images * in_pad^2");
+    } else {
+      LA_CHECK_ARG(rows_total >= static_cast<long long>(n_seq) * 196, "la_attention_window_bf16: rows_total too small");
+    }
+    LA_CHECK_ARG(rows_total < (1ll << 31), "la_attention_window_bf16: rows_total out of range");
     LA_CHECK_ARG(rel_pad == 32 && (reinterpret_cast<uintptr_t>(rel_table) & 15) == 0,
                  "la_attention_window_bf16: rel_table is the 16-byte aligned [64][64] operand with rel_pad 32");
     LA_CHECK_ARG(out_mode == 0 || (nwin > 0 && img_hw > 0 && n_seq % (nwin * nwin) == 0),
@@ -1344,8 +1351,9 @@ extern "C" int la_attention_window_bf16(void* stream, const void* q, long long l
     long long* const trace = nullptr;
 #endif
     return la_attention_window_v2(stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total, n_seq, n_heads, scale,
-                                  rel_table, rel_pad, out, ld_out, out_mode, nwin, img_hw, trace);
+                                  rel_table, rel_pad, out, ld_out, out_mode, nwin, img_hw, in_pad, trace);
   }
+  LA_CHECK_ARG(in_pad == 0, "la_attention_window_bf16: the first-generation kernel reads window-partitioned rows only");
   return attention_dispatch("la_attention_window_bf16", stream, q, ld_q, q_off, kv, ld_kv, k_off, v_off, rows_total,
                             n_seq, 196, n_heads, scale, nullptr, nullptr, LA_DTYPE_F32, 0, rel_table, rel_pad, 14, out, ld_out,
                             out_mode, nwin, img_hw);

@@ -29,6 +29,9 @@
 //     into 16 spare TMEM columns per Q tile, so the softmax threads do no fp32 accumulation of their own (98 packed
 //     adds per row: a fifth of the dispatch cycles of the exponential pass, which is what bounds an item) and the
 //     normaliser is the sum of exactly the bf16 P values the numerator uses.
+//   * padded-grid input (in_pad > 0): Q, K and V of a window are one 4-D TMA box each out of [image][70][70][C]
+//     projections whose padding positions hold the bias row, so the windowed blocks project 64 x 64 tokens per image
+//     instead of the partitioned 70 x 70 and no window-partition copy exists anywhere.
 //   * loads: Q (2 x 128 rows), K and V (208 rows each: the 12 rows past the window are the next window's, finite,
 //     and are masked / multiplied by P = 0) through a 2-stage ring.
 //   warp 0: TMA producer; warps 1 / 3: MMA issuers of Q tile A / B; warp 2: TMEM allocation;
@@ -71,6 +74,8 @@ struct WinParams {
   __nv_bfloat16* out;
   long long ld_out;
   int out_mode, nwin, img_hw;
+  int in_pad;         // > 0: q / kv are padded-grid tensors [image][in_pad][in_pad][ld] (la_gemm_bf16_to_grid): a window is
+                      // one 4-D box (64 channels, 14 x, 14 y, 1 image); 0: window-partitioned rows (196 per window)
   long long* trace;   // -DLA_ATT_TRACE builds: clock64 stamps of CTA 0, [role][item][event]; else nullptr
 };
 
@@ -160,6 +165,15 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     tmem_relinquish();
   }
   for (int i = threadIdx.x; i < 2048 / 4; i += WA_THREADS) reinterpret_cast<uint32_t*>(smem + WA_OFF_ONES)[i] = 0x3f803f80u;
+  if (p.in_pad > 0) {
+    // the 4-D boxes bring 196 rows: rows 196..207 of every K / V tile are never written -- make them zero once
+    constexpr int TAIL = (WA_N - WA_KEYS) * 128 / 16;   // uint4 per tile
+    for (int i = threadIdx.x; i < 4 * TAIL; i += WA_THREADS) {
+      const int tile = i / TAIL;   // (stage, K | V)
+      uint8_t* base = smem + (tile >> 1) * WA_STAGE + WA_Q_BYTES + (tile & 1) * WA_KV_BYTES + WA_KEYS * 128;
+      reinterpret_cast<uint4*>(base)[i - tile * TAIL] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -201,11 +215,22 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             tma_store_wait_read<0>();   // the copy engine has read the stage: it may be refilled
           }
           uint8_t* base = smem + st * WA_STAGE;
-          mbar_arrive_expect_tx(&full[st], WA_STAGE);
-          tma_load_2d(base, &tm_q, &full[st], p.q_off + head * 64, row0);
-          tma_load_2d(base + 16384, &tm_q, &full[st], p.q_off + head * 64, row0 + 128);
-          tma_load_2d(base + WA_Q_BYTES, &tm_kv, &full[st], p.k_off + head * 64, row0);
-          tma_load_2d(base + WA_Q_BYTES + WA_KV_BYTES, &tm_kv, &full[st], p.v_off + head * 64, row0);
+          if (p.in_pad > 0) {
+            const int per_img = p.nwin * p.nwin;
+            const int img = seq / per_img, wi = seq - img * per_img;
+            const int wy = wi / p.nwin;
+            const int x0 = (wi - wy * p.nwin) * WA_GW, y0 = wy * WA_GW;
+            mbar_arrive_expect_tx(&full[st], 3 * WA_KEYS * 128);
+            tma_load_4d(base, &tm_q, &full[st], p.q_off + head * 64, x0, y0, img);
+            tma_load_4d(base + WA_Q_BYTES, &tm_kv, &full[st], p.k_off + head * 64, x0, y0, img);
+            tma_load_4d(base + WA_Q_BYTES + WA_KV_BYTES, &tm_kv, &full[st], p.v_off + head * 64, x0, y0, img);
+          } else {
+            mbar_arrive_expect_tx(&full[st], WA_STAGE);
+            tma_load_2d(base, &tm_q, &full[st], p.q_off + head * 64, row0);
+            tma_load_2d(base + 16384, &tm_q, &full[st], p.q_off + head * 64, row0 + 128);
+            tma_load_2d(base + WA_Q_BYTES, &tm_kv, &full[st], p.k_off + head * 64, row0);
+            tma_load_2d(base + WA_Q_BYTES + WA_KV_BYTES, &tm_kv, &full[st], p.v_off + head * 64, row0);
+          }
         }
         for (int j = n_my > 2 ? n_my - 2 : 0; j < n_my; ++j) store_item(j);
         tma_store_wait_read<0>();
@@ -495,15 +520,32 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 int la_attention_window_v2(void* stream, const void* q, long long ld_q, int q_off, const void* kv, long long ld_kv,
                            int k_off, int v_off, long long rows_total, int n_seq, int n_heads, float scale,
                            const void* rel_table, int rel_pad, void* out, long long ld_out, int out_mode, int nwin,
-                           int img_hw, long long* trace) {
+                           int img_hw, int in_pad, long long* trace) {
   using namespace la;
   CUtensorMap tm_q, tm_kv, tm_rel;
-  int rc = make_tensor_map_2d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_q, (uint64_t)rows_total,
-                              (uint64_t)ld_q * 2, 64, 128, Swizzle::B128);
-  if (rc) return rc;
-  rc = make_tensor_map_2d(&tm_kv, kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_kv, (uint64_t)rows_total,
-                          (uint64_t)ld_kv * 2, 64, WA_N, Swizzle::B128);
-  if (rc) return rc;
+  int rc;
+  if (in_pad > 0) {
+    // (channel, x, y, image) over the padded grids; one window = one box
+    const uint64_t pd = static_cast<uint64_t>(in_pad), n_img = static_cast<uint64_t>(n_seq / (nwin * nwin));
+    const uint32_t box[4] = {64, WA_GW, WA_GW, 1};
+    const uint64_t dq[4] = {static_cast<uint64_t>(ld_q), pd, pd, n_img};
+    const uint64_t sq[3] = {static_cast<uint64_t>(ld_q) * 2, static_cast<uint64_t>(ld_q) * 2 * pd,
+                            static_cast<uint64_t>(ld_q) * 2 * pd * pd};
+    rc = make_tensor_map_4d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dq, sq, box, Swizzle::B128);
+    if (rc) return rc;
+    const uint64_t dk[4] = {static_cast<uint64_t>(ld_kv), pd, pd, n_img};
+    const uint64_t sk[3] = {static_cast<uint64_t>(ld_kv) * 2, static_cast<uint64_t>(ld_kv) * 2 * pd,
+                            static_cast<uint64_t>(ld_kv) * 2 * pd * pd};
+    rc = make_tensor_map_4d(&tm_kv, kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dk, sk, box, Swizzle::B128);
+    if (rc) return rc;
+  } else {
+    rc = make_tensor_map_2d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_q, (uint64_t)rows_total,
+                            (uint64_t)ld_q * 2, 64, 128, Swizzle::B128);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&tm_kv, kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)ld_kv, (uint64_t)rows_total,
+                            (uint64_t)ld_kv * 2, 64, WA_N, Swizzle::B128);
+    if (rc) return rc;
+  }
   rc = make_tensor_map_2d(&tm_rel, rel_table, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64, 64, 128, 64, 64, Swizzle::B128);
   if (rc) return rc;
   WinParams p;
@@ -519,6 +561,7 @@ int la_attention_window_v2(void* stream, const void* q, long long ld_q, int q_of
   p.out_mode = out_mode;
   p.nwin = nwin;
   p.img_hw = img_hw;
+  p.in_pad = in_pad;
   p.trace = trace;
   // the output as (channel, x, y, image) [window un-partition] or (channel, token, window sequence, 1): one box per item
   CUtensorMap tm_out;

@@ -82,7 +82,9 @@ template <int BLOCK_N, typename OutT, bool CTA2 = false, bool CONV = false, int 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                          const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N,
-                         int K, int act, int conv_c = 0, int conv_h = 0) {
+                         int K, int act, int conv_c = 0, int conv_h = 0, int out_grid = 0) {
+  // out_grid > 0: the output rows are the pixels (image, y, x) of a square out_grid x out_grid grid and `tm_out` is a
+  // 4-D map (channel, x, y, image) of a LARGER (padded) grid: every 32-row store box lies inside one grid row
   static_assert(!CONV || CTA2, "the implicit-GEMM convolution is built on the CTA-pair kernel");
   static_assert(RESID == 0 || sizeof(OutT) == 4, "the residual epilogue accumulates into an fp32 tensor");
   using S = GemmSmem<BLOCK_N, CTA2, RESID == 2>;
@@ -376,7 +378,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tm_out, buf, n0 + col0, m0 + q * 32);
+          if (out_grid > 0) {
+            const int row = m0 + q * 32;
+            const int img = row / (out_grid * out_grid);
+            const int rem = row - img * out_grid * out_grid;
+            const int gy = rem / out_grid;
+            tma_store_4d(&tm_out, buf, n0 + col0, rem - gy * out_grid, gy, img);
+          } else {
+            tma_store_2d(&tm_out, buf, n0 + col0, m0 + q * 32);
+          }
           tma_store_commit();
           if constexpr (RESID == 1) {
             if (c + 2 < NCHUNK) load_resid(c + 2);   // next chunk of this tile (after the store has read the buffer)
@@ -401,7 +411,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 template <typename OutT, bool CONV = false, int RESID = 0>
 static int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
                             const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int act,
-                            int conv_c = 0, int conv_h = 0) {
+                            int conv_c = 0, int conv_h = 0, int out_grid = 0) {
   using S = GemmSmem<256, true, RESID == 2>;
   auto kern = gemm_bf16_tcgen05_kernel<256, OutT, true, CONV, RESID>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -419,13 +429,13 @@ static int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tm_a, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_w, tm_out, bias, M, N, K, act, conv_c, conv_h));
+  LA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_w, tm_out, bias, M, N, K, act, conv_c, conv_h, out_grid));
   return LA_OK;
 }
 
 template <int BLOCK_N, typename OutT>
 static int launch_gemm(cudaStream_t stream, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
-                       const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int act) {
+                       const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int act, int out_grid = 0) {
   using S = GemmSmem<BLOCK_N>;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, OutT>;
   LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -433,7 +443,7 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tm_a, const CUten
   const int m_blks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int tiles = n_blks * m_blks;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tm_a, tm_w, tm_out, bias, M, N, K, act, 0, 0);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tm_a, tm_w, tm_out, bias, M, N, K, act, 0, 0, out_grid);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
@@ -494,6 +504,92 @@ extern "C" int la_gemm_bf16(void* stream, const void* a, long long lda, const vo
     if (block_n == 128) return launch_gemm<128, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
     return launch_gemm<64, float>(st, tm_a, tm_w, tm_out, bias, M, N, K, act);
   }
+}
+
+namespace la {
+// positions of the padded grid outside the projected grid x grid part <- the bias row (what a zero input row projects to)
+__global__ void __launch_bounds__(256)
+fill_grid_padding_kernel(__nv_bfloat16* __restrict__ out, long long ldo, const float* __restrict__ bias, int n_img,
+                         int grid, int padded, int n8) {
+  const int per_img = padded * padded - grid * grid;     // padding positions per image
+  const long long total = static_cast<long long>(n_img) * per_img * n8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % n8);
+    const long long r = i / n8;
+    const int k = static_cast<int>(r % per_img);
+    const long long img = r / per_img;
+    // k enumerates the right strip (grid rows x (padded - grid) columns), then the bottom strip (full rows)
+    const int strip = grid * (padded - grid);
+    int y, x;
+    if (k < strip) {
+      y = k / (padded - grid);
+      x = grid + k - y * (padded - grid);
+    } else {
+      const int k2 = k - strip;
+      y = grid + k2 / padded;
+      x = k2 - (k2 / padded) * padded;
+    }
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * c8);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * c8 + 1);
+      v = make_uint4(pack_bf16(b0.x, b0.y), pack_bf16(b0.z, b0.w), pack_bf16(b1.x, b1.y), pack_bf16(b1.z, b1.w));
+    }
+    reinterpret_cast<uint4*>(out + ((img * padded + y) * padded + x) * ldo)[c8] = v;
+  }
+}
+}  // namespace la
+
+extern "C" int la_gemm_bf16_to_grid(void* stream, const void* a, long long lda, const void* w, long long ldw,
+                                    const float* bias, void* out, long long ldo, int M, int N, int K, int grid,
+                                    int padded) {
+  using namespace la;
+  LA_CHECK_ARG(a && w && out, "la_gemm_bf16_to_grid: null pointer");
+  LA_CHECK_ARG(M > 0 && N > 0 && K > 0, "la_gemm_bf16_to_grid: empty problem M=%d N=%d K=%d", M, N, K);
+  LA_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && N % 8 == 0 && ldo % 8 == 0 && ldo >= N,
+               "la_gemm_bf16_to_grid: K/lda/ldw/N/ldo must be multiples of 8");
+  LA_CHECK_ARG(grid > 0 && grid % 32 == 0 && padded >= grid && M % (grid * grid) == 0,
+               "la_gemm_bf16_to_grid: grid must be a multiple of 32 (32-row store boxes stay inside a grid row), "
+               "padded >= grid and M a whole number of grid x grid images");
+  LA_CHECK_ARG((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+               "la_gemm_bf16_to_grid: pointers must be 16-byte aligned");
+  LA_CHECK_ARG(!bias || (reinterpret_cast<uintptr_t>(bias) % 16 == 0), "la_gemm_bf16_to_grid: bias must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n_img = M / (grid * grid);
+  const int block_n = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+  const bool pair = block_n == 256 && M >= 2048 && !LA_GEMM_1CTA;
+  CUtensorMap tm_a, tm_w, tm_out;
+  int rc = make_tensor_map_2d(&tm_a, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)M,
+                              (uint64_t)lda * 2, GEMM_BLOCK_K, GEMM_BLOCK_M, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_w, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2,
+                          GEMM_BLOCK_K, (uint32_t)(pair ? 128 : block_n), Swizzle::B128);
+  if (rc) return rc;
+  {
+    const uint64_t row_bytes = static_cast<uint64_t>(ldo) * 2, pd = static_cast<uint64_t>(padded);
+    const uint64_t dims[4] = {static_cast<uint64_t>(N), static_cast<uint64_t>(grid), static_cast<uint64_t>(grid),
+                              static_cast<uint64_t>(n_img)};   // only the projected part is addressable
+    const uint64_t strides[3] = {row_bytes, row_bytes * pd, row_bytes * pd * pd};
+    const uint32_t box[4] = {64, 32, 1, 1};
+    rc = make_tensor_map_4d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dims, strides, box, Swizzle::B128);
+    if (rc) return rc;
+  }
+  if (pair) rc = launch_gemm_2cta<__nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE, 0, 0, grid);
+  else if (block_n == 256) rc = launch_gemm<256, __nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE, grid);
+  else if (block_n == 128) rc = launch_gemm<128, __nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE, grid);
+  else rc = launch_gemm<64, __nv_bfloat16>(st, tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE, grid);
+  if (rc) return rc;
+  if (padded > grid) {
+    const long long total = static_cast<long long>(n_img) * (padded * padded - grid * grid) * (N / 8);
+    long long blocks = (total + 255) / 256;
+    const long long cap = 8ll * sm_count();
+    if (blocks > cap) blocks = cap;
+    fill_grid_padding_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<__nv_bfloat16*>(out), ldo, bias, n_img,
+                                                                     grid, padded, N / 8);
+    LA_CHECK_CUDA(cudaGetLastError());
+  }
+  return LA_OK;
 }
 
 extern "C" int la_conv3x3_bf16(void* stream, const void* x, int n_img, int H, int W, int C, const void* w,

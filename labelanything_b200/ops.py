@@ -198,6 +198,24 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act
     return out
 
 
+def gemm_to_grid(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, grid: int, padded: int) -> torch.Tensor:
+    """bf16 [images * padded^2, N]: row (image, y, x) of a @ w.T + bias at position (image, y, x) of a padded x padded
+    grid, the positions outside the grid x grid part = the bias row (the projection of the reference's zero padding)."""
+    _require_cuda(a, w, bias)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.shape[1] == w.shape[1] and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert grid % 32 == 0 and padded >= grid and M % (grid * grid) == 0, (M, grid, padded)
+    n_img = M // (grid * grid)
+    assert bias is None or (bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous())
+    out = torch.empty((n_img * padded * padded, N), dtype=torch.bfloat16, device=a.device)
+    _cost(2.0 * M * N * K, 2.0 * (M * K + N * K) + 2.0 * out.numel())
+    _call(f"gemm.n{N}.k{K}" if _PROF is not None else "gemm", "la_gemm_bf16_to_grid", a, a.stride(0), w, w.stride(0),
+          bias, out, out.stride(0), M, N, K, grid, padded)
+    return out
+
+
 _NO_GEMM_ACCUMULATE = bool(__import__("os").environ.get("LA_NO_GEMM_ACCUMULATE"))   # experiment switch
 
 
@@ -245,9 +263,10 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, n_img: 
 
 def attention_window(q: torch.Tensor, kv: torch.Tensor, n_seq: int, n_heads: int, scale: float, out: torch.Tensor,
                      q_off: int, k_off: int, v_off: int, rel_table: torch.Tensor, rel_pad: int, out_mode: int = 0,
-                     nwin: int = 0, img_hw: int = 0) -> torch.Tensor:
+                     nwin: int = 0, img_hw: int = 0, in_pad: int = 0) -> torch.Tensor:
     """Fused MHSA over 14x14 windows (196 tokens, head_dim 64) with the decomposed rel-pos bias formed in-kernel from
-    rel_table = bf16 [2 * rel_pad, 64] (reversed rel_pos_h rows, then reversed rel_pos_w rows; see the C header)."""
+    rel_table = bf16 [2 * rel_pad, 64] (reversed rel_pos_h rows, then reversed rel_pos_w rows; see the C header).
+    in_pad > 0: q / kv are the padded-grid projections of `gemm_to_grid` ([images * in_pad^2, ld])."""
     _require_cuda(q, kv, out, rel_table)
     for t in (q, kv, out):
         assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
@@ -258,7 +277,7 @@ def attention_window(q: torch.Tensor, kv: torch.Tensor, n_seq: int, n_heads: int
           2.0 * 4 * n_seq * L * n_heads * 64)
     _call(f"attention.L{L}" if _PROF is not None else "attention", "la_attention_window_bf16", q,
           q.stride(0), q_off, kv, kv.stride(0), k_off, v_off, q.shape[0], n_seq, n_heads, float(scale),
-          rel_table, rel_pad, out, out.stride(0), out_mode, nwin, img_hw)
+          rel_table, rel_pad, out, out.stride(0), out_mode, nwin, img_hw, in_pad)
     return out
 
 

@@ -56,6 +56,8 @@ class VitSpec:
 
 # experiment switch: also take the attention branch's residual add in the proj GEMM epilogue (prefetching variant)
 _FUSE_PROJ = bool(__import__("os").environ.get("LA_FUSE_PROJ"))
+# experiment switch (import time): 0 keeps the window-partitioned projections of round 1 for A/B runs
+_GRID_ROUTE = __import__("os").environ.get("LA_WINDOW_GRID_ROUTE", "1") != "0"
 # element type of the global blocks' rel-pos tables q . rel_pos (the rel_w half is rounded to fp16 inside the attention
 # kernel either way; fp16 halves the table traffic).  LA_REL_TABLE_F32=1 keeps the fp32 tables.
 _TABLE_DTYPE = torch.float32 if __import__("os").environ.get("LA_REL_TABLE_F32") else torch.float16
@@ -90,24 +92,39 @@ def run_vit(spec: VitSpec, x: torch.Tensor, n_img: int, out_dtype: torch.dtype) 
             nwin = (g + win - 1) // win
             seq_len, n_seq = win * win, n_img * nwin * nwin
             r_att = n_seq * seq_len
-            y = torch.empty((r_att, d), dtype=torch.bfloat16, device=dev)
-            ops.add_layernorm(x, delta, bw.ln1_w, bw.ln1_b, spec.eps, rows=r_att, d=d,
-                              x_out=x if delta is not None else None, y_out=y,
-                              map_mode=1, win=win, nwin=nwin, hw=g)
+            # Padded-grid route (g % 32 == 0, 14 x 14 windows): norm1 in image order, the projections store their
+            # g x g tokens into a (nwin * win)^2 grid whose padding positions get the bias row -- what the reference's
+            # F.pad after norm1 projects to (image_encoder.py:183-192) -- and the attention kernel fetches every window
+            # as one 4-D box: 16 % fewer projected rows and no window-partition copy.
+            grid_route = _GRID_ROUTE and g % 32 == 0 and win == 14 and bw.rel_table is not None
+            if grid_route:
+                y = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
+                ops.add_layernorm(x, delta, bw.ln1_w, bw.ln1_b, spec.eps, rows=rows, d=d,
+                                  x_out=x if delta is not None else None, y_out=y)
+            else:
+                y = torch.empty((r_att, d), dtype=torch.bfloat16, device=dev)
+                ops.add_layernorm(x, delta, bw.ln1_w, bw.ln1_b, spec.eps, rows=r_att, d=d,
+                                  x_out=x if delta is not None else None, y_out=y,
+                                  map_mode=1, win=win, nwin=nwin, hw=g)
         else:
+            grid_route = False
             win, nwin, seq_len, n_seq, r_att = 0, 0, T, n_img, rows
             y = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
             ops.add_layernorm(x, delta, bw.ln1_w, bw.ln1_b, spec.eps, rows=rows, d=d,
                               x_out=x if delta is not None else None, y_out=y)
-        q = ops.gemm(y, bw.wq, bw.bq)
-        kv = ops.gemm(y, bw.wkv, bw.bkv)
+        if grid_route:
+            q = ops.gemm_to_grid(y, bw.wq, bw.bq, g, nwin * win)
+            kv = ops.gemm_to_grid(y, bw.wkv, bw.bkv, g, nwin * win)
+        else:
+            q = ops.gemm(y, bw.wq, bw.bq)
+            kv = ops.gemm(y, bw.wkv, bw.bkv)
         del y
         att = torch.empty((rows, d), dtype=torch.bfloat16, device=dev)
         if bw.rel_table is not None and win > 0:
             # windowed block: the rel-pos table products are formed inside the attention kernel
             assert win == 14, "native windowed attention is built for 14x14 windows"
             ops.attention_window(q, kv, n_seq, heads, scale, att, 0, 0, d, bw.rel_table, bw.rel_pad, out_mode=1,
-                                 nwin=nwin, img_hw=g)
+                                 nwin=nwin, img_hw=g, in_pad=nwin * win if grid_route else 0)
         else:
             bias_h = bias_w = None
             grid_hw = 0

@@ -45,11 +45,13 @@ def test_bad_arguments_are_rejected_with_a_message():
     assert lib.la_gemm_bf16_accumulate(None, p, 64, p, 64, None, p, 256, 128, 256, 64) == -1
     assert b"CTA-pair kernel" in lib.la_last_error()
     assert lib.la_attention_window_bf16(None, p, 2304, 0, p, 2304, 768, 1536, 196, 1, 12, 0.125, p, 16, p, 768, 0, 0,
-                                        0) == -1
+                                        0, 0) == -1
     assert b"rel_pad 32" in lib.la_last_error()
     assert lib.la_attention_window_bf16(None, p, 2304, 0, p, 2304, 768, 1536, 196, 1, 12, 0.125, None, 32, p, 768, 0,
-                                        0, 0) == -1
+                                        0, 0, 0) == -1
     assert b"rel_table is required" in lib.la_last_error()
+    assert lib.la_gemm_bf16_to_grid(None, p, 64, p, 64, None, p, 64, 4096, 64, 64, 48, 70) == -1   # grid % 32 != 0
+    assert b"multiple of 32" in lib.la_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -225,6 +225,41 @@ def test_window_attention_unpartition_drops_padding():
     assert torch.equal(out, r.reshape(n_img * hw * hw, -1))      # same arithmetic, only the row mapping differs
 
 
+def test_window_attention_from_padded_grid_equals_partitioned_rows():
+    """Windowed block without the 70 x 70 projection: la_gemm_bf16_to_grid stores the 64 x 64 projected tokens into a
+    padded grid whose padding positions hold the bias row, the window kernel fetches each window as one 4-D box.
+    Same arithmetic as LayerNorm-with-window-partition (zero rows) -> GEMM -> partitioned attention: identical bits."""
+    ops = _ops()
+    n_img, nwin, hw, heads, d = 2, 5, 64, 12, 768
+    P = nwin * 14
+    n_seq = n_img * nwin * nwin
+    g = _gen(33)
+    y = torch.randn(n_img * hw * hw, d, device="cuda", generator=g).to(torch.bfloat16)      # LayerNorm output, image order
+    wq = (torch.randn(d, d, device="cuda", generator=g) * 0.03).to(torch.bfloat16)
+    wkv = (torch.randn(2 * d, d, device="cuda", generator=g) * 0.03).to(torch.bfloat16)
+    bq = torch.randn(d, device="cuda", generator=g) * 0.5
+    bkv = torch.randn(2 * d, device="cuda", generator=g) * 0.5
+    rel = torch.randn(27, 64, device="cuda", generator=g) * 0.1
+    op = _rel_operand(rel, rel, 32)
+    # reference route: zero-padded window partition, projection of all 70 x 70 tokens, partitioned attention
+    yp = torch.zeros(n_img, P, P, d, device="cuda", dtype=torch.bfloat16)
+    yp[:, :hw, :hw] = y.view(n_img, hw, hw, d)
+    ywin = yp.view(n_img, nwin, 14, nwin, 14, d).permute(0, 1, 3, 2, 4, 5).reshape(n_seq * 196, d).contiguous()
+    q_ref, kv_ref = ops.gemm(ywin, wq, bq), ops.gemm(ywin, wkv, bkv)
+    out_ref = torch.zeros(n_img * hw * hw, d, device="cuda", dtype=torch.bfloat16)
+    ops.attention_window(q_ref, kv_ref, n_seq, heads, 0.125, out_ref, 0, 0, d, op, 32, out_mode=1, nwin=nwin, img_hw=hw)
+    # padded-grid route
+    q, kv = ops.gemm_to_grid(y, wq, bq, hw, P), ops.gemm_to_grid(y, wkv, bkv, hw, P)
+    assert q.shape == (n_img * P * P, d) and kv.shape == (n_img * P * P, 2 * d)
+    qg = q.view(n_img, P, P, d)
+    assert torch.equal(qg[:, :hw, :hw].reshape(-1, d), ops.gemm(y, wq, bq))
+    assert torch.equal(qg[:, hw:, :], bq.to(torch.bfloat16).expand(n_img, P - hw, P, d))
+    assert torch.equal(qg[:, :, hw:], bq.to(torch.bfloat16).expand(n_img, P, P - hw, d))
+    out = torch.zeros(n_img * hw * hw, d, device="cuda", dtype=torch.bfloat16)
+    ops.attention_window(q, kv, n_seq, heads, 0.125, out, 0, 0, d, op, 32, out_mode=1, nwin=nwin, img_hw=hw, in_pad=P)
+    assert torch.equal(out, out_ref)
+
+
 # ---------------------------------------------------------------------------------------------- row kernels
 def test_add_layernorm_modes():
     ops = _ops()
