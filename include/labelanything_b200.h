@@ -330,6 +330,98 @@ int la_rasterize_masks_u8(void* stream, const void* masks, int n, int H, int W, 
  * double, rounded once to fp32 (the reference assigns the float64 result into a float32 tensor). */
 int la_scale_coords_f64(void* stream, const void* coords, long long n, double sx, double sy, float* out);
 
+/* ---- training step (BASELINE config 4: frozen / pre-computed encoder, MAE-L-256) --------------
+ * Backward passes of the ops between the image embeddings and the loss, the fp32 forward variants the training path
+ * keeps its activations in, and the optimiser update.  The reference gets all of this from torch.autograd over
+ * label_anything/models/{lam,prompt_encoder,transformer,mask_decoder,common}.py, driven by
+ * label_anything/experiment/run.py:359-361 (accelerator.backward) and :425-590 (train loop, AdamW step).  The
+ * contractions (dgrad / wgrad of every nn.Linear / Conv2d / ConvTranspose2d) are la_gemm_bf16 launches on operands
+ * transposed by la_cast_transpose_bf16; everything below is elementwise / row / reduction work in fp32.
+ * Outputs documented as "accumulated" are added to (+=); all others are overwritten (zeroed inside where the kernel
+ * scatters with atomics). */
+/* out = bf16(in), n elements (GEMM operand of an fp32 activation) */
+int la_cast_bf16(void* stream, const float* in, void* out, long long n);
+/* hi = bf16(in), lo = bf16(in - hi): the operand split of the fp32-accurate GEMM mode (a w^T = hi_a hi_w^T + hi_a lo_w^T
+ * + lo_a hi_w^T up to 2^-16 relative, three la_gemm_bf16 launches with fp32 accumulation) -- north_star's fp32 tolerance
+ * for the training path and the yardstick the bf16 gradients are checked against */
+int la_split_bf16(void* stream, const float* in, void* hi, void* lo, long long n);
+/* out = a + b, n elements (residual adds; backward is the identity) */
+int la_add_f32(void* stream, const float* a, const float* b, float* out, long long n);
+/* dx = dy where y > 0 else 0 (nn.ReLU behind lin1 / class_mlp: transformer.py:164, mask_decoder.py:797) */
+int la_relu_bwd_f32(void* stream, const float* dy, const float* y, float* dx, long long n);
+/* y = GELU(x) (exact erf form, nn.GELU()) and dx = dy * GELU'(x): the activation of AttentionMLPBlock's MLP
+ * (common.py:19-37,151-184), kept apart from its GEMM so that the pre-activation is available to the backward pass */
+int la_gelu_f32(void* stream, const float* x, float* y, long long n);
+int la_gelu_bwd_f32(void* stream, const float* dy, const float* x, float* dx, long long n);
+/* out[c][r] = bf16(in[r][c]), in fp32 or bf16 [rows, cols] (row stride ld_in), out bf16 [cols, ld_out] with columns
+ * [rows, ld_out) zero: the K-major operands of the weight-gradient GEMM dW[N, K] = dY^T[N, rows] @ X^T[K, rows]^T. */
+int la_cast_transpose_bf16(void* stream, const void* in, int in_dtype, long long ld_in, void* out, long long ld_out,
+                           long long rows, int cols);
+/* out[(r / row_div) % b_mod][:] (+)= dy[r][:]: bias gradients (row_div = 1, b_mod = 1 -> column sum), gradients of
+ * broadcast addends (class codes, no_sparse_embedding, positional tables).  accumulate = 0 zeroes out first. */
+int la_bcast_reduce_f32(void* stream, const float* dy, float* out, long long rows, int d, long long row_div,
+                        long long b_mod, int accumulate);
+/* y = act(LayerNorm(x) * gamma + beta) per row of fp32 [rows, d] (biased variance; gamma = beta = NULL: no affine),
+ * act = LA_ACT_NONE / LA_ACT_GELU.  nn.LayerNorm and LayerNorm2d (+ the GELU behind it): common.py:42-54,
+ * transformer.py:298-329, prompt_encoder.py:61-69, mask_decoder.py:206-255, build_lam.py:150-171.  d <= 1024. */
+int la_layernorm_f32(void* stream, const float* x, const float* gamma, const float* beta, float eps, int act, float* y,
+                     long long rows, int d);
+/* its backward: dx overwritten, dgamma / dbeta ACCUMULATED (may be NULL together); statistics are recomputed from x */
+int la_layernorm_f32_bwd(void* stream, const float* x, const float* gamma, const float* beta, float eps, int act,
+                         const float* dy, float* dx, float* dgamma, float* dbeta, long long rows, int d);
+/* out = softmax(scale q k^T) v per (sequence, head) on fp32 [n_seq * nq | nk, heads * head_dim] rows; lse fp32
+ * [n_seq, heads, nq] = log-sum-exp of the scaled scores (kept for the backward pass).  common.py:97-148 after the
+ * projections (the reference's masks are no-ops).  head_dim <= 64. */
+int la_attention_f32(void* stream, const float* q, const float* k, const float* v, float* out, float* lse,
+                     long long n_seq, int nq, int nk, int heads, int head_dim, float scale);
+/* its backward: dq / dk / dv overwritten; delta fp32 [n_seq, heads, nq] is scratch (rowsum(dout * out)) */
+int la_attention_f32_bwd(void* stream, const float* q, const float* k, const float* v, const float* out, const float* lse,
+                         const float* dout, float* delta, float* dq, float* dk, float* dv, long long n_seq, int nq, int nk,
+                         int heads, int head_dim, float scale);
+/* adjoint of la_im2col_3x3: dcol fp32 [n_img*H*W, 9*C] -> dx fp32 [n_img*H*W, C] (spatial_convs, neck 3x3) */
+int la_col2im_3x3_f32(void* stream, const float* dcol, float* dx, long long n_img, int height, int width, int channels);
+/* la_mask_downscale with the weights in DEVICE memory (they change every step): weights = 332 floats, the flattened
+ * parameters mask_downscaling.{0.weight, 0.bias, 1.weight, 1.bias, 3.weight, 3.bias, 4.weight, 4.bias} in this order
+ * (prompt_encoder.py:61-69) -> out fp32 [n_seq, H/4, W/4, 16] */
+int la_mask_downscale_dev(void* stream, const float* masks, const float* weights, float eps1, float eps2, float* out,
+                          long long n_seq, int height, int width);
+/* parameter gradients of the above (the masks are inputs, not differentiated): dweights 332 floats, overwritten */
+int la_mask_downscale_bwd(void* stream, const float* masks, const float* weights, float eps1, float eps2,
+                          const float* dout, float* dweights, long long n_seq, int height, int width);
+/* adjoint of la_resize_bilinear: dout [n, out_h, out_w, c] -> din [n, in_h, in_w, c] (overwritten) */
+int la_resize_bilinear_bwd(void* stream, const float* dout, float* din, long long n, int in_h, int in_w, int out_h,
+                           int out_w, int channels);
+/* src[s, t, :] = feat[s / n_classes, t, :] + (dense != NULL && (mask_flags == NULL || mask_flags[s]) ? dense[s, t, :]
+ * : alt[:]) in fp32 -- prompt_encoder.py:783-803 with alt = not_a_mask_embed (masks given) / no_mask_embed (none) */
+int la_src_combine_f32(void* stream, const float* feat, const float* dense, const unsigned char* mask_flags,
+                       const float* alt, float* out, long long n_seq, int tokens, int d, int n_classes);
+/* its backward: dfeat [n_seq / n_classes, tokens, d] = sum over the classes, ddense (may be NULL) = dsrc of the
+ * sequences that used dense (else 0), dalt_rows (may be NULL) [n_seq / n_classes, tokens, d] = sum over the sequences
+ * that used alt (column-summed into the embedding's gradient by la_bcast_reduce_f32) */
+int la_src_combine_bwd(void* stream, const float* dsrc, const unsigned char* mask_flags, int has_dense, float* dfeat,
+                       float* ddense, float* dalt_rows, long long n_seq, int tokens, int d, int n_classes);
+/* gradients of la_embed_sparse's learned vectors: dtable [4, d] (point_embeddings.0-3), dnot_a_point [d], both
+ * overwritten; dout [n_seq, n, d] with n as in la_embed_sparse (prompt_encoder.py:83-114) */
+int la_embed_sparse_bwd(void* stream, const float* point_labels, int n_points, const float* box_flags, int n_boxes,
+                        int has_points, const float* dout, float* dtable, float* dnot_a_point, long long n_seq, int d);
+/* out[s, :] = mean over the seg_rows rows of segment s (fused.mean(dim=(2, 3)), prompt_encoder.py:733-735) + backward */
+int la_segment_mean_f32(void* stream, const float* x, float* out, long long n_seg, int seg_rows, int d);
+int la_segment_mean_bwd(void* stream, const float* dout, float* dx, long long n_seg, int seg_rows, int d);
+/* backward of la_masked_mean: demb[b, m, c, :] = flags[b, m, c] * dout[b, c, :] / max(sum_m flags, 1) */
+int la_masked_mean_bwd(void* stream, const float* dout, const unsigned char* flags, float* demb, int batch, int examples,
+                       int classes, int d);
+/* backward of la_classify: dx fp32 [batch*pixels, dk], dcls fp32 [batch, classes, dk] (mask_decoder.py:309) */
+int la_classify_bwd(void* stream, const float* dlogits, const void* x, const float* cls, float* dx, float* dcls, int batch,
+                    long long pixels, int classes, int dk);
+/* adjoint of la_postprocess_masks: dout [batch, classes, out_h, out_w] -> din [batch, classes, low_h, low_w]; padded
+ * pixels and flag_gts-masked classes carry no gradient (lam.py:383-453) */
+int la_postprocess_masks_bwd(void* stream, const float* dout, const int* sizes, const unsigned char* flag_gts, float* din,
+                             int batch, int classes, int low_h, int low_w, int image_size, int out_h, int out_w);
+/* torch.optim.AdamW step t = step (>= 1) over one flat fp32 bucket: g = grads * grad_scale; decoupled weight decay
+ * (experiment/run.py:172-200 builds AdamW over get_learnable_params) */
+int la_adamw_f32(void* stream, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale);
+
 #ifdef __cplusplus
 }
 #endif

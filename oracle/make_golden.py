@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference); the fixtures it writes are
 what travels.  Usage:  python oracle/make_golden.py [tiny] [mae256] [samvit] [sam512] [mael256] [sam20w] [samragged] [samneck]
-        [preprocess] [points] [metrics] [loss]
+        [preprocess] [points] [metrics] [loss] [train]
 
 Every fixture stores: the oracle `cfg`, the inputs, the reference outputs and either the full state dict
 (tiny models) or the synthetic-weight seed (real-size models; weights are a pure function of
@@ -515,6 +515,100 @@ def loss_f1(models):
     print("loss_f1.pt", [(tuple(c["logits"].shape), float(c["value"])) for c in cases])
 
 
+def grad_sample(g, n=4096):
+    """{"norm", "values"}: the whole tensor when it has at most n entries, else the n evenly strided entries at
+    `sample_index(numel, n)` (tests/test_training_*.py compare the same positions)."""
+    flat = g.reshape(-1)
+    return {"norm": flat.double().norm().float(), "values": flat[sample_index(flat.numel(), n)].clone()}
+
+
+def sample_index(numel, n=4096):
+    return torch.arange(numel) if numel <= n else torch.linspace(0, numel - 1, n).long()
+
+
+def train_f1(models):
+    """Training step of the pre-computed-embeddings configuration: loss value and the autograd
+    gradient of EVERY parameter of the unmodified reference `Lam` (neck + prompt encoder + mask decoder, `embeddings`
+    key) under the unmodified `LabelAnythingLoss` (focal + class weighting, parameters/trainval/coco/mael.yaml:24-28).
+    Case `mixed`: all prompt types, pinned RandomMatrixEncoder rows, all three merge attentions, mask resize, ragged
+    original sizes with the un-pad crop, flag_gts.  Case `masks_only`: mael.yaml's shape of model (no class encoder,
+    class_example_attention only), mask prompts only (one sparse token per sequence)."""
+    from label_anything.loss import LabelAnythingLoss
+    from label_anything.models.build_lam import build_lam_no_vit
+
+    S, D, Ce, g = 128, 128, 64, 8
+    cases = {}
+    for name in ("mixed", "masks_only"):
+        mixed = name == "mixed"
+        torch.manual_seed(3 if mixed else 4)
+        build = dict(image_embed_dim=Ce, embed_dim=D, image_size=S, spatial_convs=3, class_attention=mixed,
+                     example_attention=mixed, example_class_attention=True, custom_preprocess=mixed,
+                     class_encoder={"name": "RandomMatrixEncoder", "bank_size": 10, "embed_dim": D} if mixed else None)
+        lam = build_lam_no_vit(**build).train()          # the reference's own builder (models/build_lam.py:81-86)
+        load_synth_weights(lam, seed=21 if mixed else 22)
+        rows = torch.tensor([0, 4, 2, 7]) if mixed else None
+        if mixed:
+            _pin_rows(lam, rows)
+        B, M, C = 2, 2, 3
+        dims = (torch.tensor([[[100, 128], [128, 128], [128, 128]], [[128, 80], [128, 128], [128, 128]]],
+                             dtype=torch.int64) if mixed else None)
+        ep = _tiny_episode(B, M, C, S, 48 if mixed else 32, 2, 1, seed=31 if mixed else 32, with_points=mixed,
+                           with_boxes=mixed, dims=dims)
+        del ep["images"]
+        gen = torch.Generator().manual_seed(33)
+        ep["embeddings"] = torch.randn(B, M + 1, Ce, g, g, generator=gen)
+        if mixed:
+            ep["flag_gts"] = torch.tensor([[True, True, False], [True, True, True]])
+        out = lam(ep)
+        logits = out["logits"]
+        Hm, Wm = logits.shape[-2:]
+        gt = torch.randint(0, C, (B, Hm, Wm), generator=gen)
+        if mixed:
+            gt[0][gt[0] == 2] = 1                       # class 2 is absent from episode 0 (flag_gts)
+            for b in range(B):                          # padded pixels are ignored, as the data pipeline pads the gt
+                oh, ow = (int(v) for v in dims[b, 0])
+                gt[b, oh:, :] = -100
+                gt[b, :, ow:] = -100
+        loss_fn = LabelAnythingLoss({"focal": {"weight": 1.0, "gamma": 2.0}}, class_weighting=True)
+        loss = loss_fn(out, gt)
+        loss["value"].backward()
+        # every gradient in full would be 30 MB per case: small tensors are stored whole, large ones as their norm
+        # + 4096 evenly strided entries (`grad_sample`); the weights are a pure function of (name, shape, seed)
+        grads = {k: (None if p.grad is None else grad_sample(p.grad.detach())) for k, p in lam.named_parameters()}
+        # how much the reference's OWN fp32 gradients move when its weight matrices and the input embeddings are rounded
+        # to bf16 once (nothing else changes): the scale of "bf16 rounding noise" for this model and episode, against
+        # which the bf16 training path is judged (the fp32-accurate bf16x3 mode is judged against the gradients)
+        full = {k: p.grad.detach().clone() for k, p in lam.named_parameters() if p.grad is not None}
+        with torch.no_grad():
+            for p in lam.parameters():
+                if p.dim() >= 2:
+                    p.copy_(p.to(torch.bfloat16).float())
+        lam.zero_grad(set_to_none=True)
+        ep_r = dict(ep, embeddings=ep["embeddings"].to(torch.bfloat16).float())
+        loss_fn(lam(ep_r), gt)["value"].backward()
+        rels, num, den = [], 0.0, 0.0
+        for k, p in lam.named_parameters():
+            if k in full and float(full[k].double().norm()) > 1e-6:
+                d2 = float((p.grad.double() - full[k].double()).pow(2).sum())
+                r2 = float(full[k].double().pow(2).sum())
+                rels.append((d2 / r2) ** 0.5)
+                num, den = num + d2, den + r2
+        rels.sort()
+        sens = {"total": (num / den) ** 0.5, "median": rels[len(rels) // 2], "p90": rels[int(0.9 * len(rels))],
+                "worst": rels[-1]}
+        print(f"train_f1[{name}]: gradient change under one bf16 rounding of weights + inputs: {sens}")
+        cfg = {"image_size": S, "image_embedding_size": (g, g), "has_neck": True, "spatial_convs": 3,
+               "class_attention": mixed, "example_attention": mixed, "example_class_attention": True,
+               "custom_preprocess": mixed}
+        cases[name] = {"bf16_sensitivity": sens, "cfg": cfg, "weights_seed": 21 if mixed else 22, "episode": ep, "class_rows": rows, "gt": gt, "logits": logits.detach().clone(),
+                       "loss": loss["value"].detach().clone(), "grads": grads,
+                       "build": build}
+        used = sum(v is not None for v in grads.values())
+        print(f"train_f1[{name}]: loss {float(loss['value']):.6f}, {used}/{len(grads)} parameters with a gradient, "
+              f"logits {tuple(logits.shape)}")
+    torch.save({"meta": _meta(), "cases": cases}, GOLD / "train_f1.pt")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["tiny", "mae256", "samvit", "metrics", "loss"]
     models = ref_import.import_reference()
@@ -544,3 +638,5 @@ if __name__ == "__main__":
         metrics_f4(models)
     if "loss" in which:
         loss_f1(models)
+    if "train" in which:
+        train_f1(models)

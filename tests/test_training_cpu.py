@@ -1,0 +1,121 @@
+"""Row f1 (training step) without a GPU: the gradient oracle is pinned to the autograd gradients of the UNMODIFIED
+reference (tests/golden/train_f1.pt, oracle/make_golden.py train), and the host logic of the flat-bucket optimiser
+(run formation, one all-reduce of [gradients | used counters] over two gloo ranks) is exercised on CPU tensors."""
+import os
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "oracle"))
+
+import lam_oracle as O  # noqa: E402  (checker only)
+import loss_oracle as LO  # noqa: E402
+
+from labelanything_b200.build_lam import build_lam_no_vit  # noqa: E402
+from labelanything_b200.synthetic import load_synth_weights  # noqa: E402
+from labelanything_b200.training import FlatAdamW  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden" / "train_f1.pt"
+
+
+def sample_index(numel, n=4096):          # oracle/make_golden.py::sample_index
+    return torch.arange(numel) if numel <= n else torch.linspace(0, numel - 1, n).long()
+
+
+def reference_loss(logits, gt):
+    """LabelAnythingLoss({"focal": {"weight": 1, "gamma": 2}}, class_weighting=True) restated with torch ops
+    (loss/__init__.py:67-92, loss/focal.py:17-25); the weight map comes from the pinned numpy oracle."""
+    wm, _ = LO.get_weight_matrix_from_labels(gt.numpy().copy(), logits.shape[1])
+    ce = F.cross_entropy(logits, gt, reduction="none")
+    pt = torch.exp(-ce)
+    return (torch.pow(1 - pt, 2.0) * torch.from_numpy(wm) * ce).mean()
+
+
+def build_case(case):
+    lam = build_lam_no_vit(**case["build"])
+    load_synth_weights(lam, seed=case["weights_seed"])
+    if case["class_rows"] is not None:
+        lam.prompt_encoder.class_encoder.fixed_rows = case["class_rows"]
+    return lam
+
+
+@pytest.mark.parametrize("name", ["mixed", "masks_only"])
+def test_oracle_gradients_match_the_reference_autograd(name):
+    case = torch.load(GOLD, weights_only=False)["cases"][name]
+    lam = build_case(case)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in lam.state_dict().items()}
+    out = O.lam_forward(sd, case["cfg"], dict(case["episode"]), case["class_rows"])
+    ref = case["logits"]
+    fin = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(out["logits"]), fin)
+    assert (out["logits"][fin] - ref[fin]).abs().max() < 5e-5 * max(1.0, float(ref[fin].abs().max()))
+    loss = reference_loss(out["logits"], case["gt"])
+    assert abs(float(loss) - float(case["loss"])) < 1e-5 * max(1.0, abs(float(case["loss"])))
+    loss.backward()
+    names = dict(lam.named_parameters()).keys()
+    checked = 0
+    for k in names:
+        want = case["grads"][k]
+        got = sd[k].grad
+        if want is None:
+            assert got is None or float(got.abs().max()) == 0.0, k
+            continue
+        g = got.reshape(-1)
+        assert abs(float(g.double().norm()) - float(want["norm"])) <= 2e-3 * float(want["norm"]) + 1e-7, k
+        v = g[sample_index(g.numel())]
+        assert (v - want["values"]).abs().max() <= 2e-3 * float(want["values"].abs().max()) + 1e-7, k
+        checked += 1
+    assert checked > 200
+
+
+def test_used_runs_group_consecutive_parameters_with_equal_step_counts():
+    opt = object.__new__(FlatAdamW)
+    opt.params = [None] * 6
+    opt.offsets = [0, 8, 12, 40, 44, 100]
+    opt.numel = 120
+    opt.steps = [3, 3, 3, 1, 3, 3]
+    assert opt.used_runs([True] * 6) == [(0, 40, 3), (40, 44, 1), (44, 120, 3)]
+    assert opt.used_runs([True, False, True, True, False, True]) == [(0, 8, 3), (12, 40, 3), (40, 44, 1), (100, 120, 3)]
+    assert opt.used_runs([False] * 6) == []
+
+
+def _rank(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(3, 2)), torch.nn.Parameter(torch.randn(7))]
+    opt = FlatAdamW(params)
+    opt.zero_grad()
+    # rank 0 uses parameters 0 and 1, rank 1 only parameter 1; parameter 2 is unused everywhere
+    loss = (params[1] * (rank + 1)).sum() + (params[0].sum() * 2 if rank == 0 else 0)
+    loss.backward()
+    used, w = opt.reduce_gradients()
+    q.put((rank, used, w, params[0].grad.clone(), params[1].grad.clone(), params[2].grad.clone(),
+           params[0].grad.data_ptr() == opt.flat_g.data_ptr()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_bucket_allreduce():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, used, w, g0, g1, g2, in_bucket in res:
+        assert w == 2 and used == [True, True, False]          # used on ANY rank
+        assert torch.allclose(g0, torch.full((5,), 2.0))       # summed over ranks (the update divides by the world size)
+        assert torch.allclose(g1, torch.full((3, 2), 3.0))
+        assert float(g2.abs().max()) == 0.0
+        assert in_bucket                                       # autograd accumulated straight into the flat bucket
