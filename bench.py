@@ -377,6 +377,74 @@ def parity_drift(lam) -> dict | None:
             "against": "tests/golden/sam512_5w5s.pt: logits of the unmodified fp32 reference, same weights and episode"}
 
 
+def training_measurement(rank: int, world: int, steps: int = 5, warmup: int = 3) -> dict:
+    """BASELINE.json configs[3]: one optimisation step of `lam_no_vit` on pre-computed ViT-MAE-L
+    embeddings (parameters/trainval/coco/mael.yaml: image_embed_dim 1024, embed_dim 256, 480 px, focal loss + class
+    weighting, AdamW), 2 episodes of 2-way 5-shot per GPU with point + box + mask prompts.  Runs on EVERY rank: forward,
+    loss, backward, ONE all-reduce of the flat gradient bucket over NCCL, one AdamW launch.  Timed like the headline
+    (barrier + synchronize, CUDA events, max over ranks); the all-reduce is timed in separate steps (its event pair
+    costs a host sync)."""
+    import torch
+    import torch.distributed as dist
+
+    from labelanything_b200 import ops
+    from labelanything_b200.build_lam import build_lam_no_vit
+    from labelanything_b200.loss import LabelAnythingLoss
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+    from labelanything_b200.training import FlatAdamW, train_step
+
+    B, N, K, S = 2, 2, 5, 480
+    lam = build_lam_no_vit(image_embed_dim=1024, embed_dim=256, image_size=S, spatial_convs=3, class_attention=False,
+                           example_attention=False, example_class_attention=True, custom_preprocess=False)
+    load_synth_weights(lam, seed=4)
+    lam = lam.cuda().train()
+    ep = {k: v.cuda() for k, v in make_episode(B, N, K, S, seed=400 + rank, prompts="mixed", embeddings=(1024, 30)).items()}
+    g = torch.Generator().manual_seed(500 + rank)
+    gt = torch.randint(0, N + 1, (B, S // 16, S // 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2).cuda()
+    loss_fn = LabelAnythingLoss({"focal": {"weight": 1.0, "gamma": 2.0}}, class_weighting=True)
+    opt = FlatAdamW(lam.parameters(), lr=5e-5)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for _ in range(warmup):
+        losses.append(float(train_step(lam, loss_fn, opt, ep, gt)["loss"]["value"]))
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = train_step(lam, loss_fn, opt, ep, gt)
+    e1.record()
+    sync()
+    losses.append(float(r["loss"]["value"]))
+    ms = e0.elapsed_time(e1) / steps
+    with ops.profile() as prof:
+        train_step(lam, loss_fn, opt, ep, gt)
+        torch.cuda.synchronize()
+    kernel_ms = sum(a.elapsed_time(b) for _, _, _, a, b in prof.records)
+    gemm_ms = sum(a.elapsed_time(b) for n, _, _, a, b in prof.records if n.startswith("gemm"))
+    ar = []
+    for _ in range(3):
+        train_step(lam, loss_fn, opt, ep, gt, timed=True)
+        if opt.last_allreduce_ms is not None:
+            ar.append(opt.last_allreduce_ms)
+    t = torch.tensor([ms, max(ar) if ar else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = float(t[0]), float(t[1])
+    return {"workload": f"BASELINE configs[3]: lam_no_vit on pre-computed ViT-MAE-L embeddings (1024 x 30 x 30), embed 256, "
+                        f"480 px, {N}-way {K}-shot, {B} episodes per GPU, point + box + mask prompts; forward + focal loss "
+                        f"+ backward + gradient all-reduce + AdamW, bf16 GEMM operands / fp32 accumulation and state",
+            "ms_per_step": ms, "episodes_per_s": B * world / ms * 1e3, "n_gpus": world,
+            "allreduce_ms": ar_ms if world > 1 else None, "grad_bucket_bytes": int(opt.flat_g.numel() * 4),
+            "trainable_parameters": int(sum(p.numel() for p in opt.params)),
+            "native_launches_per_step": prof.launches, "kernel_ms_per_step": kernel_ms, "gemm_ms_per_step": gemm_ms,
+            "loss_first_last": [losses[0], losses[-1]]}
+
+
 def run_native(args) -> None:
     import torch
     import torch.distributed as dist
@@ -550,6 +618,12 @@ def run_native(args) -> None:
                 print(f"# {k:34s} {v['launches'] // prof_steps:5d} launches/step {v['ms'] / prof_steps:8.2f} ms/step "
                       f"{(v['flops'] / v['ms'] / 1e9) if v['flops'] else 0:8.1f} TFLOP/s {v['bytes'] / v['ms'] / 1e6:8.0f} GB/s",
                       file=sys.stderr)
+    training = None
+    if not args.no_training:
+        del dev
+        torch.cuda.empty_cache()
+        training = training_measurement(rank, world)
+    if rank == 0:
         secondary = parity = cpu = None
         if world == 1:
             del dev2
@@ -571,7 +645,7 @@ def run_native(args) -> None:
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                         "pipeline": "double-buffered inputs: H2D of step k+1 on a copy stream overlaps step k; D2H of the logits on a third stream overlaps step k+1"},
                 "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "parity": parity,
-                "secondary": secondary, "cpu_baseline": cpu, "clocks": clocks}
+                "secondary": secondary, "training": training, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -585,6 +659,7 @@ def main() -> None:
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="episodes per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-training", action="store_true", help="skip the training-step measurement (BASELINE configs[3])")
     ap.add_argument("--no-secondary", action="store_true", help="skip the labelled secondary measurements (N = 1)")
     ap.add_argument("--full-episode", action="store_true",
                     help="--impl reference: time ONE whole episode through the reference (minutes) instead of K samples")

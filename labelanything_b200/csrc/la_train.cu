@@ -153,6 +153,36 @@ __global__ void __launch_bounds__(256) bcast_reduce_kernel(const float* __restri
   }
 }
 
+// plain column sum (b_mod == 1: bias gradients over up to S*T rows): 32 columns x 8 row-lanes per CTA over a chunk of
+// COLSUM_ROWS rows, shared-memory reduction over the row-lanes, one atomic per column per CTA (the generic kernel above
+// issued one atomic per column per 64 rows: 844 per address for the 54 000 image-token rows of a training step)
+constexpr int COLSUM_ROWS = 512;
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, float* __restrict__ out, long long rows,
+                                                     int d) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long long r0 = static_cast<long long>(blockIdx.y) * COLSUM_ROWS;
+  const long long r1 = r0 + COLSUM_ROWS < rows ? r0 + COLSUM_ROWS : rows;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < d) {
+    long long r = r0 + ty;
+    for (; r + 8 < r1; r += 16) {
+      a0 += dy[r * d + c];
+      a1 += dy[(r + 8) * d + c];
+    }
+    if (r < r1) a0 += dy[r * d + c];
+  }
+  part[ty][tx] = a0 + a1;
+  __syncthreads();
+  if (ty == 0 && c < d) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][tx];
+    atomicAdd(out + c, s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // LayerNorm (nn.LayerNorm / LayerNorm2d on token-major rows: biased variance) with an optional GELU behind it
 // ------------------------------------------------------------------------------------------------------------------
@@ -288,168 +318,183 @@ struct AttnParams {
   float scale;
 };
 
+// rows are read as 16-byte vectors (head_dim % 4 == 0, 16-byte aligned rows): with lanes over keys every lane walks its
+// own row, and scalar loads made these kernels LSU-bound (32 sectors per 4-byte load instruction)
 template <int DH>
+__device__ __forceinline__ void load_row(float (&r)[DH], const float* __restrict__ p, int dh) {
+#pragma unroll
+  for (int e = 0; e < DH; e += 4) {
+    if (e < dh) {
+      const float4 t = *reinterpret_cast<const float4*>(p + e);
+      r[e] = t.x; r[e + 1] = t.y; r[e + 2] = t.z; r[e + 3] = t.w;
+    } else {
+      r[e] = r[e + 1] = r[e + 2] = r[e + 3] = 0.f;
+    }
+  }
+}
+template <int DH>
+__device__ __forceinline__ void store_row(float* __restrict__ p, const float (&r)[DH], int dh) {
+#pragma unroll
+  for (int e = 0; e < DH; e += 4)
+    if (e < dh) *reinterpret_cast<float4*>(p + e) = make_float4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+}
+template <int DH>
+__device__ __forceinline__ float dot_row(const float (&a)[DH], const float (&b)[DH]) {
+  float s = 0.f;
+#pragma unroll
+  for (int e = 0; e < DH; ++e) s = fmaf(a[e], b[e], s);   // entries past head_dim are zero
+  return s;
+}
+
+// ROW = false: one warp per row, lanes over the inner side, shuffle reductions (long inner side);
+// ROW = true : one thread per row, serial inner loop (inner side <= 32: the image->token attention of the two-way
+//              blocks has 900 queries against 1..30 keys per (sequence, head) -- lanes over keys would idle and every
+//              output would need a shuffle reduction; the rows of a warp share their (sequence, head), so the
+//              inner-side rows are broadcast loads)
+template <int DH, bool ROW>
 __global__ void __launch_bounds__(128) attn_f32_fwd_kernel(const AttnParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int lane = ROW ? 0 : (threadIdx.x & 31);
+  const int step = ROW ? 1 : 32;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long total = p.n_seq * p.heads * p.nq;
   const int ld = p.heads * p.dh;
-  for (long long w = warp; w < total; w += n_warps) {
+  for (long long w = ROW ? tid : (tid >> 5); w < total; w += ROW ? nthr : (nthr >> 5)) {
     const int i = static_cast<int>(w % p.nq);
     const int h = static_cast<int>((w / p.nq) % p.heads);
     const long long s = w / (static_cast<long long>(p.nq) * p.heads);
-    const float* qr = p.q + (s * p.nq + i) * ld + h * p.dh;
-    float q[DH];
+    float q[DH], o[DH], kk[DH];
+    load_row<DH>(q, p.q + (s * p.nq + i) * ld + h * p.dh, p.dh);
 #pragma unroll
-    for (int e = 0; e < DH; ++e) q[e] = e < p.dh ? qr[e] * p.scale : 0.f;
+    for (int e = 0; e < DH; ++e) {
+      q[e] *= p.scale;
+      o[e] = 0.f;
+    }
     const float* kb = p.k + s * p.nk * ld + h * p.dh;
     const float* vb = p.v + s * p.nk * ld + h * p.dh;
     float m = -INFINITY;
-    for (int j = lane; j < p.nk; j += 32) {
-      const float* kr = kb + static_cast<long long>(j) * ld;
-      float sc = 0.f;
-#pragma unroll
-      for (int e = 0; e < DH; ++e)
-        if (e < p.dh) sc = fmaf(q[e], kr[e], sc);
-      m = fmaxf(m, sc);
+    for (int j = lane; j < p.nk; j += step) {
+      load_row<DH>(kk, kb + static_cast<long long>(j) * ld, p.dh);
+      m = fmaxf(m, dot_row<DH>(q, kk));
     }
-    m = warp_max(m);
-    float l = 0.f, o[DH];
-#pragma unroll
-    for (int e = 0; e < DH; ++e) o[e] = 0.f;
-    for (int j = lane; j < p.nk; j += 32) {
-      const float* kr = kb + static_cast<long long>(j) * ld;
-      const float* vr = vb + static_cast<long long>(j) * ld;
-      float sc = 0.f;
-#pragma unroll
-      for (int e = 0; e < DH; ++e)
-        if (e < p.dh) sc = fmaf(q[e], kr[e], sc);
-      const float pj = __expf(sc - m);
+    if (!ROW) m = warp_max(m);
+    float l = 0.f;
+    for (int j = lane; j < p.nk; j += step) {
+      load_row<DH>(kk, kb + static_cast<long long>(j) * ld, p.dh);
+      const float pj = __expf(dot_row<DH>(q, kk) - m);
       l += pj;
+      load_row<DH>(kk, vb + static_cast<long long>(j) * ld, p.dh);
+#pragma unroll
+      for (int e = 0; e < DH; ++e) o[e] = fmaf(pj, kk[e], o[e]);
+    }
+    if (!ROW) {
+      l = warp_sum(l);
 #pragma unroll
       for (int e = 0; e < DH; ++e)
-        if (e < p.dh) o[e] = fmaf(pj, vr[e], o[e]);
+        if (e < p.dh) o[e] = warp_sum(o[e]);
     }
-    l = warp_sum(l);
     const float inv = 1.f / l;
-    float* orow = p.out + (s * p.nq + i) * ld + h * p.dh;
 #pragma unroll
-    for (int e = 0; e < DH; ++e) {
-      if (e < p.dh) {
-        const float t = warp_sum(o[e]);
-        if (lane == 0) orow[e] = t * inv;
-      }
+    for (int e = 0; e < DH; ++e) o[e] *= inv;
+    if (lane == 0) {
+      store_row<DH>(p.out + (s * p.nq + i) * ld + h * p.dh, o, p.dh);
+      p.lse[w] = m + __logf(l);
     }
-    if (lane == 0) p.lse[w] = m + __logf(l);
   }
 }
 
-// dq (and delta = rowsum(dout * out), consumed by the dk / dv kernel): one warp per (sequence, head, query)
-template <int DH>
+// dq (and delta = rowsum(dout * out), consumed by the dk / dv kernel)
+template <int DH, bool ROW>
 __global__ void __launch_bounds__(128) attn_f32_bwd_q_kernel(const AttnParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int lane = ROW ? 0 : (threadIdx.x & 31);
+  const int step = ROW ? 1 : 32;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long total = p.n_seq * p.heads * p.nq;
   const int ld = p.heads * p.dh;
-  for (long long w = warp; w < total; w += n_warps) {
+  for (long long w = ROW ? tid : (tid >> 5); w < total; w += ROW ? nthr : (nthr >> 5)) {
     const int i = static_cast<int>(w % p.nq);
     const int h = static_cast<int>((w / p.nq) % p.heads);
     const long long s = w / (static_cast<long long>(p.nq) * p.heads);
     const long long row = (s * p.nq + i) * ld + h * p.dh;
-    float q[DH], go[DH], dq[DH];
-    float dl = 0.f;
+    float q[DH], go[DH], dq[DH], kk[DH];
+    load_row<DH>(q, p.q + row, p.dh);
+    load_row<DH>(go, p.dout + row, p.dh);
+    load_row<DH>(kk, p.out + row, p.dh);
+    const float dl = dot_row<DH>(go, kk);
 #pragma unroll
     for (int e = 0; e < DH; ++e) {
-      q[e] = e < p.dh ? p.q[row + e] * p.scale : 0.f;
-      go[e] = e < p.dh ? p.dout[row + e] : 0.f;
-      dl += e < p.dh ? go[e] * p.out[row + e] : 0.f;
+      q[e] *= p.scale;
       dq[e] = 0.f;
     }
     const float lse = p.lse[w];
     const float* kb = p.k + s * p.nk * ld + h * p.dh;
     const float* vb = p.v + s * p.nk * ld + h * p.dh;
-    for (int j = lane; j < p.nk; j += 32) {
-      const float* kr = kb + static_cast<long long>(j) * ld;
-      const float* vr = vb + static_cast<long long>(j) * ld;
-      float sc = 0.f, dp = 0.f;
+    for (int j = lane; j < p.nk; j += step) {
+      load_row<DH>(kk, vb + static_cast<long long>(j) * ld, p.dh);
+      const float dp = dot_row<DH>(go, kk);
+      load_row<DH>(kk, kb + static_cast<long long>(j) * ld, p.dh);
+      const float ds = __expf(dot_row<DH>(q, kk) - lse) * (dp - dl) * p.scale;
 #pragma unroll
-      for (int e = 0; e < DH; ++e) {
-        if (e < p.dh) {
-          sc = fmaf(q[e], kr[e], sc);
-          dp = fmaf(go[e], vr[e], dp);
-        }
-      }
-      const float ds = __expf(sc - lse) * (dp - dl) * p.scale;
+      for (int e = 0; e < DH; ++e) dq[e] = fmaf(ds, kk[e], dq[e]);
+    }
+    if (!ROW) {
 #pragma unroll
       for (int e = 0; e < DH; ++e)
-        if (e < p.dh) dq[e] = fmaf(ds, kr[e], dq[e]);
+        if (e < p.dh) dq[e] = warp_sum(dq[e]);
     }
-#pragma unroll
-    for (int e = 0; e < DH; ++e) {
-      if (e < p.dh) {
-        const float t = warp_sum(dq[e]);
-        if (lane == 0) p.dq[row + e] = t;
-      }
+    if (lane == 0) {
+      store_row<DH>(p.dq + row, dq, p.dh);
+      p.delta[w] = dl;
     }
-    if (lane == 0) p.delta[w] = dl;
   }
 }
 
-// dk, dv: one warp per (sequence, head, key), lanes over queries
-template <int DH>
+// dk, dv: rows are the keys, the inner side are the queries
+template <int DH, bool ROW>
 __global__ void __launch_bounds__(128) attn_f32_bwd_kv_kernel(const AttnParams p) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int lane = ROW ? 0 : (threadIdx.x & 31);
+  const int step = ROW ? 1 : 32;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long total = p.n_seq * p.heads * p.nk;
   const int ld = p.heads * p.dh;
-  for (long long w = warp; w < total; w += n_warps) {
+  for (long long w = ROW ? tid : (tid >> 5); w < total; w += ROW ? nthr : (nthr >> 5)) {
     const int j = static_cast<int>(w % p.nk);
     const int h = static_cast<int>((w / p.nk) % p.heads);
     const long long s = w / (static_cast<long long>(p.nk) * p.heads);
     const long long row = (s * p.nk + j) * ld + h * p.dh;
-    float k[DH], v[DH], dk[DH], dv[DH];
+    float k[DH], v[DH], dk[DH], dv[DH], qq[DH], gg[DH];
+    load_row<DH>(k, p.k + row, p.dh);
+    load_row<DH>(v, p.v + row, p.dh);
 #pragma unroll
-    for (int e = 0; e < DH; ++e) {
-      k[e] = e < p.dh ? p.k[row + e] : 0.f;
-      v[e] = e < p.dh ? p.v[row + e] : 0.f;
-      dk[e] = dv[e] = 0.f;
-    }
+    for (int e = 0; e < DH; ++e) dk[e] = dv[e] = 0.f;
     const float* qb = p.q + s * p.nq * ld + h * p.dh;
     const float* gb = p.dout + s * p.nq * ld + h * p.dh;
     const long long stat = (s * p.heads + h) * p.nq;
-    for (int i = lane; i < p.nq; i += 32) {
-      const float* qr = qb + static_cast<long long>(i) * ld;
-      const float* gr = gb + static_cast<long long>(i) * ld;
-      float sc = 0.f, dp = 0.f;
+    for (int i = lane; i < p.nq; i += step) {
+      load_row<DH>(qq, qb + static_cast<long long>(i) * ld, p.dh);
+      load_row<DH>(gg, gb + static_cast<long long>(i) * ld, p.dh);
+      const float pij = __expf(dot_row<DH>(qq, k) * p.scale - p.lse[stat + i]);
+      const float ds = pij * (dot_row<DH>(gg, v) - p.delta[stat + i]) * p.scale;
 #pragma unroll
       for (int e = 0; e < DH; ++e) {
-        if (e < p.dh) {
-          sc = fmaf(qr[e], k[e], sc);
-          dp = fmaf(gr[e], v[e], dp);
-        }
+        dv[e] = fmaf(pij, gg[e], dv[e]);
+        dk[e] = fmaf(ds, qq[e], dk[e]);
       }
-      const float pij = __expf(sc * p.scale - p.lse[stat + i]);
-      const float ds = pij * (dp - p.delta[stat + i]) * p.scale;
+    }
+    if (!ROW) {
 #pragma unroll
       for (int e = 0; e < DH; ++e) {
         if (e < p.dh) {
-          dv[e] = fmaf(pij, gr[e], dv[e]);
-          dk[e] = fmaf(ds, qr[e], dk[e]);
+          dk[e] = warp_sum(dk[e]);
+          dv[e] = warp_sum(dv[e]);
         }
       }
     }
-#pragma unroll
-    for (int e = 0; e < DH; ++e) {
-      if (e < p.dh) {
-        const float a = warp_sum(dk[e]), b = warp_sum(dv[e]);
-        if (lane == 0) {
-          p.dk[row + e] = a;
-          p.dv[row + e] = b;
-        }
-      }
+    if (lane == 0) {
+      store_row<DH>(p.dk + row, dk, p.dh);
+      store_row<DH>(p.dv + row, dv, p.dh);
     }
   }
 }
@@ -1030,8 +1075,13 @@ int la_bcast_reduce_f32(void* stream, const float* dy, float* out, long long row
                         long long b_mod, int accumulate) {
   LA_CHECK_ARG(dy && out && rows > 0 && d > 0 && row_div > 0 && b_mod > 0, "la_bcast_reduce_f32: bad arguments");
   if (!accumulate) LA_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * b_mod * d, ST(stream)));
-  const long long items = (rows + RED_ROWS - 1) / RED_ROWS * d;
-  bcast_reduce_kernel<<<train_grid(items), 256, 0, ST(stream)>>>(dy, out, rows, d, row_div, b_mod);
+  if (b_mod == 1 && (rows + COLSUM_ROWS - 1) / COLSUM_ROWS <= 65535) {
+    dim3 grid(static_cast<unsigned>((d + 31) / 32), static_cast<unsigned>((rows + COLSUM_ROWS - 1) / COLSUM_ROWS));
+    colsum_kernel<<<grid, 256, 0, ST(stream)>>>(dy, out, rows, d);
+  } else {
+    const long long items = (rows + RED_ROWS - 1) / RED_ROWS * d;
+    bcast_reduce_kernel<<<train_grid(items), 256, 0, ST(stream)>>>(dy, out, rows, d, row_div, b_mod);
+  }
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
@@ -1088,15 +1138,23 @@ int la_layernorm_f32_bwd(void* stream, const float* x, const float* gamma, const
 
 int la_attention_f32(void* stream, const float* q, const float* k, const float* v, float* out, float* lse,
                      long long n_seq, int nq, int nk, int heads, int head_dim, float scale) {
-  LA_CHECK_ARG(q && k && v && out && lse && n_seq > 0 && nq > 0 && nk > 0 && heads > 0 && head_dim > 0 && head_dim <= 64,
-               "la_attention_f32: bad arguments (head_dim <= 64)");
+  LA_CHECK_ARG(q && k && v && out && lse && n_seq > 0 && nq > 0 && nk > 0 && heads > 0 && head_dim > 0 && head_dim <= 64 &&
+                   head_dim % 4 == 0,
+               "la_attention_f32: bad arguments (head_dim <= 64, a multiple of 4)");
   AttnParams p{};
   p.q = q; p.k = k; p.v = v; p.out = out; p.lse = lse;
   p.n_seq = n_seq; p.nq = nq; p.nk = nk; p.heads = heads; p.dh = head_dim; p.scale = scale;
-  const unsigned grid = train_grid(n_seq * heads * nq * 32, 128);
-#define CALL(DH) attn_f32_fwd_kernel<DH><<<grid, 128, 0, ST(stream)>>>(p)
-  LA_DH_DISPATCH(head_dim, CALL);
+  if (nk <= 32) {
+    const unsigned grid = train_grid(n_seq * heads * nq, 128);
+#define CALL(DH) attn_f32_fwd_kernel<DH, true><<<grid, 128, 0, ST(stream)>>>(p)
+    LA_DH_DISPATCH(head_dim, CALL);
 #undef CALL
+  } else {
+    const unsigned grid = train_grid(n_seq * heads * nq * 32, 128);
+#define CALL(DH) attn_f32_fwd_kernel<DH, false><<<grid, 128, 0, ST(stream)>>>(p)
+    LA_DH_DISPATCH(head_dim, CALL);
+#undef CALL
+  }
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
@@ -1105,18 +1163,35 @@ int la_attention_f32_bwd(void* stream, const float* q, const float* k, const flo
                          const float* dout, float* delta, float* dq, float* dk, float* dv, long long n_seq, int nq, int nk,
                          int heads, int head_dim, float scale) {
   LA_CHECK_ARG(q && k && v && out && lse && dout && delta && dq && dk && dv && n_seq > 0 && nq > 0 && nk > 0 &&
-                   heads > 0 && head_dim > 0 && head_dim <= 64,
-               "la_attention_f32_bwd: bad arguments (head_dim <= 64)");
+                   heads > 0 && head_dim > 0 && head_dim <= 64 && head_dim % 4 == 0,
+               "la_attention_f32_bwd: bad arguments (head_dim <= 64, a multiple of 4)");
   AttnParams p{};
   p.q = q; p.k = k; p.v = v; p.out = const_cast<float*>(out); p.lse = const_cast<float*>(lse);
   p.dout = dout; p.delta = delta; p.dq = dq; p.dk = dk; p.dv = dv;
   p.n_seq = n_seq; p.nq = nq; p.nk = nk; p.heads = heads; p.dh = head_dim; p.scale = scale;
-  const unsigned gq = train_grid(n_seq * heads * nq * 32, 128), gk = train_grid(n_seq * heads * nk * 32, 128);
-#define CALL(DH)                                              \
-  attn_f32_bwd_q_kernel<DH><<<gq, 128, 0, ST(stream)>>>(p);   \
-  attn_f32_bwd_kv_kernel<DH><<<gk, 128, 0, ST(stream)>>>(p)
-  LA_DH_DISPATCH(head_dim, CALL);
+  // dq (+ delta) first: the dk / dv kernels read delta
+  if (nk <= 32) {
+    const unsigned gq = train_grid(n_seq * heads * nq, 128);
+#define CALL(DH) attn_f32_bwd_q_kernel<DH, true><<<gq, 128, 0, ST(stream)>>>(p)
+    LA_DH_DISPATCH(head_dim, CALL);
 #undef CALL
+  } else {
+    const unsigned gq = train_grid(n_seq * heads * nq * 32, 128);
+#define CALL(DH) attn_f32_bwd_q_kernel<DH, false><<<gq, 128, 0, ST(stream)>>>(p)
+    LA_DH_DISPATCH(head_dim, CALL);
+#undef CALL
+  }
+  if (nq <= 32) {
+    const unsigned gk = train_grid(n_seq * heads * nk, 128);
+#define CALL(DH) attn_f32_bwd_kv_kernel<DH, true><<<gk, 128, 0, ST(stream)>>>(p)
+    LA_DH_DISPATCH(head_dim, CALL);
+#undef CALL
+  } else {
+    const unsigned gk = train_grid(n_seq * heads * nk * 32, 128);
+#define CALL(DH) attn_f32_bwd_kv_kernel<DH, false><<<gk, 128, 0, ST(stream)>>>(p)
+    LA_DH_DISPATCH(head_dim, CALL);
+#undef CALL
+  }
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }

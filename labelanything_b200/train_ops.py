@@ -14,6 +14,7 @@ There is no CPU / torch fallback: CPU tensors raise.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional
 
 import torch
@@ -98,20 +99,47 @@ class precision:
         _PRECISION = self.prev
 
 
+# Operands derived from a tensor (its bf16 split, the transposes of those) are shared between the ops that consume the
+# same tensor -- `keys + pe` feeds two projections per two-way layer, the input of an attention block three; each of
+# them would cast it in the forward and transpose it in the backward pass again.  Entries are keyed on the storage
+# address + shape + version of the (contiguous) source and dropped when the source tensor dies, so an address the
+# allocator hands out again can never hit a stale entry.
+_DERIVED: dict = {}
+
+
+def _derived(tag: str, src: torch.Tensor, build):
+    key = (tag, src.data_ptr(), tuple(src.shape), src.dtype, src._version)
+    hit = _DERIVED.get(key)
+    if hit is not None and hit[0]() is not None:
+        return hit[1]
+    val = build()
+    try:
+        ref = weakref.ref(src, lambda _r, k=key: _DERIVED.pop(k, None))
+    except TypeError:
+        return val
+    _DERIVED[key] = (ref, val)
+    return val
+
+
 def _split(x: torch.Tensor, mode: Optional[str] = None) -> tuple:
     """fp32 tensor -> GEMM operand (tuple of bf16 tensors of the same shape)."""
-    if (mode or _PRECISION) == "bf16":
-        return (cast_bf16(x),)
+    mode = mode or _PRECISION
     _require_cuda(x)
     x = _f32c(x)
-    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _call("split_bf16", "la_split_bf16", x, hi, lo, x.numel())
-    return (hi, lo)
+
+    def build():
+        if mode == "bf16":
+            return (cast_bf16(x),)
+        hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        _call("split_bf16", "la_split_bf16", x, hi, lo, x.numel())
+        return (hi, lo)
+
+    return _derived("split:" + mode, x, build)
 
 
 def _tr(op: tuple) -> tuple:
-    return tuple(cast_transpose(t) for t in op)
+    return tuple(_derived("T", t, lambda t=t: cast_transpose(t)) for t in op)
 
 
 def _relu_f32(x: torch.Tensor) -> torch.Tensor:
@@ -350,7 +378,8 @@ class _Attention(Function):
         out = torch.empty_like(q)
         lse = torch.empty((n_seq, heads, nq), dtype=torch.float32, device=q.device)
         scale = dh ** -0.5
-        _call("attention_f32", "la_attention_f32", q, k, v, out, lse, n_seq, nq, nk, heads, dh, scale)
+        _call(f"attention_f32.s{n_seq}.q{nq}.k{nk}.d{dh}" if ops._PROF is not None else "attention_f32", "la_attention_f32",
+              q, k, v, out, lse, n_seq, nq, nk, heads, dh, scale)
         ctx.cfg = (n_seq, nq, nk, heads, dh, scale)
         ctx.save_for_backward(q, k, v, out, lse)
         return out
@@ -362,8 +391,8 @@ class _Attention(Function):
         n_seq, nq, nk, heads, dh, scale = ctx.cfg
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         delta = torch.empty_like(lse)
-        _call("attention_f32_bwd", "la_attention_f32_bwd", q, k, v, out, lse, _f32c(dout), delta, dq, dk, dv, n_seq, nq, nk,
-              heads, dh, scale)
+        _call(f"attention_f32_bwd.s{n_seq}.q{nq}.k{nk}.d{dh}" if ops._PROF is not None else "attention_f32_bwd",
+              "la_attention_f32_bwd", q, k, v, out, lse, _f32c(dout), delta, dq, dk, dv, n_seq, nq, nk, heads, dh, scale)
         return dq, dk, dv, None, None, None, None
 
 
