@@ -47,9 +47,9 @@ EPISODE_GFLOP = 26 * (965.64 + 22.55) + 150 * 10.855 + 28.7
 # DRAM traffic per launch (MB) of the kernels that can dominate the step, from the committed `ncu --set full` captures
 # (profiles/r01_ncu_{attention,gemm,layernorm}_v3.txt) taken at the bench's launch size (one 32-image encoder chunk)
 NCU_TRAFFIC_SOURCE = ("ncu --set full dram__bytes_read.sum + dram__bytes_write.sum on a 32-image launch "
-                      "(profiles/r01_ncu_attention_v4.txt, r01_ncu_{gemm,layernorm}_v3.txt), scaled to this run's images "
-                      "per chunk")
-NCU_TRAFFIC_MB = {"attention.L4096": 1600.9, "attention.L196": 904.8, "gemm.n3072.k768": 964.0, "gemm.n768.k3072": 1007.2,
+                      "(profiles/r02_ncu_attention_global_v2.txt: q/k/v/out 805 MB + the fp16 rel-pos table 805 MB; "
+                      "r01_ncu_attention_window_v2.txt, r01_ncu_{gemm,layernorm}_v3.txt), scaled to this run's images per chunk")
+NCU_TRAFFIC_MB = {"attention.L4096": 1608.5, "attention.L196": 904.8, "gemm.n3072.k768": 964.0, "gemm.n768.k3072": 1007.2,
                   "gemm.n768.k768": 361.7, "gemm.n1536.k768": 554.9, "add_layernorm.d768.map0": 1151.0}
 
 
