@@ -32,7 +32,7 @@ from .prompt_encoder import PromptImageEncoder, RandomMatrixEncoder
 from .transformer import TwoWayTransformer
 from .utils import BatchKeys, ResultDict, get_preprocess_shape
 
-__all__ = ["train_forward", "FlatAdamW", "train_step"]
+__all__ = ["train_forward", "make_plan", "FlatAdamW", "train_step", "GraphedTrainStep"]
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -104,7 +104,7 @@ def _neck(neck: nn.Sequential, x: torch.Tensor, n_img: int, g: int) -> torch.Ten
 
 
 def _prompt_encoder(pe_mod: PromptImageEncoder, feat: torch.Tensor, B: int, M: int, points, boxes, masks,
-                    flag_examples: torch.Tensor) -> Dict[str, torch.Tensor]:
+                    flag_examples: torch.Tensor, class_rows: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """prompt_encoder.py:752-827 (+ 564-669, 696-750).  feat fp32 [B*M*T, D] support features."""
     any_prompt = points[0] if points is not None else boxes[0] if boxes is not None else \
         masks[0] if masks is not None else None
@@ -141,7 +141,7 @@ def _prompt_encoder(pe_mod: PromptImageEncoder, feat: torch.Tensor, B: int, M: i
     code = None
     ce = pe_mod.class_encoder
     if isinstance(ce, RandomMatrixEncoder):
-        rows = ce.sample_rows(C, dev)
+        rows = class_rows if class_rows is not None else ce.sample_rows(C, dev)
         code = ce.pos_embedding[0, 0].index_select(0, rows)              # [C, D], differentiable gather of the bank
         sparse = T.add_bcast(sparse, code, n, C)
     elif isinstance(ce, nn.Module):
@@ -218,13 +218,39 @@ def _mask_decoder(md, query: torch.Tensor, pe: torch.Tensor, class_emb: torch.Te
 # ----------------------------------------------------------------------------------------------------------------
 # Lam.forward(embeddings) with gradients
 # ----------------------------------------------------------------------------------------------------------------
-def train_forward(lam: Lam, batched_input: Dict[str, Any]) -> Dict[str, torch.Tensor]:
+def make_plan(lam: Lam, batched_input: Dict[str, Any]) -> Dict[str, Any]:
+    """Everything `train_forward` needs from the HOST side of a batch, computed once: which prompt types are present
+    (lam.py:214-239 reads the flags back), the per-episode sizes of `postprocess_masks` (lam.py:383-453 reads `dims`
+    back) and the class-code rows.  A plan can be reused for every batch of the same geometry -- which is what a captured
+    CUDA graph of the step requires (`GraphedTrainStep`)."""
+    points, boxes, masks, _ = lam.prepare_prompts(batched_input)
+    dims = batched_input["dims"]
+    sizes_host = dims.detach().to("cpu", torch.int64)
+    max_h, max_w = (int(v) for v in sizes_host.view(-1, 2).max(dim=0).values)
+    rows = []
+    for oh, ow in sizes_host[:, 0, :].tolist():
+        ih, iw = get_preprocess_shape(oh, ow, lam.image_size) if lam.custom_preprocess else (lam.image_size, lam.image_size)
+        rows.append((oh, ow, ih, iw))
+    dev = batched_input["embeddings"].device
+    plan = {"points": points is not None, "boxes": boxes is not None, "masks": masks is not None,
+            "sizes": torch.tensor(rows, dtype=torch.int32).to(dev), "out_hw": (max_h, max_w), "class_rows": None}
+    ce = lam.prompt_encoder.class_encoder
+    if isinstance(ce, RandomMatrixEncoder):
+        C = batched_input[BatchKeys.FLAG_EXAMPLES].shape[2]
+        plan["class_rows"] = ce.sample_rows(C, dev)
+    return plan
+
+
+def train_forward(lam: Lam, batched_input: Dict[str, Any], plan: Optional[Dict[str, Any]] = None) -> Dict[str, torch.Tensor]:
     """Differentiable `Lam.forward` on pre-computed embeddings (lam.py:57-170 with the `embeddings` key): returns
     {"logits" [B, C, Hmax, Wmax], "class_examples_embeddings" [B, M, C, D]} attached to the autograd graph of the
-    parameters of lam.neck / lam.prompt_encoder / lam.mask_decoder."""
+    parameters of lam.neck / lam.prompt_encoder / lam.mask_decoder.  With a `plan` (make_plan) the call performs no
+    host synchronisation at all."""
     if "embeddings" not in batched_input:
         raise NotImplementedError("the native training step covers the pre-computed-embeddings configuration "
                                   "(lam_no_vit, parameters/trainval/coco/mael.yaml); the ViT has no backward kernels")
+    if plan is None:
+        plan = make_plan(lam, batched_input)
     emb = batched_input["embeddings"]
     ops._require_cuda(emb)
     B, N, Ce, H, W = emb.shape
@@ -237,24 +263,18 @@ def train_forward(lam: Lam, batched_input: Dict[str, Any]) -> Dict[str, torch.Te
     per_ep = feats.view(B, N * Tn * D)
     query = per_ep[:, :Tn * D].reshape(B * Tn, D)                    # image 0 of every episode
     support = per_ep[:, Tn * D:].reshape(B * M * Tn, D)
-    points, boxes, masks, flag_examples = lam.prepare_prompts(batched_input)
-    pe_result = _prompt_encoder(lam.prompt_encoder, support, B, M, points, boxes, masks, flag_examples)
+    bi = batched_input
+    points = (bi[BatchKeys.PROMPT_POINTS], bi[BatchKeys.FLAG_POINTS]) if plan["points"] else None
+    boxes = (bi[BatchKeys.PROMPT_BBOXES], bi[BatchKeys.FLAG_BBOXES]) if plan["boxes"] else None
+    masks = (bi[BatchKeys.PROMPT_MASKS], bi[BatchKeys.FLAG_MASKS]) if plan["masks"] else None
+    pe_result = _prompt_encoder(lam.prompt_encoder, support, B, M, points, boxes, masks, bi[BatchKeys.FLAG_EXAMPLES],
+                                class_rows=plan["class_rows"])
     seg = _mask_decoder(lam.mask_decoder, query, lam.prompt_encoder.dense_pe_tokens(), pe_result[ResultDict.CLASS_EMBS],
                         B, g, g)
-
-    # postprocess_masks (lam.py:383-453)
-    dims = batched_input["dims"]
-    sizes_host = dims.detach().to("cpu", torch.int64)
-    max_h, max_w = (int(v) for v in sizes_host.view(-1, 2).max(dim=0).values)
-    rows = []
-    for oh, ow in sizes_host[:, 0, :].tolist():
-        ih, iw = get_preprocess_shape(oh, ow, lam.image_size) if lam.custom_preprocess else (lam.image_size, lam.image_size)
-        rows.append((oh, ow, ih, iw))
-    sizes = torch.tensor(rows, dtype=torch.int32).to(seg.device)
     fg = batched_input.get("flag_gts")
     if fg is not None:
         fg = (fg != 0).to(device=seg.device, dtype=torch.uint8).contiguous()
-    logits = T.postprocess_masks(seg, sizes, fg, lam.image_size, max_h, max_w)
+    logits = T.postprocess_masks(seg, plan["sizes"], fg, lam.image_size, *plan["out_hw"])    # lam.py:383-453
     return {ResultDict.LOGITS: logits, ResultDict.EXAMPLES_CLASS_EMBS: pe_result[ResultDict.EXAMPLES_CLASS_EMBS]}
 
 
@@ -314,16 +334,19 @@ class FlatAdamW:
     def used_runs(self, used: List[bool]) -> List[Tuple[int, int, int]]:
         """Maximal runs [(first offset, one-past-last offset, step count)] of consecutive used parameters that share a
         step count."""
+        return self.used_runs_for(self.steps, used)
+
+    def used_runs_for(self, steps: List[int], used: List[bool]) -> List[Tuple[int, int, int]]:
         runs, i, n = [], 0, len(self.params)
         while i < n:
             if not used[i]:
                 i += 1
                 continue
             j = i
-            while j + 1 < n and used[j + 1] and self.steps[j + 1] == self.steps[i]:
+            while j + 1 < n and used[j + 1] and steps[j + 1] == steps[i]:
                 j += 1
             end = self.offsets[j + 1] if j + 1 < n else self.numel
-            runs.append((self.offsets[i], end, self.steps[i]))
+            runs.append((self.offsets[i], end, steps[i]))
             i = j + 1
         return runs
 
@@ -350,6 +373,10 @@ class FlatAdamW:
 
     def step(self, timed: bool = False) -> None:
         used, world = self.reduce_gradients(timed)
+        self.apply(used, world)
+
+    def apply(self, used: List[bool], world: int) -> None:
+        """AdamW update of the parameters in `used` from the (already reduced) gradient bucket."""
         for i, u in enumerate(used):
             if u:
                 self.steps[i] += 1
@@ -371,3 +398,138 @@ def train_step(lam: Lam, loss_fn, opt: FlatAdamW, batched_input: Dict[str, Any],
     value.backward()
     opt.step(timed=timed)
     return {"loss": loss, **result}
+
+
+def _loss_value(loss_fn, logits: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """`LabelAnythingLoss.logits_loss` (loss/__init__.py:67-92) without the `.item()` of its logging dictionary: the
+    summed value only, as a device tensor (the component weight applied twice, like the reference)."""
+    from .loss import FROM_CLASS_WEIGHTS
+
+    wm = cw = None
+    if loss_fn.class_weighting:
+        cw, _ = ops.label_class_weights(gt.contiguous(), logits.shape[1])
+        wm = FROM_CLASS_WEIGHTS
+    total = None
+    for k, comp in loss_fn.components.items():
+        v = loss_fn.weights[k] * (loss_fn.weights[k] * comp(logits, gt, weight_matrix=wm, class_weights=cw))
+        total = v if total is None else total + v
+    return total
+
+
+class GraphedTrainStep:
+    """The whole optimisation step -- forward, loss, backward, gradient all-reduce, AdamW -- captured ONCE in a CUDA
+    graph and replayed per batch.  The eager step issues ~960 native launches plus autograd bookkeeping and is bound by
+    the host (27.6 ms against ~12 ms of GPU work for BASELINE configs[3]); a replay is one launch.
+
+    What a graph fixes, and how each piece is handled:
+      * geometry (shapes, prompt types present, original sizes): the `plan` of the example batch; `__call__` copies a new
+        batch of the same geometry into the static input tensors;
+      * which parameters receive a gradient: taken from eager warm-up steps, constant for a geometry;
+      * the optimiser's step count: the bias corrections live in device memory (`la_adamw_f32_dev`) and are refreshed
+        before every replay;
+      * RandomMatrixEncoder rows: drawn before every replay into a static tensor.
+    The loss value and the outputs are static device tensors (no `.item()` inside the step)."""
+
+    def __init__(self, lam: Lam, loss_fn, opt: FlatAdamW, example_input: Dict[str, Any], example_gt: torch.Tensor,
+                 warmup: int = 3) -> None:
+        import torch.distributed as dist
+
+        self.lam, self.loss_fn, self.opt = lam, loss_fn, opt
+        self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_input.items()}
+        self.gt = example_gt.clone()
+        self.plan = make_plan(lam, self.static)
+        self.world = dist.get_world_size(opt.group) if (dist.is_available() and dist.is_initialized()) else 1
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                     # eager warm-up steps on a side stream (torch.cuda.graph protocol)
+            for _ in range(max(1, warmup)):
+                opt.zero_grad()
+                out = train_forward(lam, self.static, self.plan)
+                _loss_value(loss_fn, out[ResultDict.LOGITS], self.gt).backward()
+                used, _ = opt.reduce_gradients()
+                opt.apply(used, self.world)
+        torch.cuda.current_stream().wait_stream(side)
+        self.used = used
+        dev = opt.flat_p.device
+        self.runs = opt.used_runs_for([s + 1 if u else s for s, u in zip(opt.steps, used)], used)
+        n_runs = max(1, len(self.runs))
+        self.bc = torch.ones((n_runs, 2), dtype=torch.float32, device=dev)
+        # ring of pinned staging rows for the bias corrections: a slot is rewritten only after its last upload finished
+        self._bc_host = [torch.ones((n_runs, 2), dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._bc_done = [torch.cuda.Event() for _ in range(4)]
+        self._bc_slot = 0
+        self._run_steps = [st for _, _, st in self.runs]
+        torch.cuda.synchronize()
+        # Inside the graph the gradients are taken with torch.autograd.grad w.r.t. fresh leaf ALIASES of the parameters
+        # (same storage) and copied into the bucket.  The parameters themselves cannot be differentiated under capture
+        # once an eager step has used them: their AccumulateGrad nodes stay bound to the stream of their first use (the
+        # legacy stream), and autograd buffers incoming gradients on that stream ("operation would make the legacy stream
+        # depend on a capturing blocking stream").
+        views = [opt.flat_g[o:o + p.numel()].view(p.shape) for p, o, u in zip(opt.params, opt.offsets, used) if u]
+        alias = {id(p): p.detach().requires_grad_(True) for p, u in zip(opt.params, used) if u}
+        swapped = []
+        for mod in lam.modules():
+            for name, p in list(mod._parameters.items()):
+                if p is not None and id(p) in alias:
+                    mod._parameters[name] = alias[id(p)]
+                    swapped.append((mod, name, p))
+        T._DERIVED.clear()                    # no operand cached by the eager steps may stand in for a captured launch
+        opt.flat_g.zero_()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(self.graph):
+                out = train_forward(lam, self.static, self.plan)
+                self.loss = _loss_value(loss_fn, out[ResultDict.LOGITS], self.gt)
+                grads = torch.autograd.grad(self.loss, [alias[id(p)] for p, u in zip(opt.params, used) if u])
+                torch._foreach_copy_(views, list(grads))
+                del grads
+                if self.world > 1:
+                    dist.all_reduce(opt.flat_g[:opt.numel], group=opt.group)   # the step's one collective, in the graph
+                for i, (lo, hi, _) in enumerate(self.runs):
+                    T.adamw_step_dev(opt.flat_p[lo:hi], opt.flat_g[lo:hi], opt.exp_avg[lo:hi], opt.exp_avg_sq[lo:hi],
+                                     opt.lr, opt.betas[0], opt.betas[1], opt.eps, opt.weight_decay, self.bc[i],
+                                     1.0 / self.world)
+        finally:
+            for mod, name, p in swapped:
+                mod._parameters[name] = p
+        self.loss = self.loss.detach()
+        out = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}
+        self.out = out
+
+    def _fill_bc(self) -> None:
+        b1, b2 = self.opt.betas
+        slot = self._bc_slot
+        self._bc_slot = (slot + 1) % len(self._bc_host)
+        self._bc_done[slot].synchronize()
+        host = self._bc_host[slot]
+        for i, st in enumerate(self._run_steps):
+            host[i, 0] = 1.0 - b1 ** st
+            host[i, 1] = (1.0 - b2 ** st) ** 0.5
+        self.bc.copy_(host, non_blocking=True)
+        self._bc_done[slot].record()
+
+    def __call__(self, batched_input: Optional[Dict[str, Any]] = None, gt: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+        """One step on `batched_input` / `gt` (same geometry as the example; None = the tensors already in place)."""
+        if batched_input is not None:
+            for k, v in batched_input.items():
+                if torch.is_tensor(v):
+                    dst = self.static[k]
+                    if v.shape != dst.shape:
+                        raise ValueError(f"GraphedTrainStep: '{k}' has shape {tuple(v.shape)}, the captured step "
+                                         f"{tuple(dst.shape)}; capture a new step for a new geometry")
+                    dst.copy_(v, non_blocking=True)
+        if gt is not None:
+            self.gt.copy_(gt, non_blocking=True)
+        if self.plan["class_rows"] is not None:
+            ce = self.lam.prompt_encoder.class_encoder
+            self.plan["class_rows"].copy_(ce.sample_rows(self.plan["class_rows"].numel(), self.plan["class_rows"].device))
+        self._fill_bc()
+        self.graph.replay()
+        opt = self.opt
+        for i, u in enumerate(self.used):
+            if u:
+                opt.steps[i] += 1
+        self._run_steps = [st + 1 for st in self._run_steps]
+        torch.autograd.graph.increment_version([p for p, u in zip(opt.params, self.used) if u])
+        return {"loss": {"value": self.loss}, **self.out}

@@ -479,3 +479,68 @@ def test_train_step_reduces_the_loss_and_keeps_inference_in_sync():
         b = train_forward(lam, ep)["logits"]
     fin = torch.isfinite(b)
     assert float((a[fin] - b[fin]).abs().max()) < 0.12 * float(b[fin].std())
+
+
+def test_graphed_train_step_equals_the_eager_step():
+    """One CUDA-graph replay of the whole step (forward, loss, backward, AdamW with device-side bias corrections) against
+    one eager step from the SAME parameters and optimiser state on a new batch of the same geometry: same loss, same
+    gradients and moments up to the reordering of a few atomic fp32 sums.  (Trajectories over several steps are not
+    comparable: the first Adam updates are lr * sign(g), so a gradient entry at the noise level flips a weight by 2 lr.)"""
+    from labelanything_b200.build_lam import build_lam_no_vit
+    from labelanything_b200.loss import LabelAnythingLoss
+    from labelanything_b200.synthetic import load_synth_weights
+    from labelanything_b200.training import FlatAdamW, GraphedTrainStep, train_step
+
+    case = torch.load(ROOT / "tests" / "golden" / "train_f1.pt", weights_only=False)["cases"]["mixed"]
+    loss_fn = LabelAnythingLoss({"focal": {"weight": 1.0, "gamma": 2.0}}, class_weighting=True)
+
+    def fresh():
+        lam = build_lam_no_vit(**case["build"])
+        load_synth_weights(lam, seed=case["weights_seed"])
+        lam.prompt_encoder.class_encoder.fixed_rows = case["class_rows"]
+        return lam.cuda().train()
+
+    ep = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in case["episode"].items()}
+    gt = case["gt"].cuda()
+    ep2 = dict(ep, embeddings=ep["embeddings"].flip(0).contiguous())          # a second batch of the same geometry
+    lr = 1e-4
+    a = fresh()
+    opt_a = FlatAdamW(a.parameters(), lr=lr)
+    train_step(a, loss_fn, opt_a, ep, gt)                                     # step 1, eager
+    b = fresh()
+    opt_b = FlatAdamW(b.parameters(), lr=lr)
+    step = GraphedTrainStep(b, loss_fn, opt_b, ep, gt, warmup=1)              # its warm-up is step 1 on the same batch
+    assert opt_a.steps == opt_b.steps
+    with torch.no_grad():                                                     # identical state before step 2
+        opt_b.flat_p.copy_(opt_a.flat_p)
+        opt_b.exp_avg.copy_(opt_a.exp_avg)
+        opt_b.exp_avg_sq.copy_(opt_a.exp_avg_sq)
+    c = fresh()                                                               # a second EAGER run: the noise yardstick
+    opt_c = FlatAdamW(c.parameters(), lr=lr)
+    train_step(c, loss_fn, opt_c, ep, gt)
+    with torch.no_grad():
+        opt_c.flat_p.copy_(opt_a.flat_p)
+        opt_c.exp_avg.copy_(opt_a.exp_avg)
+        opt_c.exp_avg_sq.copy_(opt_a.exp_avg_sq)
+    p_before = opt_a.flat_p.clone()
+    la = float(train_step(a, loss_fn, opt_a, ep2, gt)["loss"]["value"])       # step 2, eager
+    lc = float(train_step(c, loss_fn, opt_c, ep2, gt)["loss"]["value"])       # step 2, eager again
+    lb = float(step(ep2, gt)["loss"]["value"])                                # step 2, one graph replay
+    assert opt_a.steps == opt_b.steps and max(opt_a.steps) == 2
+    assert abs(la - lb) <= 1e-5 * abs(la) and abs(la - lc) <= 1e-5 * abs(la), (la, lb, lc)
+    n = opt_a.numel
+    # the backward pass scatters with atomics (bilinear / postprocess adjoints, bias and LayerNorm sums): two EAGER runs
+    # from the same state differ in the last bits of d loss / d logits, which the bf16 roundings of the backward GEMMs
+    # amplify; the replay must sit inside that run-to-run noise
+    scale = float(opt_a.flat_g[:n].abs().max())
+    noise = float((opt_c.flat_g[:n] - opt_a.flat_g[:n]).abs().max())
+    diff = float((opt_b.flat_g[:n] - opt_a.flat_g[:n]).abs().max())
+    print(f"graphed step: gradient max diff vs eager {diff / scale:.2e} of the largest gradient; eager vs eager {noise / scale:.2e}")
+    assert diff <= 3.0 * noise + 1e-5 * scale, (diff / scale, noise / scale)
+    m_noise = float((opt_c.exp_avg - opt_a.exp_avg).abs().max())
+    assert float((opt_b.exp_avg - opt_a.exp_avg).abs().max()) <= 3.0 * m_noise + 1e-6 * float(opt_a.exp_avg.abs().max())
+    da = opt_a.flat_p - p_before
+    db = opt_b.flat_p - p_before
+    assert float(da.abs().max()) > 0.5 * lr                                   # the step moved the weights ...
+    assert float((da - db).abs().max()) <= 2.1 * lr                           # ... both ways alike: at most a sign flip
+    assert float((da - db).abs().mean()) <= 0.05 * lr, float((da - db).abs().mean()) / lr
