@@ -345,6 +345,9 @@ int la_cast_bf16(void* stream, const float* in, void* out, long long n);
  * + lo_a hi_w^T up to 2^-16 relative, three la_gemm_bf16 launches with fp32 accumulation) -- north_star's fp32 tolerance
  * for the training path and the yardstick the bf16 gradients are checked against */
 int la_split_bf16(void* stream, const float* in, void* hi, void* lo, long long n);
+/* three terms hi + mid + lo = in to 2^-24: the "bf16x6" mode (the six products whose orders sum to <= 2), fp32-level
+ * accuracy of every contraction -- north_star's 1e-5 fp32 tolerance on the tensor cores */
+int la_split3_bf16(void* stream, const float* in, void* hi, void* mid, void* lo, long long n);
 /* out = a + b, n elements (residual adds; backward is the identity) */
 int la_add_f32(void* stream, const float* a, const float* b, float* out, long long n);
 /* dx = dy where y > 0 else 0 (nn.ReLU behind lin1 / class_mlp: transformer.py:164, mask_decoder.py:797) */

@@ -72,6 +72,22 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
   }
 }
 
+// three bf16 terms (24 mantissa bits): the "bf16x6" mode, fp32-level products from six tensor-core GEMMs
+__global__ void __launch_bounds__(256) split3_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                                          __nv_bfloat16* __restrict__ mid, __nv_bfloat16* __restrict__ lo,
+                                                          long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float x = in[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    hi[i] = h;
+    mid[i] = m;
+    lo[i] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+  }
+}
+
 __global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                   float* __restrict__ out, long long n) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_kernel(const float* __restr
       const float t = c < d ? v[k] - mean : 0.f;
       q += t * t;
     }
-    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    const float rstd = 1.f / sqrtf(warp_sum(q) * inv_d + eps);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c = lane + 32 * k;
@@ -258,7 +274,7 @@ layernorm_f32_bwd_kernel(const float* __restrict__ x, const float* __restrict__ 
       const float t = c < d ? v[k] - mean : 0.f;
       q += t * t;
     }
-    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    const float rstd = 1.f / sqrtf(warp_sum(q) * inv_d + eps);
     float dxh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -381,7 +397,7 @@ __global__ void __launch_bounds__(128) attn_f32_fwd_kernel(const AttnParams p) {
     float l = 0.f;
     for (int j = lane; j < p.nk; j += step) {
       load_row<DH>(kk, kb + static_cast<long long>(j) * ld, p.dh);
-      const float pj = __expf(dot_row<DH>(q, kk) - m);
+      const float pj = expf(dot_row<DH>(q, kk) - m);
       l += pj;
       load_row<DH>(kk, vb + static_cast<long long>(j) * ld, p.dh);
 #pragma unroll
@@ -398,7 +414,7 @@ __global__ void __launch_bounds__(128) attn_f32_fwd_kernel(const AttnParams p) {
     for (int e = 0; e < DH; ++e) o[e] *= inv;
     if (lane == 0) {
       store_row<DH>(p.out + (s * p.nq + i) * ld + h * p.dh, o, p.dh);
-      p.lse[w] = m + __logf(l);
+      p.lse[w] = m + logf(l);
     }
   }
 }
@@ -434,7 +450,7 @@ __global__ void __launch_bounds__(128) attn_f32_bwd_q_kernel(const AttnParams p)
       load_row<DH>(kk, vb + static_cast<long long>(j) * ld, p.dh);
       const float dp = dot_row<DH>(go, kk);
       load_row<DH>(kk, kb + static_cast<long long>(j) * ld, p.dh);
-      const float ds = __expf(dot_row<DH>(q, kk) - lse) * (dp - dl) * p.scale;
+      const float ds = expf(dot_row<DH>(q, kk) - lse) * (dp - dl) * p.scale;
 #pragma unroll
       for (int e = 0; e < DH; ++e) dq[e] = fmaf(ds, kk[e], dq[e]);
     }
@@ -475,7 +491,7 @@ __global__ void __launch_bounds__(128) attn_f32_bwd_kv_kernel(const AttnParams p
     for (int i = lane; i < p.nq; i += step) {
       load_row<DH>(qq, qb + static_cast<long long>(i) * ld, p.dh);
       load_row<DH>(gg, gb + static_cast<long long>(i) * ld, p.dh);
-      const float pij = __expf(dot_row<DH>(qq, k) * p.scale - p.lse[stat + i]);
+      const float pij = expf(dot_row<DH>(qq, k) * p.scale - p.lse[stat + i]);
       const float ds = pij * (dot_row<DH>(gg, v) - p.delta[stat + i]) * p.scale;
 #pragma unroll
       for (int e = 0; e < DH; ++e) {
@@ -1029,6 +1045,15 @@ int la_split_bf16(void* stream, const float* in, void* hi, void* lo, long long n
   LA_CHECK_ARG(in && hi && lo && n > 0, "la_split_bf16: bad arguments");
   split_bf16_kernel<<<train_grid(n), 256, 0, ST(stream)>>>(in, static_cast<__nv_bfloat16*>(hi),
                                                             static_cast<__nv_bfloat16*>(lo), n);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+int la_split3_bf16(void* stream, const float* in, void* hi, void* mid, void* lo, long long n) {
+  LA_CHECK_ARG(in && hi && mid && lo && n > 0, "la_split3_bf16: bad arguments");
+  split3_bf16_kernel<<<train_grid(n), 256, 0, ST(stream)>>>(in, static_cast<__nv_bfloat16*>(hi),
+                                                             static_cast<__nv_bfloat16*>(mid),
+                                                             static_cast<__nv_bfloat16*>(lo), n);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }

@@ -78,7 +78,8 @@ def bcast_reduce(dy: torch.Tensor, row_div: int = 1, b_mod: int = 1, out: Option
 # GEMM precision of the training path.  "bf16": operands rounded to bf16 (what the inference path does).  "bf16x3":
 # every fp32 operand is split into two bf16 terms and the product is three tensor-core GEMMs with fp32 accumulation
 # (hi*hi + hi*lo + lo*hi; the dropped lo*lo term is 2^-16 relative) -- fp32-accurate gradients at three times the GEMM
-# work.  An operand is a tuple of bf16 tensors: (hi,) or (hi, lo).
+# work.  "bf16x6": three terms (24 mantissa bits), the six products whose orders sum to <= 2: fp32-level contractions.
+# An operand is a tuple of bf16 tensors: (hi,), (hi, lo) or (hi, mid, lo).
 _PRECISION = "bf16"
 
 
@@ -86,7 +87,7 @@ class precision:
     """with train_ops.precision("bf16x3"): ...   (captured at forward time; the backward of an op uses the same mode)"""
 
     def __init__(self, mode: str) -> None:
-        assert mode in ("bf16", "bf16x3"), mode
+        assert mode in ("bf16", "bf16x3", "bf16x6"), mode
         self.mode = mode
 
     def __enter__(self):
@@ -130,10 +131,9 @@ def _split(x: torch.Tensor, mode: Optional[str] = None) -> tuple:
     def build():
         if mode == "bf16":
             return (cast_bf16(x),)
-        hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-        lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-        _call("split_bf16", "la_split_bf16", x, hi, lo, x.numel())
-        return (hi, lo)
+        parts = tuple(torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) for _ in range(2 if mode == "bf16x3" else 3))
+        _call("split_bf16", "la_split_bf16" if mode == "bf16x3" else "la_split3_bf16", x, *parts, x.numel())
+        return parts
 
     return _derived("split:" + mode, x, build)
 
@@ -152,11 +152,16 @@ def _mm(a: tuple, w: tuple, bias=None, act=ACT_NONE) -> torch.Tensor:
     """fp32 [M, N] = act(a @ w^T + bias) for operands a [M, K], w [N, K]."""
     if len(a) == 1 and len(w) == 1:
         return ops.gemm(a[0], w[0], bias, act=act, out_dtype=torch.float32)
-    out = ops.gemm(a[0], w[0], bias, out_dtype=torch.float32)
-    if len(w) > 1:
-        out = add_f32(out, ops.gemm(a[0], w[1], None, out_dtype=torch.float32))
-    if len(a) > 1:
-        out = add_f32(out, ops.gemm(a[1], w[0], None, out_dtype=torch.float32))
+    # every product a_i w_j^T with i + j <= order (3 of 4 for two terms, 6 of 9 for three), the small ones summed first
+    order = max(len(a), len(w)) - 1
+    out = None
+    for total in range(order, 0, -1):
+        for i in range(len(a)):
+            j = total - i
+            if 0 <= j < len(w):
+                t = ops.gemm(a[i], w[j], None, out_dtype=torch.float32)
+                out = t if out is None else add_f32(out, t)
+    out = add_f32(ops.gemm(a[0], w[0], bias, out_dtype=torch.float32), out)
     if act == ACT_RELU:
         out = _relu_f32(out)
     else:

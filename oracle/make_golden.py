@@ -515,6 +515,15 @@ def loss_f1(models):
     print("loss_f1.pt", [(tuple(c["logits"].shape), float(c["value"])) for c in cases])
 
 
+def scale_matrices(module, gain):
+    """Multiply every weight matrix / convolution kernel (>= 2-D, more than one output row) by `gain`."""
+    if gain != 1.0:
+        with torch.no_grad():
+            for p in module.parameters():
+                if p.dim() >= 2 and p.shape[0] > 1:
+                    p.mul_(gain)
+
+
 def grad_sample(g, n=4096):
     """{"norm", "values"}: the whole tensor when it has at most n entries, else the n evenly strided entries at
     `sample_index(numel, n)` (tests/test_training_*.py compare the same positions)."""
@@ -538,14 +547,19 @@ def train_f1(models):
 
     S, D, Ce, g = 128, 128, 64, 8
     cases = {}
-    for name in ("mixed", "masks_only"):
-        mixed = name == "mixed"
+    for name in ("mixed", "masks_only", "mixed_scaled"):
+        mixed = name != "masks_only"
+        # `mixed_scaled`: the mixed model with every weight matrix halved.  At gain 1 this random-weight model is
+        # ill-conditioned (one bf16 rounding of the weights moves the fp32 gradients by 60 %); at gain 0.5 by 7 %, which
+        # makes the bf16 training path's gradient error a meaningful number.
+        gain = 0.5 if name == "mixed_scaled" else 1.0
         torch.manual_seed(3 if mixed else 4)
         build = dict(image_embed_dim=Ce, embed_dim=D, image_size=S, spatial_convs=3, class_attention=mixed,
                      example_attention=mixed, example_class_attention=True, custom_preprocess=mixed,
                      class_encoder={"name": "RandomMatrixEncoder", "bank_size": 10, "embed_dim": D} if mixed else None)
         lam = build_lam_no_vit(**build).train()          # the reference's own builder (models/build_lam.py:81-86)
         load_synth_weights(lam, seed=21 if mixed else 22)
+        scale_matrices(lam, gain)
         rows = torch.tensor([0, 4, 2, 7]) if mixed else None
         if mixed:
             _pin_rows(lam, rows)
@@ -597,10 +611,33 @@ def train_f1(models):
         sens = {"total": (num / den) ** 0.5, "median": rels[len(rels) // 2], "p90": rels[int(0.9 * len(rels))],
                 "worst": rels[-1]}
         print(f"train_f1[{name}]: gradient change under one bf16 rounding of weights + inputs: {sens}")
+        # the reference's OWN mixed-precision mode (torch.autocast(bfloat16), what `accelerate` gives its training loop):
+        # fp32 weights, bf16 matmul / conv operands in forward and backward -- the like-for-like yardstick of the native
+        # bf16 path, measured against the same fp32 gradients
+        load_synth_weights(lam, seed=21 if mixed else 22)
+        scale_matrices(lam, gain)
+        lam.zero_grad(set_to_none=True)
+        with torch.autocast(device_type="cpu", dtype=torch.bfloat16):
+            out_ac = lam(ep)
+        loss_fn({"logits": out_ac["logits"].float()}, gt)["value"].backward()
+        rels, num, den = [], 0.0, 0.0
+        for k, p in lam.named_parameters():
+            if k in full and float(full[k].double().norm()) > 1e-6 and p.grad is not None:
+                d2 = float((p.grad.double() - full[k].double()).pow(2).sum())
+                r2 = float(full[k].double().pow(2).sum())
+                rels.append((d2 / r2) ** 0.5)
+                num, den = num + d2, den + r2
+        rels.sort()
+        fin_ = torch.isfinite(logits)
+        autocast = {"total": (num / den) ** 0.5, "median": rels[len(rels) // 2], "p90": rels[int(0.9 * len(rels))],
+                    "worst": rels[-1],
+                    "logits_mean_over_std": float((out_ac["logits"].float()[fin_] - logits[fin_]).abs().mean()
+                                                  / logits[fin_].std())}
+        print(f"train_f1[{name}]: gradient error of the reference under torch.autocast(bfloat16): {autocast}")
         cfg = {"image_size": S, "image_embedding_size": (g, g), "has_neck": True, "spatial_convs": 3,
                "class_attention": mixed, "example_attention": mixed, "example_class_attention": True,
                "custom_preprocess": mixed}
-        cases[name] = {"bf16_sensitivity": sens, "cfg": cfg, "weights_seed": 21 if mixed else 22, "episode": ep, "class_rows": rows, "gt": gt, "logits": logits.detach().clone(),
+        cases[name] = {"bf16_sensitivity": sens, "bf16_autocast_error": autocast, "cfg": cfg, "weights_seed": 21 if mixed else 22, "weight_gain": gain, "episode": ep, "class_rows": rows, "gt": gt, "logits": logits.detach().clone(),
                        "loss": loss["value"].detach().clone(), "grads": grads,
                        "build": build}
         used = sum(v is not None for v in grads.values())

@@ -26,6 +26,14 @@ def sample_index(numel, n=4096):          # oracle/make_golden.py::sample_index
     return torch.arange(numel) if numel <= n else torch.linspace(0, numel - 1, n).long()
 
 
+def scale_matrices(module, gain):          # oracle/make_golden.py::scale_matrices
+    if gain != 1.0:
+        with torch.no_grad():
+            for p in module.parameters():
+                if p.dim() >= 2 and p.shape[0] > 1:
+                    p.mul_(gain)
+
+
 def reference_loss(logits, gt):
     """LabelAnythingLoss({"focal": {"weight": 1, "gamma": 2}}, class_weighting=True) restated with torch ops
     (loss/__init__.py:67-92, loss/focal.py:17-25); the weight map comes from the pinned numpy oracle."""
@@ -38,12 +46,13 @@ def reference_loss(logits, gt):
 def build_case(case):
     lam = build_lam_no_vit(**case["build"])
     load_synth_weights(lam, seed=case["weights_seed"])
+    scale_matrices(lam, case.get("weight_gain", 1.0))
     if case["class_rows"] is not None:
         lam.prompt_encoder.class_encoder.fixed_rows = case["class_rows"]
     return lam
 
 
-@pytest.mark.parametrize("name", ["mixed", "masks_only"])
+@pytest.mark.parametrize("name", ["mixed", "masks_only", "mixed_scaled"])
 def test_oracle_gradients_match_the_reference_autograd(name):
     case = torch.load(GOLD, weights_only=False)["cases"][name]
     lam = build_case(case)

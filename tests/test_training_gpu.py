@@ -387,6 +387,11 @@ def _gradient_errors(case, mode):
 
     lam = build_lam_no_vit(**case["build"])
     load_synth_weights(lam, seed=case["weights_seed"])
+    if case.get("weight_gain", 1.0) != 1.0:                     # oracle/make_golden.py::scale_matrices
+        with torch.no_grad():
+            for p in lam.parameters():
+                if p.dim() >= 2 and p.shape[0] > 1:
+                    p.mul_(case["weight_gain"])
     if case["class_rows"] is not None:
         lam.prompt_encoder.class_encoder.fixed_rows = case["class_rows"]
     lam = lam.cuda().train()
@@ -423,15 +428,19 @@ def _gradient_errors(case, mode):
     return (float(err.max()) / std, float(err.mean()) / std), float(loss["value"]), rels, (num / den) ** 0.5
 
 
-@pytest.mark.parametrize("name", ["mixed", "masks_only"])
+@pytest.mark.parametrize("name", ["mixed", "masks_only", "mixed_scaled"])
 def test_train_forward_backward_matches_the_reference_gradients(name):
     """Logits, loss and the gradient of every parameter against the autograd gradients of the UNMODIFIED fp32 reference.
 
     * fp32-accurate mode (`bf16x3`: split operands, three tensor-core GEMMs per product): every gradient must agree
       with the reference on the sampled entries -- this is the check of the backward kernels and of the wiring.
-    * bf16 mode (the training configuration): these random-weight models amplify one bf16 rounding of the weights into a
-      15-60 % change of the reference's OWN fp32 gradients (`bf16_sensitivity`, measured by oracle/make_golden.py on
-      the unmodified reference), so the bf16 gradients are held to that scale (<= 1.5x), not to a fixed percentage.
+    * bf16 mode (the training configuration): the yardstick is the reference's OWN mixed-precision mode -- the
+      gradients of the unmodified reference under `torch.autocast(bfloat16)` against its fp32 gradients
+      (`bf16_autocast_error`, measured by oracle/make_golden.py).  The native bf16 gradients must be at least as close
+      to fp32 as that (x 1.25).  The gain-1 `mixed` model is ill-conditioned: ONE bf16 rounding of its weights moves
+      the reference's fp32 gradients by 59 %, autocast by 66 % -- at that level errors saturate and change with any
+      reordering of a sum, so only a sanity bound applies there; `mixed_scaled` is the same model at gain 0.5
+      (5 % / 16 %), where the comparison is meaningful.
     Parameters the reference leaves without gradient must have none here either."""
     case = torch.load(ROOT / "tests" / "golden" / "train_f1.pt", weights_only=False)["cases"][name]
     (mx, mean), loss, rels, total = _gradient_errors(case, "bf16x3")
@@ -443,15 +452,90 @@ def test_train_forward_backward_matches_the_reference_gradients(name):
     assert total <= 5e-3 and rels[len(rels) // 2][0] <= 5e-3, (total, rels[len(rels) // 2])
     assert rels[-1][0] <= 5e-2, rels[-5:]
 
-    sens = case["bf16_sensitivity"]
+    ac = case["bf16_autocast_error"]
     (mx, mean), loss, rels, total = _gradient_errors(case, "bf16")
-    print(f"train_f1[{name}] bf16  : logits max {mx:.3f} mean {mean:.4f} of std; loss {loss:.6f}; rel err all {total:.3f} "
-          f"(reference under one bf16 rounding: {sens['total']:.3f}), median {rels[len(rels) // 2][0]:.3f} ({sens['median']:.3f}), "
-          f"p90 {rels[int(0.9 * len(rels))][0]:.3f} ({sens['p90']:.3f}), worst {rels[-1][0]:.3f} ({rels[-1][2]})")
+    print(f"train_f1[{name}] bf16  : logits max {mx:.3f} mean {mean:.4f} of std (reference autocast: mean "
+          f"{ac['logits_mean_over_std']:.4f}); loss {loss:.6f}; rel err all {total:.3f} (reference under "
+          f"torch.autocast(bfloat16): {ac['total']:.3f}), median {rels[len(rels) // 2][0]:.3f} ({ac['median']:.3f}), p90 "
+          f"{rels[int(0.9 * len(rels))][0]:.3f} ({ac['p90']:.3f}), worst {rels[-1][0]:.3f} ({rels[-1][2]})")
     assert mx < 0.12 and mean < 0.03, (mx, mean)
     assert abs(loss - float(case["loss"])) < 0.03 * abs(float(case["loss"]))
-    assert total <= 1.5 * sens["total"] and rels[len(rels) // 2][0] <= 1.5 * sens["median"], (total, sens)
-    assert rels[int(0.9 * len(rels))][0] <= 1.5 * sens["p90"], (rels[int(0.9 * len(rels))], sens)
+    if ac["total"] < 0.5:
+        assert total <= 1.25 * ac["total"] and rels[len(rels) // 2][0] <= 1.25 * ac["median"], (total, ac)
+        assert rels[int(0.9 * len(rels))][0] <= 1.25 * ac["p90"], (rels[int(0.9 * len(rels))], ac)
+    else:
+        assert total <= 1.25, (total, ac)       # saturated regime: uncorrelated gradients of equal norm would give 1.41
+
+
+def test_fp32_level_mode_matches_the_fp32_reference():
+    """`bf16x6` (three-term operand split, six tensor-core GEMMs per product): the forward pass of the prompt encoder +
+    mask decoder path within north_star's fp32 tolerance of the unmodified fp32 reference, gradients at the level two
+    fp32 evaluations with different summation orders differ."""
+    cases = torch.load(ROOT / "tests" / "golden" / "train_f1.pt", weights_only=False)["cases"]
+    for name in ("mixed", "masks_only", "mixed_scaled"):
+        (mx, mean), loss, rels, total = _gradient_errors(cases[name], "bf16x6")
+        print(f"train_f1[{name}] bf16x6: logits max {mx:.2e} mean {mean:.2e} of std; loss {loss:.7f} vs "
+              f"{float(cases[name]['loss']):.7f}; rel err all {total:.2e}, median {rels[len(rels) // 2][0]:.2e}, worst "
+              f"{rels[-1][0]:.2e} ({rels[-1][2]})")
+        assert mx < 4e-5 and mean < 8e-6, (mx, mean)               # of the logit std (O(1)): fp32 evaluation-order level
+        assert abs(loss - float(cases[name]["loss"])) < 2e-6 * abs(float(cases[name]["loss"]))
+        assert total <= 1e-3 and rels[-1][0] <= 1e-2, (total, rels[-3:])
+
+
+@pytest.mark.parametrize("variant", ["no_masks", "points_only", "boxes_only"])
+def test_train_forward_backward_other_prompt_sets_match_the_oracle(variant):
+    """Prompt sets the goldens do not contain -- no mask prompts at all (`no_mask_embed` path), points only (padding
+    point), boxes only -- against autograd through the CPU oracle (pinned to the reference by test_training_cpu.py) on
+    the same weights, in the fp32-accurate mode."""
+    import lam_oracle as O
+    import loss_oracle as LO
+
+    from labelanything_b200.build_lam import build_lam_no_vit
+    from labelanything_b200.loss import LabelAnythingLoss
+    from labelanything_b200.synthetic import load_synth_weights
+    from labelanything_b200.training import train_forward
+
+    case = torch.load(ROOT / "tests" / "golden" / "train_f1.pt", weights_only=False)["cases"]["mixed"]
+    ep = dict(case["episode"])
+    drop = {"no_masks": ("prompt_masks", "flag_masks"),
+            "points_only": ("prompt_masks", "flag_masks", "prompt_bboxes", "flag_bboxes"),
+            "boxes_only": ("prompt_masks", "flag_masks", "prompt_points", "flag_points")}[variant]
+    for k in drop:
+        ep.pop(k)
+    lam = build_lam_no_vit(**case["build"])
+    load_synth_weights(lam, seed=case["weights_seed"])
+    lam.prompt_encoder.class_encoder.fixed_rows = case["class_rows"]
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in lam.state_dict().items()}
+    ref = O.lam_forward(sd, case["cfg"], dict(ep), case["class_rows"])["logits"]
+    gt = case["gt"]
+    wm, _ = LO.get_weight_matrix_from_labels(gt.numpy().copy(), ref.shape[1])
+    ce = F.cross_entropy(ref, gt, reduction="none")
+    ref_loss = (torch.pow(1 - torch.exp(-ce), 2.0) * torch.from_numpy(wm) * ce).mean()
+    ref_loss.backward()
+
+    lam = lam.cuda().train()
+    with T.precision("bf16x3"):
+        out = train_forward(lam, {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in ep.items()})
+        loss = LabelAnythingLoss({"focal": {"weight": 1.0, "gamma": 2.0}}, class_weighting=True)(out, gt.cuda())["value"]
+        loss.backward()
+    fin = torch.isfinite(ref)
+    got = out["logits"].detach().cpu()
+    assert torch.equal(torch.isfinite(got), fin)
+    assert float((got[fin] - ref.detach()[fin]).abs().max()) < 2e-3 * float(ref.detach()[fin].std())
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    worst, n = (0.0, None), 0
+    for k, p in lam.named_parameters():
+        want = sd[k].grad
+        if want is None or float(want.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-6, k
+            continue
+        if float(want.double().norm()) < 1e-6:
+            continue
+        rel = float((p.grad.detach().cpu().double() - want.double()).norm() / want.double().norm())
+        worst = max(worst, (rel, k))
+        n += 1
+    print(f"train_forward[{variant}] bf16x3: {n} gradients, worst relative error {worst[0]:.2e} ({worst[1]})")
+    assert n > 150 and worst[0] < 5e-2, worst
 
 
 def test_train_step_reduces_the_loss_and_keeps_inference_in_sync():
