@@ -319,6 +319,22 @@ class FlatAdamW:
                 p.register_post_accumulate_grad_hook(self._mark(i))
         self.last_allreduce_ms: Optional[float] = None
 
+    def attach(self, module: nn.Module) -> None:
+        """Keep `module.state_dict()` checkpoint-friendly: the parameters are views of ONE flat storage now, which
+        `safetensors.torch.save_model` (huggingface_hub's `save_pretrained`, accelerate's `save_state`) refuses ("none is
+        covering the entire storage").  A state-dict hook hands out copies of such views instead.  Idempotent; called by
+        `train_step` / `GraphedTrainStep`."""
+        if module.__dict__.get("_la_flat_state_dict_hook"):
+            return
+
+        def hook(mod, state_dict, prefix, local_metadata):
+            for k, v in list(state_dict.items()):
+                if torch.is_tensor(v) and v.untyped_storage().nbytes() > v.numel() * v.element_size():
+                    state_dict[k] = v.detach().clone()
+
+        module.register_state_dict_post_hook(hook)
+        module.__dict__["_la_flat_state_dict_hook"] = True
+
     def _mark(self, i: int):
         def hook(_p):
             self._used[i] = True
@@ -391,6 +407,7 @@ class FlatAdamW:
 def train_step(lam: Lam, loss_fn, opt: FlatAdamW, batched_input: Dict[str, Any], gt: torch.Tensor,
                timed: bool = False) -> Dict[str, Any]:
     """One optimisation step: forward, LabelAnythingLoss, backward, gradient all-reduce, AdamW (run.py:425-590)."""
+    opt.attach(lam)
     opt.zero_grad()
     result = train_forward(lam, batched_input)
     loss = loss_fn(result, gt)
@@ -435,6 +452,7 @@ class GraphedTrainStep:
         import torch.distributed as dist
 
         self.lam, self.loss_fn, self.opt = lam, loss_fn, opt
+        opt.attach(lam)
         self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_input.items()}
         self.gt = example_gt.clone()
         self.plan = make_plan(lam, self.static)

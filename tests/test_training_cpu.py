@@ -128,3 +128,23 @@ def test_two_rank_gloo_gradient_bucket_allreduce():
         assert torch.allclose(g1, torch.full((3, 2), 3.0))
         assert float(g2.abs().max()) == 0.0
         assert in_bucket                                       # autograd accumulated straight into the flat bucket
+
+
+def test_checkpoints_can_be_written_after_the_parameters_moved_into_the_flat_bucket(tmp_path):
+    """huggingface_hub's save_pretrained / accelerate's save_state go through safetensors.torch.save_model, which refuses
+    views of a larger storage: FlatAdamW.attach makes state_dict() hand out copies."""
+    from safetensors.torch import load_file, save_model
+
+    lam = build_lam_no_vit(image_embed_dim=64, embed_dim=128, image_size=128, spatial_convs=3)
+    opt = FlatAdamW(lam.parameters())
+    with pytest.raises(RuntimeError):
+        save_model(lam, str(tmp_path / "views.safetensors"))
+    opt.attach(lam)
+    opt.attach(lam)                                   # idempotent
+    save_model(lam, str(tmp_path / "m.safetensors"))
+    back = load_file(str(tmp_path / "m.safetensors"))
+    sd = lam.state_dict()
+    assert set(back) == set(sd) and all(torch.equal(back[k], v) for k, v in sd.items())
+    lam.load_state_dict(back)                         # loads in place: the parameters stay views of the bucket
+    p0 = opt.params[0]
+    assert p0.data_ptr() == opt.flat_p.data_ptr() + 4 * opt.offsets[0]
