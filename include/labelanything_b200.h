@@ -424,10 +424,11 @@ int la_postprocess_masks_bwd(void* stream, const float* dout, const int* sizes, 
  * (experiment/run.py:172-200 builds AdamW over get_learnable_params) */
 int la_adamw_f32(void* stream, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale);
-/* the same update with the bias corrections {1 - beta1^t, sqrt(1 - beta2^t)} read from device memory: the launch
- * parameters stay constant, so a captured CUDA graph of the whole training step can be replayed as t grows */
+/* the same update with the per-step scalars {1 - beta1^t, sqrt(1 - beta2^t), lr} read from device memory (fp32 [3]):
+ * the launch parameters stay constant, so a captured CUDA graph of the whole training step can be replayed as t grows
+ * and the learning-rate schedule (run.py: constant_with_warmup) moves */
 int la_adamw_f32_dev(void* stream, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
-                     float lr, float beta1, float beta2, float eps, float weight_decay, const float* bias_corrections,
+                     float beta1, float beta2, float eps, float weight_decay, const float* step_scalars,
                      float grad_scale);
 
 #ifdef __cplusplus

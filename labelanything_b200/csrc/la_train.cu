@@ -1002,8 +1002,9 @@ postprocess_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ s
 // ------------------------------------------------------------------------------------------------------------------
 // AdamW (torch.optim.AdamW, decoupled weight decay) over one flat fp32 parameter bucket
 // ------------------------------------------------------------------------------------------------------------------
-// bias corrections either by value or (bc_dev != nullptr: {1 - beta1^t, sqrt(1 - beta2^t)}) from device memory, so
-// that a captured CUDA graph of the step can be replayed with a growing step count
+// bias corrections and learning rate either by value or (bc_dev != nullptr: {1 - beta1^t, sqrt(1 - beta2^t), lr}) from
+// device memory, so that a captured CUDA graph of the step can be replayed with a growing step count and a scheduled
+// learning rate
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
              float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale,
@@ -1011,6 +1012,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   if (bc_dev) {
     bc1 = bc_dev[0];
     bc2_sqrt = bc_dev[1];
+    lr = bc_dev[2];
   }
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1372,11 +1374,11 @@ int la_adamw_f32(void* stream, float* params, const float* grads, float* exp_avg
 }
 
 int la_adamw_f32_dev(void* stream, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
-                     float lr, float beta1, float beta2, float eps, float weight_decay, const float* bias_corrections,
+                     float beta1, float beta2, float eps, float weight_decay, const float* step_scalars,
                      float grad_scale) {
-  LA_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && bias_corrections && n > 0, "la_adamw_f32_dev: bad arguments");
-  adamw_kernel<<<train_grid(n), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                      weight_decay, 1.f, 1.f, grad_scale, bias_corrections);
+  LA_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && step_scalars && n > 0, "la_adamw_f32_dev: bad arguments");
+  adamw_kernel<<<train_grid(n), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, 0.f, beta1, beta2, eps,
+                                                      weight_decay, 1.f, 1.f, grad_scale, step_scalars);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }

@@ -643,11 +643,10 @@ def adamw_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor,
           float(eps), float(weight_decay), int(step), float(grad_scale))
 
 
-def adamw_step_dev(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: float,
-                   beta1: float, beta2: float, eps: float, weight_decay: float, bias_corrections: torch.Tensor,
-                   grad_scale: float = 1.0) -> None:
-    """`adamw_step` with {1 - beta1^t, sqrt(1 - beta2^t)} read from the device tensor `bias_corrections` (fp32 [2])."""
-    _require_cuda(params, grads, exp_avg, exp_avg_sq, bias_corrections)
-    assert bias_corrections.dtype == torch.float32 and bias_corrections.numel() == 2 and bias_corrections.is_contiguous()
-    _call("adamw", "la_adamw_f32_dev", params, grads, exp_avg, exp_avg_sq, params.numel(), float(lr), float(beta1),
-          float(beta2), float(eps), float(weight_decay), bias_corrections, float(grad_scale))
+def adamw_step_dev(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, beta1: float,
+                   beta2: float, eps: float, weight_decay: float, step_scalars: torch.Tensor, grad_scale: float = 1.0) -> None:
+    """`adamw_step` with {1 - beta1^t, sqrt(1 - beta2^t), lr} read from the device tensor `step_scalars` (fp32 [3])."""
+    _require_cuda(params, grads, exp_avg, exp_avg_sq, step_scalars)
+    assert step_scalars.dtype == torch.float32 and step_scalars.numel() == 3 and step_scalars.is_contiguous()
+    _call("adamw", "la_adamw_f32_dev", params, grads, exp_avg, exp_avg_sq, params.numel(), float(beta1), float(beta2),
+          float(eps), float(weight_decay), step_scalars, float(grad_scale))

@@ -442,8 +442,8 @@ class GraphedTrainStep:
       * geometry (shapes, prompt types present, original sizes): the `plan` of the example batch; `__call__` copies a new
         batch of the same geometry into the static input tensors;
       * which parameters receive a gradient: taken from eager warm-up steps, constant for a geometry;
-      * the optimiser's step count: the bias corrections live in device memory (`la_adamw_f32_dev`) and are refreshed
-        before every replay;
+      * the optimiser's step count and learning rate: bias corrections and `opt.lr` live in device memory
+        (`la_adamw_f32_dev`) and are refreshed before every replay, so a scheduler that sets `opt.lr` keeps working;
       * RandomMatrixEncoder rows: drawn before every replay into a static tensor.
     The loss value and the outputs are static device tensors (no `.item()` inside the step)."""
 
@@ -471,9 +471,9 @@ class GraphedTrainStep:
         dev = opt.flat_p.device
         self.runs = opt.used_runs_for([s + 1 if u else s for s, u in zip(opt.steps, used)], used)
         n_runs = max(1, len(self.runs))
-        self.bc = torch.ones((n_runs, 2), dtype=torch.float32, device=dev)
+        self.bc = torch.ones((n_runs, 3), dtype=torch.float32, device=dev)
         # ring of pinned staging rows for the bias corrections: a slot is rewritten only after its last upload finished
-        self._bc_host = [torch.ones((n_runs, 2), dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._bc_host = [torch.ones((n_runs, 3), dtype=torch.float32).pin_memory() for _ in range(4)]
         self._bc_done = [torch.cuda.Event() for _ in range(4)]
         self._bc_slot = 0
         self._run_steps = [st for _, _, st in self.runs]
@@ -506,8 +506,7 @@ class GraphedTrainStep:
                     dist.all_reduce(opt.flat_g[:opt.numel], group=opt.group)   # the step's one collective, in the graph
                 for i, (lo, hi, _) in enumerate(self.runs):
                     T.adamw_step_dev(opt.flat_p[lo:hi], opt.flat_g[lo:hi], opt.exp_avg[lo:hi], opt.exp_avg_sq[lo:hi],
-                                     opt.lr, opt.betas[0], opt.betas[1], opt.eps, opt.weight_decay, self.bc[i],
-                                     1.0 / self.world)
+                                     opt.betas[0], opt.betas[1], opt.eps, opt.weight_decay, self.bc[i], 1.0 / self.world)
         finally:
             for mod, name, p in swapped:
                 mod._parameters[name] = p
@@ -524,6 +523,7 @@ class GraphedTrainStep:
         for i, st in enumerate(self._run_steps):
             host[i, 0] = 1.0 - b1 ** st
             host[i, 1] = (1.0 - b2 ** st) ** 0.5
+            host[i, 2] = self.opt.lr                      # read per replay: learning-rate schedules keep working
         self.bc.copy_(host, non_blocking=True)
         self._bc_done[slot].record()
 

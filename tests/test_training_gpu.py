@@ -628,3 +628,9 @@ def test_graphed_train_step_equals_the_eager_step():
     assert float(da.abs().max()) > 0.5 * lr                                   # the step moved the weights ...
     assert float((da - db).abs().max()) <= 2.1 * lr                           # ... both ways alike: at most a sign flip
     assert float((da - db).abs().mean()) <= 0.05 * lr, float((da - db).abs().mean()) / lr
+    # a scheduler that changes opt.lr is honoured by the next replay (the learning rate is read from device memory)
+    before = opt_b.flat_p.clone()
+    opt_b.lr = 0.0
+    step(ep, gt)
+    torch.cuda.synchronize()
+    assert float((opt_b.flat_p - before).abs().max()) == 0.0
