@@ -51,6 +51,14 @@ int la_device_check(void); /* LA_OK iff the current device is sm_100 */
 int la_gemm_bf16(void* stream, const void* a, long long lda, const void* w, long long ldw, const float* bias,
                  void* out, long long ldo, int out_dtype, int M, int N, int K, int act);
 
+/* out[M,N] (fp32, zeroed by the call) = a @ w^T + bias with the CONTRACTION split over the SMs: work items are (output
+ * tile, K range), partial tiles are added with TMA reduce stores (fp32 adds in L2: the summation order, not the
+ * operands, varies from run to run).  For products with few output tiles and a long K -- the weight gradients
+ * dW[N_out, K_in] = dY^T X of the training step, whose contraction runs over up to S*T = 54 000 token rows
+ * (label_anything/experiment/run.py:359-361: autograd's grad-weight GEMMs). */
+int la_gemm_bf16_splitk(void* stream, const void* a, long long lda, const void* w, long long ldw, const float* bias,
+                        float* out, long long ldo, int M, int N, int K);
+
 /* The same product stored into a PADDED GRID: the M rows of `a` are the pixels (image, y, x) of M / grid^2 square
  * grid x grid token maps; `out` (bf16, row stride ldo) is [M / grid^2][padded][padded][ldo] and receives row
  * (image, y, x) at position (image, y, x) of the padded grid (4-D TMA stores), while the padded^2 - grid^2 positions

@@ -78,11 +78,16 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // RESID == 2: the residual chunk is fetched into a buffer of its own, ONE CHUNK AHEAD (also across tiles), so the
 // epilogue never waits for a load -- what the short-K proj GEMM needs (its tile lasts 3 us, four exposed L2/HBM
 // round trips per tile would make it epilogue bound).
-template <int BLOCK_N, typename OutT, bool CTA2 = false, bool CONV = false, int RESID = 0>
+// SPLITK (one-CTA variant, fp32 output, no activation): the work items are (output tile, K split); every CTA contracts
+// its range of k-blocks and ADDS its partial tile to the zeroed output with TMA reduce stores (split 0 adds the bias).
+// The weight-gradient GEMMs of the training step have one or two output tiles and K = 54 000 image-token rows: without
+// the split ONE CTA walks 844 k-blocks (330 us per launch, a quarter of the whole step).
+template <int BLOCK_N, typename OutT, bool CTA2 = false, bool CONV = false, int RESID = 0, bool SPLITK = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                          const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N,
-                         int K, int act, int conv_c = 0, int conv_h = 0, int out_grid = 0) {
+                         int K, int act, int conv_c = 0, int conv_h = 0, int out_grid = 0, int splits = 1) {
+  static_assert(!SPLITK || (!CTA2 && !CONV && RESID == 0 && sizeof(OutT) == 4), "split-K: one-CTA fp32 kernel only");
   // out_grid > 0: the output rows are the pixels (image, y, x) of a square out_grid x out_grid grid and `tm_out` is a
   // 4-D map (channel, x, y, image) of a LARGER (padded) grid: every 32-row store box lies inside one grid row
   static_assert(!CONV || CTA2, "the implicit-GEMM convolution is built on the CTA-pair kernel");
@@ -114,6 +119,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const int num_tiles = n_blks * m_blks;
   const int k_blks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int act_code = act;
+  const int num_work = SPLITK ? num_tiles * splits : num_tiles;     // work item = split * num_tiles + tile
+  auto kb_first = [&](int sp) { return SPLITK ? static_cast<int>(static_cast<long long>(sp) * k_blks / splits) : 0; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -152,10 +159,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int wi = tile0; wi < num_work; wi += tile_step) {
+        const int tile = SPLITK ? wi % num_tiles : wi;
+        const int kb_lo = kb_first(SPLITK ? wi / num_tiles : 0);
+        const int kb_n = SPLITK ? kb_first(wi / num_tiles + 1) - kb_lo : k_blks;
         const int m0 = (tile / n_blks) * TILE_M + rank * GEMM_BLOCK_M;
         const int n0 = (tile % n_blks) * BLOCK_N + rank * S::B_ROWS * (CTA2 ? 1 : 0);
-        for (int kb = 0; kb < k_blks; ++kb) {
+        for (int kb = 0; kb < kb_n; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * S::STAGE_BYTES;
           uint8_t* b_dst = a_dst + S::A_BYTES;
@@ -173,8 +183,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             tma_load_2d_2cta(b_dst, &tm_w, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-            tma_load_2d(a_dst, &tm_a, &full_bar[stage], kb * GEMM_BLOCK_K, m0);
-            tma_load_2d(b_dst, &tm_w, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+            tma_load_2d(a_dst, &tm_a, &full_bar[stage], (kb_lo + kb) * GEMM_BLOCK_K, m0);
+            tma_load_2d(b_dst, &tm_w, &full_bar[stage], (kb_lo + kb) * GEMM_BLOCK_K, n0);
           }
           if (++stage == S::STAGES) {
             stage = 0;
@@ -193,13 +203,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+      for (int wi = tile0; wi < num_work; wi += tile_step, ++it) {
+        const int kb_n = SPLITK ? kb_first(wi / num_tiles + 1) - kb_first(wi / num_tiles) : k_blks;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tm + acc * BLOCK_N;
-        for (int kb = 0; kb < k_blks; ++kb) {
+        for (int kb = 0; kb < kb_n; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * S::STAGE_BYTES);
@@ -214,10 +225,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             }
             if constexpr (CTA2) {
               umma_commit_2cta_mc(&empty_bar[stage], 3);                         // frees the slot in both CTAs
-              if (kb == k_blks - 1) umma_commit_2cta_mc(&tmem_full[acc], 3);     // both epilogues
+              if (kb == kb_n - 1) umma_commit_2cta_mc(&tmem_full[acc], 3);       // both epilogues
             } else {
               umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-              if (kb == k_blks - 1) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+              if (kb == kb_n - 1) umma_commit(&tmem_full[acc]);    // accumulator complete -> epilogue
             }
           }
           __syncwarp();
@@ -250,7 +261,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       if (lane == 0 && half < NCHUNK && tile0 < num_tiles) prefetch_resid(tile0, half);
     }
     int it = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
+    for (int wi = tile0; wi < num_work; wi += tile_step, ++it) {
+      const int tile = SPLITK ? wi % num_tiles : wi;
+      const bool add_bias = bias != nullptr && (!SPLITK || wi < num_tiles);     // split 0 carries the bias
       const int m0 = (tile / n_blks) * TILE_M + rank * GEMM_BLOCK_M;
       const int n0 = (tile % n_blks) * BLOCK_N;
       const int acc = it & 1;
@@ -296,7 +309,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           else mbar_arrive(&tmem_empty[acc]);
         }
         }
-        if (bias != nullptr) {
+        if (add_bias) {
 #pragma unroll
           for (int i = 0; i < CHUNK; i += 4) {
             const int col = n0 + col0 + i;
@@ -384,6 +397,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             const int rem = row - img * out_grid * out_grid;
             const int gy = rem / out_grid;
             tma_store_4d(&tm_out, buf, n0 + col0, rem - gy * out_grid, gy, img);
+          } else if constexpr (SPLITK) {
+            tma_reduce_add_2d(&tm_out, buf, n0 + col0, m0 + q * 32);
           } else {
             tma_store_2d(&tm_out, buf, n0 + col0, m0 + q * 32);
           }
@@ -429,7 +444,7 @@ static int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tm_a, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_w, tm_out, bias, M, N, K, act, conv_c, conv_h, out_grid));
+  LA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_w, tm_out, bias, M, N, K, act, conv_c, conv_h, out_grid, 1));
   return LA_OK;
 }
 
@@ -443,12 +458,59 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tm_a, const CUten
   const int m_blks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int tiles = n_blks * m_blks;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tm_a, tm_w, tm_out, bias, M, N, K, act, 0, 0, out_grid);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tm_a, tm_w, tm_out, bias, M, N, K, act, 0, 0, out_grid, 1);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+// split-K launch (one-CTA kernel, fp32 output zeroed here): tiles x splits work items over the SMs
+template <int BLOCK_N>
+static int launch_gemm_splitk(cudaStream_t stream, const CUtensorMap& tm_a, const CUtensorMap& tm_w,
+                              const CUtensorMap& tm_out, const float* bias, int M, int N, int K, int splits) {
+  using S = GemmSmem<BLOCK_N>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, float, false, false, 0, true>;
+  LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  const int tiles = ((N + BLOCK_N - 1) / BLOCK_N) * ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  const int work = tiles * splits;
+  const int grid = work < sm_count() ? work : sm_count();
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tm_a, tm_w, tm_out, bias, M, N, K, LA_ACT_NONE, 0, 0, 0, splits);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }
 
 }  // namespace la
+
+extern "C" int la_gemm_bf16_splitk(void* stream, const void* a, long long lda, const void* w, long long ldw,
+                                   const float* bias, float* out, long long ldo, int M, int N, int K) {
+  using namespace la;
+  LA_CHECK_ARG(a && w && out && M > 0 && N > 0 && K > 0, "la_gemm_bf16_splitk: bad arguments");
+  LA_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && N % 8 == 0 && ldo % 4 == 0 && ldo >= N,
+               "la_gemm_bf16_splitk: K / lda / ldw / N must be multiples of 8, ldo of 4");
+  LA_CHECK_ARG((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) %
+                       16 == 0, "la_gemm_bf16_splitk: pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int block_n = N >= 256 ? 256 : (N > 64 ? 128 : 64);
+  const int tiles = ((N + block_n - 1) / block_n) * ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  const int k_blks = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  // enough splits to fill the SMs once, at least 8 k-blocks per split
+  int splits = (sm_count() + tiles - 1) / tiles;
+  if (splits > k_blks / 8) splits = k_blks / 8;
+  if (splits < 1) splits = 1;
+  LA_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * static_cast<size_t>(M - 1) * ldo + sizeof(float) * N, st));
+  CUtensorMap tm_a, tm_w, tm_out;
+  int rc = make_tensor_map_2d(&tm_a, a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2,
+                              GEMM_BLOCK_K, GEMM_BLOCK_M, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_w, w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2,
+                          GEMM_BLOCK_K, (uint32_t)block_n, Swizzle::B128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tm_out, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 4, 32,
+                          32, Swizzle::B128);
+  if (rc) return rc;
+  if (block_n == 256) return launch_gemm_splitk<256>(st, tm_a, tm_w, tm_out, bias, M, N, K, splits);
+  if (block_n == 128) return launch_gemm_splitk<128>(st, tm_a, tm_w, tm_out, bias, M, N, K, splits);
+  return launch_gemm_splitk<64>(st, tm_a, tm_w, tm_out, bias, M, N, K, splits);
+}
 
 extern "C" int la_gemm_bf16(void* stream, const void* a, long long lda, const void* w, long long ldw,
                             const float* bias, void* out, long long ldo, int out_dtype, int M, int N, int K,

@@ -198,6 +198,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act
     return out
 
 
+def gemm_splitk(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 [M, N] = a @ w.T + bias with the contraction split over the SMs (few output tiles, long K: the weight
+    gradients of the training step).  a [M, K] bf16, w [N, K] bf16; partial tiles are added by TMA reduce stores."""
+    _require_cuda(a, w, bias)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.shape[1] == w.shape[1] and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert bias is None or (bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous())
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _cost(2.0 * M * N * K, 2.0 * (M * K + N * K) + 4.0 * M * N)
+    _call(f"gemm_splitk.n{N}.k{K}" if _PROF is not None else "gemm_splitk", "la_gemm_bf16_splitk", a, a.stride(0), w,
+          w.stride(0), bias, out, out.stride(0), M, N, K)
+    return out
+
+
 def gemm_to_grid(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, grid: int, padded: int) -> torch.Tensor:
     """bf16 [images * padded^2, N]: row (image, y, x) of a @ w.T + bias at position (image, y, x) of a padded x padded
     grid, the positions outside the grid x grid part = the bias row (the projection of the reference's zero padding)."""

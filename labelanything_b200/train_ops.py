@@ -148,10 +148,21 @@ def _relu_f32(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def _gemm_f32(a16: torch.Tensor, w16: torch.Tensor, bias=None, act=ACT_NONE) -> torch.Tensor:
+    """One fp32-output GEMM; products with a long contraction and too few output tiles to fill the GPU (the weight
+    gradients over the image-token rows: [N_out, 54 000] x [K_in, 54 000]^T) go through the split-K kernel."""
+    M, K = a16.shape
+    N = w16.shape[0]
+    tiles = -(-M // 128) * -(-N // (256 if N >= 256 else 128 if N > 64 else 64))
+    if act == ACT_NONE and K >= 2048 and tiles <= 32:
+        return ops.gemm_splitk(a16, w16, bias)
+    return ops.gemm(a16, w16, bias, act=act, out_dtype=torch.float32)
+
+
 def _mm(a: tuple, w: tuple, bias=None, act=ACT_NONE) -> torch.Tensor:
     """fp32 [M, N] = act(a @ w^T + bias) for operands a [M, K], w [N, K]."""
     if len(a) == 1 and len(w) == 1:
-        return ops.gemm(a[0], w[0], bias, act=act, out_dtype=torch.float32)
+        return _gemm_f32(a[0], w[0], bias, act)
     # every product a_i w_j^T with i + j <= order (3 of 4 for two terms, 6 of 9 for three), the small ones summed first
     order = max(len(a), len(w)) - 1
     out = None
@@ -159,9 +170,9 @@ def _mm(a: tuple, w: tuple, bias=None, act=ACT_NONE) -> torch.Tensor:
         for i in range(len(a)):
             j = total - i
             if 0 <= j < len(w):
-                t = ops.gemm(a[i], w[j], None, out_dtype=torch.float32)
+                t = _gemm_f32(a[i], w[j])
                 out = t if out is None else add_f32(out, t)
-    out = add_f32(ops.gemm(a[0], w[0], bias, out_dtype=torch.float32), out)
+    out = add_f32(_gemm_f32(a[0], w[0], bias), out)
     if act == ACT_RELU:
         out = _relu_f32(out)
     else:
