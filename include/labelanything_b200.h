@@ -368,6 +368,12 @@ int la_gelu_bwd_f32(void* stream, const float* dy, const float* x, float* dx, lo
  * [rows, ld_out) zero: the K-major operands of the weight-gradient GEMM dW[N, K] = dY^T[N, rows] @ X^T[K, rows]^T. */
 int la_cast_transpose_bf16(void* stream, const void* in, int in_dtype, long long ld_in, void* out, long long ld_out,
                            long long rows, int cols);
+/* One pass over an output gradient dy fp32 [rows, cols] (row stride ld) for everything a Linear's backward needs from
+ * it (each output optional): out_bf16 [rows, cols] = bf16(dy) (data-gradient GEMM operand), out_t_bf16 [cols, ld_t] =
+ * its transpose, columns [rows, ld_t) zero (weight-gradient GEMM operand), colsum fp32 [cols] = column sums (bias
+ * gradient; overwritten). */
+int la_grad_prep_bf16(void* stream, const float* dy, long long ld, void* out_bf16, void* out_t_bf16, long long ld_t,
+                      float* colsum, long long rows, int cols);
 /* out[(r / row_div) % b_mod][:] (+)= dy[r][:]: bias gradients (row_div = 1, b_mod = 1 -> column sum), gradients of
  * broadcast addends (class codes, no_sparse_embedding, positional tables).  accumulate = 0 zeroes out first. */
 int la_bcast_reduce_f32(void* stream, const float* dy, float* out, long long rows, int d, long long row_div,

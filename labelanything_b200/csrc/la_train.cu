@@ -142,6 +142,57 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const T* __restrict
   }
 }
 
+// One pass over an output gradient dy fp32 [rows, cols] for the three things a Linear's backward needs from it: the bf16
+// copy (A operand of the data-gradient GEMM), the bf16 transpose padded to 8 rows (A operand of the weight-gradient
+// GEMM) and the column sums (bias gradient).  Separately these were three kernels reading dy three times.
+constexpr int PREP_TILES = 16;   // 32-row tiles per CTA: 512 rows -> one atomic per column per CTA
+__global__ void __launch_bounds__(256)
+grad_prep_kernel(const float* __restrict__ dy, long long ld, __nv_bfloat16* __restrict__ out16,
+                 __nv_bfloat16* __restrict__ outT, long long ldT, float* __restrict__ colsum, long long rows, int cols) {
+  __shared__ float tile[32][33];
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * 32;
+  const long long rbase = static_cast<long long>(blockIdx.x) * (32 * PREP_TILES);
+  float csum = 0.f;
+  for (int t = 0; t < PREP_TILES; ++t) {
+    const long long r0 = rbase + 32ll * t;
+    if (r0 >= ldT) break;                 // ldT >= rows: the padding rows of the transpose are written (as zeros) too
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long r = r0 + ty + 8 * k;
+      const int c = c0 + tx;
+      float v = 0.f;
+      if (r < rows && c < cols) {
+        v = dy[r * ld + c];
+        if (out16) out16[r * cols + c] = __float2bfloat16_rn(v);
+      }
+      csum += v;
+      tile[ty + 8 * k][tx] = v;
+    }
+    __syncthreads();
+    if (outT) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k;
+        const long long r = r0 + tx;
+        if (c < cols && r < ldT) outT[c * ldT + r] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
+      }
+    }
+    __syncthreads();
+  }
+  if (colsum) {
+    part[ty][tx] = csum;
+    __syncthreads();
+    if (ty == 0 && c0 + tx < cols) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += part[k][tx];
+      atomicAdd(colsum + c0 + tx, a);
+    }
+  }
+}
+
 // out[(r / row_div) % b_mod][c] += sum of dy[r][c] over the rows r of one chunk (runs of equal targets are added
 // locally, one atomic per run)
 constexpr int RED_ROWS = 64;
@@ -1101,6 +1152,22 @@ int la_cast_transpose_bf16(void* stream, const void* in, int in_dtype, long long
   else
     cast_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(in), ld_in,
                                                                        static_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
+  LA_CHECK_CUDA(cudaGetLastError());
+  return LA_OK;
+}
+
+int la_grad_prep_bf16(void* stream, const float* dy, long long ld, void* out_bf16, void* out_t_bf16, long long ld_t,
+                      float* colsum, long long rows, int cols) {
+  LA_CHECK_ARG(dy && rows > 0 && cols > 0 && ld >= cols && (out_bf16 || out_t_bf16 || colsum), "la_grad_prep_bf16: bad arguments");
+  LA_CHECK_ARG(!out_t_bf16 || ld_t >= rows, "la_grad_prep_bf16: ld_t must cover the rows");
+  const long long span = out_t_bf16 ? ld_t : rows;
+  const long long gx = (span + 32 * PREP_TILES - 1) / (32 * PREP_TILES);
+  LA_CHECK_ARG(gx < (1ll << 31) && (cols + 31) / 32 <= 65535, "la_grad_prep_bf16: matrix too large");
+  if (colsum) LA_CHECK_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * cols, ST(stream)));
+  dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>((cols + 31) / 32));
+  grad_prep_kernel<<<grid, 256, 0, ST(stream)>>>(dy, ld, static_cast<__nv_bfloat16*>(out_bf16),
+                                                 static_cast<__nv_bfloat16*>(out_t_bf16), out_t_bf16 ? ld_t : rows, colsum,
+                                                 rows, cols);
   LA_CHECK_CUDA(cudaGetLastError());
   return LA_OK;
 }

@@ -148,6 +148,29 @@ def _relu_f32(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def grad_prep(dy: torch.Tensor, want16: bool, want_t: bool, want_sum: bool):
+    """(bf16(dy), bf16(dy)^T padded to 8 rows, column sums) of an fp32 [rows, cols] gradient in one pass."""
+    _require_cuda(dy)
+    dy = _f32c(dy)
+    rows, cols = dy.shape
+    r8 = (rows + 7) // 8 * 8
+    o16 = torch.empty((rows, cols), dtype=torch.bfloat16, device=dy.device) if want16 else None
+    ot = torch.empty((cols, r8), dtype=torch.bfloat16, device=dy.device) if want_t else None
+    cs = torch.empty(cols, dtype=torch.float32, device=dy.device) if want_sum else None
+    _call("grad_prep", "la_grad_prep_bf16", dy, dy.stride(0), o16, ot, r8, cs, rows, cols)
+    return o16, ot, cs
+
+
+def _backward_operands(dy: torch.Tensor, mode: str, need_dx: bool, need_dw: bool, need_db: bool):
+    """-> (dy as a GEMM operand | None, its transpose as a GEMM operand | None, bias gradient | None).  bf16 mode: one
+    fused pass over dy; split-operand modes: the generic split / transpose / column-sum kernels."""
+    if mode == "bf16":
+        o16, ot, cs = grad_prep(dy, need_dx, need_dw, need_db)
+        return (None if o16 is None else (o16,)), (None if ot is None else (ot,)), cs
+    dyb = _split(dy, mode) if (need_dx or need_dw) else None
+    return (dyb if need_dx else None), (_tr(dyb) if need_dw else None), (bcast_reduce(dy).view(-1) if need_db else None)
+
+
 def _gemm_f32(a16: torch.Tensor, w16: torch.Tensor, bias=None, act=ACT_NONE) -> torch.Tensor:
     """One fp32-output GEMM; products with a long contraction and too few output tiles to fill the GPU (the weight
     gradients over the image-token rows: [N_out, 54 000] x [K_in, 54 000]^T) go through the split-K kernel."""
@@ -210,14 +233,13 @@ class _Linear(Function):
             g = torch.empty_like(dy)
             _call("relu_bwd", "la_relu_bwd_f32", dy, y, g, dy.numel())
             dy = g
-        dyb = _split(dy, ctx.mode)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        need = ctx.needs_input_grad
+        dyb, dyt, db = _backward_operands(dy, ctx.mode, need[0], need[1], ctx.has_bias and need[2])
+        dx = dw = None
+        if need[0]:
             dx = _mm(dyb, _tr(wb))                                    # [M, N] @ [K, N]^T
-        if ctx.needs_input_grad[1]:
-            dw = _mm(_tr(dyb), _tr(xb))                               # [N, M8] @ [K, M8]^T
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = bcast_reduce(dy).view(-1)
+        if need[1]:
+            dw = _mm(dyt, _tr(xb))                                    # [N, M8] @ [K, M8]^T
         return dx, dw, db, None
 
 
@@ -252,16 +274,15 @@ class _Conv3x3(Function):
         col, wb = tuple(parts[:n]), tuple(parts[n:])
         n_img, h, w, c = ctx.geom
         dy = _f32c(dy)
-        dyb = _split(dy, ctx.mode)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        need = ctx.needs_input_grad
+        dyb, dyt, db = _backward_operands(dy, ctx.mode, need[0], need[1], ctx.has_bias and need[2])
+        dx = dw = None
+        if need[0]:
             dcol = _mm(dyb, _tr(wb))                                  # [rows, 9c] fp32
             dx = torch.empty((n_img * h * w, c), dtype=torch.float32, device=dy.device)
             _call("col2im_3x3", "la_col2im_3x3_f32", dcol, dx, n_img, h, w, c)
-        if ctx.needs_input_grad[1]:
-            dw = _mm(_tr(dyb), _tr(col))
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = bcast_reduce(dy).view(-1)
+        if need[1]:
+            dw = _mm(dyt, _tr(col))
         return dx, dw, db, None, None, None
 
 

@@ -625,7 +625,9 @@ def test_graphed_train_step_equals_the_eager_step():
     lc = float(train_step(c, loss_fn, opt_c, ep2, gt)["loss"]["value"])       # step 2, eager again
     lb = float(step(ep2, gt)["loss"]["value"])                                # step 2, one graph replay
     assert opt_a.steps == opt_b.steps and max(opt_a.steps) == 2
-    assert abs(la - lb) <= 1e-5 * abs(la) and abs(la - lc) <= 1e-5 * abs(la), (la, lb, lc)
+    # the split-K GEMMs add their partial tiles in whatever order the CTAs finish: already the forward pass differs in its
+    # last bits from run to run, and the bf16 roundings behind it amplify that (4e-4 of the loss on this model)
+    assert abs(la - lb) <= 2e-3 * abs(la) and abs(la - lc) <= 2e-3 * abs(la), (la, lb, lc)
     n = opt_a.numel
     # the backward pass scatters with atomics (bilinear / postprocess adjoints, bias and LayerNorm sums): two EAGER runs
     # from the same state differ in the last bits of d loss / d logits, which the bf16 roundings of the backward GEMMs
