@@ -454,7 +454,9 @@ def training_measurement(rank: int, world: int, steps: int = 5, warmup: int = 3)
                         f"480 px, {N}-way {K}-shot, {B} episodes per GPU, point + box + mask prompts; forward + focal loss "
                         f"+ backward + gradient all-reduce + AdamW, bf16 GEMM operands / fp32 accumulation and state",
             "ms_per_step": ms_graph, "episodes_per_s": B * world / ms_graph * 1e3, "n_gpus": world,
-            "step": "one CUDA-graph replay per step (GraphedTrainStep); eager launch sequence: see eager_ms_per_step",
+            "step": ("one CUDA-graph replay per step (GraphedTrainStep)" if world == 1 else
+                     "two CUDA-graph replays per step (forward + backward | AdamW) with the NCCL all-reduce of the "
+                     "gradient bucket between them (GraphedTrainStep)") + "; eager launch sequence: see eager_ms_per_step",
             "eager_ms_per_step": ms, "eager_episodes_per_s": B * world / ms * 1e3,
             "allreduce_ms": ar_ms if world > 1 else None, "grad_bucket_bytes": int(opt.flat_g.numel() * 4),
             "trainable_parameters": int(sum(p.numel() for p in opt.params)),

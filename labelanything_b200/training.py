@@ -448,7 +448,7 @@ class GraphedTrainStep:
     The loss value and the outputs are static device tensors (no `.item()` inside the step)."""
 
     def __init__(self, lam: Lam, loss_fn, opt: FlatAdamW, example_input: Dict[str, Any], example_gt: torch.Tensor,
-                 warmup: int = 3) -> None:
+                 warmup: int = 3, collective_in_graph: bool = False) -> None:
         import torch.distributed as dist
 
         self.lam, self.loss_fn, self.opt = lam, loss_fn, opt
@@ -494,7 +494,16 @@ class GraphedTrainStep:
         T._DERIVED.clear()                    # no operand cached by the eager steps may stand in for a captured launch
         opt.flat_g.zero_()
         torch.cuda.synchronize()
+        def update():
+            for i, (lo, hi, _) in enumerate(self.runs):
+                T.adamw_step_dev(opt.flat_p[lo:hi], opt.flat_g[lo:hi], opt.exp_avg[lo:hi], opt.exp_avg_sq[lo:hi],
+                                 opt.betas[0], opt.betas[1], opt.eps, opt.weight_decay, self.bc[i], 1.0 / self.world)
+
+        # world > 1: by default the all-reduce is launched BETWEEN two graphs (forward + backward | update) -- one more
+        # launch per step; `collective_in_graph=True` makes it a node of a single graph (NCCL supports capture; verified
+        # on 2 GPUs here)
         self.graph = torch.cuda.CUDAGraph()
+        self.graph_update = None
         try:
             with torch.cuda.graph(self.graph):
                 out = train_forward(lam, self.static, self.plan)
@@ -502,11 +511,14 @@ class GraphedTrainStep:
                 grads = torch.autograd.grad(self.loss, [alias[id(p)] for p, u in zip(opt.params, used) if u])
                 torch._foreach_copy_(views, list(grads))
                 del grads
-                if self.world > 1:
-                    dist.all_reduce(opt.flat_g[:opt.numel], group=opt.group)   # the step's one collective, in the graph
-                for i, (lo, hi, _) in enumerate(self.runs):
-                    T.adamw_step_dev(opt.flat_p[lo:hi], opt.flat_g[lo:hi], opt.exp_avg[lo:hi], opt.exp_avg_sq[lo:hi],
-                                     opt.betas[0], opt.betas[1], opt.eps, opt.weight_decay, self.bc[i], 1.0 / self.world)
+                if self.world > 1 and collective_in_graph:
+                    dist.all_reduce(opt.flat_g[:opt.numel], group=opt.group)
+                if self.world == 1 or collective_in_graph:
+                    update()
+            if self.world > 1 and not collective_in_graph:
+                self.graph_update = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_update, pool=self.graph.pool()):
+                    update()
         finally:
             for mod, name, p in swapped:
                 mod._parameters[name] = p
@@ -544,6 +556,11 @@ class GraphedTrainStep:
             self.plan["class_rows"].copy_(ce.sample_rows(self.plan["class_rows"].numel(), self.plan["class_rows"].device))
         self._fill_bc()
         self.graph.replay()
+        if self.graph_update is not None:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.opt.flat_g[:self.opt.numel], group=self.opt.group)   # the step's one collective
+            self.graph_update.replay()
         opt = self.opt
         for i, u in enumerate(self.used):
             if u:
