@@ -388,7 +388,7 @@ int la_layernorm_f32_bwd(void* stream, const float* x, const float* gamma, const
                          const float* dy, float* dx, float* dgamma, float* dbeta, long long rows, int d);
 /* out = softmax(scale q k^T) v per (sequence, head) on fp32 [n_seq * nq | nk, heads * head_dim] rows; lse fp32
  * [n_seq, heads, nq] = log-sum-exp of the scaled scores (kept for the backward pass).  common.py:97-148 after the
- * projections (the reference's masks are no-ops).  head_dim <= 64. */
+ * projections (the reference's masks are no-ops).  head_dim <= 64 and a multiple of 4 (16-byte row loads). */
 int la_attention_f32(void* stream, const float* q, const float* k, const float* v, float* out, float* lse,
                      long long n_seq, int nq, int nk, int heads, int head_dim, float scale);
 /* its backward: dq / dk / dv overwritten; delta fp32 [n_seq, heads, nq] is scratch (rowsum(dout * out)) */
