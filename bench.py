@@ -295,7 +295,15 @@ def secondary_measurements(lam, steps: int = 3) -> dict:
         out["mode_B_embeddings"] = {
             "workload": f"SAM-512 5-way 5-shot, Lam.forward(embeddings): neck + prompt encoder + decoder, batch {B}",
             "ms_per_step": ms, "episodes_per_s": B / ms * 1e3, "gflop_per_episode": gf, "tflops": gf * B / ms}
-        del ep
+        # the same with point + box + mask prompts (9 sparse tokens per sequence instead of 1): the token <-> image
+        # attentions run on la_attention_tokens (CUDA cores) instead of the pooled single-token path
+        epm = cuda(make_episode(B, N_WAYS, K_SHOTS, IMAGE_SIZE, seed=7, prompts="mixed", embeddings=(768, 64)))
+        ms = _timed(lambda: lam(epm)["logits"], steps)
+        out["mode_B_mixed_prompts"] = {
+            "workload": f"SAM-512 5-way 5-shot, Lam.forward(embeddings) with 5 points + 2 boxes + 1 mask per (example, "
+                        f"class): 9 sparse tokens per sequence, batch {B}",
+            "ms_per_step": ms, "episodes_per_s": B / ms * 1e3}
+        del ep, epm
         # ---- mode C: class embeddings once, then predict per query (lam.py:349-381) ----
         sup = make_episode(1, N_WAYS, K_SHOTS, IMAGE_SIZE, seed=8)
         sup_in = cuda({k: (v[:, 1:] if k in ("images", "dims") else v) for k, v in sup.items()})

@@ -148,14 +148,93 @@ __global__ void __launch_bounds__(256) attn_query_parallel_kernel(const TokAttPa
 }
 
 // ------------------------------------------------------------------------------------------------------
+// query-parallel, few keys (<= 16: the image -> token attention of the two-way blocks, 4096 queries against the 1..16
+// sparse tokens of their sequence): ONE THREAD per (sequence, query, head), all scores first, then the softmax, then
+// the values -- no shuffles, no running rescale; the key / value rows of a sequence are shared by every thread that
+// works on it (L1 broadcast).  The G-lanes-per-unit kernel above spent 3.5 ms on 2.5 GB of queries + outputs
+// (0.7 TB/s, profiles/r02_ncu_modeb_v1.txt): nine serial online-softmax steps with two shuffles each per lane.
+// ------------------------------------------------------------------------------------------------------
+constexpr int QR_MAX_KEYS = 16;
+
+template <int DH>
+__global__ void __launch_bounds__(256) attn_query_row_kernel(const TokAttParams p) {
+  const long long total = static_cast<long long>(p.n_seq) * p.nq * p.n_heads;
+  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
+       g += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int h = static_cast<int>(g % p.n_heads);
+    const long long sq = g / p.n_heads;  // seq * nq + query
+    const int qi = static_cast<int>(sq % p.nq);
+    const long long seq = sq / p.nq;
+    const int col = h * DH;
+    float q[DH];
+#pragma unroll
+    for (int c = 0; c < DH / 8; ++c) {
+      float t[8];
+      load8(p.q + sq * p.ld_q + col + 8 * c, t);
+      if (p.q_add) add8(p.q_add + static_cast<long long>(qi) * p.ld_qadd + col + 8 * c, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[8 * c + i] = t[i] * p.scale_log2;
+    }
+    const __nv_bfloat16* kp = p.k + seq * p.nk * p.ld_k + col;
+    const __nv_bfloat16* vp = p.v + seq * p.nk * p.ld_v + col;
+    float s[QR_MAX_KEYS];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < QR_MAX_KEYS; ++j) {
+      s[j] = -INFINITY;
+      if (j < p.nk) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+          float t[8];
+          load8(kp + static_cast<long long>(j) * p.ld_k + 8 * c, t);
+          if (p.k_add) add8(p.k_add + static_cast<long long>(j) * p.ld_kadd + col + 8 * c, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc = fmaf(q[8 * c + i], t[i], acc);
+        }
+        s[j] = acc;
+        m = fmaxf(m, acc);
+      }
+    }
+    float l = 0.f, o[DH];
+#pragma unroll
+    for (int i = 0; i < DH; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < QR_MAX_KEYS; ++j) {
+      if (j < p.nk) {
+        const float pj = ex2f(s[j] - m);
+        l += pj;
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+          float t[8];
+          load8(vp + static_cast<long long>(j) * p.ld_v + 8 * c, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[8 * c + i] = fmaf(pj, t[i], o[8 * c + i]);
+        }
+      }
+    }
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int c = 0; c < DH / 8; ++c) {
+      float t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = o[8 * c + i];
+      store8(p.out + sq * p.ld_out + col + 8 * c, t, inv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // key-parallel: one warp per (sequence, split, head); QB queries per pass
 // ------------------------------------------------------------------------------------------------------
 // KP_QB: queries handled per pass over the keys (1 for the single-token sequences of mask-only prompts, which keeps
 // the register count low enough for KP_UNROLL key groups of loads in flight per warp -- the kernel is a pure HBM
 // stream and was latency bound with one group in flight).
-constexpr int KP_UNROLL = 4;
-
-template <int DH, int KP_QB>
+// With several tokens per sequence (point / box prompts: 9 tokens; the decoder's class tokens) ALL queries ride in ONE
+// pass over the keys when they fit the register budget (KP_QB up to 10 with two key groups in flight): with KP_QB = 4
+// nine queries meant three passes, i.e. K and V of all S*T image tokens read three times (7.6 GB instead of 2.5 GB per
+// four episodes, profiles/r02_ncu_modeb_v1.txt).
+template <int DH, int KP_QB, int KP_UNROLL>
 __global__ void __launch_bounds__(256) attn_key_parallel_kernel(const TokAttParams p) {
   constexpr int G = DH / 8;
   constexpr int KG = 32 / G;  // keys per warp iteration
@@ -316,8 +395,10 @@ static int launch_tokens(cudaStream_t st, const TokAttParams& p, bool key_parall
   if (key_parallel) {
     const long long grid = static_cast<long long>(p.n_seq) * p.splits;
     const int threads = 32 * (p.n_heads < 8 ? p.n_heads : 8);
-    if (p.nq == 1) attn_key_parallel_kernel<DH, 1><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
-    else attn_key_parallel_kernel<DH, 4><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
+    if (p.nq == 1) attn_key_parallel_kernel<DH, 1, 4><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
+    else if (p.nq <= 4) attn_key_parallel_kernel<DH, 4, 4><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
+    else if (p.nq <= 6) attn_key_parallel_kernel<DH, 6, 2><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
+    else attn_key_parallel_kernel<DH, 10, 2><<<static_cast<unsigned>(grid), threads, 0, st>>>(p);
     LA_CHECK_CUDA(cudaGetLastError());
     if (p.splits > 1) {
       const long long total = static_cast<long long>(p.n_seq) * p.n_heads * p.nq * DH;
@@ -327,6 +408,13 @@ static int launch_tokens(cudaStream_t st, const TokAttParams& p, bool key_parall
       attn_merge_splits_kernel<DH><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
       LA_CHECK_CUDA(cudaGetLastError());
     }
+  } else if (p.nk <= QR_MAX_KEYS && p.nq >= 64) {
+    const long long units = static_cast<long long>(p.n_seq) * p.nq * p.n_heads;
+    long long blocks = (units + 255) / 256;
+    const long long cap = static_cast<long long>(sm_count()) * 32;
+    if (blocks > cap) blocks = cap;
+    attn_query_row_kernel<DH><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
+    LA_CHECK_CUDA(cudaGetLastError());
   } else {
     constexpr int G = DH / 8;
     const long long units = static_cast<long long>(p.n_seq) * p.nq * p.n_heads;

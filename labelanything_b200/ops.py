@@ -432,7 +432,8 @@ def attention_tokens(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, n_seq: i
     ws_bytes = _attention_tokens_workspace_bytes(n_seq, nq, nk, n_heads, head_dim)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes > 0 else None
     _cost(4.0 * n_seq * nq * nk * w, 2.0 * n_seq * (2 * nq + 2 * nk) * w)
-    _call("attention_tokens", "la_attention_tokens", q, q.stride(0), k, k.stride(0), v, v.stride(0), q_add,
+    _call(f"attention_tokens.s{n_seq}.q{nq}.k{nk}.d{head_dim}" if _PROF is not None else "attention_tokens",
+          "la_attention_tokens", q, q.stride(0), k, k.stride(0), v, v.stride(0), q_add,
         q_add.stride(0) if q_add is not None else 0, k_add, k_add.stride(0) if k_add is not None else 0,
         out, out.stride(0), n_seq, nq, nk, n_heads, head_dim, head_dim ** -0.5, ws)
     return out

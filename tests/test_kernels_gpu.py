@@ -374,7 +374,13 @@ def test_layout_and_index_kernels_are_exact():
 @pytest.mark.parametrize("n_seq,nq,nk,dh,with_tables", [
     (7, 1, 4096, 32, True),     # token -> image, one token per sequence (key-parallel with splits)
     (3, 6, 900, 16, True),      # class tokens -> 30x30 image (MAE-256 decoder)
-    (2, 4096, 9, 32, True),     # image -> tokens (query-parallel)
+    (2, 4096, 9, 32, True),     # image -> tokens (one thread per query row: <= 16 keys)
+    (3, 900, 3, 16, True),      # image -> class tokens (MAE-256 decoder)
+    (2, 300, 16, 64, False),    # 16 keys, head_dim 64 (row kernel at its register limit)
+    (2, 40, 9, 32, True),       # few queries, few keys: the lanes-per-unit kernel
+    (3, 9, 4096, 32, True),     # nine prompt tokens -> image: all queries in ONE pass over the keys (KP_QB 10)
+    (2, 21, 900, 16, True),     # 20-way decoder: 21 class tokens, three passes of 10
+    (2, 6, 4096, 64, False),    # six class tokens (KP_QB 6), head_dim 64
     (4, 150, 150, 64, False),   # example attention over M*C tokens
     (5, 9, 9, 8, False),        # tiny self-attention
 ])
