@@ -155,16 +155,47 @@ __global__ void __launch_bounds__(256) attn_query_parallel_kernel(const TokAttPa
 // (0.7 TB/s, profiles/r02_ncu_modeb_v1.txt): nine serial online-softmax steps with two shuffles each per lane.
 // ------------------------------------------------------------------------------------------------------
 constexpr int QR_MAX_KEYS = 16;
+constexpr int QR_ITERS = 8;     // query rows per thread: one CTA stages a sequence's keys / values once for 2048 units
 
+// A CTA works on ONE sequence: it stages that sequence's (k + k_add) * scale and v as fp32 in shared memory (rows padded
+// by 4 floats per head: the eight heads of a warp's lanes hit eight different bank groups), then every thread walks
+// QR_ITERS (query, head) units: the only global traffic of the inner loop is the unit's q row (+ table row) in and its
+// output row out.  The first version read k / v through L1 inside the loop and sat at 0.6 TB/s with 7.9 warps stalled
+// on loads per issued instruction.
 template <int DH>
-__global__ void __launch_bounds__(256) attn_query_row_kernel(const TokAttParams p) {
-  const long long total = static_cast<long long>(p.n_seq) * p.nq * p.n_heads;
-  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
-       g += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int h = static_cast<int>(g % p.n_heads);
-    const long long sq = g / p.n_heads;  // seq * nq + query
-    const int qi = static_cast<int>(sq % p.nq);
-    const long long seq = sq / p.nq;
+__global__ void __launch_bounds__(256) attn_query_row_kernel(const TokAttParams p, int chunks) {
+  extern __shared__ float s_kv[];                       // [2][nk][heads][DH + 4]
+  constexpr int HS = DH + 4;
+  const int H = p.n_heads;
+  const long long seq = blockIdx.x / chunks;
+  const int chunk = blockIdx.x % chunks;
+  float* ks = s_kv;
+  float* vs = s_kv + p.nk * H * HS;
+  for (int i = threadIdx.x; i < p.nk * H * (DH / 8); i += blockDim.x) {
+    const int c = i % (DH / 8);
+    const int h = (i / (DH / 8)) % H;
+    const int j = i / ((DH / 8) * H);
+    const int col = h * DH + 8 * c;
+    float t[8];
+    load8(p.k + (seq * p.nk + j) * p.ld_k + col, t);
+    if (p.k_add) add8(p.k_add + static_cast<long long>(j) * p.ld_kadd + col, t);
+    float* kd = ks + (j * H + h) * HS + 8 * c;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) kd[e] = t[e] * p.scale_log2;
+    load8(p.v + (seq * p.nk + j) * p.ld_v + col, t);
+    float* vd = vs + (j * H + h) * HS + 8 * c;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) vd[e] = t[e];
+  }
+  __syncthreads();
+  const long long units = static_cast<long long>(p.nq) * H;        // (query, head) units of this sequence
+  const long long u0 = static_cast<long long>(chunk) * (256 * QR_ITERS);
+  for (int it = 0; it < QR_ITERS; ++it) {
+    const long long u = u0 + it * 256 + threadIdx.x;
+    if (u >= units) break;
+    const int h = static_cast<int>(u % H);
+    const int qi = static_cast<int>(u / H);
+    const long long sq = seq * p.nq + qi;
     const int col = h * DH;
     float q[DH];
 #pragma unroll
@@ -173,24 +204,23 @@ __global__ void __launch_bounds__(256) attn_query_row_kernel(const TokAttParams 
       load8(p.q + sq * p.ld_q + col + 8 * c, t);
       if (p.q_add) add8(p.q_add + static_cast<long long>(qi) * p.ld_qadd + col + 8 * c, t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[8 * c + i] = t[i] * p.scale_log2;
+      for (int i = 0; i < 8; ++i) q[8 * c + i] = t[i];
     }
-    const __nv_bfloat16* kp = p.k + seq * p.nk * p.ld_k + col;
-    const __nv_bfloat16* vp = p.v + seq * p.nk * p.ld_v + col;
     float s[QR_MAX_KEYS];
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < QR_MAX_KEYS; ++j) {
       s[j] = -INFINITY;
       if (j < p.nk) {
+        const float4* kr = reinterpret_cast<const float4*>(ks + (j * H + h) * HS);
         float acc = 0.f;
 #pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
-          float t[8];
-          load8(kp + static_cast<long long>(j) * p.ld_k + 8 * c, t);
-          if (p.k_add) add8(p.k_add + static_cast<long long>(j) * p.ld_kadd + col + 8 * c, t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc = fmaf(q[8 * c + i], t[i], acc);
+        for (int c = 0; c < DH / 4; ++c) {
+          const float4 t = kr[c];
+          acc = fmaf(q[4 * c], t.x, acc);
+          acc = fmaf(q[4 * c + 1], t.y, acc);
+          acc = fmaf(q[4 * c + 2], t.z, acc);
+          acc = fmaf(q[4 * c + 3], t.w, acc);
         }
         s[j] = acc;
         m = fmaxf(m, acc);
@@ -204,12 +234,14 @@ __global__ void __launch_bounds__(256) attn_query_row_kernel(const TokAttParams 
       if (j < p.nk) {
         const float pj = ex2f(s[j] - m);
         l += pj;
+        const float4* vr = reinterpret_cast<const float4*>(vs + (j * H + h) * HS);
 #pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
-          float t[8];
-          load8(vp + static_cast<long long>(j) * p.ld_v + 8 * c, t);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[8 * c + i] = fmaf(pj, t[i], o[8 * c + i]);
+        for (int c = 0; c < DH / 4; ++c) {
+          const float4 t = vr[c];
+          o[4 * c] = fmaf(pj, t.x, o[4 * c]);
+          o[4 * c + 1] = fmaf(pj, t.y, o[4 * c + 1]);
+          o[4 * c + 2] = fmaf(pj, t.z, o[4 * c + 2]);
+          o[4 * c + 3] = fmaf(pj, t.w, o[4 * c + 3]);
         }
       }
     }
@@ -408,12 +440,14 @@ static int launch_tokens(cudaStream_t st, const TokAttParams& p, bool key_parall
       attn_merge_splits_kernel<DH><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
       LA_CHECK_CUDA(cudaGetLastError());
     }
-  } else if (p.nk <= QR_MAX_KEYS && p.nq >= 64) {
-    const long long units = static_cast<long long>(p.n_seq) * p.nq * p.n_heads;
-    long long blocks = (units + 255) / 256;
-    const long long cap = static_cast<long long>(sm_count()) * 32;
-    if (blocks > cap) blocks = cap;
-    attn_query_row_kernel<DH><<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
+  } else if (p.nk <= QR_MAX_KEYS && p.nq >= 64 &&
+             static_cast<long long>(p.n_seq) * ((static_cast<long long>(p.nq) * p.n_heads + 256 * QR_ITERS - 1) /
+                                                (256 * QR_ITERS)) < (1ll << 31)) {
+    const int chunks = static_cast<int>((static_cast<long long>(p.nq) * p.n_heads + 256 * QR_ITERS - 1) / (256 * QR_ITERS));
+    const size_t smem = sizeof(float) * 2 * p.nk * p.n_heads * (DH + 4);
+    auto kern = attn_query_row_kernel<DH>;
+    if (smem > 48 * 1024) LA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<static_cast<unsigned>(p.n_seq * chunks), 256, smem, st>>>(p, chunks);
     LA_CHECK_CUDA(cudaGetLastError());
   } else {
     constexpr int G = DH / 8;
