@@ -91,6 +91,10 @@ class ImageEncoderViT(NativeModule):
             nn.Conv2d(out_chans, out_chans, kernel_size=3, padding=1, bias=False), LayerNorm2d(out_chans))
         #: images per launch group; bounds the workspace (~125 MB per 1024-px image)
         self.max_images_per_chunk = 64   # upper bound; chunks are balanced (see encode_tokens)
+        #: optional hook `chunk_ready(first_image, n_images)` called before a chunk's first launch: an input pipeline that
+        #: uploads the image batch in slices makes the stream wait for just the slice the chunk reads (bench.py e2e), so
+        #: the encoder starts on the first images while the rest of the batch is still crossing PCIe
+        self.chunk_ready = None
 
     # ------------------------------------------------------------------ weight packing
     def _spec(self, grid: int) -> VitSpec:
@@ -144,6 +148,8 @@ class ImageEncoderViT(NativeModule):
         per_chunk = -(-I // n_chunks)
         for s in range(0, I, per_chunk):
             n = min(per_chunk, I - s)
+            if self.chunk_ready is not None:
+                self.chunk_ready(s, n)
             cols = ops.im2col_patch16(images[s:s + n])
             patch = ops.gemm(cols, w_pe, b_pe)
             del cols
