@@ -99,3 +99,28 @@ def test_sam_vit_with_neck_and_last_block_state_matches_reference_golden():
     assert torch.equal(plain, out["last_hidden_state"])
     _check("SAM ViT-B last_block_state", out["last_block_state"][0, ::16], g["last_block_state_sub"])
     _check("SAM ViT-B + neck last_hidden_state", out["last_hidden_state"][0, ::8], g["last_hidden_state_sub"])
+
+
+def test_chunk_ready_hook_is_called_once_per_encoder_chunk_and_changes_nothing():
+    """ImageEncoderViT.chunk_ready (the input pipeline's per-slice wait, bench.py e2e): called with the image range of
+    every balanced chunk before its first launch; the features are those of the un-hooked call."""
+    from functools import partial
+
+    from labelanything_b200.image_encoder import ImageEncoderViT
+    from labelanything_b200.synthetic import load_synth_weights
+
+    vit = ImageEncoderViT(depth=2, embed_dim=128, img_size=256, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                          num_heads=2, patch_size=16, qkv_bias=True, use_rel_pos=True, global_attn_indexes=[1],
+                          project_last_hidden=False, window_size=14, out_chans=256)
+    load_synth_weights(vit, seed=3)
+    vit = vit.cuda()
+    x = torch.randn(5, 3, 256, 256, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    vit.max_images_per_chunk = 2
+    with torch.no_grad():
+        ref = vit(x)
+        calls = []
+        vit.chunk_ready = lambda first, n: calls.append((first, n))
+        got = vit(x)
+        vit.chunk_ready = None
+    assert calls == [(0, 2), (2, 2), (4, 1)]
+    assert torch.equal(got, ref)
