@@ -109,12 +109,12 @@ def test_chunk_ready_hook_is_called_once_per_encoder_chunk_and_changes_nothing()
     from labelanything_b200.image_encoder import ImageEncoderViT
     from labelanything_b200.synthetic import load_synth_weights
 
-    vit = ImageEncoderViT(depth=2, embed_dim=128, img_size=256, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+    vit = ImageEncoderViT(depth=2, embed_dim=128, img_size=1024, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
                           num_heads=2, patch_size=16, qkv_bias=True, use_rel_pos=True, global_attn_indexes=[1],
                           project_last_hidden=False, window_size=14, out_chans=256)
     load_synth_weights(vit, seed=3)
     vit = vit.cuda()
-    x = torch.randn(5, 3, 256, 256, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    x = torch.randn(5, 3, 1024, 1024, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
     vit.max_images_per_chunk = 2
     with torch.no_grad():
         ref = vit(x)
