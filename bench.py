@@ -454,10 +454,36 @@ def training_measurement(rank: int, world: int, steps: int = 5, warmup: int = 3)
     sync()
     losses.append(float(r["loss"]["value"]))
     ms_graph = g0.elapsed_time(g1) / steps
-    t = torch.tensor([ms, max(ar) if ar else 0.0, ms_graph], dtype=torch.float64, device="cuda")
+    # the same configuration from IMAGES through a frozen ViT-MAE-L (BASELINE configs[3] as worded: the encoder runs on its
+    # inference kernels inside the captured step, only neck + prompt encoder + decoder are trained)
+    del gstep
+    from labelanything_b200.build_encoder import build_vit_from_config
+    from labelanything_b200.build_lam import build_lam
+
+    lam_l = build_lam(build_vit=lambda project_last_hidden: build_vit_from_config(
+        hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096, image_size=224),
+        image_embed_dim=1024, embed_dim=256, image_size=S, spatial_convs=3, class_attention=False, example_attention=False,
+        example_class_attention=True, custom_preprocess=False)
+    load_synth_weights(lam_l, seed=4)
+    lam_l = lam_l.cuda().train()
+    ep_i = {k: v.cuda() for k, v in make_episode(B, N, K, S, seed=400 + rank, prompts="mixed").items()}
+    opt_l = FlatAdamW(lam_l.get_learnable_params({"freeze_backbone": True}), lr=5e-5)
+    gstep_l = GraphedTrainStep(lam_l, loss_fn, opt_l, ep_i, gt, warmup=2)
+    for _ in range(warmup):
+        gstep_l()
+    sync()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(steps):
+        gstep_l()
+    i1.record()
+    sync()
+    ms_images = i0.elapsed_time(i1) / steps
+    del gstep_l, lam_l, opt_l
+    t = torch.tensor([ms, max(ar) if ar else 0.0, ms_graph, ms_images], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ar_ms, ms_graph = float(t[0]), float(t[1]), float(t[2])
+    ms, ar_ms, ms_graph, ms_images = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     return {"workload": f"BASELINE configs[3]: lam_no_vit on pre-computed ViT-MAE-L embeddings (1024 x 30 x 30), embed 256, "
                         f"480 px, {N}-way {K}-shot, {B} episodes per GPU, point + box + mask prompts; forward + focal loss "
                         f"+ backward + gradient all-reduce + AdamW, bf16 GEMM operands / fp32 accumulation and state",
@@ -466,6 +492,9 @@ def training_measurement(rank: int, world: int, steps: int = 5, warmup: int = 3)
                      "two CUDA-graph replays per step (forward + backward | AdamW) with the NCCL all-reduce of the "
                      "gradient bucket between them (GraphedTrainStep)") + "; eager launch sequence: see eager_ms_per_step",
             "eager_ms_per_step": ms, "eager_episodes_per_s": B * world / ms * 1e3,
+            "from_images_frozen_vit_l": {"workload": f"the same step from images [{B}, {N * K + 1}, 3, {S}, {S}] through a "
+                                                     "frozen ViT-MAE-L (1024 / 24 / 16) inside the captured graph",
+                                         "ms_per_step": ms_images, "episodes_per_s": B * world / ms_images * 1e3},
             "allreduce_ms": ar_ms if world > 1 else None, "grad_bucket_bytes": int(opt.flat_g.numel() * 4),
             "trainable_parameters": int(sum(p.numel() for p in opt.params)),
             "native_launches_per_step": prof.launches, "kernel_ms_per_step": kernel_ms, "gemm_ms_per_step": gemm_ms,

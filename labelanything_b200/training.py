@@ -231,7 +231,7 @@ def make_plan(lam: Lam, batched_input: Dict[str, Any]) -> Dict[str, Any]:
     for oh, ow in sizes_host[:, 0, :].tolist():
         ih, iw = get_preprocess_shape(oh, ow, lam.image_size) if lam.custom_preprocess else (lam.image_size, lam.image_size)
         rows.append((oh, ow, ih, iw))
-    dev = batched_input["embeddings"].device
+    dev = (batched_input["embeddings"] if "embeddings" in batched_input else batched_input["images"]).device
     plan = {"points": points is not None, "boxes": boxes is not None, "masks": masks is not None,
             "sizes": torch.tensor(rows, dtype=torch.int32).to(dev), "out_hw": (max_h, max_w), "class_rows": None}
     ce = lam.prompt_encoder.class_encoder
@@ -242,21 +242,35 @@ def make_plan(lam: Lam, batched_input: Dict[str, Any]) -> Dict[str, Any]:
 
 
 def train_forward(lam: Lam, batched_input: Dict[str, Any], plan: Optional[Dict[str, Any]] = None) -> Dict[str, torch.Tensor]:
-    """Differentiable `Lam.forward` on pre-computed embeddings (lam.py:57-170 with the `embeddings` key): returns
+    """Differentiable `Lam.forward` on pre-computed embeddings (lam.py:57-170 with the `embeddings` key) or on images
+    through a FROZEN image encoder: returns
     {"logits" [B, C, Hmax, Wmax], "class_examples_embeddings" [B, M, C, D]} attached to the autograd graph of the
     parameters of lam.neck / lam.prompt_encoder / lam.mask_decoder.  With a `plan` (make_plan) the call performs no
     host synchronisation at all."""
-    if "embeddings" not in batched_input:
-        raise NotImplementedError("the native training step covers the pre-computed-embeddings configuration "
-                                  "(lam_no_vit, parameters/trainval/coco/mael.yaml); the ViT has no backward kernels")
     if plan is None:
         plan = make_plan(lam, batched_input)
-    emb = batched_input["embeddings"]
-    ops._require_cuda(emb)
-    B, N, Ce, H, W = emb.shape
-    assert H == W, "native kernels expect square feature maps"
-    g, Tn, M = H, H * W, N - 1
-    feats, _ = ops.nchw_to_tokens(emb.reshape(B * N, Ce, H, W).float().contiguous())      # [B*N*T, Ce] (input: no grad)
+    if "embeddings" in batched_input:
+        emb = batched_input["embeddings"]
+        ops._require_cuda(emb)
+        B, N, Ce, H, W = emb.shape
+        assert H == W, "native kernels expect square feature maps"
+        g, Tn, M = H, H * W, N - 1
+        feats, _ = ops.nchw_to_tokens(emb.reshape(B * N, Ce, H, W).float().contiguous())   # [B*N*T, Ce] (input: no grad)
+    elif "images" in batched_input and lam.image_encoder is not None:
+        # FROZEN encoder (train_params.freeze_backbone, lam.py:321-347): the ViT runs on its inference kernels without an
+        # autograd graph -- it has no backward kernels -- and hands its token-major features to the differentiable part
+        images = batched_input["images"]
+        ops._require_cuda(images)
+        B, N = images.shape[:2]
+        if any(p.requires_grad for p in lam.image_encoder.parameters()):
+            raise NotImplementedError("the native training step trains neck + prompt encoder + mask decoder; freeze the "
+                                      "image encoder (get_learnable_params({'freeze_backbone': True})) or pass "
+                                      "pre-computed 'embeddings' (the ViT has no backward kernels)")
+        with torch.no_grad():
+            feats, g = lam.image_encoder.encode_tokens(images.reshape(B * N, *images.shape[2:]), torch.float32)
+        Tn, M = g * g, N - 1
+    else:
+        raise ValueError("Either 'images' or 'embeddings' must be provided.")  # lam.py:165
     if lam.neck is not None:
         feats = _neck(lam.neck, feats, B * N, g)
     D = feats.shape[1]

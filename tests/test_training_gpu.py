@@ -652,3 +652,58 @@ def test_graphed_train_step_equals_the_eager_step():
     step(ep, gt)
     torch.cuda.synchronize()
     assert float((opt_b.flat_p - before).abs().max()) == 0.0
+
+
+def test_train_forward_from_images_through_a_frozen_encoder():
+    """`train_forward(images)` = the frozen ViT on its inference kernels (no autograd graph) + the differentiable neck /
+    prompt encoder / decoder: same logits and gradients as feeding the encoder's output through the `embeddings` key; an
+    encoder that still requires gradients is refused."""
+    from labelanything_b200.build_encoder import build_vit_from_config
+    from labelanything_b200.build_lam import build_lam
+    from labelanything_b200.loss import LabelAnythingLoss
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+    from labelanything_b200.training import FlatAdamW, train_forward, train_step
+
+    lam = build_lam(build_vit=lambda project_last_hidden: build_vit_from_config(
+        hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, image_size=128),
+        image_embed_dim=128, embed_dim=128, image_size=128, spatial_convs=3, class_attention=False, example_attention=False,
+        example_class_attention=True, custom_preprocess=False)
+    load_synth_weights(lam, seed=5)
+    lam = lam.cuda().train()
+    ep = {k: v.cuda() for k, v in make_episode(2, 2, 1, 128, seed=3, prompts="mixed").items()}
+    gt = torch.randint(0, 3, (2, 128, 128), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    loss_fn = LabelAnythingLoss({"focal": {"weight": 1.0, "gamma": 2.0}}, class_weighting=True)
+    with pytest.raises(NotImplementedError):
+        train_forward(lam, ep)                                   # the encoder still wants gradients
+    params = lam.get_learnable_params({"freeze_backbone": True})
+    assert all(not p.requires_grad for p in lam.image_encoder.parameters())
+
+    def grads(batch):
+        for p in params:
+            p.grad = None
+        out = train_forward(lam, batch)
+        loss = loss_fn(out, gt)["value"]
+        loss.backward()
+        return out["logits"].detach().clone(), float(loss), [None if p.grad is None else p.grad.detach().clone() for p in params]
+
+    lo_i, loss_i, g_i = grads(ep)
+    with torch.no_grad():
+        B, N = ep["images"].shape[:2]
+        emb = lam.image_encoder(ep["images"].flatten(0, 1))
+    ep_e = {k: v for k, v in ep.items() if k != "images"}
+    ep_e["embeddings"] = emb.view(B, N, *emb.shape[1:])
+    lo_e, loss_e, g_e = grads(ep_e)
+    # same arithmetic on both routes; the split-K GEMMs of the forward pass sum in a run-dependent order and the bf16
+    # roundings behind them amplify the last bits (measured 1.5 % of the logit std)
+    assert float((lo_i - lo_e).abs().max()) <= 0.06 * float(lo_e.std())
+    assert abs(loss_i - loss_e) <= 1e-2 * abs(loss_e)
+    for a, b in zip(g_i, g_e):
+        assert (a is None) == (b is None)
+        if a is not None and float(b.norm()) > 1e-6:
+            assert float((a * b).sum() / (a.norm() * b.norm())) > 0.9
+    # and a whole optimisation step runs on it
+    opt = FlatAdamW(params, lr=1e-4)
+    l0 = float(train_step(lam, loss_fn, opt, ep, gt)["loss"]["value"])
+    for _ in range(4):
+        l1 = float(train_step(lam, loss_fn, opt, ep, gt)["loss"]["value"])
+    assert l1 < l0
