@@ -148,3 +148,36 @@ def test_checkpoints_can_be_written_after_the_parameters_moved_into_the_flat_buc
     lam.load_state_dict(back)                         # loads in place: the parameters stay views of the bucket
     p0 = opt.params[0]
     assert p0.data_ptr() == opt.flat_p.data_ptr() + 4 * opt.offsets[0]
+
+
+def test_derived_operand_cache_follows_tensor_identity_version_and_lifetime():
+    """train_ops._derived: operands derived from a tensor (bf16 splits, transposes) are shared between the ops that
+    consume the same tensor, recomputed after an in-place update, and dropped when the source dies (so an address the
+    allocator hands out again cannot hit a stale entry)."""
+    import gc
+
+    from labelanything_b200 import train_ops as T
+
+    T._DERIVED.clear()
+    calls = []
+
+    def build(tag):
+        calls.append(tag)
+        return object()
+
+    x = torch.zeros(4, 8)
+    a = T._derived("t", x, lambda: build("a"))
+    assert T._derived("t", x, lambda: build("a2")) is a and calls == ["a"]          # shared
+    assert T._derived("other", x, lambda: build("b")) is not a                       # another derivation of the same tensor
+    x.add_(1)                                                                        # in-place update: new version
+    assert T._derived("t", x, lambda: build("c")) is not a and calls == ["a", "b", "c"]
+    n = len(T._DERIVED)
+    del x
+    gc.collect()
+    assert len(T._DERIVED) < n and all(ref() is not None for ref, _ in T._DERIVED.values())
+    with T.precision("bf16x3"):
+        assert T._PRECISION == "bf16x3"
+        with T.precision("bf16x6"):
+            assert T._PRECISION == "bf16x6"
+        assert T._PRECISION == "bf16x3"
+    assert T._PRECISION == "bf16"
