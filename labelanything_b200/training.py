@@ -354,7 +354,15 @@ class FlatAdamW:
             self._used[i] = True
         return hook
 
+    def _check_views(self) -> None:
+        for i in (0, len(self.params) - 1):
+            if self.params[i].data_ptr() != self.flat_p.data_ptr() + 4 * self.offsets[i]:
+                raise RuntimeError("FlatAdamW: the parameters no longer live in the optimiser's flat bucket (the model was "
+                                   "moved / re-materialised, e.g. model.to(...) or load_state_dict(assign=True), after the "
+                                   "optimiser was built); build a new FlatAdamW")
+
     def zero_grad(self) -> None:
+        self._check_views()
         self.flat_g.zero_()
         self._used = [False] * len(self.params)
         for p, o in zip(self.params, self.offsets):     # autograd may have replaced .grad (it does not when one is set)

@@ -181,3 +181,12 @@ def test_derived_operand_cache_follows_tensor_identity_version_and_lifetime():
             assert T._PRECISION == "bf16x6"
         assert T._PRECISION == "bf16x3"
     assert T._PRECISION == "bf16"
+
+
+def test_flat_adamw_notices_parameters_that_left_the_bucket():
+    lin = torch.nn.Linear(4, 3)
+    opt = FlatAdamW(lin.parameters())
+    opt.zero_grad()
+    lin.weight.data = lin.weight.data.clone()            # what model.to(other_device) does to a parameter
+    with pytest.raises(RuntimeError, match="flat bucket"):
+        opt.zero_grad()
