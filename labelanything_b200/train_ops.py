@@ -177,7 +177,9 @@ def _gemm_f32(a16: torch.Tensor, w16: torch.Tensor, bias=None, act=ACT_NONE) -> 
     M, K = a16.shape
     N = w16.shape[0]
     tiles = -(-M // 128) * -(-N // (256 if N >= 256 else 128 if N > 64 else 64))
-    if act == ACT_NONE and K >= 2048 and tiles <= 32:
+    # K >= 8192 singles out the weight gradients (contraction over token rows); forward and data-gradient products
+    # (K <= 2304 features) stay on the unsplit kernel, whose summation order is fixed: the forward pass is reproducible
+    if act == ACT_NONE and K >= 8192 and tiles <= 32:
         return ops.gemm_splitk(a16, w16, bias)
     return ops.gemm(a16, w16, bias, act=act, out_dtype=torch.float32)
 
