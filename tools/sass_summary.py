@@ -1,5 +1,5 @@
 """Per-kernel counts of the SASS mnemonics that prove a Blackwell-native path (B200_PROFILING.md): UTC*MMA =
-tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTCCP = tcgen05.cp, UTMALDG / UTMASTG / UBLKCP = TMA, HMMA = legacy
+tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTCCP = tcgen05.cp, UTMALDG / UTMASTG / UTMAREDG / UBLKCP = TMA (REDG: reduce store), HMMA = legacy
 mma.sync.   python tools/sass_summary.py > profiles/rNN_sass_summary.txt   (runs here: cuobjdump needs no GPU)"""
 import re
 import subprocess
@@ -9,7 +9,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "labelanything_b200" / "liblabelanything_b200.so"
-PAT = re.compile(r"\b(UTC[A-Z]*MMA|UTCCP|LDTM|STTM|UTMALDG|UTMASTG|UBLKCP|UTMAPF|HMMA|SYNCS|MUFU)\b")
+PAT = re.compile(r"\b(UTC[A-Z]*MMA|UTCCP|LDTM|STTM|UTMALDG|UTMASTG|UTMAREDG|UBLKCP|UTMAPF|HMMA|SYNCS|MUFU)\b")
 
 out = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True, check=True).stdout
 kernels: "OrderedDict[str, Counter]" = OrderedDict()
