@@ -32,7 +32,7 @@ from .prompt_encoder import PromptImageEncoder, RandomMatrixEncoder
 from .transformer import TwoWayTransformer
 from .utils import BatchKeys, ResultDict, get_preprocess_shape
 
-__all__ = ["train_forward", "make_plan", "FlatAdamW", "train_step", "GraphedTrainStep"]
+__all__ = ["train_forward", "make_plan", "FlatAdamW", "train_step", "GraphedTrainStep", "ConstantWithWarmup"]
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -427,16 +427,38 @@ class FlatAdamW:
 
 
 def train_step(lam: Lam, loss_fn, opt: FlatAdamW, batched_input: Dict[str, Any], gt: torch.Tensor,
-               timed: bool = False) -> Dict[str, Any]:
-    """One optimisation step: forward, LabelAnythingLoss, backward, gradient all-reduce, AdamW (run.py:425-590)."""
+               timed: bool = False, loss_normalizer: float = 1.0) -> Dict[str, Any]:
+    """One optimisation step: forward, LabelAnythingLoss, backward, gradient all-reduce, AdamW (run.py:425-590).
+    `loss_normalizer` divides the loss before backward, as `Run._backward` does (run.py:359-361)."""
     opt.attach(lam)
     opt.zero_grad()
     result = train_forward(lam, batched_input)
     loss = loss_fn(result, gt)
     value = loss["value"] if isinstance(loss, dict) else loss
-    value.backward()
+    (value if loss_normalizer == 1.0 else value / loss_normalizer).backward()
     opt.step(timed=timed)
     return {"loss": loss, **result}
+
+
+class ConstantWithWarmup:
+    """The reference's default schedule (`scheduler: constant_with_warmup`, parameters/trainval/coco/mael.yaml:34-37,
+    transformers.get_constant_schedule_with_warmup): lr = base * min(1, step / num_warmup_steps).  `step()` sets `opt.lr`,
+    which eager steps pass by value and `GraphedTrainStep` uploads before every replay."""
+
+    def __init__(self, opt: FlatAdamW, num_warmup_steps: int) -> None:
+        self.opt, self.base_lr, self.num_warmup_steps, self.last_step = opt, opt.lr, int(num_warmup_steps), 0
+        self._set()
+
+    def _set(self) -> None:
+        w = self.num_warmup_steps
+        self.opt.lr = self.base_lr * (min(1.0, self.last_step / max(1.0, w)) if w > 0 else 1.0)
+
+    def step(self) -> None:
+        self.last_step += 1
+        self._set()
+
+    def get_last_lr(self) -> List[float]:
+        return [self.opt.lr]
 
 
 def _loss_value(loss_fn, logits: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:

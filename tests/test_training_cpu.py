@@ -190,3 +190,21 @@ def test_flat_adamw_notices_parameters_that_left_the_bucket():
     lin.weight.data = lin.weight.data.clone()            # what model.to(other_device) does to a parameter
     with pytest.raises(RuntimeError, match="flat bucket"):
         opt.zero_grad()
+
+
+def test_constant_with_warmup_matches_the_transformers_schedule():
+    """lr_lambda of transformers.get_constant_schedule_with_warmup: step / max(1, warmup) below the warm-up, then 1."""
+    from transformers import get_constant_schedule_with_warmup
+
+    from labelanything_b200.training import ConstantWithWarmup
+
+    lin = torch.nn.Linear(4, 3)
+    ref_opt = torch.optim.AdamW(lin.parameters(), lr=5e-5)
+    ref = get_constant_schedule_with_warmup(ref_opt, num_warmup_steps=4)
+    opt = FlatAdamW(torch.nn.Linear(4, 3).parameters(), lr=5e-5)
+    sched = ConstantWithWarmup(opt, 4)
+    for _ in range(7):
+        assert abs(sched.get_last_lr()[0] - ref.get_last_lr()[0]) < 1e-12
+        ref_opt.step()
+        ref.step()
+        sched.step()
