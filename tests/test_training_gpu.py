@@ -707,3 +707,57 @@ def test_train_forward_from_images_through_a_frozen_encoder():
     for _ in range(4):
         l1 = float(train_step(lam, loss_fn, opt, ep, gt)["loss"]["value"])
     assert l1 < l0
+
+
+def test_config4_size_gradients_match_the_oracle():
+    """BASELINE configs[3] at its real size -- ViT-MAE-L embeddings 1024 x 30 x 30, embed 256, 480 px, 2-way 5-shot (30
+    sequences of 900 tokens, nine sparse tokens each, prompt masks resized 64 -> 30, 120 x 120 decoder maps): every
+    gradient of the fp32-accurate mode against autograd through the pinned CPU oracle on the same weights."""
+    import lam_oracle as O
+    import loss_oracle as LO
+
+    from labelanything_b200.build_lam import build_lam_no_vit
+    from labelanything_b200.loss import LabelAnythingLoss
+    from labelanything_b200.synthetic import load_synth_weights, make_episode
+    from labelanything_b200.training import train_forward
+
+    lam = build_lam_no_vit(image_embed_dim=1024, embed_dim=256, image_size=480, spatial_convs=3, class_attention=False,
+                           example_attention=False, example_class_attention=True, custom_preprocess=False)
+    load_synth_weights(lam, seed=4)
+    ep = make_episode(1, 2, 5, 480, seed=11, prompts="mixed", embeddings=(1024, 30))
+    cfg = {"image_size": 480, "image_embedding_size": (30, 30), "has_neck": True, "spatial_convs": 3,
+           "class_attention": False, "example_attention": False, "example_class_attention": True, "custom_preprocess": False}
+    gt = torch.randint(0, 3, (1, 30, 30), generator=torch.Generator().manual_seed(3)).repeat_interleave(16, 1) \
+        .repeat_interleave(16, 2)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in lam.state_dict().items()}
+    ref = O.lam_forward(sd, cfg, dict(ep), None)["logits"]
+    wm, _ = LO.get_weight_matrix_from_labels(gt.numpy().copy(), 3)
+    ce = F.cross_entropy(ref, gt, reduction="none")
+    ref_loss = (torch.pow(1 - torch.exp(-ce), 2.0) * torch.from_numpy(wm) * ce).mean()
+    ref_loss.backward()
+
+    lam = lam.cuda().train()
+    with T.precision("bf16x3"):
+        out = train_forward(lam, {k: v.cuda() for k, v in ep.items()})
+        loss = LabelAnythingLoss({"focal": {"weight": 1.0, "gamma": 2.0}}, class_weighting=True)(out, gt.cuda())["value"]
+        loss.backward()
+    got = out["logits"].detach().cpu()
+    std = float(ref.detach().std())
+    assert float((got - ref.detach()).abs().max()) < 2e-3 * std
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss))
+    rels, num, den = [], 0.0, 0.0
+    for k, p in lam.named_parameters():
+        want = sd[k].grad
+        if want is None or float(want.double().norm()) < 1e-7:
+            assert p.grad is None or float(p.grad.double().norm()) < 1e-4, k
+            continue
+        d2 = float((p.grad.detach().cpu().double() - want.double()).pow(2).sum())
+        r2 = float(want.double().pow(2).sum())
+        num, den = num + d2, den + r2
+        rels.append(((d2 / r2) ** 0.5, k))
+    rels.sort()
+    total = (num / den) ** 0.5
+    print(f"config 4 size, bf16x3: logits max {float((got - ref.detach()).abs().max()) / std:.2e} of std, loss {float(loss):.6f} "
+          f"vs {float(ref_loss):.6f}, {len(rels)} gradients, rel err all {total:.2e}, median {rels[len(rels) // 2][0]:.2e}, "
+          f"worst {rels[-1][0]:.2e} ({rels[-1][1]})")
+    assert len(rels) > 200 and total < 5e-3 and rels[len(rels) // 2][0] < 5e-3 and rels[-1][0] < 0.1, (total, rels[-3:])
